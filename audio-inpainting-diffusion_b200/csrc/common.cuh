@@ -1,0 +1,112 @@
+// Shared device/host types for the B200 denoiser path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aid {
+
+// A [B, C, F, T] fp32 activation view.  T is contiguous and the (F, T) plane of one channel is
+// contiguous (F-slices of a wider buffer keep that property), so only batch and channel strides are free.
+// `stats` (optional) points at this tensor's group-norm accumulators: [B][8][2] doubles = (sum, sum of squares)
+// over the 8 channel groups of the *whole* logical tensor the view belongs to (unet.py:147-163).
+struct TV {
+    float* p = nullptr;
+    int B = 0, C = 0, F = 0, T = 0;
+    long long sb = 0, sc = 0;  // element strides
+    double* stats = nullptr;
+};
+
+static inline TV make_tv(float* p, int B, int C, int F, int T) {
+    TV v; v.p = p; v.B = B; v.C = C; v.F = F; v.T = T; v.sc = (long long)F * T; v.sb = v.sc * C; return v;
+}
+// rows [f0, f0+nf) of v
+static inline TV slice_f(const TV& v, int f0, int nf) {
+    TV r = v; r.p = v.p + (long long)f0 * v.T; r.F = nf; r.stats = nullptr; return r;
+}
+// channels [c0, c0+nc) of v
+static inline TV slice_c(const TV& v, int c0, int nc) {
+    TV r = v; r.p = v.p + (long long)c0 * v.sc; r.C = nc; r.stats = nullptr; return r;
+}
+
+struct ConvEpilogue {
+    // out = alpha * (acc * gate[c] + R) + beta * R2        (unet.py:482, 470, 491, 794, 817)
+    const float* gate = nullptr;  // per-channel gate vector (adaLN gate Linear output), or null => 1
+    long long gate_bstride = 0;   // 0 when sigma is shared by the batch
+    TV R;                         // R.p == nullptr => no residual
+    TV R2;                        // R2.p == nullptr => none
+    float alpha = 1.f, beta = 0.f;
+    double* stats = nullptr;      // accumulate (sum, sumsq) of `out` per (b, group of Cout/8 channels)
+};
+
+#define AID_CUDA_CHECK(expr)                                                         \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) throw aid::CudaError(_e, #expr, __FILE__, __LINE__);   \
+    } while (0)
+
+struct CudaError {
+    cudaError_t code; const char* expr; const char* file; int line;
+    CudaError(cudaError_t c, const char* e, const char* f, int l) : code(c), expr(e), file(f), line(l) {}
+};
+
+extern unsigned long long g_launch_count;  // kernels launched by this library (bench.py's gpu_launches)
+#define AID_COUNT_LAUNCH(n) (aid::g_launch_count += (n))
+
+// ---- launchers (defined in the .cu files) ---------------------------------------------------------
+void launch_group_stats(const TV& x, double* stats, cudaStream_t s);
+void launch_gn_act(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
+                   long long affine_bstride, bool gelu, const TV& out, cudaStream_t s);
+void launch_combine(const TV& a, const TV& b, float alpha, float beta, const TV& out, double* stats, cudaStream_t s);
+void launch_resample_down(const TV& x, const TV& out, cudaStream_t s);
+void launch_resample_up(const TV& x, const TV& out, cudaStream_t s);
+void launch_conv_simt(const TV& a, const float* wp, int KF, int KT, int dil, const TV& out, const ConvEpilogue& ep,
+                      cudaStream_t s);
+void launch_attention(const TV& h, const float* qk, const TV& out, cudaStream_t s);
+void launch_embedding(const float* c_noise, int n_sigma, const float* rff, const float* w0, const float* b0,
+                      const float* w1, const float* b1, const float* w2, const float* b2, float* emb, cudaStream_t s);
+void launch_mod_vectors(const float* emb, int n_sigma, const float* W, const float* bias, int total, float* out,
+                        cudaStream_t s);
+
+// FFT / CQT
+struct FftPlan {
+    int L = 0, N1 = 0, N2 = 0;
+    const float2* tw = nullptr;  // W_L^k = exp(-2*pi*i*k/L), k in [0, L)
+};
+// batched length-L complex FFT via the four-step split L = N1*N2.
+//  in_real != null : input is real [B][in_stride], scaled by in_scale
+//  in_cplx != null : input complex [B][L]
+//  out_cplx != null: complex output [B][L] (unscaled)
+//  out_real != null: out_real[b][n] = out_scale * Re(result) + skip_scale * skip[b][n]   (skip may be null)
+void launch_fft_big(const FftPlan& plan, int B, bool inverse, const float* in_real, long long in_stride, float in_scale,
+                    const float2* in_cplx, float2* tmp, float2* out_cplx, float* out_real, long long out_stride,
+                    float out_scale, const float* skip, long long skip_stride, float skip_scale, cudaStream_t s);
+
+struct CqtTables {
+    int L = 0, K = 0, bins = 0, nocts = 0;
+    const int* centre = nullptr;   // [K] centre bin of band k (bands 1..K of the plan)
+    const int* Lg = nullptr;       // [K] window length
+    const int* woff = nullptr;     // [K] offset of band k's window in win / dual
+    const float* win = nullptr;    // analysis windows, "peak at index 0" order
+    const float* dual = nullptr;   // synthesis windows * M_o / D
+    const int* klo = nullptr;      // [L/2+1] first band covering bin n (or K if none)
+    const int* khi = nullptr;      // [L/2+1] last band covering bin n (or -1)
+    const float* hhpf = nullptr;   // [L]
+    int M[16] = {0};               // coefficients per band for octave o
+    long long yoff[16] = {0};      // offset of octave o in the per-clip synthesis scratch (complex elements)
+    long long ytotal = 0;          // complex elements per clip in the synthesis scratch
+};
+// spec [B][L] complex -> one octave's coefficients, written as C[b, 0/1, band_in_oct, frame] (re, im channels)
+void launch_cqt_analysis_oct(const CqtTables& t, const FftPlan& fp, int oct, const float2* spec, const TV& C, cudaStream_t s);
+// C (re, im channels) of one octave -> FFT_M of every band into scratch Y [B][ytotal]
+void launch_cqt_synth_oct(const CqtTables& t, const FftPlan& fp, int oct, const TV& C, float2* Y, cudaStream_t s);
+// gather Y into the Hermitian full spectrum fr [B][L]
+void launch_cqt_synth_gather(const CqtTables& t, int B, const float2* Y, float2* fr, cudaStream_t s);
+void launch_spec_mul_real(int B, int L, float2* spec, const float* h, cudaStream_t s);
+
+// EDM sampler element-wise steps (sampler.py:214, 141-147, 230-251)
+void launch_axpy_noise(float* x, const float* eps, float scale, long long n, cudaStream_t s);
+void launch_edm_step(const float* xin, const float* xhat, const float* y, const float* mask, long long mask_n, long long n,
+                     float sigma, float h, int mode, const float* d_prev, const float* xbase, float* d_out, float* x_out,
+                     cudaStream_t s);
+
+}  // namespace aid

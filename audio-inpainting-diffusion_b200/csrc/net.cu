@@ -1,0 +1,764 @@
+// Network executor + C ABI (include/aid_b200.h) for the CQT-octave U-Net denoiser.
+//
+// Host-side mirror of Unet_CQT_oct_with_attention (unet.py:583-845): the constructor builds the same
+// module tree / state-dict schema, aid_unet_forward() replays forward() as a fixed sequence of kernel
+// launches on one stream over a caller-owned workspace (first-fit planned, no allocation per call).
+// Concatenations (unet.py:769-774, 814) and slices (unet.py:821-822) are strided views, never copies.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/aid_b200.h"
+#include "common.cuh"
+#include "cqt_plan.hpp"
+
+namespace aid {
+
+unsigned long long g_launch_count = 0;
+
+static const float kInvSqrt2 = 0.70710678118654752440f;
+
+// ---- weights --------------------------------------------------------------------------------------
+struct Weight {
+    std::string name;
+    std::vector<int64_t> shape;
+    std::vector<float> host;
+    bool loaded = false;
+    bool ignored = false;  // accepted but unused (resampler kernels are constants)
+    size_t numel() const { size_t n = 1; for (auto d : shape) n *= (size_t)d; return n; }
+};
+
+struct ConvW { int widx = -1; float* wp = nullptr; int Cin = 0, Cout = 0, KF = 1, KT = 1; };
+struct LinRef { int w = -1, b = -1; int off = -1, N = 0; };
+struct NormRef { int widx = -1; float* gamma = nullptr; };
+
+struct ResBlk {
+    int dim = 0, dim_out = 0, N = 0, nd = 0, Fdim = 0;
+    bool k1x1 = false, after = false, attn = false;
+    ConvW proj_in, res_conv, proj_out, a_in, a_out, qk;
+    std::vector<ConvW> H;
+    std::vector<LinRef> affine, gate;
+    std::vector<NormRef> norm;
+    LinRef affine2, gate2;
+    NormRef norm2;
+};
+
+struct Level { ResBlk init, main; ConvW pyr; };
+
+// ---- workspace arena: first-fit over a caller-owned slab; "dry" mode only measures the peak -----------
+struct Arena {
+    char* base = nullptr; size_t cap = 0, peak = 0; bool dry = true;
+    std::map<size_t, size_t> used;  // offset -> size
+    void reset(char* b, size_t c, bool d) { base = b; cap = c; dry = d; peak = 0; used.clear(); }
+    void* alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes == 0) bytes = 256;
+        size_t off = 0;
+        for (auto& kv : used) {
+            if (kv.first >= off + bytes) break;
+            off = std::max(off, kv.first + kv.second);
+        }
+        used[off] = bytes;
+        peak = std::max(peak, off + bytes);
+        if (!dry && off + bytes > cap) throw std::runtime_error("workspace too small");
+        return dry ? reinterpret_cast<void*>(0x100000 + off) : base + off;
+    }
+    void release(void* p) {
+        const size_t off = dry ? reinterpret_cast<size_t>(p) - 0x100000 : (size_t)((char*)p - base);
+        used.erase(off);
+    }
+};
+
+struct Net {
+    aid_config cfg{};
+    int device = 0;
+    std::string err;
+    std::vector<Weight> weights;
+    std::map<std::string, int> windex;
+    std::vector<Level> downs;
+    ResBlk mid_main, mid_out;
+    std::vector<ResBlk> ups_main, ups_out;
+    std::vector<LinRef*> lin_all;  // every adaLN Linear, in mod-vector order
+    int total_mod = 0;
+    int emb_idx[7] = {-1, -1, -1, -1, -1, -1, -1};  // RFF_freq, W0,b0,W1,b1,W2,b2
+    bool finalized = false;
+    // device state
+    float* dweights = nullptr;   // packed conv weights + gammas + embedding + mod matrix
+    float* d_emb[7] = {nullptr};
+    float* d_modW = nullptr; float* d_modB = nullptr;
+    CqtPlanHost plan;
+    CqtTables tabs;
+    FftPlan fft;
+    void* d_tables = nullptr;
+    int n_stat_slots = 0;
+};
+
+static int add_weight(Net& n, const std::string& name, std::vector<int64_t> shape, bool ignored = false) {
+    Weight w; w.name = name; w.shape = std::move(shape); w.ignored = ignored;
+    n.weights.push_back(std::move(w));
+    n.windex[name] = (int)n.weights.size() - 1;
+    return (int)n.weights.size() - 1;
+}
+
+static ConvW add_conv(Net& n, const std::string& name, int Cout, int Cin, int KF, int KT, bool conv1d = false) {
+    ConvW c; c.Cin = Cin; c.Cout = Cout; c.KF = KF; c.KT = KT;
+    c.widx = conv1d ? add_weight(n, name + ".weight", {Cout, Cin, 1}) : add_weight(n, name + ".weight", {Cout, Cin, KF, KT});
+    return c;
+}
+
+static LinRef add_lin(Net& n, const std::string& name, int N) {
+    LinRef l; l.N = N;
+    l.w = add_weight(n, name + ".weight", {N, 256});
+    l.b = add_weight(n, name + ".bias", {N});
+    l.off = n.total_mod; n.total_mod += N;
+    return l;
+}
+
+// unet.py:382-448
+static void build_resblk(Net& n, ResBlk& k, const std::string& p, int dim, int dim_out, int nd, bool k1x1, bool after,
+                         bool attn, int Fdim) {
+    k.dim = dim; k.dim_out = dim_out; k.nd = nd; k.k1x1 = k1x1; k.after = after; k.attn = attn; k.Fdim = Fdim;
+    k.N = after ? dim : dim_out;
+    const int N = k.N;
+    if (N % 8 != 0) throw std::invalid_argument("block width must be a multiple of 8 (8 norm groups): " + p);
+    if (after && N != dim_out) k.proj_out = add_conv(n, p + ".proj_out", dim_out, N, 1, 1);
+    if (dim != dim_out) k.res_conv = add_conv(n, p + ".res_conv", dim_out, dim, 1, 1);
+    if (dim != N) k.proj_in = add_conv(n, p + ".proj_in", N, dim, 1, 1);
+    for (int i = 0; i < nd; ++i) {
+        const std::string si = std::to_string(i);
+        NormRef nr; nr.widx = add_weight(n, p + ".norm." + si + ".gamma", {1, N, 1, 1});
+        k.norm.push_back(nr);
+        k.affine.push_back(add_lin(n, p + ".affine." + si, N));
+        k.gate.push_back(add_lin(n, p + ".gate." + si, N));
+        k.H.push_back(k1x1 ? add_conv(n, p + ".H." + si, N, N, 1, 1) : add_conv(n, p + ".H." + si, N, N, 5, 3));
+    }
+    if (attn) {
+        const int heads = n.cfg.num_heads;
+        k.norm2.widx = add_weight(n, p + ".norm2.gamma", {1, N, 1, 1});
+        k.affine2 = add_lin(n, p + ".affine2", N);
+        k.gate2 = add_lin(n, p + ".gate2", N);
+        k.qk = add_conv(n, p + ".attn_block.qk", 2 * heads * Fdim, heads * Fdim, 1, 1, /*conv1d=*/true);
+        k.a_in = add_conv(n, p + ".attn_block.proj_in", heads, N, 1, 1);
+        k.a_out = add_conv(n, p + ".attn_block.proj_out", N, heads, 1, 1);
+    }
+}
+
+static void collect_lins(Net& n, ResBlk& k) {
+    for (auto& l : k.affine) n.lin_all.push_back(&l);
+    for (auto& l : k.gate) n.lin_all.push_back(&l);
+    if (k.attn) { n.lin_all.push_back(&k.affine2); n.lin_all.push_back(&k.gate2); }
+}
+
+// unet.py:587-721
+static void build_net(Net& n) {
+    const aid_config& c = n.cfg;
+    if (c.num_octs < 1 || c.num_octs > AID_MAX_OCTS) throw std::invalid_argument("num_octs out of range");
+    if (c.emb_dim != 256) throw std::invalid_argument("emb_dim must be 256");
+    if (c.num_bottleneck_layers != 1) throw std::invalid_argument("num_bottleneck_layers must be 1");
+    if (c.num_heads < 1) throw std::invalid_argument("num_heads must be >= 1");
+    const int no = c.num_octs, bins = c.bins_per_oct;
+    n.emb_idx[0] = add_weight(n, "embedding.RFF_freq", {1, 32});
+    const int dims[4] = {64, 128, 256, 256};
+    for (int i = 0; i < 3; ++i) {
+        n.emb_idx[1 + 2 * i] = add_weight(n, "embedding.MLP." + std::to_string(i) + ".weight", {dims[i + 1], dims[i]});
+        n.emb_idx[2 + 2 * i] = add_weight(n, "embedding.MLP." + std::to_string(i) + ".bias", {dims[i + 1]});
+    }
+    add_weight(n, "downsamplerT.kernel", {8}, true);
+    add_weight(n, "upsamplerT.kernel", {8}, true);
+    n.downs.resize(no);
+    for (int i = 0; i < no; ++i) {
+        const int din = i == 0 ? c.Ns[0] : c.Ns[i - 1], dout = c.Ns[i];
+        const std::string p = "downs." + std::to_string(i);
+        build_resblk(n, n.downs[i].init, p + ".0", 2, din, 1, true, false, false, bins);
+        n.downs[i].pyr = add_conv(n, p + ".1", dout, 2, 5, 3);
+        build_resblk(n, n.downs[i].main, p + ".2", din, dout, c.num_dils[i], false, false, c.attention_layers[i] != 0, (i + 1) * bins);
+    }
+    build_resblk(n, n.mid_out, "middle.0.0", c.Ns[no - 1], 2, 1, true, true, false, no * bins);
+    build_resblk(n, n.mid_main, "middle.0.1", c.Ns[no - 1], c.Ns[no - 1], c.num_dils[no - 1], false, false,
+                 c.attention_layers[no] != 0, no * bins);
+    n.ups_main.resize(no); n.ups_out.resize(no);
+    for (int i = 0; i < no; ++i) {
+        const int j = no - 1 - i;
+        const int din = 2 * c.Ns[j], dout = j == 0 ? c.Ns[0] : c.Ns[j - 1];
+        const std::string p = "ups." + std::to_string(i);
+        build_resblk(n, n.ups_out[i], p + ".0", dout, 2, 1, true, true, false, (j + 1) * bins);
+        build_resblk(n, n.ups_main[i], p + ".1", din, dout, c.num_dils[j], false, false, c.attention_layers[j] != 0, (j + 1) * bins);
+    }
+    for (auto& l : n.downs) { collect_lins(n, l.init); collect_lins(n, l.main); }
+    collect_lins(n, n.mid_out); collect_lins(n, n.mid_main);
+    for (int i = 0; i < no; ++i) { collect_lins(n, n.ups_out[i]); collect_lins(n, n.ups_main[i]); }
+    n.plan.build(no, bins, c.sample_rate, c.audio_len, c.window_kind, c.beta);
+}
+
+// ---- device upload / repack ---------------------------------------------------------------------------
+// w[co][ci][tap] -> wp[(ci*taps + tap)*Cout + co]
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin, int taps) {
+    const long long n = (long long)Cout * Cin * taps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        const long long k = i / Cout;
+        wp[i] = w[(long long)co * Cin * taps + k];
+    }
+}
+
+static void upload_tables(Net& n);
+
+static void finalize_net(Net& n) {
+    for (auto& w : n.weights)
+        if (!w.loaded && !w.ignored) throw std::runtime_error("missing weight: " + w.name);
+    AID_CUDA_CHECK(cudaSetDevice(n.device));
+    size_t total = 0, max_conv = 0;
+    auto al = [](size_t v) { return (v + 63) & ~(size_t)63; };
+    std::vector<ConvW*> convs;
+    std::vector<NormRef*> norms;
+    auto visit = [&](ResBlk& k) {
+        for (ConvW* c : {&k.proj_in, &k.res_conv, &k.proj_out, &k.a_in, &k.a_out, &k.qk}) if (c->widx >= 0) convs.push_back(c);
+        for (auto& c : k.H) convs.push_back(&c);
+        for (auto& nr : k.norm) norms.push_back(&nr);
+        if (k.attn) norms.push_back(&k.norm2);
+    };
+    for (auto& l : n.downs) { visit(l.init); visit(l.main); convs.push_back(&l.pyr); }
+    visit(n.mid_main); visit(n.mid_out);
+    for (auto& k : n.ups_main) visit(k);
+    for (auto& k : n.ups_out) visit(k);
+    for (auto* c : convs) { size_t e = n.weights[c->widx].numel(); total += al(e); max_conv = std::max(max_conv, e); }
+    for (auto* nr : norms) total += al(n.weights[nr->widx].numel());
+    for (int i = 0; i < 7; ++i) total += al(n.weights[n.emb_idx[i]].numel());
+    total += al((size_t)n.total_mod * 256) + al((size_t)n.total_mod);
+    AID_CUDA_CHECK(cudaMalloc(&n.dweights, total * sizeof(float)));
+    float* stage = nullptr;
+    AID_CUDA_CHECK(cudaMalloc(&stage, max_conv * sizeof(float)));
+    size_t off = 0;
+    for (auto* c : convs) {
+        Weight& w = n.weights[c->widx];
+        const size_t e = w.numel();
+        AID_CUDA_CHECK(cudaMemcpy(stage, w.host.data(), e * sizeof(float), cudaMemcpyHostToDevice));
+        c->wp = n.dweights + off;
+        pack_conv_weight_kernel<<<(int)std::min<size_t>(4096, (e + 255) / 256), 256>>>(stage, c->wp, c->Cout, c->Cin, c->KF * c->KT);
+        AID_CUDA_CHECK(cudaGetLastError());
+        AID_CUDA_CHECK(cudaDeviceSynchronize());
+        off += al(e);
+    }
+    AID_CUDA_CHECK(cudaFree(stage));
+    for (auto* nr : norms) {
+        Weight& w = n.weights[nr->widx];
+        nr->gamma = n.dweights + off;
+        AID_CUDA_CHECK(cudaMemcpy(nr->gamma, w.host.data(), w.numel() * sizeof(float), cudaMemcpyHostToDevice));
+        off += al(w.numel());
+    }
+    for (int i = 0; i < 7; ++i) {
+        Weight& w = n.weights[n.emb_idx[i]];
+        n.d_emb[i] = n.dweights + off;
+        AID_CUDA_CHECK(cudaMemcpy(n.d_emb[i], w.host.data(), w.numel() * sizeof(float), cudaMemcpyHostToDevice));
+        off += al(w.numel());
+    }
+    n.d_modW = n.dweights + off; off += al((size_t)n.total_mod * 256);
+    n.d_modB = n.dweights + off; off += al((size_t)n.total_mod);
+    for (LinRef* l : n.lin_all) {
+        AID_CUDA_CHECK(cudaMemcpy(n.d_modW + (size_t)l->off * 256, n.weights[l->w].host.data(), (size_t)l->N * 256 * sizeof(float), cudaMemcpyHostToDevice));
+        AID_CUDA_CHECK(cudaMemcpy(n.d_modB + l->off, n.weights[l->b].host.data(), (size_t)l->N * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    for (auto& w : n.weights) { std::vector<float>().swap(w.host); }
+    upload_tables(n);
+    n.finalized = true;
+}
+
+// CQT tables + FFT twiddles live in one device allocation made at create time (no weights needed).
+static void upload_tables(Net& n) {
+    if (n.d_tables) return;
+    AID_CUDA_CHECK(cudaSetDevice(n.device));
+    const CqtPlanHost& p = n.plan;
+    const int L = p.L, K = p.K;
+    std::vector<float2> tw(L);
+    for (int k = 0; k < L; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)L;
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t bytes = al(L * sizeof(float2)) + 3 * al(K * sizeof(int)) + 2 * al(p.win.size() * sizeof(float)) +
+                   2 * al((L / 2 + 1) * sizeof(int)) + al(L * sizeof(float));
+    AID_CUDA_CHECK(cudaMalloc(&n.d_tables, bytes));
+    char* d = (char*)n.d_tables;
+    auto put = [&](const void* src, size_t nb) { void* dst = d; AID_CUDA_CHECK(cudaMemcpy(dst, src, nb, cudaMemcpyHostToDevice)); d += al(nb); return dst; };
+    n.fft.tw = (const float2*)put(tw.data(), L * sizeof(float2));
+    int lg = 0; while ((1 << lg) < L) ++lg;
+    n.fft.L = L; n.fft.N1 = 1 << ((lg + 1) / 2); n.fft.N2 = L / n.fft.N1;
+    CqtTables& t = n.tabs;
+    t.L = L; t.K = K; t.bins = p.bins; t.nocts = p.nocts;
+    t.centre = (const int*)put(p.centre.data(), K * sizeof(int));
+    t.Lg = (const int*)put(p.Lg.data(), K * sizeof(int));
+    t.woff = (const int*)put(p.woff.data(), K * sizeof(int));
+    t.win = (const float*)put(p.win.data(), p.win.size() * sizeof(float));
+    t.dual = (const float*)put(p.dual.data(), p.dual.size() * sizeof(float));
+    t.klo = (const int*)put(p.klo.data(), (L / 2 + 1) * sizeof(int));
+    t.khi = (const int*)put(p.khi.data(), (L / 2 + 1) * sizeof(int));
+    t.hhpf = (const float*)put(p.hhpf.data(), L * sizeof(float));
+}
+
+static void fill_host_tables(Net& n) {
+    const CqtPlanHost& p = n.plan;
+    CqtTables& t = n.tabs;
+    t.L = p.L; t.K = p.K; t.bins = p.bins; t.nocts = p.nocts;
+    long long yo = 0;
+    for (int o = 0; o < p.nocts; ++o) { t.M[o] = p.size_per_oct[o]; t.yoff[o] = yo; yo += (long long)p.bins * t.M[o]; }
+    t.ytotal = yo;
+}
+
+// ---- forward ------------------------------------------------------------------------------------------
+struct Ctx {
+    Net* n = nullptr; Arena ar; cudaStream_t s = nullptr; int B = 0, nsig = 1;
+    float* mod = nullptr; double* stats_base = nullptr; int slot = 0;
+    bool dry() const { return ar.dry; }
+    float* allocf(long long nfl) { return (float*)ar.alloc((size_t)nfl * sizeof(float)); }
+    void release(void* p) { ar.release(p); }
+    double* new_slot() { double* r = stats_base ? stats_base + (size_t)slot * B * 16 : nullptr; ++slot; return dry() ? reinterpret_cast<double*>(0x10) : r; }
+    long long modstride() const { return nsig > 1 ? n->total_mod : 0; }
+};
+
+#define RUN(call) do { if (!c.dry()) { call; } } while (0)
+
+static void conv(Ctx& c, const TV& a, const ConvW& w, int dil, const TV& out, ConvEpilogue ep) {
+    if (a.C != w.Cin || out.C != w.Cout || a.F != out.F || a.T != out.T || a.B != out.B)
+        throw std::runtime_error("conv: shape mismatch");
+    if (ep.stats && (w.Cout % 8 != 0)) throw std::runtime_error("conv: statistics need Cout % 8 == 0");
+    RUN(launch_conv_simt(a, w.wp, w.KF, w.KT, dil, out, ep, c.s));
+}
+
+// unet.py:452-493.  `accum` (decoder out blocks, unet.py:817): out = (accum + block(x)) / sqrt(2), may alias out.
+static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = nullptr) {
+    const int B = in.B, F = in.F, T = in.T, N = k.N;
+    if (in.C != k.dim || out.C != k.dim_out) throw std::runtime_error("resblock: channel mismatch");
+    const long long plane = (long long)B * N * F * T;
+    const long long n_grp = (long long)(N / 8) * F * T;
+    float* xbuf = c.allocf(plane);
+    float* abuf = c.allocf(plane);
+    TV x = make_tv(xbuf, B, N, F, T), a = make_tv(abuf, B, N, F, T);
+    TV cur;
+    if (k.dim != N) {
+        ConvEpilogue ep; ep.stats = x.stats = c.new_slot();
+        conv(c, in, k.proj_in, 1, x, ep);
+        cur = x;
+    } else {
+        cur = in;
+        if (!cur.stats) { cur.stats = c.new_slot(); RUN(launch_group_stats(cur, cur.stats, c.s)); }
+    }
+    if (k.attn) {
+        const int heads = k.a_in.Cout;
+        RUN(launch_gn_act(cur, cur.stats, n_grp, k.norm2.gamma, c.mod + k.affine2.off, c.modstride(), false, a, c.s));
+        TV h = make_tv(c.allocf((long long)B * heads * F * T), B, heads, F, T);
+        conv(c, a, k.a_in, 1, h, ConvEpilogue());
+        TV hflat = make_tv(h.p, B, heads * F, 1, T);
+        TV qk = make_tv(c.allocf((long long)B * 2 * heads * F * T), B, 2 * heads * F, 1, T);
+        conv(c, hflat, k.qk, 1, qk, ConvEpilogue());
+        TV o = make_tv(c.allocf((long long)B * heads * F * T), B, heads, F, T);
+        RUN(launch_attention(h, qk.p, o, c.s));
+        ConvEpilogue ep;
+        ep.gate = c.mod + k.gate2.off; ep.gate_bstride = c.modstride();
+        ep.R = cur; ep.alpha = kInvSqrt2; ep.stats = c.new_slot();
+        x.stats = ep.stats;
+        conv(c, o, k.a_out, 1, x, ep);
+        c.release(h.p); c.release(qk.p); c.release(o.p);
+        cur = x;
+    }
+    for (int i = 0; i < k.nd; ++i) {
+        RUN(launch_gn_act(cur, cur.stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, a, c.s));
+        ConvEpilogue ep;
+        ep.gate = c.mod + k.gate[i].off; ep.gate_bstride = c.modstride();
+        ep.R = cur; ep.alpha = kInvSqrt2;
+        ep.stats = (i + 1 < k.nd) ? c.new_slot() : nullptr;
+        x.stats = ep.stats;
+        conv(c, a, k.H[i], k.k1x1 ? 1 : (1 << i), x, ep);
+        cur = x;
+    }
+    if (k.after && N != k.dim_out) {
+        TV t = make_tv(c.allocf((long long)B * k.dim_out * F * T), B, k.dim_out, F, T);
+        conv(c, cur, k.proj_out, 1, t, ConvEpilogue());
+        ConvEpilogue ep; ep.R = t; ep.stats = out.stats;
+        if (accum) { ep.alpha = 0.5f; ep.beta = kInvSqrt2; ep.R2 = *accum; }
+        else ep.alpha = kInvSqrt2;
+        conv(c, in, k.res_conv, 1, out, ep);
+        c.release(t.p);
+    } else {
+        if (accum) throw std::runtime_error("resblock: accum only supported for out blocks");
+        if (k.dim != k.dim_out) {
+            ConvEpilogue ep; ep.R = cur; ep.alpha = kInvSqrt2; ep.stats = out.stats;
+            conv(c, in, k.res_conv, 1, out, ep);
+        } else {
+            RUN(launch_combine(cur, in, kInvSqrt2, kInvSqrt2, out, out.stats, c.s));
+        }
+    }
+    c.release(abuf); c.release(xbuf);
+}
+
+// unet.py:730-845
+static void forward(Ctx& c, const float* x, const float* c_noise, float* out, float in_scale, float out_scale, float skip_scale) {
+    Net& n = *c.n;
+    const aid_config& cf = n.cfg;
+    const int B = c.B, L = cf.audio_len, no = cf.num_octs, bins = cf.bins_per_oct;
+    c.slot = 0;
+    c.mod = c.allocf((long long)c.nsig * n.total_mod);
+    float* emb = c.allocf((long long)c.nsig * 256);
+    RUN(launch_embedding(c_noise, c.nsig, n.d_emb[0], n.d_emb[1], n.d_emb[2], n.d_emb[3], n.d_emb[4], n.d_emb[5], n.d_emb[6], emb, c.s));
+    RUN(launch_mod_vectors(emb, c.nsig, n.d_modW, n.d_modB, n.total_mod, c.mod, c.s));
+    const size_t stat_bytes = (size_t)std::max(1, n.n_stat_slots) * B * 16 * sizeof(double);
+    c.stats_base = (double*)c.ar.alloc(stat_bytes);
+    RUN(AID_CUDA_CHECK(cudaMemsetAsync(c.stats_base, 0, stat_bytes, c.s)));
+    float2* spec = (float2*)c.ar.alloc((size_t)B * L * sizeof(float2));
+    float2* tmp = (float2*)c.ar.alloc((size_t)B * L * sizeof(float2));
+    RUN(launch_fft_big(n.fft, B, false, x, L, in_scale, nullptr, tmp, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, c.s));
+
+    auto Tof = [&](int lvl) { return n.tabs.M[no - 1 - lvl]; };
+    std::vector<TV> cat(no);
+    for (int j = 0; j < no; ++j)
+        cat[j] = make_tv(c.allocf((long long)B * 2 * cf.Ns[j] * bins * (j + 1) * Tof(j)), B, 2 * cf.Ns[j], bins * (j + 1), Tof(j));
+
+    TV Xcat, pyr, Xmid;
+    for (int i = 0; i < no; ++i) {
+        const int Ti = Tof(i), Fi = bins * (i + 1);
+        const int din = i == 0 ? cf.Ns[0] : cf.Ns[i - 1];
+        TV C = make_tv(c.allocf((long long)B * 2 * bins * Ti), B, 2, bins, Ti);
+        RUN(launch_cqt_analysis_oct(n.tabs, n.fft, no - 1 - i, spec, C, c.s));
+        if (i == 0) { Xcat = make_tv(c.allocf((long long)B * din * Fi * Ti), B, din, Fi, Ti); Xcat.stats = c.new_slot(); }
+        TV c2 = slice_f(Xcat, 0, bins); c2.stats = Xcat.stats;
+        resblock(c, n.downs[i].init, C, c2);
+        TV pyr_new;
+        if (i < no - 1) {
+            pyr_new = make_tv(c.allocf((long long)B * 2 * Fi * (Ti / 2)), B, 2, Fi, Ti / 2);
+            RUN(launch_resample_down(C, slice_f(pyr_new, 0, bins), c.s));
+            if (i > 0) RUN(launch_resample_down(pyr, slice_f(pyr_new, bins, Fi - bins), c.s));
+        } else {
+            pyr_new = make_tv(c.allocf((long long)B * 2 * Fi * Ti), B, 2, Fi, Ti);
+            RUN(launch_combine(C, TV(), 1.f, 0.f, slice_f(pyr_new, 0, bins), nullptr, c.s));
+            if (i > 0) RUN(launch_combine(pyr, TV(), 1.f, 0.f, slice_f(pyr_new, bins, Fi - bins), nullptr, c.s));
+        }
+        c.release(C.p);
+        if (i > 0) c.release(pyr.p);
+        pyr = pyr_new;
+        TV skip = slice_c(cat[i], cf.Ns[i], cf.Ns[i]);
+        resblock(c, n.downs[i].main, Xcat, skip);
+        c.release(Xcat.p);
+        ConvEpilogue ep; ep.alpha = kInvSqrt2;
+        if (i < no - 1) {
+            TV Xd = make_tv(c.allocf((long long)B * cf.Ns[i] * Fi * (Ti / 2)), B, cf.Ns[i], Fi, Ti / 2);
+            RUN(launch_resample_down(skip, Xd, c.s));
+            Xcat = make_tv(c.allocf((long long)B * cf.Ns[i] * (Fi + bins) * (Ti / 2)), B, cf.Ns[i], Fi + bins, Ti / 2);
+            Xcat.stats = c.new_slot();
+            ep.R = Xd; ep.stats = Xcat.stats;
+            conv(c, pyr, n.downs[i].pyr, 1, slice_f(Xcat, bins, Fi), ep);
+            c.release(Xd.p);
+        } else {
+            Xmid = make_tv(c.allocf((long long)B * cf.Ns[i] * Fi * Ti), B, cf.Ns[i], Fi, Ti);
+            Xmid.stats = c.new_slot();
+            ep.R = skip; ep.stats = Xmid.stats;
+            conv(c, pyr, n.downs[i].pyr, 1, Xmid, ep);
+        }
+    }
+    c.release(pyr.p);
+
+    const int Fl = bins * no, Tl = Tof(no - 1);
+    TV Xm = slice_c(cat[no - 1], 0, cf.Ns[no - 1]); Xm.stats = c.new_slot();
+    resblock(c, n.mid_main, Xmid, Xm);
+    c.release(Xmid.p);
+    TV Xout = make_tv(c.allocf((long long)B * 2 * Fl * Tl), B, 2, Fl, Tl);
+    resblock(c, n.mid_out, Xm, Xout);
+    float2* Y = (float2*)c.ar.alloc((size_t)B * n.tabs.ytotal * sizeof(float2));
+    for (int i = 0; i < no; ++i) {
+        const int j = no - 1 - i, Fj = bins * (j + 1), Tj = Tof(j);
+        const int dout = j == 0 ? cf.Ns[0] : cf.Ns[j - 1];
+        TV Xdec = make_tv(c.allocf((long long)B * dout * Fj * Tj), B, dout, Fj, Tj); Xdec.stats = c.new_slot();
+        resblock(c, n.ups_main[i], cat[j], Xdec);
+        c.release(cat[j].p);
+        resblock(c, n.ups_out[i], Xdec, Xout, &Xout);
+        RUN(launch_cqt_synth_oct(n.tabs, n.fft, i, slice_f(Xout, 0, bins), Y, c.s));
+        if (j > 0) {
+            TV Xn = slice_c(cat[j - 1], 0, cf.Ns[j - 1]);
+            RUN(launch_resample_up(slice_f(Xdec, bins, Fj - bins), Xn, c.s));
+            TV Xo2 = make_tv(c.allocf((long long)B * 2 * (Fj - bins) * 2 * Tj), B, 2, Fj - bins, 2 * Tj);
+            RUN(launch_resample_up(slice_f(Xout, bins, Fj - bins), Xo2, c.s));
+            c.release(Xout.p);
+            Xout = Xo2;
+        }
+        c.release(Xdec.p);
+    }
+    c.release(Xout.p);
+    RUN(launch_cqt_synth_gather(n.tabs, B, Y, spec, c.s));
+    RUN(launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, nullptr, out, L, out_scale / (float)L,
+                       skip_scale != 0.f ? x : nullptr, L, skip_scale, c.s));
+    if (!c.dry()) AID_CUDA_CHECK(cudaGetLastError());
+}
+
+static size_t plan_forward(Net& n, int B, int* slots) {
+    Ctx c; c.n = &n; c.B = B; c.nsig = 1; c.ar.reset(nullptr, 0, true);
+    forward(c, nullptr, nullptr, nullptr, 1.f, 1.f, 0.f);
+    if (slots) *slots = c.slot;
+    return c.ar.peak + 4096;
+}
+
+static size_t cqt_ws_bytes(const Net& n, int B) {
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    return 2 * al((size_t)B * n.cfg.audio_len * sizeof(float2)) + al((size_t)B * n.tabs.ytotal * sizeof(float2)) + 4096;
+}
+
+}  // namespace aid
+
+// =======================================================================================================
+using namespace aid;
+
+struct aid_handle { Net net; };
+static std::string g_create_error;
+
+template <class Fn>
+static int guarded(aid_handle* h, Fn&& fn) {
+    try { fn(); return AID_OK; }
+    catch (const CudaError& e) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e.code, cudaGetErrorString(e.code), e.file, e.line, e.expr);
+        if (h) h->net.err = buf; else g_create_error = buf;
+        return AID_ERR_CUDA;
+    } catch (const std::invalid_argument& e) { if (h) h->net.err = e.what(); else g_create_error = e.what(); return AID_ERR_INVALID; }
+    catch (const std::exception& e) {
+        if (h) h->net.err = e.what(); else g_create_error = e.what();
+        return std::string(e.what()).find("workspace") != std::string::npos ? AID_ERR_WORKSPACE : AID_ERR_STATE;
+    }
+}
+
+extern "C" {
+
+int aid_create(const aid_config* cfg, int device, aid_handle** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return AID_ERR_INVALID; }
+    aid_handle* h = nullptr;
+    int rc = guarded(nullptr, [&] {
+        h = new aid_handle();
+        h->net.cfg = *cfg; h->net.device = device;
+        build_net(h->net);
+        fill_host_tables(h->net);
+        int slots = 0; plan_forward(h->net, 1, &slots);
+        h->net.n_stat_slots = slots;
+        // host-only so far: device tables are uploaded by aid_finalize / the first CQT call, so that the
+        // schema (aid_weight_info) can be queried on a machine without a GPU
+    });
+    if (rc != AID_OK) { delete h; return rc; }
+    *out = h;
+    return AID_OK;
+}
+
+void aid_destroy(aid_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->net.device);
+    if (h->net.dweights) cudaFree(h->net.dweights);
+    if (h->net.d_tables) cudaFree(h->net.d_tables);
+    delete h;
+}
+
+const char* aid_last_error(const aid_handle* h) { return h ? h->net.err.c_str() : g_create_error.c_str(); }
+
+int aid_num_weights(const aid_handle* h) { return h ? (int)h->net.weights.size() : 0; }
+
+int aid_weight_info(const aid_handle* h, int index, const char** name, int64_t* shape4, int* ndim) {
+    if (!h || index < 0 || index >= (int)h->net.weights.size()) return AID_ERR_INVALID;
+    const Weight& w = h->net.weights[index];
+    if (name) *name = w.name.c_str();
+    if (ndim) *ndim = (int)w.shape.size();
+    if (shape4) for (size_t i = 0; i < w.shape.size() && i < 4; ++i) shape4[i] = w.shape[i];
+    return AID_OK;
+}
+
+int aid_load_weight(aid_handle* h, const char* name, const float* host, const int64_t* shape, int ndim) {
+    if (!h || !name || !host || !shape) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        if (h->net.finalized) throw std::runtime_error("aid_load_weight after aid_finalize");
+        auto it = h->net.windex.find(name);
+        if (it == h->net.windex.end()) throw std::invalid_argument(std::string("unexpected key in state dict: ") + name);
+        Weight& w = h->net.weights[it->second];
+        if ((int)w.shape.size() != ndim) throw std::invalid_argument(std::string("rank mismatch for ") + name);
+        for (int i = 0; i < ndim; ++i)
+            if (w.shape[i] != shape[i]) throw std::invalid_argument(std::string("size mismatch for ") + name);
+        if (!w.ignored) w.host.assign(host, host + w.numel());
+        w.loaded = true;
+    });
+}
+
+int aid_finalize(aid_handle* h) {
+    if (!h) return AID_ERR_INVALID;
+    return guarded(h, [&] { if (h->net.finalized) throw std::runtime_error("already finalized"); finalize_net(h->net); });
+}
+
+int aid_workspace_bytes(aid_handle* h, int B, size_t* bytes) {
+    if (!h || !bytes || B < 1) return AID_ERR_INVALID;
+    return guarded(h, [&] { *bytes = plan_forward(h->net, B, nullptr); });
+}
+
+int aid_unet_forward(aid_handle* h, const float* x_dev, const float* c_noise_dev, int n_sigma, float* out_dev, int B,
+                     float in_scale, float out_scale, float skip_scale, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!h || !x_dev || !c_noise_dev || !out_dev || !workspace_dev || B < 1) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!h->net.finalized) throw std::runtime_error("aid_unet_forward before aid_finalize");
+        if (n_sigma != 1 && n_sigma != B) throw std::invalid_argument("n_sigma must be 1 or B");
+        if (out_dev == x_dev && skip_scale != 0.f) throw std::invalid_argument("out may alias x only when skip_scale == 0");
+        Ctx c; c.n = &h->net; c.B = B; c.nsig = n_sigma; c.s = (cudaStream_t)stream;
+        c.ar.reset((char*)workspace_dev, workspace_bytes, false);
+        forward(c, x_dev, c_noise_dev, out_dev, in_scale, out_scale, skip_scale);
+    });
+}
+
+int aid_cqt_layout(const aid_handle* h, int B, int64_t* offsets, int32_t* frames) {
+    if (!h || !offsets) return AID_ERR_INVALID;
+    const Net& n = h->net;
+    int64_t off = 0;
+    for (int o = 0; o < n.cfg.num_octs; ++o) {
+        offsets[o] = off;
+        if (frames) frames[o] = n.tabs.M[o];
+        off += (int64_t)B * 2 * n.cfg.bins_per_oct * n.tabs.M[o];
+    }
+    offsets[n.cfg.num_octs] = off;
+    return AID_OK;
+}
+
+int aid_cqt_workspace_bytes(const aid_handle* h, int B, size_t* bytes) {
+    if (!h || !bytes || B < 1) return AID_ERR_INVALID;
+    *bytes = cqt_ws_bytes(h->net, B);
+    return AID_OK;
+}
+
+static void cqt_ws_split(Net& n, int B, void* ws, size_t ws_bytes, float2** spec, float2** tmp, float2** Y) {
+    upload_tables(n);
+    if (ws_bytes < cqt_ws_bytes(n, B)) throw std::runtime_error("workspace too small");
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    char* p = (char*)ws;
+    *spec = (float2*)p; p += al((size_t)B * n.cfg.audio_len * sizeof(float2));
+    *tmp = (float2*)p; p += al((size_t)B * n.cfg.audio_len * sizeof(float2));
+    *Y = (float2*)p;
+}
+
+int aid_cqt_fwd(aid_handle* h, const float* x_dev, float* coef_dev, int B, void* ws, size_t ws_bytes, void* stream) {
+    if (!h || !x_dev || !coef_dev || !ws) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        Net& n = h->net; cudaStream_t s = (cudaStream_t)stream;
+        float2 *spec, *tmp, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &Y);
+        const int L = n.cfg.audio_len, bins = n.cfg.bins_per_oct;
+        launch_fft_big(n.fft, B, false, x_dev, L, 1.f, nullptr, tmp, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
+        int64_t off = 0;
+        for (int o = 0; o < n.cfg.num_octs; ++o) {
+            TV C = make_tv(coef_dev + off, B, 2, bins, n.tabs.M[o]);
+            launch_cqt_analysis_oct(n.tabs, n.fft, o, spec, C, s);
+            off += (int64_t)B * 2 * bins * n.tabs.M[o];
+        }
+        AID_CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int aid_cqt_bwd(aid_handle* h, const float* coef_dev, float* x_dev, int B, void* ws, size_t ws_bytes, void* stream) {
+    if (!h || !x_dev || !coef_dev || !ws) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        Net& n = h->net; cudaStream_t s = (cudaStream_t)stream;
+        float2 *spec, *tmp, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &Y);
+        const int L = n.cfg.audio_len, bins = n.cfg.bins_per_oct;
+        int64_t off = 0;
+        for (int o = 0; o < n.cfg.num_octs; ++o) {
+            TV C = make_tv(const_cast<float*>(coef_dev) + off, B, 2, bins, n.tabs.M[o]);
+            launch_cqt_synth_oct(n.tabs, n.fft, o, C, Y, s);
+            off += (int64_t)B * 2 * bins * n.tabs.M[o];
+        }
+        launch_cqt_synth_gather(n.tabs, B, Y, spec, s);
+        launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, nullptr, x_dev, L, 1.f / (float)L, nullptr, 0, 0.f, s);
+        AID_CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int aid_hpf_dc(aid_handle* h, const float* x_dev, float* out_dev, int B, void* ws, size_t ws_bytes, void* stream) {
+    if (!h || !x_dev || !out_dev || !ws) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        Net& n = h->net; cudaStream_t s = (cudaStream_t)stream;
+        float2 *spec, *tmp, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &Y);
+        const int L = n.cfg.audio_len;
+        launch_fft_big(n.fft, B, false, x_dev, L, 1.f, nullptr, tmp, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
+        launch_spec_mul_real(B, L, spec, n.tabs.hhpf, s);
+        launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, nullptr, out_dev, L, 1.f / (float)L, nullptr, 0, 0.f, s);
+        AID_CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int aid_edm_add_noise(float* x_dev, const float* eps_dev, float scale, int64_t n, void* stream) {
+    if (!x_dev || !eps_dev || n < 0) return AID_ERR_INVALID;
+    launch_axpy_noise(x_dev, eps_dev, scale, n, (cudaStream_t)stream);
+    return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+int aid_edm_step(const float* xin, const float* xhat, const float* y, const float* mask, int64_t mask_n, int64_t n, float sigma,
+                 float hstep, int mode, const float* d_prev, const float* xbase, float* d_out, float* x_out, void* stream) {
+    if (!xin || !xhat || !x_out || n < 0 || (mask && (!y || mask_n <= 0)) || (mode == 1 && (!d_prev || !xbase)) || (mode != 0 && mode != 1))
+        return AID_ERR_INVALID;
+    launch_edm_step(xin, xhat, y, mask, mask_n, n, sigma, hstep, mode, d_prev, xbase, d_out, x_out, (cudaStream_t)stream);
+    return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+// ---- single-operator entry points -----------------------------------------------------------------------
+int aid_op_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
+                  const float* gate_dev, const float* R_dev, const float* R2_dev, float alpha, float beta, float* out_dev,
+                  double* stats_dev, int mode, void* stream) {
+    if (!a_dev || !w_dev || !out_dev) return AID_ERR_INVALID;
+    static std::string err;
+    try {
+        cudaStream_t s = (cudaStream_t)stream;
+        float* wp = nullptr;
+        const size_t e = (size_t)Cout * Cin * KF * KT;
+        AID_CUDA_CHECK(cudaMalloc(&wp, e * sizeof(float)));
+        pack_conv_weight_kernel<<<(int)std::min<size_t>(4096, (e + 255) / 256), 256, 0, s>>>(w_dev, wp, Cout, Cin, KF * KT);
+        TV a = make_tv(const_cast<float*>(a_dev), B, Cin, F, T), out = make_tv(out_dev, B, Cout, F, T);
+        ConvEpilogue ep; ep.gate = gate_dev; ep.gate_bstride = 0; ep.alpha = alpha; ep.beta = beta; ep.stats = stats_dev;
+        if (R_dev) ep.R = make_tv(const_cast<float*>(R_dev), B, Cout, F, T);
+        if (R2_dev) ep.R2 = make_tv(const_cast<float*>(R2_dev), B, Cout, F, T);
+        if (mode != 0) throw std::invalid_argument("conv mode not built");
+        launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
+        AID_CUDA_CHECK(cudaGetLastError());
+        AID_CUDA_CHECK(cudaStreamSynchronize(s));
+        AID_CUDA_CHECK(cudaFree(wp));
+        return AID_OK;
+    } catch (const CudaError& e) { return AID_ERR_CUDA; }
+    catch (const std::exception&) { return AID_ERR_INVALID; }
+}
+
+int aid_op_groupnorm_act(const float* x_dev, const float* gamma_dev, const float* affine_dev, int B, int C, int F, int T, int gelu,
+                         float* out_dev, double* stats_scratch_dev, void* stream) {
+    if (!x_dev || !gamma_dev || !out_dev || !stats_scratch_dev || C % 8 != 0) return AID_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    TV x = make_tv(const_cast<float*>(x_dev), B, C, F, T), out = make_tv(out_dev, B, C, F, T);
+    if (cudaMemsetAsync(stats_scratch_dev, 0, (size_t)B * 16 * sizeof(double), s) != cudaSuccess) return AID_ERR_CUDA;
+    launch_group_stats(x, stats_scratch_dev, s);
+    launch_gn_act(x, stats_scratch_dev, (long long)(C / 8) * F * T, gamma_dev, affine_dev, 0, gelu != 0, out, s);
+    return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+int aid_op_resample(const float* x_dev, int B, int C, int F, int T, int up, float* out_dev, void* stream) {
+    if (!x_dev || !out_dev || T < 4 || (T & 1)) return AID_ERR_INVALID;
+    TV x = make_tv(const_cast<float*>(x_dev), B, C, F, T);
+    TV out = make_tv(out_dev, B, C, F, up ? 2 * T : T / 2);
+    if (up) launch_resample_up(x, out, (cudaStream_t)stream); else launch_resample_down(x, out, (cudaStream_t)stream);
+    return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+int aid_op_attention(const float* h_dev, const float* qk_dev, int B, int heads, int F, int T, float* out_dev, void* stream) {
+    if (!h_dev || !qk_dev || !out_dev) return AID_ERR_INVALID;
+    try {
+        TV h = make_tv(const_cast<float*>(h_dev), B, heads, F, T), out = make_tv(out_dev, B, heads, F, T);
+        launch_attention(h, qk_dev, out, (cudaStream_t)stream);
+        return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+    } catch (...) { return AID_ERR_INVALID; }
+}
+
+int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float* emb_dev, void* stream) {
+    if (!h || !c_noise_dev || !emb_dev || !h->net.finalized) return AID_ERR_INVALID;
+    Net& n = h->net;
+    launch_embedding(c_noise_dev, n_sigma, n.d_emb[0], n.d_emb[1], n.d_emb[2], n.d_emb[3], n.d_emb[4], n.d_emb[5], n.d_emb[6], emb_dev,
+                     (cudaStream_t)stream);
+    return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+uint64_t aid_launch_count(void) { return aid::g_launch_count; }
+
+}  // extern "C"

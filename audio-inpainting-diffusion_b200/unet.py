@@ -1,0 +1,289 @@
+"""Host-side mirror of the reference denoiser's plugin surface.
+
+`Unet_CQT_oct_with_attention(args, device)` is a `torch.nn.Module` with the reference's constructor and
+`forward(inputs[B,L], sigma[B|1,1]) -> [B,L]` signature (unet.py:587, 730-737), the reference state-dict key
+schema, and a `CQTransform` attribute exposing `fwd / bwd / apply_hpf_DC`
+(unet.py:620, sampler.py:63,123).  Select it with
+    network.callable: "audio-inpainting-diffusion_b200.unet.Unet_CQT_oct_with_attention"
+All arithmetic runs in libaid_b200.so (hand-written sm_100a kernels); torch only owns device memory and streams.
+Forward-only: a call with grad enabled on an input that requires grad raises (the reference's guidance
+branch, sampler.py:57-113, needs a VJP that this path does not provide).
+"""
+import ctypes as C
+import math
+import zlib
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .config import NetConfig
+
+
+def schema_from_lib(cfg: NetConfig):
+    """[(name, shape)] of the reference state dict for `cfg`, as the C library builds it (host only, no GPU)."""
+    L = _lib.lib()
+    h = C.c_void_p()
+    c = cfg.to_c()
+    _lib.check(L.aid_create(C.byref(c), 0, C.byref(h)))
+    try:
+        out = []
+        name, shape, nd = C.c_char_p(), (C.c_int64 * 4)(), C.c_int()
+        for i in range(L.aid_num_weights(h)):
+            _lib.check(L.aid_weight_info(h, i, C.byref(name), shape, C.byref(nd)), h)
+            out.append((name.value.decode(), tuple(int(shape[j]) for j in range(nd.value))))
+        return out
+    finally:
+        L.aid_destroy(h)
+
+
+_BUFFERS = ("downsamplerT.kernel", "upsamplerT.kernel")
+_CUBIC = [-0.01171875, -0.03515625, 0.11328125, 0.43359375, 0.43359375, 0.11328125, -0.03515625, -0.01171875]
+
+
+def _fan_in(shape):
+    f = 1
+    for d in shape[1:]:
+        f *= d
+    return f
+
+
+def init_tensor(name, shape, gen, test_mode=False):
+    """Reference initialisation (unet.py:20-25, 599-600): kaiming_uniform * sqrt(1/3) == U(-1,1)/sqrt(fan_in);
+    gates * 1e-7; biases 0; gamma 1; RFF_freq = 16*randn.
+
+    test_mode re-randomises what the default init makes numerically invisible (SURVEY.md finding 6):
+    gates get O(1/sqrt(256)) weights and O(1) biases, gammas are spread around 1, biases are non-zero.
+    """
+    if name in _BUFFERS:
+        return torch.tensor(_CUBIC, dtype=torch.float32)
+    if name == "embedding.RFF_freq":
+        return 16.0 * torch.randn(shape, generator=gen)
+    leaf = name.rsplit(".", 1)[-1]
+    is_gate = ".gate" in name
+    if leaf == "gamma":
+        return 1.0 + 0.25 * torch.randn(shape, generator=gen) if test_mode else torch.ones(shape)
+    if leaf == "bias":
+        if not test_mode:
+            return torch.zeros(shape)
+        return (0.6 + 0.2 * torch.randn(shape, generator=gen)) if is_gate else 0.2 * torch.randn(shape, generator=gen)
+    u = (torch.rand(shape, generator=gen) * 2 - 1) / math.sqrt(_fan_in(shape))
+    if is_gate:
+        return u if test_mode else u * (1e-7 * math.sqrt(3.0))
+    return u
+
+
+def random_state_dict(cfg: NetConfig, seed=1234, test_mode=True):
+    """Deterministic, name-keyed random weights in the reference schema (same values on any machine)."""
+    sd = {}
+    for name, shape in schema_from_lib(cfg):
+        gen = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
+        sd[name] = init_tensor(name, shape, gen, test_mode=test_mode)
+    return sd
+
+
+class _Node(nn.Module):
+    pass
+
+
+class CQTDevice:
+    """`model.CQTransform` (unet.py:620): fwd / bwd / apply_hpf_DC on the GPU through the C ABI."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def _ws(self, B, dev):
+        L = _lib.lib()
+        n = C.c_size_t()
+        _lib.check(L.aid_cqt_workspace_bytes(self._o._handle, B, C.byref(n)), self._o._handle)
+        return torch.empty(n.value, dtype=torch.uint8, device=dev)
+
+    def _layout(self, B):
+        L = _lib.lib()
+        no = self._o.cfg.num_octs
+        offs, frames = (C.c_int64 * (no + 1))(), (C.c_int32 * no)()
+        _lib.check(L.aid_cqt_layout(self._o._handle, B, offs, frames), self._o._handle)
+        return list(offs), list(frames)
+
+    def fwd(self, x):
+        """real [B,1,L] -> list (ascending frequency) of complex64 [B,1,bins,T_o]   (unet.py:743)"""
+        o = self._o
+        o._ensure_handle(x.device)
+        B = x.shape[0]
+        assert x.shape[1] == 1 and x.shape[-1] == o.cfg.audio_len
+        xin = x.reshape(B, -1).contiguous().float()
+        offs, frames = self._layout(B)
+        coef = torch.empty(offs[-1], dtype=torch.float32, device=x.device)
+        ws = self._ws(B, x.device)
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().aid_cqt_fwd(o._handle, _lib.ptr(xin), _lib.ptr(coef), B, _lib.ptr(ws), ws.numel(), st), o._handle)
+        out = []
+        for i, T in enumerate(frames):
+            c = coef[offs[i]:offs[i + 1]].view(B, 2, o.cfg.bins_per_oct, T)
+            out.append(torch.complex(c[:, 0], c[:, 1]).unsqueeze(1))
+        return out
+
+    def bwd(self, coefs):
+        """list of complex [B,1,bins,T_o] -> real [B,1,L]   (unet.py:841)"""
+        o = self._o
+        dev = coefs[0].device
+        o._ensure_handle(dev)
+        B = coefs[0].shape[0]
+        offs, frames = self._layout(B)
+        coef = torch.empty(offs[-1], dtype=torch.float32, device=dev)
+        for i, c in enumerate(coefs):
+            assert c.shape[-1] == frames[i], "octave frame count mismatch"
+            dst = coef[offs[i]:offs[i + 1]].view(B, 2, o.cfg.bins_per_oct, frames[i])
+            cc = c.reshape(B, o.cfg.bins_per_oct, frames[i])
+            dst[:, 0].copy_(cc.real)
+            dst[:, 1].copy_(cc.imag)
+        x = torch.empty(B, o.cfg.audio_len, dtype=torch.float32, device=dev)
+        ws = self._ws(B, dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().aid_cqt_bwd(o._handle, _lib.ptr(coef), _lib.ptr(x), B, _lib.ptr(ws), ws.numel(), st), o._handle)
+        return x.unsqueeze(1)
+
+    def apply_hpf_DC(self, x):
+        """[B,L'] (L' <= L, zero padded) -> [B,L']   (sampler.py:63,123)"""
+        o = self._o
+        o._ensure_handle(x.device)
+        Lin, L = x.shape[-1], o.cfg.audio_len
+        if Lin > L:
+            raise ValueError("Input signal is longer than the maximum length")
+        xin = x.reshape(-1, Lin).float()
+        if Lin < L:
+            xin = torch.nn.functional.pad(xin, (0, L - Lin))
+        xin = xin.contiguous()
+        B = xin.shape[0]
+        out = torch.empty_like(xin)
+        ws = self._ws(B, x.device)
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().aid_hpf_dc(o._handle, _lib.ptr(xin), _lib.ptr(out), B, _lib.ptr(ws), ws.numel(), st), o._handle)
+        return out[:, :Lin].reshape(x.shape)
+
+
+class Unet_CQT_oct_with_attention(nn.Module):
+    """Drop-in for networks.unet_cqt_oct_with_projattention_adaLN_2.Unet_CQT_oct_with_attention."""
+
+    def __init__(self, args, device, conv_mode=None):
+        super().__init__()
+        self.args = args
+        self.cfg = args if isinstance(args, NetConfig) else NetConfig.from_args(args, conv_mode=conv_mode)
+        if conv_mode is not None:
+            self.cfg.conv_mode = int(conv_mode)
+        self.device = torch.device(device)
+        self.depth = self.cfg.num_octs
+        self.emb_dim = self.cfg.emb_dim
+        self.bins_per_oct, self.num_octs = self.cfg.bins_per_oct, self.cfg.num_octs
+        self._handle = None
+        self._handle_dev = None
+        self._weights_loaded = False
+        self._ws = {}
+        gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 31))
+        for name, shape in schema_from_lib(self.cfg):
+            node = self
+            *path, leaf = name.split(".")
+            for part in path:
+                if not hasattr(node, part):
+                    node.add_module(part, _Node())
+                node = getattr(node, part)
+            t = init_tensor(name, shape, gen)
+            if name in _BUFFERS:
+                node.register_buffer(leaf, t)
+            else:
+                node.register_parameter(leaf, nn.Parameter(t, requires_grad=(name != "embedding.RFF_freq")))
+        self.CQTransform = CQTDevice(self)
+
+    # ---- handle / weights -------------------------------------------------------------------------
+    def _dev_index(self, dev):
+        dev = torch.device(dev)
+        if dev.type != "cuda":
+            raise _lib.AidError("this denoiser runs on a CUDA device only (no CPU fallback); got device " + str(dev))
+        return dev.index if dev.index is not None else torch.cuda.current_device()
+
+    def _ensure_handle(self, dev):
+        idx = self._dev_index(dev)
+        if self._handle is not None and self._handle_dev == idx:
+            return
+        self._release()
+        h = C.c_void_p()
+        c = self.cfg.to_c()
+        _lib.check(_lib.lib().aid_create(C.byref(c), idx, C.byref(h)))
+        self._handle, self._handle_dev, self._weights_loaded = h, idx, False
+
+    def _ensure_weights(self, dev):
+        self._ensure_handle(dev)
+        if self._weights_loaded:
+            return
+        L = _lib.lib()
+        for name, t in self.state_dict().items():
+            if name in _BUFFERS:
+                continue
+            t = t.detach().to("cpu", torch.float32).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(L.aid_load_weight(self._handle, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()), self._handle)
+        _lib.check(L.aid_finalize(self._handle), self._handle)
+        self._weights_loaded = True
+
+    def refresh_weights(self):
+        """Re-upload the parameters after they were modified in place."""
+        self._release()
+
+    def _release(self):
+        if self._handle is not None:
+            _lib.lib().aid_destroy(self._handle)
+        self._handle, self._handle_dev, self._weights_loaded = None, None, False
+        self._ws = {}
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        r = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._release()
+        return r
+
+    def _workspace(self, B, dev):
+        key = (B, str(dev))
+        if key not in self._ws:
+            n = C.c_size_t()
+            _lib.check(_lib.lib().aid_workspace_bytes(self._handle, B, C.byref(n)), self._handle)
+            self._ws = {key: torch.empty(n.value, dtype=torch.uint8, device=dev)}
+        return self._ws[key]
+
+    # ---- forward ----------------------------------------------------------------------------------
+    def denoise_fused(self, x, c_noise, in_scale=1.0, out_scale=1.0, skip_scale=0.0, out=None):
+        """out = out_scale * net(in_scale * x, c_noise) + skip_scale * x  (EDM.denoiser fused, edm.py:133-148)."""
+        if x.dim() != 2 or x.shape[1] != self.cfg.audio_len:
+            raise AssertionError("bad shapes")  # unet.py:844
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        dev = x.device
+        self._ensure_weights(dev)
+        B = x.shape[0]
+        cn = c_noise.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+        if cn.numel() not in (1, B):
+            raise ValueError("sigma must have 1 or B entries")
+        if out is None:
+            out = torch.empty_like(x)
+        ws = self._workspace(B, dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().aid_unet_forward(self._handle, _lib.ptr(x), _lib.ptr(cn), cn.numel(), _lib.ptr(out), B,
+                                                   float(in_scale), float(out_scale), float(skip_scale),
+                                                   _lib.ptr(ws), ws.numel(), st), self._handle)
+        return out
+
+    def forward(self, inputs, sigma):
+        """inputs [B,T] time-domain signal, sigma [B,1] or [1,1] noise-level embedding input (c_noise)."""
+        if torch.is_grad_enabled() and inputs.requires_grad:
+            raise RuntimeError("this denoiser is forward-only: it cannot back-propagate to its input "
+                               "(reconstruction guidance, xi > 0, is not supported; use xi = 0)")
+        return self.denoise_fused(inputs, sigma)

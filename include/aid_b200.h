@@ -1,0 +1,120 @@
+/* C ABI of the B200-native denoiser path (libaid_b200.so).
+ *
+ * Drop-in boundary for ONE path of eloimoliner/audio-inpainting-diffusion: the denoiser forward
+ * driven by the EDM inpainting sampler.  The reference is pure Python; the "FFI" a maintainer would
+ * bind is ctypes.  Every entry point names the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only.  `*_dev` pointers are device pointers on the GPU the
+ * handle was created for; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * All entry points return 0 on success or a negative aid_status; aid_last_error() gives the message.
+ * Calls are stream-ordered, never synchronise the device and never allocate device memory after
+ * aid_finalize() (the caller owns the workspace).  One handle = one GPU = one host thread at a time.
+ */
+#ifndef AID_B200_H
+#define AID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AID_MAX_OCTS 16
+
+typedef enum aid_status {
+    AID_OK = 0,
+    AID_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+    AID_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+    AID_ERR_STATE = -3,     /* wrong call order (e.g. denoise before finalize, missing weights) */
+    AID_ERR_WORKSPACE = -4  /* caller-provided workspace too small */
+} aid_status;
+
+/* Mirrors what Unet_CQT_oct_with_attention.__init__ reads from `args` (unet.py:595-655):
+ * args.network.{cqt.num_octs,cqt.bins_per_oct,cqt.window,cqt.beta,emb_dim,Ns,num_dils,attention_layers,
+ * attention_dict.num_heads,num_bottleneck_layers} and args.exp.{sample_rate,audio_len}. */
+typedef struct aid_config {
+    int32_t num_octs;
+    int32_t bins_per_oct;
+    int32_t audio_len;            /* power of two >= 4096 */
+    int32_t window_kind;          /* 0 = "hann", 1 = ("kaiser", beta) */
+    double sample_rate;
+    double beta;
+    int32_t emb_dim;              /* must be 256 (RFF_MLP_Block 64->128->256->emb_dim) */
+    int32_t num_heads;            /* attention_dict.num_heads */
+    int32_t Ns[AID_MAX_OCTS];
+    int32_t num_dils[AID_MAX_OCTS];
+    int32_t attention_layers[AID_MAX_OCTS + 1]; /* num_octs entries + bottleneck */
+    int32_t num_bottleneck_layers; /* must be 1 */
+    int32_t conv_mode;            /* 0 = exact fp32 CUDA cores; 1 = tcgen05 split-fp16 tensor cores for the 5x3 layers */
+} aid_config;
+
+typedef struct aid_handle aid_handle;
+
+/* Unet_CQT_oct_with_attention(args, device)                                   unet.py:587 */
+int aid_create(const aid_config* cfg, int device, aid_handle** out);
+void aid_destroy(aid_handle* h);
+const char* aid_last_error(const aid_handle* h); /* h may be NULL: error of the last failed aid_create */
+
+/* model.load_state_dict(sd): one call per tensor, reference key names   tester_inpainting.py:202
+ * `host` is a host pointer to contiguous fp32 data. */
+int aid_load_weight(aid_handle* h, const char* name, const float* host, const int64_t* shape, int ndim);
+/* number of tensors the schema expects / names by index (for state_dict()/strict loading) */
+int aid_num_weights(const aid_handle* h);
+int aid_weight_info(const aid_handle* h, int index, const char** name, int64_t* shape4, int* ndim);
+/* repack weights into kernel layouts and upload; required before any compute call */
+int aid_finalize(aid_handle* h);
+
+/* bytes of caller-owned scratch aid_unet_forward needs for a batch of B clips */
+int aid_workspace_bytes(aid_handle* h, int B, size_t* bytes);
+
+/* Unet_CQT_oct_with_attention.forward(inputs[B,L], sigma[B|1,1]) -> [B,L]      unet.py:730-845
+ * fused with EDM.denoiser's preconditioning (edm.py:133-148):
+ *     out = out_scale * net(in_scale * x, c_noise) + skip_scale * x
+ * (in_scale=1, out_scale=1, skip_scale=0 is the bare nn.Module forward).
+ * c_noise_dev holds n_sigma (1 or B) values.  out_dev may alias x_dev only if skip_scale == 0. */
+int aid_unet_forward(aid_handle* h, const float* x_dev, const float* c_noise_dev, int n_sigma, float* out_dev, int B,
+                     float in_scale, float out_scale, float skip_scale, void* workspace_dev, size_t workspace_bytes,
+                     void* stream);
+
+/* CQT_nsgt.fwd / bwd / apply_hpf_DC                         unet.py:743, unet.py:841, sampler.py:63,123
+ * coefficient layout: per octave o (ascending frequency) a [B, 2, bins, T_o] fp32 tensor (re, im planes),
+ * octave tensors concatenated in one buffer at offsets aid_cqt_layout() reports (in floats, for batch B). */
+int aid_cqt_layout(const aid_handle* h, int B, int64_t* offsets /*[num_octs+1]*/, int32_t* frames /*[num_octs]*/);
+int aid_cqt_fwd(aid_handle* h, const float* x_dev, float* coef_dev, int B, void* workspace_dev, size_t workspace_bytes, void* stream);
+int aid_cqt_bwd(aid_handle* h, const float* coef_dev, float* x_dev, int B, void* workspace_dev, size_t workspace_bytes, void* stream);
+int aid_hpf_dc(aid_handle* h, const float* x_dev, float* out_dev, int B, void* workspace_dev, size_t workspace_bytes, void* stream);
+int aid_cqt_workspace_bytes(const aid_handle* h, int B, size_t* bytes);
+
+/* Sampler element-wise steps on [B, L] buffers                          sampler.py:214, 141-147, 230-251 */
+int aid_edm_add_noise(float* x_dev, const float* eps_dev, float scale, int64_t n, void* stream);
+/* xh = mask ? mask*y + (1-mask)*xhat : xhat;  d = (xin - xh)/sigma;
+ * mode 0: d_out = d (if non-NULL), x_out = xin + h*d;   mode 1: x_out = xbase + h*(d_prev + d)/2 */
+int aid_edm_step(const float* xin_dev, const float* xhat_dev, const float* y_dev, const float* mask_dev, int64_t mask_n,
+                 int64_t n, float sigma, float h, int mode, const float* d_prev_dev, const float* xbase_dev,
+                 float* d_out_dev, float* x_out_dev, void* stream);
+
+/* ---- single-operator entry points (unit parity tests; same kernels the forward uses) ---------------- */
+/* F.conv2d(a[B,Cin,F,T], w[Cout,Cin,KF,KT], padding="same", dilation=(dil,1)) with the fused epilogue
+ * out = alpha*(conv*gate[c] + R) + beta*R2; gate/R/R2 may be NULL.  stats_dev (may be NULL): [B][8][2] doubles
+ * accumulated with (sum, sumsq) of out per channel group.  mode as aid_config.conv_mode.   unet.py:79-88, 482 */
+int aid_op_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
+                  const float* gate_dev, const float* R_dev, const float* R2_dev, float alpha, float beta,
+                  float* out_dev, double* stats_dev, int mode, void* stream);
+/* BiasFreeGroupNorm (8 groups) * (affine+1) [+ exact GELU]                       unet.py:147-163, 479, 482 */
+int aid_op_groupnorm_act(const float* x_dev, const float* gamma_dev, const float* affine_dev, int B, int C, int F, int T,
+                         int gelu, float* out_dev, double* stats_scratch_dev /*[B][8][2]*/, void* stream);
+/* UpDownResample along T: up=0 -> [.., T/2], up=1 -> [.., 2T]                               unet.py:549-580 */
+int aid_op_resample(const float* x_dev, int B, int C, int F, int T, int up, float* out_dev, void* stream);
+/* attention core of TimeAttentionBlock: h[B,heads,F,T], qk[B,2*heads*F,T] -> out[B,heads,F,T]   unet.py:353-374 */
+int aid_op_attention(const float* h_dev, const float* qk_dev, int B, int heads, int F, int T, float* out_dev, void* stream);
+/* RFF_MLP_Block + every adaLN Linear: returns the emb [n_sigma,256]                          unet.py:184-211 */
+int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float* emb_dev, void* stream);
+
+/* kernels launched by this library since load (the bench's gpu_launches counter) */
+uint64_t aid_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AID_B200_H */
