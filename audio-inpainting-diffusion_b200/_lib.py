@@ -40,6 +40,7 @@ _SIGS = {
     "aid_cqt_fwd": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "aid_cqt_bwd": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "aid_hpf_dc": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
+    "aid_cqt_plan": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P, _P, _P, _P, _P]),
     "aid_cqt_workspace_bytes": (C.c_int, [_P, C.c_int, C.POINTER(C.c_size_t)]),
     "aid_edm_add_noise": (C.c_int, [_P, _P, C.c_float, C.c_int64, _P]),
     "aid_edm_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_int, _P, _P, _P, _P, _P]),
@@ -49,6 +50,7 @@ _SIGS = {
     "aid_op_resample": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "aid_op_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "aid_op_embedding": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "aid_debug_probe": (C.c_int, [_P, C.c_char_p, _P]),
     "aid_launch_count": (C.c_uint64, []),
 }
 EXPORTS = tuple(_SIGS)

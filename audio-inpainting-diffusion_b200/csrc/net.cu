@@ -96,6 +96,7 @@ struct Net {
     FftPlan fft;
     void* d_tables = nullptr;
     int n_stat_slots = 0;
+    std::map<std::string, float*> probes;  // debug: name -> caller buffer that receives a contiguous copy
 };
 
 static int add_weight(Net& n, const std::string& name, std::vector<int64_t> shape, bool ignored = false) {
@@ -161,6 +162,7 @@ static void build_net(Net& n) {
     if (c.emb_dim != 256) throw std::invalid_argument("emb_dim must be 256");
     if (c.num_bottleneck_layers != 1) throw std::invalid_argument("num_bottleneck_layers must be 1");
     if (c.num_heads < 1) throw std::invalid_argument("num_heads must be >= 1");
+    if (c.conv_mode != 0) throw std::invalid_argument("conv_mode 1 (tcgen05) is not built into this library yet");
     const int no = c.num_octs, bins = c.bins_per_oct;
     n.emb_idx[0] = add_weight(n, "embedding.RFF_freq", {1, 32});
     const int dims[4] = {64, 128, 256, 256};
@@ -395,14 +397,22 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
     c.release(abuf); c.release(xbuf);
 }
 
+// debug probes (parity tests localise an error to one block): contiguous copy of a named intermediate
+static void probe(Ctx& c, const std::string& name, const TV& v) {
+    if (c.dry()) return;
+    auto it = c.n->probes.find(name);
+    if (it == c.n->probes.end() || !it->second) return;
+    launch_combine(v, TV(), 1.f, 0.f, make_tv(it->second, v.B, v.C, v.F, v.T), nullptr, c.s);
+}
+
 // unet.py:730-845
 static void forward(Ctx& c, const float* x, const float* c_noise, float* out, float in_scale, float out_scale, float skip_scale) {
     Net& n = *c.n;
     const aid_config& cf = n.cfg;
     const int B = c.B, L = cf.audio_len, no = cf.num_octs, bins = cf.bins_per_oct;
     c.slot = 0;
-    c.mod = c.allocf((long long)c.nsig * n.total_mod);
-    float* emb = c.allocf((long long)c.nsig * 256);
+    c.mod = c.allocf((long long)B * n.total_mod);   // sized for per-clip sigma so the plan does not depend on n_sigma
+    float* emb = c.allocf((long long)B * 256);
     RUN(launch_embedding(c_noise, c.nsig, n.d_emb[0], n.d_emb[1], n.d_emb[2], n.d_emb[3], n.d_emb[4], n.d_emb[5], n.d_emb[6], emb, c.s));
     RUN(launch_mod_vectors(emb, c.nsig, n.d_modW, n.d_modB, n.total_mod, c.mod, c.s));
     const size_t stat_bytes = (size_t)std::max(1, n.n_stat_slots) * B * 16 * sizeof(double);
@@ -441,6 +451,7 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
         pyr = pyr_new;
         TV skip = slice_c(cat[i], cf.Ns[i], cf.Ns[i]);
         resblock(c, n.downs[i].main, Xcat, skip);
+        probe(c, "enc" + std::to_string(i), skip);
         c.release(Xcat.p);
         ConvEpilogue ep; ep.alpha = kInvSqrt2;
         if (i < no - 1) {
@@ -463,6 +474,7 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
     const int Fl = bins * no, Tl = Tof(no - 1);
     TV Xm = slice_c(cat[no - 1], 0, cf.Ns[no - 1]); Xm.stats = c.new_slot();
     resblock(c, n.mid_main, Xmid, Xm);
+    probe(c, "mid", Xm);
     c.release(Xmid.p);
     TV Xout = make_tv(c.allocf((long long)B * 2 * Fl * Tl), B, 2, Fl, Tl);
     resblock(c, n.mid_out, Xm, Xout);
@@ -472,6 +484,7 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
         const int dout = j == 0 ? cf.Ns[0] : cf.Ns[j - 1];
         TV Xdec = make_tv(c.allocf((long long)B * dout * Fj * Tj), B, dout, Fj, Tj); Xdec.stats = c.new_slot();
         resblock(c, n.ups_main[i], cat[j], Xdec);
+        probe(c, "dec" + std::to_string(i), Xdec);
         c.release(cat[j].p);
         resblock(c, n.ups_out[i], Xdec, Xout, &Xout);
         RUN(launch_cqt_synth_oct(n.tabs, n.fft, i, slice_f(Xout, 0, bins), Y, c.s));
@@ -619,6 +632,21 @@ int aid_cqt_layout(const aid_handle* h, int B, int64_t* offsets, int32_t* frames
     return AID_OK;
 }
 
+int aid_cqt_plan(const aid_handle* h, int32_t* K, int32_t* n_win, int32_t* centre, int32_t* Lg, int32_t* woff, float* win,
+                 float* dual, float* hhpf) {
+    if (!h) return AID_ERR_INVALID;
+    const CqtPlanHost& p = h->net.plan;
+    if (K) *K = p.K;
+    if (n_win) *n_win = (int32_t)p.win.size();
+    if (centre) std::copy(p.centre.begin(), p.centre.end(), centre);
+    if (Lg) std::copy(p.Lg.begin(), p.Lg.end(), Lg);
+    if (woff) std::copy(p.woff.begin(), p.woff.end(), woff);
+    if (win) std::copy(p.win.begin(), p.win.end(), win);
+    if (dual) std::copy(p.dual.begin(), p.dual.end(), dual);
+    if (hhpf) std::copy(p.hhpf.begin(), p.hhpf.end(), hhpf);
+    return AID_OK;
+}
+
 int aid_cqt_workspace_bytes(const aid_handle* h, int B, size_t* bytes) {
     if (!h || !bytes || B < 1) return AID_ERR_INVALID;
     *bytes = cqt_ws_bytes(h->net, B);
@@ -757,6 +785,12 @@ int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float
     launch_embedding(c_noise_dev, n_sigma, n.d_emb[0], n.d_emb[1], n.d_emb[2], n.d_emb[3], n.d_emb[4], n.d_emb[5], n.d_emb[6], emb_dev,
                      (cudaStream_t)stream);
     return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+int aid_debug_probe(aid_handle* h, const char* name, float* dst_dev) {
+    if (!h || !name) return AID_ERR_INVALID;
+    if (dst_dev) h->net.probes[name] = dst_dev; else h->net.probes.erase(name);
+    return AID_OK;
 }
 
 uint64_t aid_launch_count(void) { return aid::g_launch_count; }

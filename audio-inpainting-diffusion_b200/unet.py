@@ -70,6 +70,8 @@ def init_tensor(name, shape, gen, test_mode=False):
     u = (torch.rand(shape, generator=gen) * 2 - 1) / math.sqrt(_fan_in(shape))
     if is_gate:
         return u if test_mode else u * (1e-7 * math.sqrt(3.0))
+    if test_mode and name.endswith("attn_block.qk.weight"):
+        return u * 6.0  # O(1) attention logits: with the default scale the softmax is uniform and q/k bugs are invisible
     return u
 
 
@@ -280,6 +282,30 @@ class Unet_CQT_oct_with_attention(nn.Module):
                                                    float(in_scale), float(out_scale), float(skip_scale),
                                                    _lib.ptr(ws), ws.numel(), st), self._handle)
         return out
+
+    def forward_with_probes(self, inputs, sigma):
+        """Debug/parity helper: forward plus the per-block intermediates {"enc<i>", "mid", "dec<i>"} (see aid_debug_probe)."""
+        cfg, B, dev = self.cfg, inputs.shape[0], inputs.device
+        self._ensure_weights(dev)
+        no, bins = cfg.num_octs, cfg.bins_per_oct
+        _, frames = self.CQTransform._layout(1)
+        T = lambda lvl: frames[no - 1 - lvl]
+        shapes = {f"enc{i}": (B, cfg.Ns[i], bins * (i + 1), T(i)) for i in range(no)}
+        shapes["mid"] = (B, cfg.Ns[no - 1], bins * no, T(no - 1))
+        for i in range(no):
+            j = no - 1 - i
+            shapes[f"dec{i}"] = (B, cfg.Ns[0] if j == 0 else cfg.Ns[j - 1], bins * (j + 1), T(j))
+        bufs = {k: torch.empty(s, dtype=torch.float32, device=dev) for k, s in shapes.items()}
+        L = _lib.lib()
+        try:
+            for k, b in bufs.items():
+                _lib.check(L.aid_debug_probe(self._handle, k.encode(), _lib.ptr(b)), self._handle)
+            out = self.denoise_fused(inputs, sigma)
+            torch.cuda.synchronize(dev)
+        finally:
+            for k in bufs:
+                L.aid_debug_probe(self._handle, k.encode(), None)
+        return out, bufs
 
     def forward(self, inputs, sigma):
         """inputs [B,T] time-domain signal, sigma [B,1] or [1,1] noise-level embedding input (c_noise)."""

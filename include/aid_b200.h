@@ -85,6 +85,10 @@ int aid_cqt_fwd(aid_handle* h, const float* x_dev, float* coef_dev, int B, void*
 int aid_cqt_bwd(aid_handle* h, const float* coef_dev, float* x_dev, int B, void* workspace_dev, size_t workspace_bytes, void* stream);
 int aid_hpf_dc(aid_handle* h, const float* x_dev, float* out_dev, int B, void* workspace_dev, size_t workspace_bytes, void* stream);
 int aid_cqt_workspace_bytes(const aid_handle* h, int B, size_t* bytes);
+/* host-side band plan (for inspection / tests): K bands, n_win window samples in total.
+ * Any output pointer may be NULL.  centre/Lg/woff: [K]; win/dual: [n_win]; hhpf: [audio_len]. */
+int aid_cqt_plan(const aid_handle* h, int32_t* K, int32_t* n_win, int32_t* centre, int32_t* Lg, int32_t* woff,
+                 float* win, float* dual, float* hhpf);
 
 /* Sampler element-wise steps on [B, L] buffers                          sampler.py:214, 141-147, 230-251 */
 int aid_edm_add_noise(float* x_dev, const float* eps_dev, float scale, int64_t n, void* stream);
@@ -110,6 +114,11 @@ int aid_op_resample(const float* x_dev, int B, int C, int F, int T, int up, floa
 int aid_op_attention(const float* h_dev, const float* qk_dev, int B, int heads, int F, int T, float* out_dev, void* stream);
 /* RFF_MLP_Block + every adaLN Linear: returns the emb [n_sigma,256]                          unet.py:184-211 */
 int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float* emb_dev, void* stream);
+
+/* Debug: the next aid_unet_forward calls also copy the named intermediate, contiguous [B,C,F,T], into dst_dev
+ * (NULL removes the probe).  Names: "enc<i>" = encoder ResBlock output of level i (unet.py:780), "mid" = bottleneck
+ * ResBlock output (unet.py:803), "dec<i>" = decoder ResBlock output (unet.py:815). */
+int aid_debug_probe(aid_handle* h, const char* name, float* dst_dev);
 
 /* kernels launched by this library since load (the bench's gpu_launches counter) */
 uint64_t aid_launch_count(void);

@@ -1,0 +1,197 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, schema, config parsing,
+CQT band plan (C++) against the oracle's, sampler host logic, error behaviour.  No compute call needs a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from util import rel_l2, seeded
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol(aid):
+    from aid_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "aid_b200.h")).read()
+    declared = set(re.findall(r"\b(aid_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/aid_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+
+
+def test_config_from_reference_style_args(aid):
+    cfg = aid.paper_22k(262144)
+    cfg2 = aid.NetConfig.from_args(cfg.to_args())
+    assert cfg2.as_dict() == cfg.as_dict()
+    bad = cfg.to_args()
+    bad["network"]["use_fencoding"] = True
+    with pytest.raises(NotImplementedError):
+        aid.NetConfig.from_args(bad)
+
+
+def test_unsupported_length_is_a_clear_error(aid):
+    with pytest.raises(Exception, match="power of two"):
+        aid.schema_from_lib(aid.NetConfig(audio_len=184184))
+
+
+def test_module_surface_and_state_dict_roundtrip(aid):
+    cfg = aid.small_test(16384)
+    net = aid.Unet_CQT_oct_with_attention(cfg.to_args(), "cpu")
+    sd = aid.random_state_dict(cfg, seed=3)
+    assert set(net.state_dict().keys()) == set(sd.keys())
+    net.load_state_dict(sd, strict=True)
+    assert torch.equal(net.state_dict()["downs.2.2.H.1.weight"], sd["downs.2.2.H.1.weight"])
+    assert hasattr(net.CQTransform, "apply_hpf_DC") and hasattr(net.CQTransform, "fwd") and hasattr(net.CQTransform, "bwd")
+    with pytest.raises(RuntimeError):
+        net.load_state_dict({k: v for k, v in sd.items() if "gate2" not in k}, strict=True)
+    # default init keeps the reference's property: gates ~1e-7, gammas 1 (unet.py:599-600, 141)
+    fresh = aid.Unet_CQT_oct_with_attention(cfg, "cpu").state_dict()
+    assert fresh["downs.0.2.gate.0.weight"].abs().max() < 1e-6 and torch.all(fresh["downs.0.2.norm.0.gamma"] == 1)
+
+
+def test_no_cpu_fallback(aid):
+    cfg = aid.small_test(16384)
+    net = aid.Unet_CQT_oct_with_attention(cfg, "cpu")
+    from aid_b200 import _lib
+    with pytest.raises(_lib.AidError, match="CUDA device only"):
+        net(torch.zeros(1, cfg.audio_len), torch.zeros(1, 1))
+
+
+def test_workspace_plan_is_host_only_and_grows_with_batch(aid):
+    from aid_b200 import _lib
+    L = _lib.lib()
+    cfg = aid.paper_22k(262144)
+    h = C.c_void_p()
+    c = cfg.to_c()
+    _lib.check(L.aid_create(C.byref(c), 0, C.byref(h)))
+    try:
+        n1, n2, n32 = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _lib.check(L.aid_workspace_bytes(h, 1, C.byref(n1)), h)
+        _lib.check(L.aid_workspace_bytes(h, 2, C.byref(n2)), h)
+        _lib.check(L.aid_workspace_bytes(h, 32, C.byref(n32)), h)
+        assert n1.value < n2.value < n32.value < 100e9  # fits one B200 (180 GB) with room for the weights
+        assert L.aid_num_weights(h) == 662
+    finally:
+        L.aid_destroy(h)
+
+
+@pytest.mark.parametrize("L", [16384, 65536, 262144])
+def test_cqt_band_plan_matches_oracle(aid, L):
+    """The C++ band plan (csrc/cqt_plan.hpp) and the oracle's numpy plan are two writings of one definition."""
+    import cqt_oracle
+    from aid_b200 import _lib
+    Lb = _lib.lib()
+    cfg = aid.small_test(L)
+    p = cqt_oracle.CQTPlan(cfg.num_octs, cfg.bins_per_oct, ("kaiser", cfg.beta), cfg.sample_rate, L)
+    h = C.c_void_p()
+    c = cfg.to_c()
+    _lib.check(Lb.aid_create(C.byref(c), 0, C.byref(h)))
+    try:
+        K, nw = C.c_int32(), C.c_int32()
+        _lib.check(Lb.aid_cqt_plan(h, C.byref(K), C.byref(nw), None, None, None, None, None, None))
+        cen, lg, wo = np.zeros(K.value, np.int32), np.zeros(K.value, np.int32), np.zeros(K.value, np.int32)
+        win, dual, hh = np.zeros(nw.value, np.float32), np.zeros(nw.value, np.float32), np.zeros(L, np.float32)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(Lb.aid_cqt_plan(h, None, None, P(cen), P(lg), P(wo), P(win), P(dual), P(hh)))
+        offs, frames = (C.c_int64 * 8)(), (C.c_int32 * 7)()
+        _lib.check(Lb.aid_cqt_layout(h, 1, offs, frames))
+    finally:
+        Lb.aid_destroy(h)
+    assert K.value == p.K and list(frames) == p.size_per_oct
+    assert np.array_equal(cen, p.centre[1:p.K + 1]) and np.array_equal(lg, p.Lg[1:p.K + 1])
+    assert np.allclose(hh, p.Hhpf, atol=1e-6)
+    for k in (0, 1, p.K // 2, p.K - 2, p.K - 1):
+        j = k + 1
+        o = k // cfg.bins_per_oct
+        assert np.allclose(win[wo[k]:wo[k] + lg[k]], p.g[j], atol=1e-6)
+        assert np.allclose(dual[wo[k]:wo[k] + lg[k]], p.gd[j] * p.size_per_oct[o], rtol=1e-5, atol=1e-9)
+
+
+class _FakeNet(torch.nn.Module):
+    class _C:
+        @staticmethod
+        def apply_hpf_DC(x):
+            return x - x.mean(-1, keepdim=True)
+    CQTransform = _C()
+
+    def forward(self, x, cnoise):
+        return torch.tanh(3.0 * x) * (1.0 + 0.1 * cnoise)
+
+
+def _tester_args(aid, T=35, order=2):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    a = aid.AttrDict.wrap({
+        "tester": {"T": T, "order": order, "filter_out_cqt_DC_Nyq": True, "posterior_sampling": {"xi": 0, "norm": 2, "smoothl1_beta": 1},
+                   "data_consistency": {"use": True, "type": "always", "smooth": True, "hann_size": 50},
+                   "diff_params": {"same_as_training": False, "sigma_data": 0.063, "sigma_min": 1e-4, "sigma_max": 1, "ro": 13,
+                                   "Schurn": 10, "Snoise": 1.0, "Stmin": 0, "Stmax": 50}},
+        "diff_params": {"sigma_data": 0.063, "sigma_min": 1e-5, "sigma_max": 10, "ro": 13, "Schurn": 5, "Snoise": 1, "Stmin": 0, "Stmax": 50},
+    })
+    return a
+
+
+def test_sampler_host_logic_against_oracle(aid):
+    """69 denoiser evaluations for T=35 and the same trajectory as oracle/sample_oracle."""
+    import unet_oracle
+    args = _tester_args(aid)
+    net = _FakeNet()
+    calls = []
+    net.register_forward_hook(lambda m, i, o: calls.append(1))
+    s = aid.Sampler(net, aid.EDM(args), args)
+    assert s.diff_params.sigma_max == 1 and s.diff_params.Schurn == 10  # tester overrides applied (sampler.py:43-53)
+    y = seeded((2, 8192), 1, 0.063)
+    mask = torch.ones(1, 8192)
+    mask[..., 4000:4600] = 0
+
+    def stream(shape):
+        while True:
+            yield torch.randn(shape)
+
+    torch.manual_seed(11)
+    got = s.predict_inpainting(y * mask, mask)
+    assert len(calls) == 69
+    torch.manual_seed(11)
+    want = unet_oracle.sample_oracle(net, unet_oracle.EDMOracle(), (2, 8192), stream((2, 8192)), nb_steps=35, y=y * mask,
+                                     mask_s=unet_oracle.smooth_mask(mask.expand(2, -1), 50))
+    assert rel_l2(got, want) < 1e-6
+    # known samples are restored by the replacement method (the last Euler step lands on the projected estimate)
+    assert torch.allclose(got[:, :3900], (y * mask)[:, :3900], atol=1e-6)
+    torch.manual_seed(12)
+    got_u = s.predict_unconditional((2, 8192), "cpu")
+    torch.manual_seed(12)
+    want_u = unet_oracle.sample_oracle(net, unet_oracle.EDMOracle(), (2, 8192), stream((2, 8192)), nb_steps=35, hpf=net.CQTransform.apply_hpf_DC)
+    assert rel_l2(got_u, want_u) < 1e-6
+
+
+def test_sampler_guidance_is_refused(aid):
+    args = _tester_args(aid)
+    args["tester"]["posterior_sampling"]["xi"] = 0.25
+    s = aid.Sampler(_FakeNet(), aid.EDM(args), args)
+    with pytest.raises(NotImplementedError, match="xi"):
+        s.predict_inpainting(torch.zeros(1, 4096), torch.ones(1, 4096))
+
+
+def test_smooth_mask_matches_the_reference_loop(aid):
+    """sampler.py:302-325 restated as the literal loop."""
+    args = _tester_args(aid)
+    s = aid.Sampler(_FakeNet(), aid.EDM(args), args)
+    mask = torch.ones(2, 3000)
+    mask[:, 500:900] = 0
+    mask[:, 2000:2010] = 0
+    size = 50
+    hann = torch.hann_window(size * 2)
+    m, new, prev = mask[0], mask[0].clone(), 1
+    for i in range(len(m)):
+        if m[i] != prev:
+            if m[i] == 0:
+                new[i - size:i] = hann[size:]
+            if m[i] == 1:
+                new[i:i + size] = hann[:size]
+        prev = m[i]
+    assert torch.equal(s.prepare_smooth_mask(mask, size), new.unsqueeze(0).expand(2, -1))

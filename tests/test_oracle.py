@@ -1,0 +1,139 @@
+"""CPU tests of the oracle itself: pinned against the golden vectors the reference's own code produced
+(tests/golden/make_golden.py) and against the frame identities of the CQT definition."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import rel_l2, seeded, make_oracle
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(GOLD, "golden.npz")), json.load(open(os.path.join(GOLD, "golden_meta.json")))
+
+
+@pytest.fixture(scope="module")
+def small(aid):
+    cfg = aid.small_test(16384)
+    sd = aid.random_state_dict(cfg, seed=1234)
+    return cfg, sd, make_oracle(cfg, sd)
+
+
+def test_unet_oracle_matches_reference_golden(small, golden):
+    cfg, sd, orc = small
+    g, _ = golden
+    x = seeded((2, cfg.audio_len), 0)
+    for i, cn in enumerate([0.0613, -0.75, -2.3]):
+        assert rel_l2(orc(x, torch.tensor([[cn]])), torch.from_numpy(g[f"small_fwd_{i}"])) < 1e-5
+    x3 = seeded((3, cfg.audio_len), 3, 0.3)
+    out = orc(x3, torch.tensor([[0.05], [-0.8], [-1.7]]))
+    assert rel_l2(out, torch.from_numpy(g["small_fwd_persample"])) < 1e-5
+
+
+def test_fixture_is_sensitive_to_every_branch(small):
+    """Finding 6 of SURVEY.md: with default init the gated branches vanish; the test weights must not allow that."""
+    cfg, sd, orc = small
+    x = seeded((1, cfg.audio_len), 0)
+    cn = torch.tensor([[-0.5]])
+    pb = {}
+    base = orc(x, cn, probe=pb)
+    # (weight, block output it must visibly change).  Deep blocks move the waveform little with random weights,
+    # which is why the GPU parity tests also compare these block outputs (test_forward_blockwise_vs_oracle).
+    for key, where in (("downs.6.2.H.1.weight", "enc6"), ("ups.0.1.attn_block.qk.weight", "dec0"),
+                       ("downs.4.2.attn_block.qk.weight", "enc4"), ("middle.0.1.gate2.bias", "mid"),
+                       ("middle.0.1.attn_block.proj_in.weight", "mid"), ("ups.1.1.affine2.weight", "dec1"),
+                       ("downs.3.1.weight", "enc4"), ("downs.0.0.norm.0.gamma", "enc0"), ("ups.3.1.res_conv.weight", "dec3")):
+        sd2 = dict(sd)
+        sd2[key] = sd[key] * 0.0 if "gamma" not in key else sd[key] * 1.5
+        p2 = {}
+        out = make_oracle(cfg, sd2)(x, cn, probe=p2)
+        assert rel_l2(p2[where], pb[where]) > 2e-3, (key, where)  # 20x the 1e-4 block-wise GPU tolerance
+        assert rel_l2(out, base) > 5e-5, key
+
+
+def test_sampler_oracle_matches_reference_golden(small, golden):
+    import unet_oracle
+    cfg, sd, orc = small
+    g, meta = golden
+    edm = unet_oracle.EDMOracle()
+    t = edm.create_schedule(35)
+    assert torch.allclose(t, torch.tensor(meta["schedule_T35"]), rtol=0, atol=0)
+    assert torch.allclose(edm.get_gamma(t), torch.tensor(meta["gamma_T35"]), rtol=0, atol=0)
+    shape = (2, cfg.audio_len)
+
+    def stream():
+        while True:
+            yield torch.randn(shape)
+
+    torch.manual_seed(42)
+    xu = unet_oracle.sample_oracle(orc, edm, shape, stream(), nb_steps=6, hpf=orc.CQTransform.apply_hpf_DC)
+    assert rel_l2(xu, torch.from_numpy(g["small_sample_uncond_T6"])) < 1e-4
+    y = seeded(shape, 7, 0.063)
+    mask = torch.ones(1, cfg.audio_len)
+    mask[..., cfg.audio_len // 2 - 750: cfg.audio_len // 2 + 750] = 0
+    ms = unet_oracle.smooth_mask(mask.expand(2, -1), 50)
+    torch.manual_seed(43)
+    xi = unet_oracle.sample_oracle(orc, edm, shape, stream(), nb_steps=6, y=y * mask, mask_s=ms)
+    assert rel_l2(xi, torch.from_numpy(g["small_sample_inpaint_T6"])) < 1e-4
+
+
+def test_paper_network_oracle_matches_reference_golden(aid, golden):
+    """BASELINE config 1 (186 M parameters, 1 x 65536) through EDM.denoiser."""
+    import unet_oracle
+    g, meta = golden
+    cfg = aid.paper_22k(65536)
+    assert [[k, list(s)] for k, s in aid.schema_from_lib(cfg)].sort() == meta["schema_paper"].sort()
+    sd = aid.random_state_dict(cfg, seed=1234)
+    orc = make_oracle(cfg, sd)
+    edm = unet_oracle.EDMOracle()
+    x = seeded((1, 65536), 0)
+    assert rel_l2(edm.denoiser(x, orc, torch.tensor([1.0])), torch.from_numpy(g["paper_denoise_0"])) < 1e-5
+    assert rel_l2(edm.denoiser(x * 0.05, orc, torch.tensor([0.05])), torch.from_numpy(g["paper_denoise_1"])) < 1e-5
+
+
+@pytest.mark.parametrize("L,T0", [(16384, 256), (65536, 1024), (262144, 4096)])
+def test_cqt_oracle_contract(L, T0):
+    """unet.py:769-774 needs frame counts that double per octave; App. B: T0 = 4096 at L = 262144, 1024 at 65536."""
+    import cqt_oracle
+    c = cqt_oracle.CQT_nsgt(7, 64, "oct", ("kaiser", 1), fs=22050, audio_len=L)
+    assert c.size_per_oct == [T0 >> (6 - o) for o in range(7)]
+    if L > 65536:
+        return
+    x = seeded((2, 1, L), 1)
+    X = c.fwd(x)
+    assert [tuple(a.shape) for a in X] == [(2, 1, 64, T0 >> (6 - o)) for o in range(7)] and X[0].dtype == torch.complex64
+    # linearity
+    x2 = seeded((2, 1, L), 2)
+    X12 = c.fwd(2.0 * x - 0.5 * x2)
+    for a, b, d in zip(c.fwd(x), c.fwd(x2), X12):
+        assert rel_l2(torch.view_as_real(2.0 * a - 0.5 * b), torch.view_as_real(d)) < 1e-5
+    # frame identity on the half spectrum, below the Nyquist-straddling top band
+    p = c.plan
+    top = int(p.centre[p.K] - p.Lg[p.K] // 2)
+    Y = torch.fft.rfft(c.bwd(X)[:, 0].double())[:, :top]
+    Xf = torch.fft.rfft(x[:, 0].double())[:, :top]
+    H = torch.from_numpy(p.Hhpf[:top])
+    assert ((Y - Xf * H).norm() / (Xf * H).norm()).item() < 1e-5
+    # apply_hpf_DC removes DC, keeps the mid band
+    h = c.apply_hpf_DC(x[:, 0])
+    assert abs(h.mean().item()) < 1e-6
+    Hf, X0 = torch.fft.rfft(h.double()), torch.fft.rfft(x[:, 0].double())
+    mid = slice(int(p.centre[2]), top)
+    assert ((Hf[:, mid] - X0[:, mid]).norm() / X0[:, mid].norm()).item() < 1e-5
+
+
+def test_resampler_oracle_facts():
+    """down has DC gain 1 and maps an impulse at 8 to taps at outputs 2..5; up has DC gain 0.5."""
+    import unet_oracle
+    x = torch.ones(1, 1, 1, 32)
+    assert torch.allclose(unet_oracle.down_t(x), torch.ones(1, 1, 1, 16), atol=1e-6)
+    assert torch.allclose(unet_oracle.up_t(x), 0.5 * torch.ones(1, 1, 1, 64), atol=1e-6)
+    imp = torch.zeros(1, 1, 1, 32)
+    imp[..., 8] = 1
+    d = unet_oracle.down_t(imp)[0, 0, 0]
+    assert torch.allclose(d[2:6], torch.tensor([-0.01171875, 0.11328125, 0.43359375, -0.03515625]), atol=1e-7)

@@ -1,0 +1,82 @@
+"""Pins the oracle to the reference's own code, live (build container only: needs /root/reference)."""
+import sys
+
+import pytest
+import torch
+
+from util import rel_l2, seeded, make_oracle
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.path.insert(0, "/root/reference")
+    import cqt_oracle
+    cqt_oracle.install_as_cqt_nsgt_pytorch()
+    from networks.unet_cqt_oct_with_projattention_adaLN_2 import Unet_CQT_oct_with_attention
+    from diff_params.edm import EDM
+    from testing.edm_sampler_inpainting import Sampler
+    return Unet_CQT_oct_with_attention, EDM, Sampler
+
+
+def _args(aid, cfg, T):
+    sys.path.insert(0, __file__.rsplit("/", 1)[0] + "/golden")
+    from make_golden import TESTER
+    a = cfg.to_args()
+    a.update(aid.AttrDict.wrap(TESTER))
+    a["tester"]["T"] = T
+    return a
+
+
+def test_schema_and_forward(aid, ref):
+    RefNet, _, _ = ref
+    cfg = aid.NetConfig(audio_len=32768, Ns=[8, 16, 16, 24, 24, 32, 40], num_dils=[2, 1, 3, 2, 2, 3, 2],
+                        attention_layers=[0, 0, 0, 1, 0, 1, 1, 1])
+    net = RefNet(cfg.to_args(), "cpu")
+    rsd = net.state_dict()
+    assert {k: tuple(v.shape) for k, v in rsd.items()} == dict(aid.schema_from_lib(cfg))
+    sd = aid.random_state_dict(cfg, seed=99)
+    net.load_state_dict(sd, strict=True)
+    x = seeded((2, cfg.audio_len), 4, 0.7)
+    cn = torch.tensor([[-1.1], [0.02]])
+    with torch.no_grad():
+        want = net(x, cn)
+    assert rel_l2(make_oracle(cfg, sd)(x, cn), want) < 1e-6
+
+
+def test_sampler_mirror_equals_reference_sampler(aid, ref):
+    """Our Sampler (host logic, torch ops on CPU) against the reference Sampler with the same cheap fake denoiser."""
+    _, RefEDM, RefSampler = ref
+    cfg = aid.small_test(16384)
+
+    class FakeNet(torch.nn.Module):
+        class _C:
+            @staticmethod
+            def apply_hpf_DC(x):
+                return x - x.mean(-1, keepdim=True)
+        CQTransform = _C()
+
+        def forward(self, x, cnoise):
+            return torch.tanh(3.0 * x) * (1.0 + 0.1 * cnoise)
+
+    net = FakeNet()
+    for T, order in ((35, 2), (5, 1)):
+        args = _args(aid, cfg, T)
+        args["tester"]["order"] = order
+        y = seeded((3, 4096), 1, 0.063)
+        mask = torch.ones(1, 4096)
+        mask[..., 1000:1400] = 0
+        mask[..., 3000:3100] = 0
+        torch.manual_seed(5)
+        want_i = RefSampler(net, RefEDM(args), args).predict_inpainting(y * mask, mask)
+        torch.manual_seed(5)
+        got_i = aid.Sampler(net, aid.EDM(args), args).predict_inpainting(y * mask, mask)
+        assert torch.equal(got_i, want_i)
+        torch.manual_seed(6)
+        want_u = RefSampler(net, RefEDM(args), args).predict_unconditional((2, 4096), "cpu")
+        torch.manual_seed(6)
+        got_u = aid.Sampler(net, aid.EDM(args), args).predict_unconditional((2, 4096), "cpu")
+        assert torch.equal(got_u, want_u)
+    s = aid.Sampler(net, aid.EDM(args), args)
+    assert torch.equal(s.prepare_smooth_mask(mask.expand(3, -1), 50), RefSampler(net, RefEDM(args), args).prepare_smooth_mask(mask.expand(3, -1), 50))
