@@ -97,6 +97,11 @@ struct Net {
     void* d_tables = nullptr;
     int n_stat_slots = 0;
     std::map<std::string, float*> probes;  // debug: name -> caller buffer that receives a contiguous copy
+    // optional per-launch timing of the convolution kernels (bench.py roofline): CUDA events on the launching stream
+    struct ProfRec { cudaEvent_t e0, e1; int kind; double flops, bytes; };
+    bool prof = false;
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
 };
 
 static int add_weight(Net& n, const std::string& name, std::vector<int64_t> shape, bool ignored = false) {
@@ -328,7 +333,20 @@ static void conv(Ctx& c, const TV& a, const ConvW& w, int dil, const TV& out, Co
     if (a.C != w.Cin || out.C != w.Cout || a.F != out.F || a.T != out.T || a.B != out.B)
         throw std::runtime_error("conv: shape mismatch");
     if (ep.stats && (w.Cout % 8 != 0)) throw std::runtime_error("conv: statistics need Cout % 8 == 0");
-    RUN(launch_conv_simt(a, w.wp, w.KF, w.KT, dil, out, ep, c.s));
+    if (c.dry()) return;
+    Net& n = *c.n;
+    Net::ProfRec rec{};
+    if (n.prof) {
+        auto get = [&]() { cudaEvent_t e; if (n.prof_pool.empty()) { AID_CUDA_CHECK(cudaEventCreate(&e)); } else { e = n.prof_pool.back(); n.prof_pool.pop_back(); } return e; };
+        rec.e0 = get(); rec.e1 = get();
+        rec.kind = (w.KF == 5 && w.Cin > 2) ? 0 : 1;   // 0 = dilated 5x3 residual layers (K1), 1 = everything else
+        const double px = (double)a.B * a.F * a.T;
+        rec.flops = 2.0 * w.Cin * w.Cout * w.KF * w.KT * px;
+        rec.bytes = 4.0 * (px * (w.Cin + w.Cout + (ep.R.p ? w.Cout : 0) + (ep.R2.p ? w.Cout : 0)) + (double)w.Cin * w.Cout * w.KF * w.KT);
+        AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
+    }
+    launch_conv_simt(a, w.wp, w.KF, w.KT, dil, out, ep, c.s);
+    if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
 // unet.py:452-493.  `accum` (decoder out blocks, unet.py:817): out = (accum + block(x)) / sqrt(2), may alias out.
@@ -785,6 +803,32 @@ int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float
     launch_embedding(c_noise_dev, n_sigma, n.d_emb[0], n.d_emb[1], n.d_emb[2], n.d_emb[3], n.d_emb[4], n.d_emb[5], n.d_emb[6], emb_dev,
                      (cudaStream_t)stream);
     return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+int aid_profile(aid_handle* h, int enable) {
+    if (!h) return AID_ERR_INVALID;
+    for (auto& r : h->net.prof_recs) { h->net.prof_pool.push_back(r.e0); h->net.prof_pool.push_back(r.e1); }
+    h->net.prof_recs.clear();
+    h->net.prof = enable != 0;
+    return AID_OK;
+}
+
+int aid_profile_read(aid_handle* h, int kind, uint64_t* launches, double* ms, double* flops, double* bytes) {
+    if (!h) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        uint64_t nl = 0; double t = 0, f = 0, b = 0;
+        for (auto& r : h->net.prof_recs) {
+            if (r.kind != kind) continue;
+            AID_CUDA_CHECK(cudaEventSynchronize(r.e1));
+            float e = 0.f;
+            AID_CUDA_CHECK(cudaEventElapsedTime(&e, r.e0, r.e1));
+            ++nl; t += e; f += r.flops; b += r.bytes;
+        }
+        if (launches) *launches = nl;
+        if (ms) *ms = t;
+        if (flops) *flops = f;
+        if (bytes) *bytes = b;
+    });
 }
 
 int aid_debug_probe(aid_handle* h, const char* name, float* dst_dev) {

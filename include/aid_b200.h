@@ -115,6 +115,13 @@ int aid_op_attention(const float* h_dev, const float* qk_dev, int B, int heads, 
 /* RFF_MLP_Block + every adaLN Linear: returns the emb [n_sigma,256]                          unet.py:184-211 */
 int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float* emb_dev, void* stream);
 
+/* Per-launch timing of the convolution kernels with CUDA events on the launching stream (bench.py's roofline).
+ * aid_profile(h, 1) clears and starts recording, aid_profile(h, 0) stops; aid_profile_read sums the recorded launches
+ * of one kind (0 = dilated 5x3 residual-layer convolutions, 1 = all other convolutions): count, device ms, algorithmic
+ * FLOPs (2*Cin*Cout*taps*pixels) and algorithmic bytes (operand + result + residual tensors + weights, fp32). */
+int aid_profile(aid_handle* h, int enable);
+int aid_profile_read(aid_handle* h, int kind, uint64_t* launches, double* ms, double* flops, double* bytes);
+
 /* Debug: the next aid_unet_forward calls also copy the named intermediate, contiguous [B,C,F,T], into dst_dev
  * (NULL removes the probe).  Names: "enc<i>" = encoder ResBlock output of level i (unet.py:780), "mid" = bottleneck
  * ResBlock output (unet.py:803), "dec<i>" = decoder ResBlock output (unet.py:815). */
