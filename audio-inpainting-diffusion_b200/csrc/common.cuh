@@ -1,5 +1,6 @@
 // Shared device/host types for the B200 denoiser path.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -66,6 +67,16 @@ void launch_embedding(const float* c_noise, int n_sigma, const float* rff, const
                       const float* w1, const float* b1, const float* w2, const float* b2, float* emb, cudaStream_t s);
 void launch_mod_vectors(const float* emb, int n_sigma, const float* W, const float* bias, int total, float* out,
                         cudaStream_t s);
+
+// tcgen05 path for the dilated 5x3 convolutions (conv_tc.cu).  Operands are split-fp16 planar: [B][C/8][F][T+2][8].
+
+bool conv_tc_supported(int Cin, int Cout, int KF, int KT);
+void launch_pack_weight_tc(const float* w, __half* wp, int N, int Cin, cudaStream_t s);
+void launch_gn_act_tc(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
+                      long long affine_bstride, bool gelu, __half* a_hi, __half* a_lo, cudaStream_t s);
+void launch_to_planar_tc(const TV& x, __half* a_hi, __half* a_lo, cudaStream_t s);
+void launch_conv_tc(const __half* a_hi, const __half* a_lo, const __half* wp, int B, int Cin, int F, int T, int dil, const TV& out,
+                    const ConvEpilogue& ep, int num_sms, cudaStream_t s);
 
 // FFT / CQT
 struct FftPlan {

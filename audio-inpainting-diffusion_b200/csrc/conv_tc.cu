@@ -1,0 +1,423 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM kernel for the dilated 5x3 residual-layer convolutions
+// (unet.py:433-436, 482) -- 95 % of the forward's FLOPs -- with the gate/residual/statistics epilogue fused.
+//
+// Precision: error-compensated split fp16.  The normalise/modulate/GELU pass writes every activation as
+// a = a_hi + a_lo (two fp16, scaled by 2^4), weights are pre-split the same way (scaled by 2^10); the kernel issues
+// a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (kind::f16, fp32 accumulation in TMEM).  The dropped a_lo*w_lo term is 2^-22
+// relative, so the result is fp32-grade (the 1e-3 parity bar rules out single bf16/tf32 products over 75 layers).
+//
+// GEMM view per "unit" = 128 consecutive pixels of one (clip, frequency row):
+//     D[128 px, N=Cout] += A[128 px, 16 ch] * B[N, 16 ch]^T     for every (kf, kt, 16-channel step)
+// Layouts (all K-major, SWIZZLE_NONE canonical: core matrix = 8 rows x 16 B, SBO = 128 B, LBO = plane stride):
+//   activations in HBM : [B][C/8][F][T+2][8] fp16 (hi and lo arrays); one zero pixel each side of T = the conv's zero
+//                        padding along T.  A 130-pixel window of one row is ONE contiguous 2080-byte run, fetched with
+//                        cp.async.bulk; the three kt taps are the same window with the descriptor start advanced by 16 B.
+//   weights in HBM     : [kf][Cin/16][hi|lo][kt][2 chunks][N][8] fp16 -> one contiguous bulk copy per pipeline stage.
+//   zero padding along F: a tap row outside [0,F) is skipped (no MMA issued), never loaded.
+// One CTA = 2 units (two accumulators in TMEM share every weight stage), persistent over tiles; warp 0 = bulk-copy
+// producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> coalesced NCHW stores).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace aid {
+
+static constexpr int TC_THREADS = 192;
+static constexpr int TC_PLANE = 130 * 16;     // bytes of one (16 B chunk) x (130 pixel) plane of A in smem
+static constexpr int TC_A_BYTES = 8 * TC_PLANE;  // 2 units x (hi, lo) x 2 chunks
+static constexpr float TC_A_SCALE = 16.f, TC_W_SCALE = 1024.f, TC_OUT_SCALE = 1.f / (16.f * 1024.f);
+
+struct TcConvArgs {
+    const __half* a_hi; const __half* a_lo; const __half* w;
+    TV out, R;
+    const float* gate; long long gate_bstride;
+    float alpha; double* stats;
+    int B, Cin, N, F, T, Tp, dil, tiles_t, n_units, n_tiles, nstages, acc_bufs, ncol_stride, b_bytes, stage_bytes;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct UnitInfo { int exists, b, f, t0, seg_px; };
+
+__device__ __forceinline__ UnitInfo unit_info(const TcConvArgs& p, int u) {
+    UnitInfo i;
+    i.exists = u < p.n_units;
+    const int tt = u % p.tiles_t, r = u / p.tiles_t;
+    i.f = r % p.F; i.b = r / p.F; i.t0 = tt * 128;
+    i.seg_px = min(130, p.Tp - i.t0);
+    return i;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv5x3_tc_kernel(TcConvArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* bar_base = smem + (size_t)p.nstages * p.stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* empty = full + 8;
+    uint64_t* tmem_full = empty + 8;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < p.nstages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 128); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int KS = p.Cin >> 4;
+    const int c8_total = p.Cin >> 3;
+
+    if (warp == 0) {
+        // ===================== producer: bulk copies HBM/L2 -> shared =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const UnitInfo u0 = unit_info(p, 2 * tile), u1 = unit_info(p, 2 * tile + 1);
+                for (int kf = 0; kf < 5; ++kf) {
+                    const int f0 = u0.f + (kf - 2) * p.dil, f1 = u1.f + (kf - 2) * p.dil;
+                    const bool v0 = u0.exists && f0 >= 0 && f0 < p.F, v1 = u1.exists && f1 >= 0 && f1 < p.F;
+                    if (!(v0 || v1)) continue;
+                    for (int ks = 0; ks < KS; ++ks) {
+                        mbar_wait(empty + stage, phase ^ 1);
+                        uint8_t* sb = smem + (size_t)stage * p.stage_bytes;
+                        const uint32_t bytes = (uint32_t)p.b_bytes + (v0 ? 4u * u0.seg_px * 16u : 0u) + (v1 ? 4u * u1.seg_px * 16u : 0u);
+                        mbar_expect_tx(full + stage, bytes);
+                        bulk_g2s(sb, p.w + (size_t)(kf * KS + ks) * (p.b_bytes >> 1), (uint32_t)p.b_bytes, full + stage);
+                        uint8_t* sa = sb + p.b_bytes;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const UnitInfo& u = i ? u1 : u0;
+                            if (!(i ? v1 : v0)) continue;
+                            const int ff = i ? f1 : f0;
+#pragma unroll
+                            for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+                                for (int c = 0; c < 2; ++c) {
+                                    const size_t off = ((((size_t)u.b * c8_total + (2 * ks + c)) * p.F + ff) * p.Tp + u.t0) * 8;
+                                    bulk_g2s(sa + ((i * 2 + hl) * 2 + c) * TC_PLANE, (hl ? p.a_lo : p.a_hi) + off, (uint32_t)u.seg_px * 16u,
+                                             full + stage);
+                                }
+                        }
+                        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);  // F16 x F16 -> F32, K-major A/B
+            const uint32_t b_lbo = (uint32_t)p.N * 16u;
+            int stage = 0; uint32_t phase = 0; int ab = 0; uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const UnitInfo u0 = unit_info(p, 2 * tile), u1 = unit_info(p, 2 * tile + 1);
+                mbar_wait(tmem_empty + ab, aphase ^ 1);
+                tc_fence_after();
+                uint32_t started[2] = {0u, 0u};
+                for (int kf = 0; kf < 5; ++kf) {
+                    const int f0 = u0.f + (kf - 2) * p.dil, f1 = u1.f + (kf - 2) * p.dil;
+                    const bool v0 = u0.exists && f0 >= 0 && f0 < p.F, v1 = u1.exists && f1 >= 0 && f1 < p.F;
+                    if (!(v0 || v1)) continue;
+                    for (int ks = 0; ks < KS; ++ks) {
+                        mbar_wait(full + stage, phase);
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                        const uint32_t sa = sb + (uint32_t)p.b_bytes;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            if (!(i ? v1 : v0)) continue;
+                            const uint32_t d = tmem_base + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride);
+#pragma unroll
+                            for (int kt = 0; kt < 3; ++kt) {
+                                const uint64_t a_hi = make_desc(sa + (uint32_t)((i * 2 + 0) * 2) * TC_PLANE + kt * 16, TC_PLANE, 128);
+                                const uint64_t a_lo = make_desc(sa + (uint32_t)((i * 2 + 1) * 2) * TC_PLANE + kt * 16, TC_PLANE, 128);
+                                const uint64_t b_hi = make_desc(sb + (uint32_t)((0 * 3 + kt) * 2) * b_lbo, b_lbo, 128);
+                                const uint64_t b_lo = make_desc(sb + (uint32_t)((1 * 3 + kt) * 2) * b_lbo, b_lbo, 128);
+                                tc_mma_f16(d, a_hi, b_hi, idesc, started[i]);
+                                started[i] = 1u;
+                                tc_mma_f16(d, a_lo, b_hi, idesc, 1u);
+                                tc_mma_f16(d, a_hi, b_lo, idesc, 1u);
+                            }
+                        }
+                        tc_commit(empty + stage);  // frees the smem slot when these MMAs have read it
+                        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                tc_commit(tmem_full + ab);  // accumulators of this tile are complete
+                if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> out = alpha*(acc*gate + R), statistics =====================
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int ab = 0; uint32_t aphase = 0;
+        const int gcn = p.N / 8;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(tmem_full + ab, aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int i = 0; i < 2; ++i) {
+                const UnitInfo u = unit_info(p, 2 * tile + i);
+                if (!u.exists) continue;
+                const int t = u.t0 + q * 32 + lane;
+                const bool ok = t < p.T;
+                const long long po = (long long)u.b * p.out.sb + (long long)u.f * p.T + t;
+                const long long pr = (long long)u.b * p.R.sb + (long long)u.f * p.T + t;
+                const float* gate = p.gate ? p.gate + (long long)u.b * p.gate_bstride : nullptr;
+                float ssum = 0.f, ssq = 0.f;
+                int sgroup = 0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < p.N; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride + c0), r);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int co = c0 + j;
+                        if (p.stats && co / gcn != sgroup) {
+                            // flush the finished group: warp-reduce, one double atomic per warp
+                            float s = ssum, qq = ssq;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
+                            if (lane == 0) {
+                                atomicAdd(p.stats + ((long long)u.b * 8 + sgroup) * 2 + 0, (double)s);
+                                atomicAdd(p.stats + ((long long)u.b * 8 + sgroup) * 2 + 1, (double)qq);
+                            }
+                            ssum = 0.f; ssq = 0.f; sgroup = co / gcn;
+                        }
+                        if (ok) {
+                            const float g = (gate ? gate[co] : 1.f) * TC_OUT_SCALE;
+                            float v = __uint_as_float(r[j]) * g;
+                            if (p.R.p) v += p.R.p[pr + (long long)co * p.R.sc];
+                            v *= p.alpha;
+                            p.out.p[po + (long long)co * p.out.sc] = v;
+                            ssum += v; ssq += v * v;
+                        }
+                    }
+                }
+                if (p.stats) {
+                    float s = ssum, qq = ssq;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
+                    if (lane == 0) {
+                        atomicAdd(p.stats + ((long long)u.b * 8 + sgroup) * 2 + 0, (double)s);
+                        atomicAdd(p.stats + ((long long)u.b * 8 + sgroup) * 2 + 1, (double)qq);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty + ab);
+            if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- operand preparation ---------------------------------------------------------------------------------
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+    v = fminf(fmaxf(v, -60000.f), 60000.f);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// w[co][ci][kf][kt] (fp32) -> [kf][Cin/16][hi|lo][kt][2][N][8] fp16, scaled by 2^10
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, __half* __restrict__ wp, int N, int Cin) {
+    const int KS = Cin >> 4;
+    const long long total = (long long)5 * KS * 3 * 2 * N * 8;  // (hi, lo) pairs
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int e = (int)(r % 8); r /= 8;
+        const int n = (int)(r % N); r /= N;
+        const int c = (int)(r % 2); r /= 2;
+        const int kt = (int)(r % 3); r /= 3;
+        const int ks = (int)(r % KS); r /= KS;
+        const int kf = (int)r;
+        const int ci = ks * 16 + c * 8 + e;
+        const float v = w[(((long long)n * Cin + ci) * 5 + kf) * 3 + kt] * TC_W_SCALE;
+        __half hi, lo;
+        split_half(v, hi, lo);
+        const long long blk = (long long)(kf * KS + ks) * (2 * 3 * 2 * N * 8);
+        const long long in_blk = (((long long)kt * 2 + c) * N + n) * 8 + e;
+        wp[blk + 0 * (3 * 2 * N * 8) + in_blk] = hi;
+        wp[blk + 1 * (3 * 2 * N * 8) + in_blk] = lo;
+    }
+}
+
+void launch_pack_weight_tc(const float* w, __half* wp, int N, int Cin, cudaStream_t s) {
+    const long long total = (long long)5 * (Cin / 16) * 3 * 2 * N * 8;
+    pack_weight_tc_kernel<<<(int)min((long long)4096, (total + 255) / 256), 256, 0, s>>>(w, wp, N, Cin);
+    AID_COUNT_LAUNCH(1);
+}
+
+__device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+
+// Normalise / modulate / GELU (unet.py:159-163, 479, 482) writing the split-fp16 planar operand:
+//   a[b][c/8][f][1+t][c%8] = split(16 * act(x[b,c,f,t] * scale_c)),  pad pixels (index 0 and T+1) = 0
+// grid: (ceil(Tp/128), F, B*C/8), block 128: one thread per padded pixel, 8 channels each.
+__global__ void __launch_bounds__(128)
+gn_act_tc_kernel(TV x, const double* __restrict__ stats, double n_per_group, const float* __restrict__ gamma,
+                 const float* __restrict__ affine, long long affine_bstride, int gelu, __half* __restrict__ a_hi,
+                 __half* __restrict__ a_lo) {
+    const int C8 = x.C >> 3;
+    const int c8 = blockIdx.z % C8, b = blockIdx.z / C8, f = blockIdx.y;
+    const int Tp = x.T + 2;
+    const int tp = blockIdx.x * 128 + threadIdx.x;
+    __shared__ float s_scale[8];
+    if (threadIdx.x < 8) {
+        const int c = c8 * 8 + threadIdx.x;
+        const int g = c / (x.C / 8);
+        const double s1 = stats[((long long)b * 8 + g) * 2 + 0], s2 = stats[((long long)b * 8 + g) * 2 + 1];
+        double var = (s2 - s1 * s1 / n_per_group) / (n_per_group - 1.0);
+        var = var > 0.0 ? var : 0.0;
+        const float stdv = (float)sqrt(var);
+        const float mod = affine ? (1.f + affine[b * affine_bstride + c]) : 1.f;
+        s_scale[threadIdx.x] = gamma[c] * mod / (stdv + 1e-7f);
+    }
+    __syncthreads();
+    if (tp >= Tp) return;
+    __align__(16) __half hi[8], lo[8];
+    const int t = tp - 1;
+    if (t < 0 || t >= x.T) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { hi[j] = __float2half_rn(0.f); lo[j] = __float2half_rn(0.f); }
+    } else {
+        const float* src = x.p + (long long)b * x.sb + (long long)(c8 * 8) * x.sc + (long long)f * x.T + t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = __ldg(src + (long long)j * x.sc) * s_scale[j];
+            if (gelu) v = gelu_erf_tc(v);
+            split_half(v * TC_A_SCALE, hi[j], lo[j]);
+        }
+    }
+    const long long o = ((((long long)b * C8 + c8) * x.F + f) * Tp + tp) * 8;
+    *reinterpret_cast<uint4*>(a_hi + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(a_lo + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+void launch_gn_act_tc(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
+                      long long affine_bstride, bool gelu, __half* a_hi, __half* a_lo, cudaStream_t s) {
+    dim3 grid((x.T + 2 + 127) / 128, x.F, x.B * (x.C / 8));
+    gn_act_tc_kernel<<<grid, 128, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, a_hi, a_lo);
+    AID_COUNT_LAUNCH(1);
+}
+
+bool conv_tc_supported(int Cin, int Cout, int KF, int KT) {
+    return KF == 5 && KT == 3 && Cin % 16 == 0 && Cin >= 16 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256;
+}
+
+void launch_conv_tc(const __half* a_hi, const __half* a_lo, const __half* wp, int B, int Cin, int F, int T, int dil, const TV& out,
+                    const ConvEpilogue& ep, int num_sms, cudaStream_t s) {
+    if (ep.R2.p) throw CudaError(cudaErrorInvalidValue, "conv_tc: R2 is not supported", __FILE__, __LINE__);
+    TcConvArgs p{};
+    p.a_hi = a_hi; p.a_lo = a_lo; p.w = wp; p.out = out; p.R = ep.R; p.gate = ep.gate; p.gate_bstride = ep.gate_bstride;
+    p.alpha = ep.alpha; p.stats = ep.stats;
+    p.B = B; p.Cin = Cin; p.N = out.C; p.F = F; p.T = T; p.Tp = T + 2; p.dil = dil;
+    p.tiles_t = (T + 127) / 128;
+    p.n_units = B * F * p.tiles_t;
+    p.n_tiles = (p.n_units + 1) / 2;
+    p.b_bytes = 192 * p.N;  // (hi, lo) x 3 kt x 2 chunks x N x 16 B
+    p.stage_bytes = ((p.b_bytes + 127) & ~127) + TC_A_BYTES;
+    p.nstages = min(6, (220 * 1024) / p.stage_bytes);
+    p.ncol_stride = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256);
+    p.acc_bufs = p.ncol_stride <= 128 ? 2 : 1;
+    const size_t smem = (size_t)p.nstages * p.stage_bytes + 256;
+    static size_t configured = 0;
+    if (smem > configured) {
+        AID_CUDA_CHECK(cudaFuncSetAttribute(conv5x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int grid = min(p.n_tiles, num_sms);
+    conv5x3_tc_kernel<<<grid, TC_THREADS, smem, s>>>(p);
+    AID_COUNT_LAUNCH(1);
+}
+
+}  // namespace aid
+
+namespace aid {
+// plain fp32 NCHW -> split-fp16 planar operand (unit-test entry point aid_op_conv2d, mode 1)
+__global__ void __launch_bounds__(128) to_planar_tc_kernel(TV x, __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
+    const int C8 = x.C >> 3;
+    const int c8 = blockIdx.z % C8, b = blockIdx.z / C8, f = blockIdx.y;
+    const int Tp = x.T + 2;
+    const int tp = blockIdx.x * 128 + threadIdx.x;
+    if (tp >= Tp) return;
+    __align__(16) __half hi[8], lo[8];
+    const int t = tp - 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v = 0.f;
+        if (t >= 0 && t < x.T) v = x.p[(long long)b * x.sb + (long long)(c8 * 8 + j) * x.sc + (long long)f * x.T + t];
+        split_half(v * TC_A_SCALE, hi[j], lo[j]);
+    }
+    const long long o = ((((long long)b * C8 + c8) * x.F + f) * Tp + tp) * 8;
+    *reinterpret_cast<uint4*>(a_hi + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(a_lo + o) = *reinterpret_cast<const uint4*>(lo);
+}
+void launch_to_planar_tc(const TV& x, __half* a_hi, __half* a_lo, cudaStream_t s) {
+    dim3 grid((x.T + 2 + 127) / 128, x.F, x.B * (x.C / 8));
+    to_planar_tc_kernel<<<grid, 128, 0, s>>>(x, a_hi, a_lo);
+    AID_COUNT_LAUNCH(1);
+}
+}  // namespace aid

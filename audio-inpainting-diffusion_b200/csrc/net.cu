@@ -33,7 +33,7 @@ struct Weight {
     size_t numel() const { size_t n = 1; for (auto d : shape) n *= (size_t)d; return n; }
 };
 
-struct ConvW { int widx = -1; float* wp = nullptr; int Cin = 0, Cout = 0, KF = 1, KT = 1; };
+struct ConvW { int widx = -1; float* wp = nullptr; __half* wtc = nullptr; int Cin = 0, Cout = 0, KF = 1, KT = 1; };
 struct LinRef { int w = -1, b = -1; int off = -1, N = 0; };
 struct NormRef { int widx = -1; float* gamma = nullptr; };
 
@@ -96,6 +96,8 @@ struct Net {
     FftPlan fft;
     void* d_tables = nullptr;
     int n_stat_slots = 0;
+    int num_sms = 148;
+    __half* dweights_tc = nullptr;  // split-fp16 packed weights of the tcgen05 convolutions (conv_mode 1)
     std::map<std::string, float*> probes;  // debug: name -> caller buffer that receives a contiguous copy
     // optional per-launch timing of the convolution kernels (bench.py roofline): CUDA events on the launching stream
     struct ProfRec { cudaEvent_t e0, e1; int kind; double flops, bytes; };
@@ -167,7 +169,7 @@ static void build_net(Net& n) {
     if (c.emb_dim != 256) throw std::invalid_argument("emb_dim must be 256");
     if (c.num_bottleneck_layers != 1) throw std::invalid_argument("num_bottleneck_layers must be 1");
     if (c.num_heads < 1) throw std::invalid_argument("num_heads must be >= 1");
-    if (c.conv_mode != 0) throw std::invalid_argument("conv_mode 1 (tcgen05) is not built into this library yet");
+    if (c.conv_mode != 0 && c.conv_mode != 1) throw std::invalid_argument("conv_mode must be 0 (fp32 CUDA cores) or 1 (tcgen05 split-fp16)");
     const int no = c.num_octs, bins = c.bins_per_oct;
     n.emb_idx[0] = add_weight(n, "embedding.RFF_freq", {1, 32});
     const int dims[4] = {64, 128, 256, 256};
@@ -250,6 +252,23 @@ static void finalize_net(Net& n) {
         AID_CUDA_CHECK(cudaGetLastError());
         AID_CUDA_CHECK(cudaDeviceSynchronize());
         off += al(e);
+    }
+    if (n.cfg.conv_mode == 1) {
+        AID_CUDA_CHECK(cudaDeviceGetAttribute(&n.num_sms, cudaDevAttrMultiProcessorCount, n.device));
+        size_t tc_total = 0;
+        for (auto* c : convs) if (conv_tc_supported(c->Cin, c->Cout, c->KF, c->KT)) tc_total += al(2 * n.weights[c->widx].numel());
+        if (tc_total) AID_CUDA_CHECK(cudaMalloc(&n.dweights_tc, tc_total * sizeof(__half)));
+        size_t toff = 0;
+        for (auto* c : convs) {
+            if (!conv_tc_supported(c->Cin, c->Cout, c->KF, c->KT)) continue;
+            Weight& w = n.weights[c->widx];
+            AID_CUDA_CHECK(cudaMemcpy(stage, w.host.data(), w.numel() * sizeof(float), cudaMemcpyHostToDevice));
+            c->wtc = n.dweights_tc + toff;
+            launch_pack_weight_tc(stage, c->wtc, c->Cout, c->Cin, 0);
+            AID_CUDA_CHECK(cudaGetLastError());
+            AID_CUDA_CHECK(cudaDeviceSynchronize());
+            toff += al(2 * w.numel());
+        }
     }
     AID_CUDA_CHECK(cudaFree(stage));
     for (auto* nr : norms) {
@@ -349,6 +368,23 @@ static void conv(Ctx& c, const TV& a, const ConvW& w, int dil, const TV& out, Co
     if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
+static void conv_tc(Ctx& c, const __half* a_hi, const __half* a_lo, const ConvW& w, int dil, const TV& out, ConvEpilogue ep) {
+    if (out.C != w.Cout) throw std::runtime_error("conv_tc: shape mismatch");
+    if (c.dry()) return;
+    Net& n = *c.n;
+    Net::ProfRec rec{};
+    if (n.prof) {
+        auto get = [&]() { cudaEvent_t e; if (n.prof_pool.empty()) { AID_CUDA_CHECK(cudaEventCreate(&e)); } else { e = n.prof_pool.back(); n.prof_pool.pop_back(); } return e; };
+        rec.e0 = get(); rec.e1 = get(); rec.kind = 0;
+        const double px = (double)out.B * out.F * out.T;
+        rec.flops = 2.0 * w.Cin * w.Cout * 15 * px;
+        rec.bytes = 4.0 * (px * (w.Cin + w.Cout + (ep.R.p ? w.Cout : 0)) + (double)w.Cin * w.Cout * 15);
+        AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
+    }
+    launch_conv_tc(a_hi, a_lo, w.wtc, out.B, w.Cin, out.F, out.T, dil, out, ep, n.num_sms, c.s);
+    if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
+}
+
 // unet.py:452-493.  `accum` (decoder out blocks, unet.py:817): out = (accum + block(x)) / sqrt(2), may alias out.
 static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = nullptr) {
     const int B = in.B, F = in.F, T = in.T, N = k.N;
@@ -356,7 +392,11 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
     const long long plane = (long long)B * N * F * T;
     const long long n_grp = (long long)(N / 8) * F * T;
     float* xbuf = c.allocf(plane);
-    float* abuf = c.allocf(plane);
+    // operand buffer: fp32 [B,N,F,T] for the CUDA-core path, or split-fp16 planar hi|lo [B][N/8][F][T+2][8] each (tcgen05 path)
+    const long long a_halves = (long long)B * N * F * (T + 2);
+    float* abuf = c.allocf(std::max(plane, a_halves));
+    __half* a_hi = reinterpret_cast<__half*>(abuf);
+    __half* a_lo = a_hi + a_halves;
     TV x = make_tv(xbuf, B, N, F, T), a = make_tv(abuf, B, N, F, T);
     TV cur;
     if (k.dim != N) {
@@ -386,13 +426,20 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         cur = x;
     }
     for (int i = 0; i < k.nd; ++i) {
-        RUN(launch_gn_act(cur, cur.stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, a, c.s));
         ConvEpilogue ep;
         ep.gate = c.mod + k.gate[i].off; ep.gate_bstride = c.modstride();
         ep.R = cur; ep.alpha = kInvSqrt2;
         ep.stats = (i + 1 < k.nd) ? c.new_slot() : nullptr;
-        x.stats = ep.stats;
-        conv(c, a, k.H[i], k.k1x1 ? 1 : (1 << i), x, ep);
+        const double* cur_stats = cur.stats;
+        if (k.H[i].wtc) {
+            RUN(launch_gn_act_tc(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, a_hi, a_lo, c.s));
+            x.stats = ep.stats;
+            conv_tc(c, a_hi, a_lo, k.H[i], 1 << i, x, ep);
+        } else {
+            RUN(launch_gn_act(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, a, c.s));
+            x.stats = ep.stats;
+            conv(c, a, k.H[i], k.k1x1 ? 1 : (1 << i), x, ep);
+        }
         cur = x;
     }
     if (k.after && N != k.dim_out) {
@@ -582,6 +629,7 @@ void aid_destroy(aid_handle* h) {
     if (!h) return;
     cudaSetDevice(h->net.device);
     if (h->net.dweights) cudaFree(h->net.dweights);
+    if (h->net.dweights_tc) cudaFree(h->net.dweights_tc);
     if (h->net.d_tables) cudaFree(h->net.d_tables);
     delete h;
 }
@@ -759,10 +807,26 @@ int aid_op_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Co
         ConvEpilogue ep; ep.gate = gate_dev; ep.gate_bstride = 0; ep.alpha = alpha; ep.beta = beta; ep.stats = stats_dev;
         if (R_dev) ep.R = make_tv(const_cast<float*>(R_dev), B, Cout, F, T);
         if (R2_dev) ep.R2 = make_tv(const_cast<float*>(R2_dev), B, Cout, F, T);
-        if (mode != 0) throw std::invalid_argument("conv mode not built");
-        launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
-        AID_CUDA_CHECK(cudaGetLastError());
-        AID_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (mode == 1) {
+            if (!conv_tc_supported(Cin, Cout, KF, KT) || R2_dev) throw std::invalid_argument("shape not supported by the tcgen05 path");
+            int sms = 148, dev = 0;
+            AID_CUDA_CHECK(cudaGetDevice(&dev));
+            AID_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            __half *wtc = nullptr, *ah = nullptr;
+            const size_t ahalves = (size_t)B * Cin * F * (T + 2);
+            AID_CUDA_CHECK(cudaMalloc(&wtc, 2 * e * sizeof(__half)));
+            AID_CUDA_CHECK(cudaMalloc(&ah, 2 * ahalves * sizeof(__half)));
+            launch_pack_weight_tc(w_dev, wtc, Cout, Cin, s);
+            launch_to_planar_tc(a, ah, ah + ahalves, s);
+            launch_conv_tc(ah, ah + ahalves, wtc, B, Cin, F, T, dil, out, ep, sms, s);
+            AID_CUDA_CHECK(cudaGetLastError());
+            AID_CUDA_CHECK(cudaStreamSynchronize(s));
+            AID_CUDA_CHECK(cudaFree(wtc)); AID_CUDA_CHECK(cudaFree(ah));
+        } else if (mode == 0) {
+            launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
+            AID_CUDA_CHECK(cudaGetLastError());
+            AID_CUDA_CHECK(cudaStreamSynchronize(s));
+        } else throw std::invalid_argument("unknown conv mode");
         AID_CUDA_CHECK(cudaFree(wp));
         return AID_OK;
     } catch (const CudaError& e) { return AID_ERR_CUDA; }

@@ -1,0 +1,102 @@
+"""GPU parity of the tcgen05 (split-fp16 tensor-core) path for the dilated 5x3 convolutions, through the C ABI.
+
+The split a_hi*w_hi + a_lo*w_hi + a_hi*w_lo keeps ~22 mantissa bits, so the single-op tolerance is 1e-5 and the
+whole-network tolerance stays 1e-4 against the fp32 CPU oracle (published bar: 1e-3)."""
+import math
+
+import pytest
+import torch
+
+from util import rel_l2, seeded, make_oracle
+from test_gpu_ops import conv_ref, _lib
+
+pytestmark = pytest.mark.gpu
+
+TC_CASES = [
+    # B, Cin, Cout, F, T, dil, stats
+    (1, 16, 16, 3, 128, 1, False),     # smallest legal shape, one unit pair
+    (2, 64, 64, 20, 256, 1, True),     # level-0-like
+    (1, 64, 64, 20, 384, 2, True),     # 3 t-tiles per row -> units of one CTA straddle rows
+    (1, 96, 96, 33, 128, 4, True),     # N = 96 (two accumulator buffers of 128 columns), odd F
+    (1, 128, 128, 40, 64, 16, True),   # T < 128: partial unit, dilation skips taps
+    (1, 256, 256, 24, 64, 64, True),   # N = 256 (single accumulator buffer), only the centre tap row is in range
+    (3, 32, 48, 9, 16, 2, True),       # tiny T, Cin != Cout
+    (1, 256, 256, 70, 128, 32, True),  # deep level shape
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc(cuda, case):
+    B, Cin, Cout, Fd, T, dil, use_stats = case
+    L = _lib()
+    a = seeded((B, Cin, Fd, T), 1)
+    w = seeded((Cout, Cin, 5, 3), 2, 1.0 / math.sqrt(Cin * 15))
+    gate, R = seeded((Cout,), 3), seeded((B, Cout, Fd, T), 4)
+    alpha = 0.70710678
+    ref = conv_ref(a, w, dil, gate, R, None, alpha)
+    ad, wd, gd, Rd = a.to(cuda), w.to(cuda), gate.to(cuda), R.to(cuda)
+    out = torch.full((B, Cout, Fd, T), float("nan"), device=cuda)
+    stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=cuda) if use_stats else None
+    L.check(L.lib().aid_op_conv2d(L.ptr(ad), L.ptr(wd), B, Cin, Cout, Fd, T, 5, 3, dil, L.ptr(gd), L.ptr(Rd), None,
+                                  alpha, 0.0, L.ptr(out), L.ptr(stats), 1, None))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < 1e-5
+    # the convolution term alone (residual removed) to the same tolerance: the residual must not mask an MMA error
+    assert rel_l2(out.cpu().double() - alpha * R.double(), ref - alpha * R.double()) < 1e-5
+    if use_stats:
+        g = ref.reshape(B, 8, -1)
+        assert torch.allclose(stats[:, :, 0].cpu(), g.sum(-1), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(stats[:, :, 1].cpu(), (g * g).sum(-1), rtol=1e-5, atol=1e-3)
+
+
+def test_conv_tc_matches_simt_kernel(cuda):
+    """Same inputs through both CUDA paths (device-side cross-check, large enough to use every SM several times)."""
+    L = _lib()
+    B, Cn, Fd, T = 4, 64, 64, 1024
+    a, w = seeded((B, Cn, Fd, T), 1).to(cuda), seeded((Cn, Cn, 5, 3), 2, 0.03).to(cuda)
+    g, R = seeded((Cn,), 3).to(cuda), seeded((B, Cn, Fd, T), 4).to(cuda)
+    outs = []
+    for mode in (0, 1):
+        out = torch.empty(B, Cn, Fd, T, device=cuda)
+        L.check(L.lib().aid_op_conv2d(L.ptr(a), L.ptr(w), B, Cn, Cn, Fd, T, 5, 3, 2, L.ptr(g), L.ptr(R), None, 0.5, 0.0, L.ptr(out), None, mode, None))
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert rel_l2(outs[1], outs[0]) < 1e-5
+
+
+@pytest.fixture(scope="module")
+def small_tc(aid, cuda):
+    # widths that are multiples of 16 so that every dilated layer takes the tcgen05 path
+    cfg = aid.NetConfig(audio_len=16384, Ns=[16, 16, 32, 32, 32, 48, 64], num_dils=[1, 2, 2, 3, 3, 3, 2], conv_mode=1)
+    sd = aid.random_state_dict(cfg, seed=77)
+    net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+    net.load_state_dict(sd)
+    return cfg, sd, net, make_oracle(cfg, sd)
+
+
+def test_forward_tc_blockwise_vs_oracle(small_tc, cuda):
+    cfg, sd, net, orc = small_tc
+    x = seeded((2, cfg.audio_len), 21, 0.8)
+    cn = torch.tensor([[-0.9]])
+    probe = {}
+    ref = orc(x, cn, probe=probe)
+    out, got = net.forward_with_probes(x.to(cuda), cn.to(cuda))
+    assert rel_l2(out, ref) < 1e-4
+    for k in sorted(probe):
+        assert rel_l2(got[k], probe[k]) < 1e-4, k
+
+
+def test_forward_tc_paper_network_matches_reference_golden(aid, cuda):
+    """BASELINE config 1 with the tensor-core path against the numbers the reference's own code produced."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden.npz"))
+    cfg = aid.paper_22k(65536, conv_mode=1)
+    net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+    net.load_state_dict(aid.random_state_dict(cfg, seed=1234))
+    e = aid.EDM(aid.AttrDict.wrap({"diff_params": dict(sigma_min=1e-4, sigma_max=1.0, ro=13, sigma_data=0.063, Schurn=10,
+                                                        Stmin=0, Stmax=50, Snoise=1.0)}))
+    x = seeded((1, 65536), 0).to(cuda)
+    assert rel_l2(e.denoiser(x, net, torch.tensor([1.0], device=cuda)), torch.from_numpy(g["paper_denoise_0"])) < 1e-4
+    assert rel_l2(e.denoiser(x * 0.05, net, torch.tensor([0.05], device=cuda)), torch.from_numpy(g["paper_denoise_1"])) < 1e-4
