@@ -17,12 +17,13 @@
 // One CTA = 2 units (two accumulators in TMEM share every weight stage), persistent over tiles; warp 0 = bulk-copy
 // producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> coalesced NCHW stores).
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace aid {
 
-static constexpr int TC_THREADS = 192;
+static constexpr int TC_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps
 static constexpr int TC_PLANE = 130 * 16;     // bytes of one (16 B chunk) x (130 pixel) plane of A in smem
 static constexpr int TC_A_BYTES = 8 * TC_PLANE;  // 2 units x (hi, lo) x 2 chunks
 static constexpr float TC_A_SCALE = 16.f, TC_W_SCALE = 1024.f, TC_OUT_SCALE = 1.f / (16.f * 1024.f);
@@ -33,6 +34,7 @@ struct TcConvArgs {
     const float* gate; long long gate_bstride;
     float alpha; double* stats;
     int B, Cin, N, F, T, Tp, dil, tiles_t, n_units, n_tiles, nstages, acc_bufs, ncol_stride, b_bytes, stage_bytes;
+    int dbg;  // AID_TC_DEBUG bits (tuning only): 1 skip epilogue body, 2 skip MMAs, 4 skip A loads, 8 skip B loads
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -85,6 +87,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 struct UnitInfo { int exists, b, f, t0, seg_px; };
 
 __device__ __forceinline__ UnitInfo unit_info(const TcConvArgs& p, int u) {
@@ -109,7 +118,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5x3_tc_kernel(TcConvArgs p)
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < p.nstages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 128); }
+            for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 256); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -125,110 +134,129 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5x3_tc_kernel(TcConvArgs p)
     const int c8_total = p.Cin >> 3;
 
     if (warp == 0) {
-        // ===================== producer: bulk copies HBM/L2 -> shared =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const UnitInfo u0 = unit_info(p, 2 * tile), u1 = unit_info(p, 2 * tile + 1);
-                for (int kf = 0; kf < 5; ++kf) {
-                    const int f0 = u0.f + (kf - 2) * p.dil, f1 = u1.f + (kf - 2) * p.dil;
-                    const bool v0 = u0.exists && f0 >= 0 && f0 < p.F, v1 = u1.exists && f1 >= 0 && f1 < p.F;
-                    if (!(v0 || v1)) continue;
-                    for (int ks = 0; ks < KS; ++ks) {
-                        mbar_wait(empty + stage, phase ^ 1);
-                        uint8_t* sb = smem + (size_t)stage * p.stage_bytes;
-                        const uint32_t bytes = (uint32_t)p.b_bytes + (v0 ? 4u * u0.seg_px * 16u : 0u) + (v1 ? 4u * u1.seg_px * 16u : 0u);
+        // ===================== producer: bulk copies HBM/L2 -> shared (whole warp loops; lanes 0..8 issue) =====================
+        int stage = 0; uint32_t phase = 0;
+        // lane l in [1,8]: A copy of unit i, (hi|lo), chunk c
+        const int ai = (lane - 1) >> 2, ahl = ((lane - 1) >> 1) & 1, ac = (lane - 1) & 1;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const UnitInfo u0 = unit_info(p, 2 * tile), u1 = unit_info(p, 2 * tile + 1);
+            for (int kf = 0; kf < 5; ++kf) {
+                const int f0 = u0.f + (kf - 2) * p.dil, f1 = u1.f + (kf - 2) * p.dil;
+                const bool v0 = u0.exists && f0 >= 0 && f0 < p.F, v1 = u1.exists && f1 >= 0 && f1 < p.F;
+                if (!(v0 || v1)) continue;
+                for (int ks = 0; ks < KS; ++ks) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    uint8_t* sb = smem + (size_t)stage * p.stage_bytes;
+                    if (lane == 0) {
+                        uint32_t bytes = (p.dbg & 8) ? 0u : (uint32_t)p.b_bytes;
+                        if (!(p.dbg & 4)) bytes += (v0 ? 4u * u0.seg_px * 16u : 0u) + (v1 ? 4u * u1.seg_px * 16u : 0u);
                         mbar_expect_tx(full + stage, bytes);
-                        bulk_g2s(sb, p.w + (size_t)(kf * KS + ks) * (p.b_bytes >> 1), (uint32_t)p.b_bytes, full + stage);
-                        uint8_t* sa = sb + p.b_bytes;
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const UnitInfo& u = i ? u1 : u0;
-                            if (!(i ? v1 : v0)) continue;
-                            const int ff = i ? f1 : f0;
-#pragma unroll
-                            for (int hl = 0; hl < 2; ++hl)
-#pragma unroll
-                                for (int c = 0; c < 2; ++c) {
-                                    const size_t off = ((((size_t)u.b * c8_total + (2 * ks + c)) * p.F + ff) * p.Tp + u.t0) * 8;
-                                    bulk_g2s(sa + ((i * 2 + hl) * 2 + c) * TC_PLANE, (hl ? p.a_lo : p.a_hi) + off, (uint32_t)u.seg_px * 16u,
-                                             full + stage);
-                                }
-                        }
-                        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
+                        if (!(p.dbg & 8))
+                            bulk_g2s(sb, p.w + (size_t)(kf * KS + ks) * (p.b_bytes >> 1), (uint32_t)p.b_bytes, full + stage);
                     }
+                    __syncwarp();
+                    if (lane >= 1 && lane <= 8 && !(p.dbg & 4)) {
+                        const UnitInfo& u = ai ? u1 : u0;
+                        if (ai ? v1 : v0) {
+                            const int ff = ai ? f1 : f0;
+                            const size_t off = ((((size_t)u.b * c8_total + (2 * ks + ac)) * p.F + ff) * p.Tp + u.t0) * 8;
+                            bulk_g2s(sb + p.b_bytes + ((ai * 2 + ahl) * 2 + ac) * TC_PLANE, (ahl ? p.a_lo : p.a_hi) + off,
+                                     (uint32_t)u.seg_px * 16u, full + stage);
+                        }
+                    }
+                    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);  // F16 x F16 -> F32, K-major A/B
-            const uint32_t b_lbo = (uint32_t)p.N * 16u;
-            int stage = 0; uint32_t phase = 0; int ab = 0; uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const UnitInfo u0 = unit_info(p, 2 * tile), u1 = unit_info(p, 2 * tile + 1);
-                mbar_wait(tmem_empty + ab, aphase ^ 1);
-                tc_fence_after();
-                uint32_t started[2] = {0u, 0u};
-                for (int kf = 0; kf < 5; ++kf) {
-                    const int f0 = u0.f + (kf - 2) * p.dil, f1 = u1.f + (kf - 2) * p.dil;
-                    const bool v0 = u0.exists && f0 >= 0 && f0 < p.F, v1 = u1.exists && f1 >= 0 && f1 < p.F;
-                    if (!(v0 || v1)) continue;
-                    for (int ks = 0; ks < KS; ++ks) {
-                        mbar_wait(full + stage, phase);
-                        tc_fence_after();
+        // ===================== MMA issuer (whole warp loops, lane 0 issues) =====================
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);  // F16 x F16 -> F32, K-major A/B
+        const uint32_t b_lbo = (uint32_t)p.N * 16u;
+        int stage = 0; uint32_t phase = 0; int ab = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const UnitInfo u0 = unit_info(p, 2 * tile), u1 = unit_info(p, 2 * tile + 1);
+            mbar_wait(tmem_empty + ab, aphase ^ 1);
+            tc_fence_after();
+            uint32_t started[2] = {0u, 0u};
+            for (int kf = 0; kf < 5; ++kf) {
+                const int f0 = u0.f + (kf - 2) * p.dil, f1 = u1.f + (kf - 2) * p.dil;
+                const bool v0 = u0.exists && f0 >= 0 && f0 < p.F, v1 = u1.exists && f1 >= 0 && f1 < p.F;
+                if (!(v0 || v1)) continue;
+                for (int ks = 0; ks < KS; ++ks) {
+                    mbar_wait(full + stage, phase);
+                    tc_fence_after();
+                    if (lane == 0) {
                         const uint32_t sb = smem_u32(smem + (size_t)stage * p.stage_bytes);
                         const uint32_t sa = sb + (uint32_t)p.b_bytes;
+                        if (!(p.dbg & 2)) {
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            if (!(i ? v1 : v0)) continue;
-                            const uint32_t d = tmem_base + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride);
+                            for (int i = 0; i < 2; ++i) {
+                                if (!(i ? v1 : v0)) continue;
+                                const uint32_t d = tmem_base + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride);
 #pragma unroll
-                            for (int kt = 0; kt < 3; ++kt) {
-                                const uint64_t a_hi = make_desc(sa + (uint32_t)((i * 2 + 0) * 2) * TC_PLANE + kt * 16, TC_PLANE, 128);
-                                const uint64_t a_lo = make_desc(sa + (uint32_t)((i * 2 + 1) * 2) * TC_PLANE + kt * 16, TC_PLANE, 128);
-                                const uint64_t b_hi = make_desc(sb + (uint32_t)((0 * 3 + kt) * 2) * b_lbo, b_lbo, 128);
-                                const uint64_t b_lo = make_desc(sb + (uint32_t)((1 * 3 + kt) * 2) * b_lbo, b_lbo, 128);
-                                tc_mma_f16(d, a_hi, b_hi, idesc, started[i]);
-                                started[i] = 1u;
-                                tc_mma_f16(d, a_lo, b_hi, idesc, 1u);
-                                tc_mma_f16(d, a_hi, b_lo, idesc, 1u);
+                                for (int kt = 0; kt < 3; ++kt) {
+                                    const uint64_t a_hi = make_desc(sa + (uint32_t)((i * 2 + 0) * 2) * TC_PLANE + kt * 16, TC_PLANE, 128);
+                                    const uint64_t a_lo = make_desc(sa + (uint32_t)((i * 2 + 1) * 2) * TC_PLANE + kt * 16, TC_PLANE, 128);
+                                    const uint64_t b_hi = make_desc(sb + (uint32_t)((0 * 3 + kt) * 2) * b_lbo, b_lbo, 128);
+                                    const uint64_t b_lo = make_desc(sb + (uint32_t)((1 * 3 + kt) * 2) * b_lbo, b_lbo, 128);
+                                    tc_mma_f16(d, a_hi, b_hi, idesc, started[i]);
+                                    started[i] = 1u;
+                                    tc_mma_f16(d, a_lo, b_hi, idesc, 1u);
+                                    tc_mma_f16(d, a_hi, b_lo, idesc, 1u);
+                                }
                             }
                         }
                         tc_commit(empty + stage);  // frees the smem slot when these MMAs have read it
-                        if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == p.nstages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tmem_full + ab);  // accumulators of this tile are complete
-                if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
             }
+            if (lane == 0) tc_commit(tmem_full + ab);  // accumulators of this tile are complete
+            __syncwarp();
+            if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> out = alpha*(acc*gate + R), statistics =====================
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        // 8 warps: warp e handles TMEM lane quadrant (e & 3) and column half (e >> 2) of both units.
+        const int e = warp - 2;
+        const int q = warp & 3;          // TMEM lane quadrant this warp may access (warpid % 4)
+        const int half = e >> 2;
+        const int ncols = p.N >> 1;      // columns per warp (multiple of 8)
+        const int cbeg = half * ncols;
         int ab = 0; uint32_t aphase = 0;
         const int gcn = p.N / 8;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             mbar_wait(tmem_full + ab, aphase);
             tc_fence_after();
 #pragma unroll 1
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < 2 && !(p.dbg & 1); ++i) {
                 const UnitInfo u = unit_info(p, 2 * tile + i);
                 if (!u.exists) continue;
                 const int t = u.t0 + q * 32 + lane;
                 const bool ok = t < p.T;
-                const long long po = (long long)u.b * p.out.sb + (long long)u.f * p.T + t;
-                const long long pr = (long long)u.b * p.R.sb + (long long)u.f * p.T + t;
+                float* po = p.out.p + (long long)u.b * p.out.sb + (long long)u.f * p.T + t;
+                const float* pr = p.R.p ? p.R.p + (long long)u.b * p.R.sb + (long long)u.f * p.T + t : nullptr;
                 const float* gate = p.gate ? p.gate + (long long)u.b * p.gate_bstride : nullptr;
                 float ssum = 0.f, ssq = 0.f;
-                int sgroup = 0;
-#pragma unroll 1
-                for (int c0 = 0; c0 < p.N; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride + c0), r);
+                int sgroup = cbeg / gcn;
+                float rcur[8], rnext[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 8; ++j) rcur[j] = (ok && pr) ? pr[(long long)(cbeg + j) * p.R.sc] : 0.f;
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + ncols; c0 += 8) {
+                    // issue the next chunk's residual loads before touching this chunk (loads may alias the stores below,
+                    // so the compiler cannot hoist them itself)
+                    const bool more = c0 + 8 < cbeg + ncols;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rnext[j] = (ok && pr && more) ? pr[(long long)(c0 + 8 + j) * p.R.sc] : 0.f;
+                    uint32_t r[8];
+                    tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride + c0), r);
+                    float gv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) gv[j] = (gate ? __ldg(gate + c0 + j) : 1.f) * TC_OUT_SCALE;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
                         const int co = c0 + j;
                         if (p.stats && co / gcn != sgroup) {
                             // flush the finished group: warp-reduce, one double atomic per warp
@@ -242,14 +270,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5x3_tc_kernel(TcConvArgs p)
                             ssum = 0.f; ssq = 0.f; sgroup = co / gcn;
                         }
                         if (ok) {
-                            const float g = (gate ? gate[co] : 1.f) * TC_OUT_SCALE;
-                            float v = __uint_as_float(r[j]) * g;
-                            if (p.R.p) v += p.R.p[pr + (long long)co * p.R.sc];
-                            v *= p.alpha;
-                            p.out.p[po + (long long)co * p.out.sc] = v;
+                            const float v = (__uint_as_float(r[j]) * gv[j] + rcur[j]) * p.alpha;
+                            po[(long long)co * p.out.sc] = v;
                             ssum += v; ssq += v * v;
                         }
                     }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
                 }
                 if (p.stats) {
                     float s = ssum, qq = ssq;
@@ -383,6 +410,8 @@ void launch_conv_tc(const __half* a_hi, const __half* a_lo, const __half* wp, in
     p.ncol_stride = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256);
     p.acc_bufs = p.ncol_stride <= 128 ? 2 : 1;
     const size_t smem = (size_t)p.nstages * p.stage_bytes + 256;
+    static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
+    p.dbg = dbg;
     static size_t configured = 0;
     if (smem > configured) {
         AID_CUDA_CHECK(cudaFuncSetAttribute(conv5x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

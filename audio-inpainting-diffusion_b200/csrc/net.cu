@@ -792,11 +792,10 @@ int aid_edm_step(const float* xin, const float* xhat, const float* y, const floa
 }
 
 // ---- single-operator entry points -----------------------------------------------------------------------
-int aid_op_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
-                  const float* gate_dev, const float* R_dev, const float* R2_dev, float alpha, float beta, float* out_dev,
-                  double* stats_dev, int mode, void* stream) {
+static int op_conv2d_impl(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
+                          const float* gate_dev, const float* R_dev, const float* R2_dev, float alpha, float beta, float* out_dev,
+                          double* stats_dev, int mode, void* stream, int iters, float* ms_out) {
     if (!a_dev || !w_dev || !out_dev) return AID_ERR_INVALID;
-    static std::string err;
     try {
         cudaStream_t s = (cudaStream_t)stream;
         float* wp = nullptr;
@@ -807,30 +806,54 @@ int aid_op_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Co
         ConvEpilogue ep; ep.gate = gate_dev; ep.gate_bstride = 0; ep.alpha = alpha; ep.beta = beta; ep.stats = stats_dev;
         if (R_dev) ep.R = make_tv(const_cast<float*>(R_dev), B, Cout, F, T);
         if (R2_dev) ep.R2 = make_tv(const_cast<float*>(R2_dev), B, Cout, F, T);
+        cudaEvent_t e0, e1;
+        AID_CUDA_CHECK(cudaEventCreate(&e0)); AID_CUDA_CHECK(cudaEventCreate(&e1));
+        __half *wtc = nullptr, *ah = nullptr;
+        const size_t ahalves = (size_t)B * Cin * F * (T + 2);
+        int sms = 148, dev = 0;
         if (mode == 1) {
             if (!conv_tc_supported(Cin, Cout, KF, KT) || R2_dev) throw std::invalid_argument("shape not supported by the tcgen05 path");
-            int sms = 148, dev = 0;
             AID_CUDA_CHECK(cudaGetDevice(&dev));
             AID_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            __half *wtc = nullptr, *ah = nullptr;
-            const size_t ahalves = (size_t)B * Cin * F * (T + 2);
             AID_CUDA_CHECK(cudaMalloc(&wtc, 2 * e * sizeof(__half)));
             AID_CUDA_CHECK(cudaMalloc(&ah, 2 * ahalves * sizeof(__half)));
             launch_pack_weight_tc(w_dev, wtc, Cout, Cin, s);
             launch_to_planar_tc(a, ah, ah + ahalves, s);
-            launch_conv_tc(ah, ah + ahalves, wtc, B, Cin, F, T, dil, out, ep, sms, s);
-            AID_CUDA_CHECK(cudaGetLastError());
-            AID_CUDA_CHECK(cudaStreamSynchronize(s));
-            AID_CUDA_CHECK(cudaFree(wtc)); AID_CUDA_CHECK(cudaFree(ah));
-        } else if (mode == 0) {
-            launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
-            AID_CUDA_CHECK(cudaGetLastError());
-            AID_CUDA_CHECK(cudaStreamSynchronize(s));
-        } else throw std::invalid_argument("unknown conv mode");
+        } else if (mode != 0) throw std::invalid_argument("unknown conv mode");
+        (void)iters;
+        AID_CUDA_CHECK(cudaEventRecord(e0, s));
+        if (mode == 1) launch_conv_tc(ah, ah + ahalves, wtc, B, Cin, F, T, dil, out, ep, sms, s);
+        else launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
+        AID_CUDA_CHECK(cudaEventRecord(e1, s));
+        AID_CUDA_CHECK(cudaGetLastError());
+        AID_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (ms_out) AID_CUDA_CHECK(cudaEventElapsedTime(ms_out, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (wtc) AID_CUDA_CHECK(cudaFree(wtc));
+        if (ah) AID_CUDA_CHECK(cudaFree(ah));
         AID_CUDA_CHECK(cudaFree(wp));
         return AID_OK;
-    } catch (const CudaError& e) { return AID_ERR_CUDA; }
-    catch (const std::exception&) { return AID_ERR_INVALID; }
+    } catch (const CudaError& e) { fprintf(stderr, "aid_op_conv2d: CUDA error %s at %s:%d\n", cudaGetErrorString(e.code), e.file, e.line); return AID_ERR_CUDA; }
+    catch (const std::exception& e) { fprintf(stderr, "aid_op_conv2d: %s\n", e.what()); return AID_ERR_INVALID; }
+}
+
+int aid_op_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
+                  const float* gate_dev, const float* R_dev, const float* R2_dev, float alpha, float beta, float* out_dev,
+                  double* stats_dev, int mode, void* stream) {
+    return op_conv2d_impl(a_dev, w_dev, B, Cin, Cout, F, T, KF, KT, dil, gate_dev, R_dev, R2_dev, alpha, beta, out_dev, stats_dev, mode,
+                          stream, 1, nullptr);
+}
+
+/* debug/tuning: like aid_op_conv2d but returns the device time of the convolution kernel alone (one launch, after a
+ * warm-up launch); not part of the drop-in surface */
+int aid_debug_time_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
+                          const float* gate_dev, const float* R_dev, float alpha, float* out_dev, double* stats_dev, int mode,
+                          float* ms_out) {
+    int rc = op_conv2d_impl(a_dev, w_dev, B, Cin, Cout, F, T, KF, KT, dil, gate_dev, R_dev, nullptr, alpha, 0.f, out_dev, stats_dev, mode,
+                            nullptr, 1, nullptr);
+    if (rc != AID_OK) return rc;
+    return op_conv2d_impl(a_dev, w_dev, B, Cin, Cout, F, T, KF, KT, dil, gate_dev, R_dev, nullptr, alpha, 0.f, out_dev, stats_dev, mode,
+                          nullptr, 1, ms_out);
 }
 
 int aid_op_groupnorm_act(const float* x_dev, const float* gamma_dev, const float* affine_dev, int B, int C, int F, int T, int gelu,

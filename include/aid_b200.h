@@ -115,6 +115,12 @@ int aid_op_attention(const float* h_dev, const float* qk_dev, int B, int heads, 
 /* RFF_MLP_Block + every adaLN Linear: returns the emb [n_sigma,256]                          unet.py:184-211 */
 int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float* emb_dev, void* stream);
 
+/* Debug/tuning (not part of the drop-in surface): aid_op_conv2d run twice, returning the device time in ms of the
+ * second convolution launch alone. */
+int aid_debug_time_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
+                          const float* gate_dev, const float* R_dev, float alpha, float* out_dev, double* stats_dev, int mode,
+                          float* ms_out);
+
 /* Per-launch timing of the convolution kernels with CUDA events on the launching stream (bench.py's roofline).
  * aid_profile(h, 1) clears and starts recording, aid_profile(h, 0) stops; aid_profile_read sums the recorded launches
  * of one kind (0 = dilated 5x3 residual-layer convolutions, 1 = all other convolutions): count, device ms, algorithmic
