@@ -71,12 +71,12 @@ void launch_mod_vectors(const float* emb, int n_sigma, const float* W, const flo
 // tcgen05 path for the dilated 5x3 convolutions (conv_tc.cu).  Operands are split-fp16 planar: [B][C/8][F][T+2][8].
 
 bool conv_tc_supported(int Cin, int Cout, int KF, int KT);
-void launch_pack_weight_tc(const float* w, __half* wp, int N, int Cin, cudaStream_t s);
+void launch_pack_weight_tc(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s);
 void launch_gn_act_tc(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
                       long long affine_bstride, bool gelu, __half* a_hi, __half* a_lo, cudaStream_t s);
 void launch_to_planar_tc(const TV& x, __half* a_hi, __half* a_lo, cudaStream_t s);
-void launch_conv_tc(const __half* a_hi, const __half* a_lo, const __half* wp, int B, int Cin, int F, int T, int dil, const TV& out,
-                    const ConvEpilogue& ep, int num_sms, cudaStream_t s);
+void launch_conv_tc(const __half* a_hi, const __half* a_lo, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,
+                    const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s);
 
 // FFT / CQT
 struct FftPlan {

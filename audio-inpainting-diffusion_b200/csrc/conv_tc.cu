@@ -1,21 +1,24 @@
-// tcgen05 (5th-gen tensor core) implicit-GEMM kernel for the dilated 5x3 residual-layer convolutions
-// (unet.py:433-436, 482) -- 95 % of the forward's FLOPs -- with the gate/residual/statistics epilogue fused.
+// tcgen05 (5th-gen tensor core) implicit-GEMM kernel for the network's convolutions with the gate / residual /
+// statistics epilogue fused:
+//   * the dilated 5x3 residual-layer convolutions (unet.py:433-436, 482) -- 95 % of the forward's FLOPs,
+//   * the 1x1 "H" convolutions of the init / out blocks (unet.py:675, 690, 719), the block projections
+//     proj_in / res_conv (unet.py:412-415) and the attention qk Conv1d (unet.py:321, 355), all as taps = 1.
 //
-// Precision: error-compensated split fp16.  The normalise/modulate/GELU pass writes every activation as
-// a = a_hi + a_lo (two fp16, scaled by 2^4), weights are pre-split the same way (scaled by 2^10); the kernel issues
-// a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (kind::f16, fp32 accumulation in TMEM).  The dropped a_lo*w_lo term is 2^-22
-// relative, so the result is fp32-grade (the 1e-3 parity bar rules out single bf16/tf32 products over 75 layers).
+// Precision: error-compensated split fp16.  Activations are written as a = a_hi + a_lo (two fp16, scaled by 2^4),
+// weights are pre-split the same way (scaled by 2^10); the kernel issues a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+// (kind::f16, fp32 accumulation in TMEM).  The dropped a_lo*w_lo term is 2^-22 relative, so the result is fp32-grade
+// (the 1e-3 parity bar rules out single bf16/tf32 products through 75 stacked residual layers).
 //
 // GEMM view per "unit" = 128 consecutive pixels of one (clip, frequency row):
-//     D[128 px, N=Cout] += A[128 px, 16 ch] * B[N, 16 ch]^T     for every (kf, kt, 16-channel step)
+//     D[128 px, Ntile couts] += A[128 px, 16 ch] * B[Ntile, 16 ch]^T     for every (kf, kt, 16-channel step)
 // Layouts (all K-major, SWIZZLE_NONE canonical: core matrix = 8 rows x 16 B, SBO = 128 B, LBO = plane stride):
 //   activations in HBM : [B][C/8][F][T+2][8] fp16 (hi and lo arrays); one zero pixel each side of T = the conv's zero
 //                        padding along T.  A 130-pixel window of one row is ONE contiguous 2080-byte run, fetched with
-//                        cp.async.bulk; the three kt taps are the same window with the descriptor start advanced by 16 B.
-//   weights in HBM     : [kf][Cin/16][hi|lo][kt][2 chunks][N][8] fp16 -> one contiguous bulk copy per pipeline stage.
+//                        cp.async.bulk; the kt taps are the same window with the descriptor start advanced by 16 B.
+//   weights in HBM     : [n-tile][kf][Cin/16][hi|lo][kt][2 chunks][Ntile][8] fp16 -> one contiguous bulk copy per stage.
 //   zero padding along F: a tap row outside [0,F) is skipped (no MMA issued), never loaded.
-// One CTA = 2 units (two accumulators in TMEM share every weight stage), persistent over tiles; warp 0 = bulk-copy
-// producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue (TMEM -> registers -> coalesced NCHW stores).
+// One CTA tile = 2 units x one n-tile (two accumulators in TMEM share every weight stage), persistent over tiles;
+// warp 0 = bulk-copy producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = epilogue (TMEM -> registers -> NCHW).
 #include <cuda_fp16.h>
 #include <cstdlib>
 
@@ -23,9 +26,9 @@
 
 namespace aid {
 
-static constexpr int TC_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps
+static constexpr int TC_THREADS = 320;        // producer warp, MMA warp, 8 epilogue warps
 static constexpr int TC_PLANE = 130 * 16;     // bytes of one (16 B chunk) x (130 pixel) plane of A in smem
-static constexpr int TC_A_BYTES = 8 * TC_PLANE;  // 2 units x (hi, lo) x 2 chunks
+static constexpr int TC_MAX_KPS = 2;          // 16-channel k-steps per pipeline stage (1 for 5x3, 2 for 1x1)
 static constexpr float TC_A_SCALE = 16.f, TC_W_SCALE = 1024.f, TC_OUT_SCALE = 1.f / (16.f * 1024.f);
 
 struct TcConvArgs {
@@ -33,7 +36,10 @@ struct TcConvArgs {
     TV out, R;
     const float* gate; long long gate_bstride;
     float alpha; double* stats;
-    int B, Cin, N, F, T, Tp, dil, tiles_t, n_units, n_tiles, nstages, acc_bufs, ncol_stride, b_bytes, stage_bytes;
+    int B, Cin, Ntot, Ntile, n_ntiles, F, T, Tp, dil;
+    int KF, KT, kt_shift, kps;                 // taps along F / T, first tap's pixel shift inside the window, k-steps per stage
+    int tiles_t, n_units, n_pairs, n_tiles, nstages, acc_bufs, ncol_stride;
+    int b_kstep_bytes, a_bytes, stage_bytes;
     int dbg;  // AID_TC_DEBUG bits (tuning only): 1 skip epilogue body, 2 skip MMAs, 4 skip A loads, 8 skip B loads
 };
 
@@ -78,15 +84,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -105,7 +102,7 @@ __device__ __forceinline__ UnitInfo unit_info(const TcConvArgs& p, int u) {
     return i;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) conv5x3_tc_kernel(TcConvArgs p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* bar_base = smem + (size_t)p.nstages * p.stage_bytes;
@@ -132,35 +129,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5x3_tc_kernel(TcConvArgs p)
 
     const int KS = p.Cin >> 4;
     const int c8_total = p.Cin >> 3;
+    const int b_bytes_full = p.b_kstep_bytes * p.kps;
 
     if (warp == 0) {
-        // ===================== producer: bulk copies HBM/L2 -> shared (whole warp loops; lanes 0..8 issue) =====================
+        // ===================== producer: bulk copies HBM/L2 -> shared (whole warp loops; lane 0: weights, lanes 1..: A) =====================
         int stage = 0; uint32_t phase = 0;
-        // lane l in [1,8]: A copy of unit i, (hi|lo), chunk c
-        const int ai = (lane - 1) >> 2, ahl = ((lane - 1) >> 1) & 1, ac = (lane - 1) & 1;
+        // lane l >= 1: A copy of unit ai, k-step akk of the stage, (hi|lo), 16-byte chunk ac
+        const int aidx = lane - 1;
+        const int ai = aidx / (p.kps * 4), arem = aidx % (p.kps * 4);
+        const int akk = arem >> 2, ahl = (arem >> 1) & 1, ac = arem & 1;
+        const bool a_lane = lane >= 1 && aidx < 2 * p.kps * 4;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const UnitInfo u0 = unit_info(p, 2 * tile), u1 = unit_info(p, 2 * tile + 1);
-            for (int kf = 0; kf < 5; ++kf) {
-                const int f0 = u0.f + (kf - 2) * p.dil, f1 = u1.f + (kf - 2) * p.dil;
+            const int pair = tile % p.n_pairs, nt = tile / p.n_pairs;
+            const UnitInfo u0 = unit_info(p, 2 * pair), u1 = unit_info(p, 2 * pair + 1);
+            for (int kf = 0; kf < p.KF; ++kf) {
+                const int f0 = u0.f + (kf - p.KF / 2) * p.dil, f1 = u1.f + (kf - p.KF / 2) * p.dil;
                 const bool v0 = u0.exists && f0 >= 0 && f0 < p.F, v1 = u1.exists && f1 >= 0 && f1 < p.F;
                 if (!(v0 || v1)) continue;
-                for (int ks = 0; ks < KS; ++ks) {
+                for (int ks0 = 0; ks0 < KS; ks0 += p.kps) {
+                    const int nk = min(p.kps, KS - ks0);
                     mbar_wait(empty + stage, phase ^ 1);
                     uint8_t* sb = smem + (size_t)stage * p.stage_bytes;
                     if (lane == 0) {
-                        uint32_t bytes = (p.dbg & 8) ? 0u : (uint32_t)p.b_bytes;
-                        if (!(p.dbg & 4)) bytes += (v0 ? 4u * u0.seg_px * 16u : 0u) + (v1 ? 4u * u1.seg_px * 16u : 0u);
+                        const uint32_t bb = (uint32_t)(p.b_kstep_bytes * nk);
+                        uint32_t bytes = (p.dbg & 8) ? 0u : bb;
+                        if (!(p.dbg & 4)) bytes += (uint32_t)nk * ((v0 ? 4u * u0.seg_px * 16u : 0u) + (v1 ? 4u * u1.seg_px * 16u : 0u));
                         mbar_expect_tx(full + stage, bytes);
                         if (!(p.dbg & 8))
-                            bulk_g2s(sb, p.w + (size_t)(kf * KS + ks) * (p.b_bytes >> 1), (uint32_t)p.b_bytes, full + stage);
+                            bulk_g2s(sb, p.w + ((size_t)(nt * p.KF + kf) * KS + ks0) * (p.b_kstep_bytes >> 1), bb, full + stage);
                     }
                     __syncwarp();
-                    if (lane >= 1 && lane <= 8 && !(p.dbg & 4)) {
+                    if (a_lane && akk < nk && !(p.dbg & 4)) {
                         const UnitInfo& u = ai ? u1 : u0;
                         if (ai ? v1 : v0) {
                             const int ff = ai ? f1 : f0;
-                            const size_t off = ((((size_t)u.b * c8_total + (2 * ks + ac)) * p.F + ff) * p.Tp + u.t0) * 8;
-                            bulk_g2s(sb + p.b_bytes + ((ai * 2 + ahl) * 2 + ac) * TC_PLANE, (ahl ? p.a_lo : p.a_hi) + off,
+                            const size_t off = ((((size_t)u.b * c8_total + (2 * (ks0 + akk) + ac)) * p.F + ff) * p.Tp + u.t0) * 8;
+                            bulk_g2s(sb + b_bytes_full + (((ai * p.kps + akk) * 2 + ahl) * 2 + ac) * TC_PLANE, (ahl ? p.a_lo : p.a_hi) + off,
                                      (uint32_t)u.seg_px * 16u, full + stage);
                         }
                     }
@@ -170,39 +174,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5x3_tc_kernel(TcConvArgs p)
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp loops, lane 0 issues) =====================
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);  // F16 x F16 -> F32, K-major A/B
-        const uint32_t b_lbo = (uint32_t)p.N * 16u;
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Ntile >> 3) << 17) | ((128u >> 4) << 24);  // F16 x F16 -> F32, K-major A/B
+        const uint32_t b_lbo = (uint32_t)p.Ntile * 16u;
         int stage = 0; uint32_t phase = 0; int ab = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const UnitInfo u0 = unit_info(p, 2 * tile), u1 = unit_info(p, 2 * tile + 1);
+            const int pair = tile % p.n_pairs;
+            const UnitInfo u0 = unit_info(p, 2 * pair), u1 = unit_info(p, 2 * pair + 1);
             mbar_wait(tmem_empty + ab, aphase ^ 1);
             tc_fence_after();
             uint32_t started[2] = {0u, 0u};
-            for (int kf = 0; kf < 5; ++kf) {
-                const int f0 = u0.f + (kf - 2) * p.dil, f1 = u1.f + (kf - 2) * p.dil;
+            for (int kf = 0; kf < p.KF; ++kf) {
+                const int f0 = u0.f + (kf - p.KF / 2) * p.dil, f1 = u1.f + (kf - p.KF / 2) * p.dil;
                 const bool v0 = u0.exists && f0 >= 0 && f0 < p.F, v1 = u1.exists && f1 >= 0 && f1 < p.F;
                 if (!(v0 || v1)) continue;
-                for (int ks = 0; ks < KS; ++ks) {
+                for (int ks0 = 0; ks0 < KS; ks0 += p.kps) {
+                    const int nk = min(p.kps, KS - ks0);
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sb = smem_u32(smem + (size_t)stage * p.stage_bytes);
-                        const uint32_t sa = sb + (uint32_t)p.b_bytes;
+                        const uint32_t sa = sb + (uint32_t)b_bytes_full;
                         if (!(p.dbg & 2)) {
-#pragma unroll
                             for (int i = 0; i < 2; ++i) {
                                 if (!(i ? v1 : v0)) continue;
                                 const uint32_t d = tmem_base + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride);
-#pragma unroll
-                                for (int kt = 0; kt < 3; ++kt) {
-                                    const uint64_t a_hi = make_desc(sa + (uint32_t)((i * 2 + 0) * 2) * TC_PLANE + kt * 16, TC_PLANE, 128);
-                                    const uint64_t a_lo = make_desc(sa + (uint32_t)((i * 2 + 1) * 2) * TC_PLANE + kt * 16, TC_PLANE, 128);
-                                    const uint64_t b_hi = make_desc(sb + (uint32_t)((0 * 3 + kt) * 2) * b_lbo, b_lbo, 128);
-                                    const uint64_t b_lo = make_desc(sb + (uint32_t)((1 * 3 + kt) * 2) * b_lbo, b_lbo, 128);
-                                    tc_mma_f16(d, a_hi, b_hi, idesc, started[i]);
-                                    started[i] = 1u;
-                                    tc_mma_f16(d, a_lo, b_hi, idesc, 1u);
-                                    tc_mma_f16(d, a_hi, b_lo, idesc, 1u);
+                                for (int kk = 0; kk < nk; ++kk) {
+                                    const uint32_t a0 = sa + (uint32_t)(((i * p.kps + kk) * 2) * 2) * TC_PLANE;
+                                    const uint32_t b0 = sb + (uint32_t)(kk * p.b_kstep_bytes);
+                                    for (int kt = 0; kt < p.KT; ++kt) {
+                                        const uint32_t sh = (uint32_t)(kt + p.kt_shift) * 16u;
+                                        const uint64_t a_hi = make_desc(a0 + sh, TC_PLANE, 128);
+                                        const uint64_t a_lo = make_desc(a0 + 2 * TC_PLANE + sh, TC_PLANE, 128);
+                                        const uint64_t b_hi = make_desc(b0 + (uint32_t)((0 * p.KT + kt) * 2) * b_lbo, b_lbo, 128);
+                                        const uint64_t b_lo = make_desc(b0 + (uint32_t)((1 * p.KT + kt) * 2) * b_lbo, b_lbo, 128);
+                                        tc_mma_f16(d, a_hi, b_hi, idesc, started[i]);
+                                        started[i] = 1u;
+                                        tc_mma_f16(d, a_lo, b_hi, idesc, 1u);
+                                        tc_mma_f16(d, a_hi, b_lo, idesc, 1u);
+                                    }
                                 }
                             }
                         }
@@ -218,35 +227,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5x3_tc_kernel(TcConvArgs p)
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> out = alpha*(acc*gate + R), statistics =====================
-        // 8 warps: warp e handles TMEM lane quadrant (e & 3) and column half (e >> 2) of both units.
+        // 8 warps: warp e handles TMEM lane quadrant (warpid & 3) and column half (e >> 2) of both units.
         const int e = warp - 2;
-        const int q = warp & 3;          // TMEM lane quadrant this warp may access (warpid % 4)
-        const int half = e >> 2;
-        const int ncols = p.N >> 1;      // columns per warp (multiple of 8)
-        const int cbeg = half * ncols;
+        const int q = warp & 3;
+        const int ncols = p.Ntile >> 1;  // columns per warp (multiple of 8)
+        const int cbeg = (e >> 2) * ncols;
         int ab = 0; uint32_t aphase = 0;
-        const int gcn = p.N / 8;
+        const int gcn = p.Ntot / 8;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int pair = tile % p.n_pairs, nt = tile / p.n_pairs;
+            const int co_base = nt * p.Ntile;
             mbar_wait(tmem_full + ab, aphase);
             tc_fence_after();
 #pragma unroll 1
             for (int i = 0; i < 2 && !(p.dbg & 1); ++i) {
-                const UnitInfo u = unit_info(p, 2 * tile + i);
+                const UnitInfo u = unit_info(p, 2 * pair + i);
                 if (!u.exists) continue;
                 const int t = u.t0 + q * 32 + lane;
                 const bool ok = t < p.T;
-                float* po = p.out.p + (long long)u.b * p.out.sb + (long long)u.f * p.T + t;
-                const float* pr = p.R.p ? p.R.p + (long long)u.b * p.R.sb + (long long)u.f * p.T + t : nullptr;
-                const float* gate = p.gate ? p.gate + (long long)u.b * p.gate_bstride : nullptr;
+                float* po = p.out.p + (long long)u.b * p.out.sb + (long long)co_base * p.out.sc + (long long)u.f * p.T + t;
+                const float* pr = p.R.p ? p.R.p + (long long)u.b * p.R.sb + (long long)co_base * p.R.sc + (long long)u.f * p.T + t : nullptr;
+                const float* gate = p.gate ? p.gate + (long long)u.b * p.gate_bstride + co_base : nullptr;
                 float ssum = 0.f, ssq = 0.f;
-                int sgroup = cbeg / gcn;
+                int sgroup = (co_base + cbeg) / gcn;
                 float rcur[8], rnext[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) rcur[j] = (ok && pr) ? pr[(long long)(cbeg + j) * p.R.sc] : 0.f;
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cbeg + ncols; c0 += 8) {
-                    // issue the next chunk's residual loads before touching this chunk (loads may alias the stores below,
-                    // so the compiler cannot hoist them itself)
+                    // issue the next chunk's residual loads before touching this chunk (the loads may alias the stores
+                    // below -- in-place residual update -- so the compiler cannot hoist them itself)
                     const bool more = c0 + 8 < cbeg + ncols;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) rnext[j] = (ok && pr && more) ? pr[(long long)(c0 + 8 + j) * p.R.sc] : 0.f;
@@ -257,7 +267,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5x3_tc_kernel(TcConvArgs p)
                     for (int j = 0; j < 8; ++j) gv[j] = (gate ? __ldg(gate + c0 + j) : 1.f) * TC_OUT_SCALE;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int co = c0 + j;
+                        const int co = co_base + c0 + j;
                         if (p.stats && co / gcn != sgroup) {
                             // flush the finished group: warp-reduce, one double atomic per warp
                             float s = ssum, qq = ssq;
@@ -271,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv5x3_tc_kernel(TcConvArgs p)
                         }
                         if (ok) {
                             const float v = (__uint_as_float(r[j]) * gv[j] + rcur[j]) * p.alpha;
-                            po[(long long)co * p.out.sc] = v;
+                            po[(long long)(c0 + j) * p.out.sc] = v;
                             ssum += v; ssq += v * v;
                         }
                     }
@@ -309,32 +319,36 @@ __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
     lo = __float2half_rn(v - __half2float(hi));
 }
 
-// w[co][ci][kf][kt] (fp32) -> [kf][Cin/16][hi|lo][kt][2][N][8] fp16, scaled by 2^10
-__global__ void pack_weight_tc_kernel(const float* __restrict__ w, __half* __restrict__ wp, int N, int Cin) {
+static int tc_ntile(int Cout) { return Cout <= 256 ? Cout : 256; }
+
+// w[co][ci][kf][kt] (fp32) -> [n-tile][kf][Cin/16][hi|lo][kt][2][Ntile][8] fp16, scaled by 2^10
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, __half* __restrict__ wp, int Ntot, int Ntile, int Cin, int KF, int KT) {
     const int KS = Cin >> 4;
-    const long long total = (long long)5 * KS * 3 * 2 * N * 8;  // (hi, lo) pairs
+    const long long total = (long long)Ntot * Cin * KF * KT;  // one (hi, lo) pair per weight
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         long long r = i;
         const int e = (int)(r % 8); r /= 8;
-        const int n = (int)(r % N); r /= N;
+        const int n = (int)(r % Ntile); r /= Ntile;
         const int c = (int)(r % 2); r /= 2;
-        const int kt = (int)(r % 3); r /= 3;
+        const int kt = (int)(r % KT); r /= KT;
         const int ks = (int)(r % KS); r /= KS;
-        const int kf = (int)r;
-        const int ci = ks * 16 + c * 8 + e;
-        const float v = w[(((long long)n * Cin + ci) * 5 + kf) * 3 + kt] * TC_W_SCALE;
+        const int kf = (int)(r % KF); r /= KF;
+        const int nt = (int)r;
+        const int ci = ks * 16 + c * 8 + e, co = nt * Ntile + n;
+        const float v = w[(((long long)co * Cin + ci) * KF + kf) * KT + kt] * TC_W_SCALE;
         __half hi, lo;
         split_half(v, hi, lo);
-        const long long blk = (long long)(kf * KS + ks) * (2 * 3 * 2 * N * 8);
-        const long long in_blk = (((long long)kt * 2 + c) * N + n) * 8 + e;
-        wp[blk + 0 * (3 * 2 * N * 8) + in_blk] = hi;
-        wp[blk + 1 * (3 * 2 * N * 8) + in_blk] = lo;
+        const long long half_blk = (long long)KT * 2 * Ntile * 8;                       // one of (hi | lo) of a k-step block
+        const long long blk = (((long long)nt * KF + kf) * KS + ks) * (2 * half_blk);
+        const long long in_blk = (((long long)kt * 2 + c) * Ntile + n) * 8 + e;
+        wp[blk + in_blk] = hi;
+        wp[blk + half_blk + in_blk] = lo;
     }
 }
 
-void launch_pack_weight_tc(const float* w, __half* wp, int N, int Cin, cudaStream_t s) {
-    const long long total = (long long)5 * (Cin / 16) * 3 * 2 * N * 8;
-    pack_weight_tc_kernel<<<(int)min((long long)4096, (total + 255) / 256), 256, 0, s>>>(w, wp, N, Cin);
+void launch_pack_weight_tc(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s) {
+    const long long total = (long long)Cout * Cin * KF * KT;
+    pack_weight_tc_kernel<<<(int)min((long long)8192, (total + 255) / 256), 256, 0, s>>>(w, wp, Cout, tc_ntile(Cout), Cin, KF, KT);
     AID_COUNT_LAUNCH(1);
 }
 
@@ -342,6 +356,7 @@ __device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.f +
 
 // Normalise / modulate / GELU (unet.py:159-163, 479, 482) writing the split-fp16 planar operand:
 //   a[b][c/8][f][1+t][c%8] = split(16 * act(x[b,c,f,t] * scale_c)),  pad pixels (index 0 and T+1) = 0
+// With stats == nullptr it is a plain layout/precision conversion (scale_c = 1).
 // grid: (ceil(Tp/128), F, B*C/8), block 128: one thread per padded pixel, 8 channels each.
 __global__ void __launch_bounds__(128)
 gn_act_tc_kernel(TV x, const double* __restrict__ stats, double n_per_group, const float* __restrict__ gamma,
@@ -353,14 +368,18 @@ gn_act_tc_kernel(TV x, const double* __restrict__ stats, double n_per_group, con
     const int tp = blockIdx.x * 128 + threadIdx.x;
     __shared__ float s_scale[8];
     if (threadIdx.x < 8) {
-        const int c = c8 * 8 + threadIdx.x;
-        const int g = c / (x.C / 8);
-        const double s1 = stats[((long long)b * 8 + g) * 2 + 0], s2 = stats[((long long)b * 8 + g) * 2 + 1];
-        double var = (s2 - s1 * s1 / n_per_group) / (n_per_group - 1.0);
-        var = var > 0.0 ? var : 0.0;
-        const float stdv = (float)sqrt(var);
-        const float mod = affine ? (1.f + affine[b * affine_bstride + c]) : 1.f;
-        s_scale[threadIdx.x] = gamma[c] * mod / (stdv + 1e-7f);
+        float sc = 1.f;
+        if (stats) {
+            const int c = c8 * 8 + threadIdx.x;
+            const int g = c / (x.C / 8);
+            const double s1 = stats[((long long)b * 8 + g) * 2 + 0], s2 = stats[((long long)b * 8 + g) * 2 + 1];
+            double var = (s2 - s1 * s1 / n_per_group) / (n_per_group - 1.0);
+            var = var > 0.0 ? var : 0.0;
+            const float stdv = (float)sqrt(var);
+            const float mod = affine ? (1.f + affine[b * affine_bstride + c]) : 1.f;
+            sc = gamma[c] * mod / (stdv + 1e-7f);
+        }
+        s_scale[threadIdx.x] = sc;
     }
     __syncthreads();
     if (tp >= Tp) return;
@@ -390,63 +409,48 @@ void launch_gn_act_tc(const TV& x, const double* stats, long long n_per_group, c
     AID_COUNT_LAUNCH(1);
 }
 
-bool conv_tc_supported(int Cin, int Cout, int KF, int KT) {
-    return KF == 5 && KT == 3 && Cin % 16 == 0 && Cin >= 16 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256;
+// plain fp32 NCHW -> split-fp16 planar operand (inputs of proj_in / res_conv / qk)
+void launch_to_planar_tc(const TV& x, __half* a_hi, __half* a_lo, cudaStream_t s) {
+    launch_gn_act_tc(x, nullptr, 1, nullptr, nullptr, 0, false, a_hi, a_lo, s);
 }
 
-void launch_conv_tc(const __half* a_hi, const __half* a_lo, const __half* wp, int B, int Cin, int F, int T, int dil, const TV& out,
-                    const ConvEpilogue& ep, int num_sms, cudaStream_t s) {
+bool conv_tc_supported(int Cin, int Cout, int KF, int KT) {
+    const bool k = (KF == 5 && KT == 3) || (KF == 1 && KT == 1);
+    return k && Cin % 16 == 0 && Cin >= 16 && Cout % 16 == 0 && Cout >= 16 && (Cout <= 256 || Cout % 256 == 0);
+}
+
+void launch_conv_tc(const __half* a_hi, const __half* a_lo, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,
+                    const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s) {
     if (ep.R2.p) throw CudaError(cudaErrorInvalidValue, "conv_tc: R2 is not supported", __FILE__, __LINE__);
+    if (!conv_tc_supported(Cin, out.C, KF, KT)) throw CudaError(cudaErrorInvalidValue, "conv_tc: unsupported shape", __FILE__, __LINE__);
     TcConvArgs p{};
     p.a_hi = a_hi; p.a_lo = a_lo; p.w = wp; p.out = out; p.R = ep.R; p.gate = ep.gate; p.gate_bstride = ep.gate_bstride;
     p.alpha = ep.alpha; p.stats = ep.stats;
-    p.B = B; p.Cin = Cin; p.N = out.C; p.F = F; p.T = T; p.Tp = T + 2; p.dil = dil;
+    p.B = B; p.Cin = Cin; p.Ntot = out.C; p.Ntile = tc_ntile(out.C); p.n_ntiles = out.C / p.Ntile;
+    p.F = F; p.T = T; p.Tp = T + 2; p.dil = dil;
+    p.KF = KF; p.KT = KT; p.kt_shift = (KT == 1) ? 1 : 0;
+    p.kps = (KF == 1) ? min(TC_MAX_KPS, Cin / 16) : 1;
     p.tiles_t = (T + 127) / 128;
     p.n_units = B * F * p.tiles_t;
-    p.n_tiles = (p.n_units + 1) / 2;
-    p.b_bytes = 192 * p.N;  // (hi, lo) x 3 kt x 2 chunks x N x 16 B
-    p.stage_bytes = ((p.b_bytes + 127) & ~127) + TC_A_BYTES;
+    p.n_pairs = (p.n_units + 1) / 2;
+    p.n_tiles = p.n_pairs * p.n_ntiles;
+    p.b_kstep_bytes = 2 * KT * 2 * p.Ntile * 16;  // (hi, lo) x kt x 2 chunks x Ntile x 16 B
+    p.a_bytes = 2 * p.kps * 4 * TC_PLANE;         // 2 units x kps x (hi, lo) x 2 chunks
+    p.stage_bytes = p.b_kstep_bytes * p.kps + p.a_bytes;
     p.nstages = min(6, (220 * 1024) / p.stage_bytes);
-    p.ncol_stride = p.N <= 64 ? 64 : (p.N <= 128 ? 128 : 256);
+    p.ncol_stride = p.Ntile <= 64 ? 64 : (p.Ntile <= 128 ? 128 : 256);
     p.acc_bufs = p.ncol_stride <= 128 ? 2 : 1;
     const size_t smem = (size_t)p.nstages * p.stage_bytes + 256;
     static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
     p.dbg = dbg;
     static size_t configured = 0;
     if (smem > configured) {
-        AID_CUDA_CHECK(cudaFuncSetAttribute(conv5x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AID_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const int grid = min(p.n_tiles, num_sms);
-    conv5x3_tc_kernel<<<grid, TC_THREADS, smem, s>>>(p);
+    conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(p);
     AID_COUNT_LAUNCH(1);
 }
 
-}  // namespace aid
-
-namespace aid {
-// plain fp32 NCHW -> split-fp16 planar operand (unit-test entry point aid_op_conv2d, mode 1)
-__global__ void __launch_bounds__(128) to_planar_tc_kernel(TV x, __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
-    const int C8 = x.C >> 3;
-    const int c8 = blockIdx.z % C8, b = blockIdx.z / C8, f = blockIdx.y;
-    const int Tp = x.T + 2;
-    const int tp = blockIdx.x * 128 + threadIdx.x;
-    if (tp >= Tp) return;
-    __align__(16) __half hi[8], lo[8];
-    const int t = tp - 1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float v = 0.f;
-        if (t >= 0 && t < x.T) v = x.p[(long long)b * x.sb + (long long)(c8 * 8 + j) * x.sc + (long long)f * x.T + t];
-        split_half(v * TC_A_SCALE, hi[j], lo[j]);
-    }
-    const long long o = ((((long long)b * C8 + c8) * x.F + f) * Tp + tp) * 8;
-    *reinterpret_cast<uint4*>(a_hi + o) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(a_lo + o) = *reinterpret_cast<const uint4*>(lo);
-}
-void launch_to_planar_tc(const TV& x, __half* a_hi, __half* a_lo, cudaStream_t s) {
-    dim3 grid((x.T + 2 + 127) / 128, x.F, x.B * (x.C / 8));
-    to_planar_tc_kernel<<<grid, 128, 0, s>>>(x, a_hi, a_lo);
-    AID_COUNT_LAUNCH(1);
-}
 }  // namespace aid

@@ -264,7 +264,7 @@ static void finalize_net(Net& n) {
             Weight& w = n.weights[c->widx];
             AID_CUDA_CHECK(cudaMemcpy(stage, w.host.data(), w.numel() * sizeof(float), cudaMemcpyHostToDevice));
             c->wtc = n.dweights_tc + toff;
-            launch_pack_weight_tc(stage, c->wtc, c->Cout, c->Cin, 0);
+            launch_pack_weight_tc(stage, c->wtc, c->Cout, c->Cin, c->KF, c->KT, 0);
             AID_CUDA_CHECK(cudaGetLastError());
             AID_CUDA_CHECK(cudaDeviceSynchronize());
             toff += al(2 * w.numel());
@@ -377,11 +377,12 @@ static void conv_tc(Ctx& c, const __half* a_hi, const __half* a_lo, const ConvW&
         auto get = [&]() { cudaEvent_t e; if (n.prof_pool.empty()) { AID_CUDA_CHECK(cudaEventCreate(&e)); } else { e = n.prof_pool.back(); n.prof_pool.pop_back(); } return e; };
         rec.e0 = get(); rec.e1 = get(); rec.kind = 0;
         const double px = (double)out.B * out.F * out.T;
-        rec.flops = 2.0 * w.Cin * w.Cout * 15 * px;
-        rec.bytes = 4.0 * (px * (w.Cin + w.Cout + (ep.R.p ? w.Cout : 0)) + (double)w.Cin * w.Cout * 15);
+        rec.kind = (w.KF == 5) ? 0 : 1;
+        rec.flops = 2.0 * w.Cin * w.Cout * w.KF * w.KT * px;
+        rec.bytes = 4.0 * (px * (w.Cin + w.Cout + (ep.R.p ? w.Cout : 0)) + (double)w.Cin * w.Cout * w.KF * w.KT);
         AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
     }
-    launch_conv_tc(a_hi, a_lo, w.wtc, out.B, w.Cin, out.F, out.T, dil, out, ep, n.num_sms, c.s);
+    launch_conv_tc(a_hi, a_lo, w.wtc, out.B, w.Cin, out.F, out.T, w.KF, w.KT, dil, out, ep, n.num_sms, c.s);
     if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
@@ -398,10 +399,19 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
     __half* a_hi = reinterpret_cast<__half*>(abuf);
     __half* a_lo = a_hi + a_halves;
     TV x = make_tv(xbuf, B, N, F, T), a = make_tv(abuf, B, N, F, T);
+    // tcgen05 path: the block input is converted once to the split-fp16 planar operand and shared by proj_in and res_conv
+    __half* pin_hi = nullptr; __half* pin_lo = nullptr; float* pin_buf = nullptr;
+    if (k.proj_in.wtc || k.res_conv.wtc) {
+        const long long in_halves = (long long)B * k.dim * F * (T + 2);
+        pin_buf = c.allocf(in_halves);
+        pin_hi = reinterpret_cast<__half*>(pin_buf); pin_lo = pin_hi + in_halves;
+        RUN(launch_to_planar_tc(in, pin_hi, pin_lo, c.s));
+    }
     TV cur;
     if (k.dim != N) {
         ConvEpilogue ep; ep.stats = x.stats = c.new_slot();
-        conv(c, in, k.proj_in, 1, x, ep);
+        if (k.proj_in.wtc) conv_tc(c, pin_hi, pin_lo, k.proj_in, 1, x, ep);
+        else conv(c, in, k.proj_in, 1, x, ep);
         cur = x;
     } else {
         cur = in;
@@ -414,7 +424,16 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         conv(c, a, k.a_in, 1, h, ConvEpilogue());
         TV hflat = make_tv(h.p, B, heads * F, 1, T);
         TV qk = make_tv(c.allocf((long long)B * 2 * heads * F * T), B, 2 * heads * F, 1, T);
-        conv(c, hflat, k.qk, 1, qk, ConvEpilogue());
+        if (k.qk.wtc) {
+            const long long hh = (long long)B * heads * F * (T + 2);
+            float* hp = c.allocf(hh);
+            __half* h_hi = reinterpret_cast<__half*>(hp);
+            RUN(launch_to_planar_tc(hflat, h_hi, h_hi + hh, c.s));
+            conv_tc(c, h_hi, h_hi + hh, k.qk, 1, qk, ConvEpilogue());
+            c.release(hp);
+        } else {
+            conv(c, hflat, k.qk, 1, qk, ConvEpilogue());
+        }
         TV o = make_tv(c.allocf((long long)B * heads * F * T), B, heads, F, T);
         RUN(launch_attention(h, qk.p, o, c.s));
         ConvEpilogue ep;
@@ -434,7 +453,7 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         if (k.H[i].wtc) {
             RUN(launch_gn_act_tc(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, a_hi, a_lo, c.s));
             x.stats = ep.stats;
-            conv_tc(c, a_hi, a_lo, k.H[i], 1 << i, x, ep);
+            conv_tc(c, a_hi, a_lo, k.H[i], k.k1x1 ? 1 : (1 << i), x, ep);
         } else {
             RUN(launch_gn_act(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, a, c.s));
             x.stats = ep.stats;
@@ -454,12 +473,14 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         if (accum) throw std::runtime_error("resblock: accum only supported for out blocks");
         if (k.dim != k.dim_out) {
             ConvEpilogue ep; ep.R = cur; ep.alpha = kInvSqrt2; ep.stats = out.stats;
-            conv(c, in, k.res_conv, 1, out, ep);
+            if (k.res_conv.wtc) conv_tc(c, pin_hi, pin_lo, k.res_conv, 1, out, ep);
+            else conv(c, in, k.res_conv, 1, out, ep);
         } else {
             RUN(launch_combine(cur, in, kInvSqrt2, kInvSqrt2, out, out.stats, c.s));
         }
     }
     c.release(abuf); c.release(xbuf);
+    if (pin_buf) c.release(pin_buf);
 }
 
 // debug probes (parity tests localise an error to one block): contiguous copy of a named intermediate
@@ -817,12 +838,12 @@ static int op_conv2d_impl(const float* a_dev, const float* w_dev, int B, int Cin
             AID_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
             AID_CUDA_CHECK(cudaMalloc(&wtc, 2 * e * sizeof(__half)));
             AID_CUDA_CHECK(cudaMalloc(&ah, 2 * ahalves * sizeof(__half)));
-            launch_pack_weight_tc(w_dev, wtc, Cout, Cin, s);
+            launch_pack_weight_tc(w_dev, wtc, Cout, Cin, KF, KT, s);
             launch_to_planar_tc(a, ah, ah + ahalves, s);
         } else if (mode != 0) throw std::invalid_argument("unknown conv mode");
         (void)iters;
         AID_CUDA_CHECK(cudaEventRecord(e0, s));
-        if (mode == 1) launch_conv_tc(ah, ah + ahalves, wtc, B, Cin, F, T, dil, out, ep, sms, s);
+        if (mode == 1) launch_conv_tc(ah, ah + ahalves, wtc, B, Cin, F, T, KF, KT, dil, out, ep, sms, s);
         else launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
         AID_CUDA_CHECK(cudaEventRecord(e1, s));
         AID_CUDA_CHECK(cudaGetLastError());

@@ -25,6 +25,40 @@ TC_CASES = [
 ]
 
 
+TC_1x1_CASES = [
+    # B, Cin, Cout, F, T, stats      (taps = 1: init/out-block H, proj_in / res_conv, attention qk)
+    (2, 64, 64, 10, 256, True),       # init-block H
+    (1, 128, 96, 17, 128, True),      # decoder proj_in (2*Ns -> dout)
+    (1, 48, 32, 5, 40, True),         # Cin = 48: last stage holds a single k-step
+    (2, 320, 512, 1, 64, False),      # qk-like: [B, 8F, 1, T] -> 2 n-tiles of 256
+    (1, 512, 768, 1, 256, False),     # 3 n-tiles, 2 units per pair
+    (1, 16, 16, 3, 8, True),          # smallest
+]
+
+
+@pytest.mark.parametrize("case", TC_1x1_CASES)
+def test_conv_tc_1x1(cuda, case):
+    B, Cin, Cout, Fd, T, use_stats = case
+    L = _lib()
+    a = seeded((B, Cin, Fd, T), 1)
+    w = seeded((Cout, Cin, 1, 1), 2, 1.0 / math.sqrt(Cin))
+    gate, R = seeded((Cout,), 3), seeded((B, Cout, Fd, T), 4)
+    ref = conv_ref(a, w, 1, gate, R, None, 0.5)
+    ad, wd, gd, Rd = a.to(cuda), w.to(cuda), gate.to(cuda), R.to(cuda)
+    out = torch.full((B, Cout, Fd, T), float("nan"), device=cuda)
+    stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=cuda) if use_stats else None
+    L.check(L.lib().aid_op_conv2d(L.ptr(ad), L.ptr(wd), B, Cin, Cout, Fd, T, 1, 1, 1, L.ptr(gd), L.ptr(Rd), None,
+                                  0.5, 0.0, L.ptr(out), L.ptr(stats), 1, None))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert rel_l2(out, ref) < 1e-5
+    assert rel_l2(out.cpu().double() - 0.5 * R.double(), ref - 0.5 * R.double()) < 1e-5
+    if use_stats:
+        g = ref.reshape(B, 8, -1)
+        assert torch.allclose(stats[:, :, 0].cpu(), g.sum(-1), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(stats[:, :, 1].cpu(), (g * g).sum(-1), rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tc(cuda, case):
     B, Cin, Cout, Fd, T, dil, use_stats = case
