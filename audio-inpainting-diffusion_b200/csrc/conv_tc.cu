@@ -26,7 +26,7 @@
 
 namespace aid {
 
-static constexpr int TC_THREADS = 320;        // producer warp, MMA warp, 8 epilogue warps
+static constexpr int TC_THREADS = 576;        // producer warp, MMA warp, 16 epilogue warps
 static constexpr int TC_PLANE = 130 * 16;     // bytes of one (16 B chunk) x (130 pixel) plane of A in smem
 static constexpr int TC_MAX_KPS = 2;          // 16-channel k-steps per pipeline stage (1 for 5x3, 2 for 1x1)
 static constexpr float TC_A_SCALE = 16.f, TC_W_SCALE = 1024.f, TC_OUT_SCALE = 1.f / (16.f * 1024.f);
@@ -91,6 +91,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 struct UnitInfo { int exists, b, f, t0, seg_px; };
 
 __device__ __forceinline__ UnitInfo unit_info(const TcConvArgs& p, int u) {
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < p.nstages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 256); }
+            for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 512); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -227,81 +234,114 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> out = alpha*(acc*gate + R), statistics =====================
-        // 8 warps: warp e handles TMEM lane quadrant (warpid & 3) and column half (e >> 2) of both units.
+        // 16 warps: warp e owns TMEM lane quadrant (warpid & 3) and a contiguous column range (quarter, or half when the
+        // tile width is not a multiple of 32).  The loop body is kept short on purpose: the epilogue is instruction/latency
+        // bound, not bandwidth bound (few resident warps), so every per-column instruction counts.
         const int e = warp - 2;
         const int q = warp & 3;
-        const int ncols = p.Ntile >> 1;  // columns per warp (multiple of 8)
-        const int cbeg = (e >> 2) * ncols;
+        const int cw = e >> 2;
+        const int ncw = (p.Ntile & 31) ? 2 : 4;
+        const int ncols = p.Ntile / ncw;  // multiple of 8
+        const bool active = cw < ncw;
+        const int cbeg = cw * ncols;
         int ab = 0; uint32_t aphase = 0;
         const int gcn = p.Ntot / 8;
+        const float al = p.alpha, gs = TC_OUT_SCALE * p.alpha;
+        const long long osc = p.out.sc, rsc = p.R.sc;
+        double* sst = reinterpret_cast<double*>(bar_base + 256) + e * 16;  // this warp's (group, {sum, sumsq}) accumulators
+        if (lane < 16) sst[lane] = 0.0;
+        __syncwarp();
+        int b_cur = -1;
+        auto flush_global = [&]() {
+            if (p.stats && b_cur >= 0 && lane < 16) {
+                const double v = sst[lane];
+                if (v != 0.0) atomicAdd(p.stats + (long long)b_cur * 16 + lane, v);
+                sst[lane] = 0.0;
+            }
+            __syncwarp();
+        };
+        auto flush_group = [&](float s, float qq, int g) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
+            if (lane == 0) { sst[g * 2 + 0] += (double)s; sst[g * 2 + 1] += (double)qq; }
+        };
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int pair = tile % p.n_pairs, nt = tile / p.n_pairs;
             const int co_base = nt * p.Ntile;
             mbar_wait(tmem_full + ab, aphase);
             tc_fence_after();
 #pragma unroll 1
-            for (int i = 0; i < 2 && !(p.dbg & 1); ++i) {
+            for (int i = 0; i < 2 && active && !(p.dbg & 1); ++i) {
                 const UnitInfo u = unit_info(p, 2 * pair + i);
                 if (!u.exists) continue;
+                if (u.b != b_cur) { flush_global(); b_cur = u.b; }
                 const int t = u.t0 + q * 32 + lane;
                 const bool ok = t < p.T;
-                float* po = p.out.p + (long long)u.b * p.out.sb + (long long)co_base * p.out.sc + (long long)u.f * p.T + t;
-                const float* pr = p.R.p ? p.R.p + (long long)u.b * p.R.sb + (long long)co_base * p.R.sc + (long long)u.f * p.T + t : nullptr;
-                const float* gate = p.gate ? p.gate + (long long)u.b * p.gate_bstride + co_base : nullptr;
+                float* po = p.out.p + (long long)u.b * p.out.sb + (long long)(co_base + cbeg) * osc + (long long)u.f * p.T + t;
+                const float* pr = p.R.p + (long long)u.b * p.R.sb + (long long)(co_base + cbeg) * rsc + (long long)u.f * p.T + t;
+                const bool hasr = ok && p.R.p != nullptr;
+                const float* gate = p.gate ? p.gate + (long long)u.b * p.gate_bstride + co_base + cbeg : nullptr;
+                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride + cbeg);
+                int grp = (co_base + cbeg) / gcn;
+                int left = (grp + 1) * gcn - (co_base + cbeg);  // columns left in the current statistics group
                 float ssum = 0.f, ssq = 0.f;
-                int sgroup = (co_base + cbeg) / gcn;
-                float rcur[8], rnext[8];
+                float rcur[8], gcur[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) rcur[j] = (ok && pr) ? pr[(long long)(cbeg + j) * p.R.sc] : 0.f;
+                for (int j = 0; j < 8; ++j) {
+                    rcur[j] = hasr ? pr[j * rsc] : 0.f;
+                    gcur[j] = gate ? __ldg(gate + j) * gs : gs;
+                }
 #pragma unroll 1
-                for (int c0 = cbeg; c0 < cbeg + ncols; c0 += 8) {
-                    // issue the next chunk's residual loads before touching this chunk (the loads may alias the stores
-                    // below -- in-place residual update -- so the compiler cannot hoist them itself)
-                    const bool more = c0 + 8 < cbeg + ncols;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) rnext[j] = (ok && pr && more) ? pr[(long long)(c0 + 8 + j) * p.R.sc] : 0.f;
-                    uint32_t r[8];
-                    tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride + c0), r);
-                    float gv[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) gv[j] = (gate ? __ldg(gate + c0 + j) : 1.f) * TC_OUT_SCALE;
+                for (int c0 = 0; c0 < ncols; c0 += 8) {
+                    // next chunk's residual / gate loads first: the residual may alias the stores below (in-place update),
+                    // so the compiler cannot hoist these loads by itself
+                    float rn[8], gn[8];
+                    const bool more = c0 + 8 < ncols;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int co = co_base + c0 + j;
-                        if (p.stats && co / gcn != sgroup) {
-                            // flush the finished group: warp-reduce, one double atomic per warp
-                            float s = ssum, qq = ssq;
+                        rn[j] = (hasr && more) ? pr[(c0 + 8 + j) * rsc] : 0.f;
+                        gn[j] = (gate && more) ? __ldg(gate + c0 + 8 + j) * gs : gs;
+                    }
+                    uint32_t r[8];
+                    tmem_ld8(tcol + c0, r);
+                    float v[8];
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
-                            if (lane == 0) {
-                                atomicAdd(p.stats + ((long long)u.b * 8 + sgroup) * 2 + 0, (double)s);
-                                atomicAdd(p.stats + ((long long)u.b * 8 + sgroup) * 2 + 1, (double)qq);
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[j]), gcur[j], rcur[j] * al);
+                    if (ok) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) po[(c0 + j) * osc] = v[j];
+                    }
+                    if (p.stats) {
+                        if (gcn >= 8) {
+                            // at most one group boundary inside the chunk, at column `left`
+                            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float w = ok ? v[j] : 0.f;
+                                if (j < left) { a0 += w; a1 = fmaf(w, w, a1); } else { b0 += w; b1 = fmaf(w, w, b1); }
                             }
-                            ssum = 0.f; ssq = 0.f; sgroup = co / gcn;
-                        }
-                        if (ok) {
-                            const float v = (__uint_as_float(r[j]) * gv[j] + rcur[j]) * p.alpha;
-                            po[(long long)(c0 + j) * p.out.sc] = v;
-                            ssum += v; ssq += v * v;
+                            ssum += a0; ssq += a1;
+                            left -= 8;
+                            if (left <= 0) { flush_group(ssum, ssq, grp); ++grp; ssum = b0; ssq = b1; left += gcn; }
+                        } else {
+#pragma unroll 1
+                            for (int j = 0; j < 8; ++j) {
+                                const float w = ok ? v[j] : 0.f;
+                                ssum += w; ssq = fmaf(w, w, ssq);
+                                if (--left == 0) { flush_group(ssum, ssq, grp); ++grp; ssum = 0.f; ssq = 0.f; left = gcn; }
+                            }
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
+                    for (int j = 0; j < 8; ++j) { rcur[j] = rn[j]; gcur[j] = gn[j]; }
                 }
-                if (p.stats) {
-                    float s = ssum, qq = ssq;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
-                    if (lane == 0) {
-                        atomicAdd(p.stats + ((long long)u.b * 8 + sgroup) * 2 + 0, (double)s);
-                        atomicAdd(p.stats + ((long long)u.b * 8 + sgroup) * 2 + 1, (double)qq);
-                    }
-                }
+                if (p.stats && (ssum != 0.f || ssq != 0.f || true)) flush_group(ssum, ssq, min(grp, 7));
             }
             tc_fence_before();
             mbar_arrive(tmem_empty + ab);
             if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
         }
+        flush_global();
     }
 
     tc_fence_before();
@@ -319,7 +359,12 @@ __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
     lo = __float2half_rn(v - __half2float(hi));
 }
 
-static int tc_ntile(int Cout) { return Cout <= 256 ? Cout : 256; }
+static int tc_ntile_policy = -1;  // AID_TC_NTILE: 0 = 256-wide tiles, 1 = split 256 into 2 x 128 (double-buffered accumulators)
+static int tc_ntile(int Cout) {
+    if (tc_ntile_policy < 0) tc_ntile_policy = getenv("AID_TC_NTILE") ? atoi(getenv("AID_TC_NTILE")) : 0;
+    if (Cout == 256 && tc_ntile_policy == 1) return 128;
+    return Cout <= 256 ? Cout : 256;
+}
 
 // w[co][ci][kf][kt] (fp32) -> [n-tile][kf][Cin/16][hi|lo][kt][2][Ntile][8] fp16, scaled by 2^10
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __half* __restrict__ wp, int Ntot, int Ntile, int Cin, int KF, int KT) {
@@ -437,10 +482,10 @@ void launch_conv_tc(const __half* a_hi, const __half* a_lo, const __half* wp, in
     p.b_kstep_bytes = 2 * KT * 2 * p.Ntile * 16;  // (hi, lo) x kt x 2 chunks x Ntile x 16 B
     p.a_bytes = 2 * p.kps * 4 * TC_PLANE;         // 2 units x kps x (hi, lo) x 2 chunks
     p.stage_bytes = p.b_kstep_bytes * p.kps + p.a_bytes;
-    p.nstages = min(6, (220 * 1024) / p.stage_bytes);
+    p.nstages = min(6, (224 * 1024) / p.stage_bytes);
     p.ncol_stride = p.Ntile <= 64 ? 64 : (p.Ntile <= 128 ? 128 : 256);
     p.acc_bufs = p.ncol_stride <= 128 ? 2 : 1;
-    const size_t smem = (size_t)p.nstages * p.stage_bytes + 256;
+    const size_t smem = (size_t)p.nstages * p.stage_bytes + 256 + 16 * 16 * sizeof(double);  // stages + barriers + per-warp statistics
     static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
     p.dbg = dbg;
     static size_t configured = 0;

@@ -8,11 +8,22 @@ dev = torch.device("cuda:0")
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 shapes = [  # B, C, F, T, dil   (levels of the paper network at B=8)
     (8, 64, 64, 4096, 2), (8, 96, 128, 2048, 4), (8, 128, 256, 512, 16), (8, 128, 320, 256, 32), (8, 256, 384, 128, 64), (8, 256, 448, 64, 8)]
-for B, Cn, Fd, T, dil in shapes:
-    a = torch.randn(B, Cn, Fd, T, device=dev); w = torch.randn(Cn, Cn, 5, 3, device=dev) * 0.03
-    g = torch.randn(Cn, device=dev); R = torch.randn(B, Cn, Fd, T, device=dev); out = torch.empty_like(R)
-    st = torch.zeros(B * 16, dtype=torch.float64, device=dev)
+def run(B, Ci, Co, Fd, T, K, dil, useR=True):
+    KF, KT = (5, 3) if K == 5 else (1, 1)
+    a = torch.randn(B, Ci, Fd, T, device=dev); w = torch.randn(Co, Ci, KF, KT, device=dev) * 0.03
+    g = torch.randn(Co, device=dev); R = torch.randn(B, Co, Fd, T, device=dev) if useR else None; out = torch.empty(B, Co, Fd, T, device=dev)
+    st = torch.zeros(B * 16, dtype=torch.float64, device=dev) if os.environ.get('NOSTATS') is None else None
     ms = C.c_float()
-    _lib.check(L.aid_debug_time_conv2d(_lib.ptr(a), _lib.ptr(w), B, Cn, Cn, Fd, T, 5, 3, dil, _lib.ptr(g), _lib.ptr(R), 0.7071, _lib.ptr(out), _lib.ptr(st), mode, C.byref(ms)))
-    fl = 2.0 * Cn * Cn * 15 * B * Fd * T
-    print(f"mode {mode} dbg {os.environ.get('AID_TC_DEBUG','0')} B{B} C{Cn} F{Fd} T{T} d{dil}: {ms.value:8.3f} ms  {fl/ms.value/1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
+    _lib.check(L.aid_debug_time_conv2d(_lib.ptr(a), _lib.ptr(w), B, Ci, Co, Fd, T, KF, KT, dil, _lib.ptr(g), _lib.ptr(R), 0.7071, _lib.ptr(out), _lib.ptr(st), mode, C.byref(ms)))
+    fl = 2.0 * Ci * Co * KF * KT * B * Fd * T
+    gb = 4.0 * B * Fd * T * (Ci + Co * (2 if useR else 1)) / 1e9
+    print(f"mode {mode} dbg {os.environ.get('AID_TC_DEBUG','0')} nt {os.environ.get('AID_TC_NTILE','0')} nostats {int(os.environ.get('NOSTATS') is not None)} {K}x B{B} Ci{Ci} Co{Co} F{Fd} T{T} d{dil} R{int(useR)}: {ms.value:8.3f} ms  {fl/ms.value/1e9:8.1f} TFLOP/s  {gb/ms.value*1e3:7.0f} GB/s (algorithmic)", flush=True)
+
+which = sys.argv[2] if len(sys.argv) > 2 else "all"
+if which in ("all", "5x3"):
+    for B, Cn, Fd, T, dil in shapes:
+        run(B, Cn, Cn, Fd, T, 5, dil)
+if which in ("all", "1x1"):
+    for B, Ci, Co, Fd, T, useR in [(8, 64, 64, 64, 4096, True), (8, 64, 96, 128, 2048, False), (8, 128, 64, 64, 4096, True), (8, 192, 64, 128, 2048, False),
+                                   (8, 256, 256, 64, 64, True), (8, 3584, 7168, 1, 64, False), (8, 2560, 5120, 1, 256, False)]:
+        run(B, Ci, Co, Fd, T, 1, 1, useR)
