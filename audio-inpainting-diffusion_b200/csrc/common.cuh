@@ -62,6 +62,8 @@ void launch_resample_down(const TV& x, const TV& out, cudaStream_t s);
 void launch_resample_up(const TV& x, const TV& out, cudaStream_t s);
 void launch_conv_simt(const TV& a, const float* wp, int KF, int KT, int dil, const TV& out, const ConvEpilogue& ep,
                       cudaStream_t s);
+// thin convolutions (conv_thin.cu); returns false when the shape is not covered
+bool launch_conv_thin(const TV& a, const float* wp, int KF, int KT, int dil, const TV& out, const ConvEpilogue& ep, cudaStream_t s);
 void launch_attention(const TV& h, const float* qk, const TV& out, cudaStream_t s);
 void launch_embedding(const float* c_noise, int n_sigma, const float* rff, const float* w0, const float* b0,
                       const float* w1, const float* b1, const float* w2, const float* b2, float* emb, cudaStream_t s);

@@ -364,7 +364,7 @@ static void conv(Ctx& c, const TV& a, const ConvW& w, int dil, const TV& out, Co
         rec.bytes = 4.0 * (px * (w.Cin + w.Cout + (ep.R.p ? w.Cout : 0) + (ep.R2.p ? w.Cout : 0)) + (double)w.Cin * w.Cout * w.KF * w.KT);
         AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
     }
-    launch_conv_simt(a, w.wp, w.KF, w.KT, dil, out, ep, c.s);
+    if (!launch_conv_thin(a, w.wp, w.KF, w.KT, dil, out, ep, c.s)) launch_conv_simt(a, w.wp, w.KF, w.KT, dil, out, ep, c.s);
     if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
@@ -840,11 +840,11 @@ static int op_conv2d_impl(const float* a_dev, const float* w_dev, int B, int Cin
             AID_CUDA_CHECK(cudaMalloc(&ah, 2 * ahalves * sizeof(__half)));
             launch_pack_weight_tc(w_dev, wtc, Cout, Cin, KF, KT, s);
             launch_to_planar_tc(a, ah, ah + ahalves, s);
-        } else if (mode != 0) throw std::invalid_argument("unknown conv mode");
+        } else if (mode != 0 && mode != 2) throw std::invalid_argument("unknown conv mode");
         (void)iters;
         AID_CUDA_CHECK(cudaEventRecord(e0, s));
         if (mode == 1) launch_conv_tc(ah, ah + ahalves, wtc, B, Cin, F, T, KF, KT, dil, out, ep, sms, s);
-        else launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
+        else if (mode == 2 || !launch_conv_thin(a, wp, KF, KT, dil, out, ep, s)) launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
         AID_CUDA_CHECK(cudaEventRecord(e1, s));
         AID_CUDA_CHECK(cudaGetLastError());
         AID_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -101,7 +101,8 @@ int aid_edm_step(const float* xin_dev, const float* xhat_dev, const float* y_dev
 /* ---- single-operator entry points (unit parity tests; same kernels the forward uses) ---------------- */
 /* F.conv2d(a[B,Cin,F,T], w[Cout,Cin,KF,KT], padding="same", dilation=(dil,1)) with the fused epilogue
  * out = alpha*(conv*gate[c] + R) + beta*R2; gate/R/R2 may be NULL.  stats_dev (may be NULL): [B][8][2] doubles
- * accumulated with (sum, sumsq) of out per channel group.  mode as aid_config.conv_mode.   unet.py:79-88, 482 */
+ * accumulated with (sum, sumsq) of out per channel group.  mode: 0 = fp32 CUDA cores (thin-channel kernels where they apply),
+ * 1 = tcgen05 split-fp16, 2 = force the general fp32 CUDA-core kernel.                       unet.py:79-88, 482 */
 int aid_op_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
                   const float* gate_dev, const float* R_dev, const float* R2_dev, float alpha, float beta,
                   float* out_dev, double* stats_dev, int mode, void* stream);
