@@ -50,8 +50,15 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CONV_CASES)
-def test_conv2d(cuda, case):
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("case", CONV_CASES + [
+    (2, 2, 64, 9, 64, 1, 1, 1, False, True, False, True),      # thin-in 1x1 with residual + statistics (init res_conv)
+    (1, 8, 24, 5, 16, 1, 1, 1, True, True, False, True),       # thin-in 8 -> N, groups of 3 channels
+    (1, 2, 40, 20, 6, 5, 3, 1, False, True, False, True),      # thin-in 5x3, T = 6 (pair-vectorised)
+    (2, 48, 8, 7, 12, 1, 1, 1, False, False, False, False),    # thin-out N -> 8
+    (1, 24, 2, 6, 8, 1, 1, 1, False, True, True, False),       # thin-out N -> 2 with both residuals
+])
+def test_conv2d(cuda, case, mode):
     B, Cin, Cout, Fd, T, KF, KT, dil, use_gate, use_R, use_R2, use_stats = case
     L = _lib()
     a = seeded((B, Cin, Fd, T), 1)
@@ -66,7 +73,7 @@ def test_conv2d(cuda, case):
     out = torch.empty(B, Cout, Fd, T, device=cuda)
     stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=cuda) if use_stats else None
     L.check(L.lib().aid_op_conv2d(L.ptr(ad), L.ptr(wd), B, Cin, Cout, Fd, T, KF, KT, dil, L.ptr(gd), L.ptr(Rd), L.ptr(R2d),
-                                  alpha, beta, L.ptr(out), L.ptr(stats), 0, None))
+                                  alpha, beta, L.ptr(out), L.ptr(stats), mode, None))
     torch.cuda.synchronize()
     assert rel_l2(out, ref) < 2e-6
     if use_stats:
