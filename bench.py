@@ -131,7 +131,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--len", type=int, default=262144)
-    ap.add_argument("--conv-mode", type=int, default=int(os.environ.get("AID_CONV_MODE", "0")))
+    ap.add_argument("--conv-mode", type=int, default=int(os.environ.get("AID_CONV_MODE", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
