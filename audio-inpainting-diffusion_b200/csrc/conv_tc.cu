@@ -37,6 +37,7 @@ struct TcConvArgs {
     const float* gate; long long gate_bstride;
     float alpha; double* stats;
     int B, Cin, Ntot, Ntile, n_ntiles, F, T, Tp, dil;
+    int PF, rows_total, stream, units_per_b;   // zero pad rows above/below each plane; stream mode: units tile the padded pixel stream
     int KF, KT, kt_shift, kps;                 // taps along F / T, first tap's pixel shift inside the window, k-steps per stage
     int tiles_t, n_units, n_pairs, n_tiles, nstages, acc_bufs, ncol_stride;
     int b_kstep_bytes, a_bytes, stage_bytes;
@@ -98,14 +99,32 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-struct UnitInfo { int exists, b, f, t0, seg_px; };
+// A unit = 128 consecutive output positions of one clip.
+//   row mode    (T % 128 == 0): 128 pixels of one frequency row (PF = 0, taps outside [0,F) are skipped exactly);
+//   stream mode (otherwise)   : 128 consecutive positions of the padded pixel stream [F rows][T+2] -- rows shorter than
+//                               128 pixels share a tile (the pad pixels between rows are the zero padding along T, their
+//                               outputs are discarded); PF zero rows above/below make every tap address valid.
+struct UnitInfo { int exists, b, f_lo, f_hi, win_start, o0, seg_px; };
 
 __device__ __forceinline__ UnitInfo unit_info(const TcConvArgs& p, int u) {
     UnitInfo i;
     i.exists = u < p.n_units;
-    const int tt = u % p.tiles_t, r = u / p.tiles_t;
-    i.f = r % p.F; i.b = r / p.F; i.t0 = tt * 128;
-    i.seg_px = min(130, p.Tp - i.t0);
+    if (p.stream) {
+        const int k = u % p.units_per_b;
+        i.b = u / p.units_per_b;
+        i.o0 = k * 128;                               // first output position, relative to row 0 of the real rows
+        i.f_lo = i.o0 / p.Tp;
+        i.f_hi = min(p.F - 1, (i.o0 + 127) / p.Tp);
+        i.win_start = p.PF * p.Tp + i.o0 - 1;         // window = positions [o0-1, o0+129) of the padded plane
+        i.seg_px = 130;
+    } else {
+        const int tt = u % p.tiles_t, r = u / p.tiles_t;
+        const int f = r % p.F, t0 = tt * 128;
+        i.b = r / p.F; i.f_lo = i.f_hi = f;
+        i.o0 = f * p.Tp + t0 + 1;
+        i.win_start = f * p.Tp + t0;
+        i.seg_px = min(130, p.Tp - t0);
+    }
     return i;
 }
 
@@ -150,8 +169,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
             const int pair = tile % p.n_pairs, nt = tile / p.n_pairs;
             const UnitInfo u0 = unit_info(p, 2 * pair), u1 = unit_info(p, 2 * pair + 1);
             for (int kf = 0; kf < p.KF; ++kf) {
-                const int f0 = u0.f + (kf - p.KF / 2) * p.dil, f1 = u1.f + (kf - p.KF / 2) * p.dil;
-                const bool v0 = u0.exists && f0 >= 0 && f0 < p.F, v1 = u1.exists && f1 >= 0 && f1 < p.F;
+                const int foff = (kf - p.KF / 2) * p.dil;
+                const bool v0 = u0.exists && u0.f_hi + foff >= 0 && u0.f_lo + foff < p.F;
+                const bool v1 = u1.exists && u1.f_hi + foff >= 0 && u1.f_lo + foff < p.F;
                 if (!(v0 || v1)) continue;
                 for (int ks0 = 0; ks0 < KS; ks0 += p.kps) {
                     const int nk = min(p.kps, KS - ks0);
@@ -169,8 +189,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
                     if (a_lane && akk < nk && !(p.dbg & 4)) {
                         const UnitInfo& u = ai ? u1 : u0;
                         if (ai ? v1 : v0) {
-                            const int ff = ai ? f1 : f0;
-                            const size_t off = ((((size_t)u.b * c8_total + (2 * (ks0 + akk) + ac)) * p.F + ff) * p.Tp + u.t0) * 8;
+                            const size_t off = (((size_t)u.b * c8_total + (2 * (ks0 + akk) + ac)) * p.rows_total * p.Tp +
+                                                (size_t)(u.win_start + foff * p.Tp)) * 8;
                             bulk_g2s(sb + b_bytes_full + (((ai * p.kps + akk) * 2 + ahl) * 2 + ac) * TC_PLANE, (ahl ? p.a_lo : p.a_hi) + off,
                                      (uint32_t)u.seg_px * 16u, full + stage);
                         }
@@ -191,8 +211,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
             tc_fence_after();
             uint32_t started[2] = {0u, 0u};
             for (int kf = 0; kf < p.KF; ++kf) {
-                const int f0 = u0.f + (kf - p.KF / 2) * p.dil, f1 = u1.f + (kf - p.KF / 2) * p.dil;
-                const bool v0 = u0.exists && f0 >= 0 && f0 < p.F, v1 = u1.exists && f1 >= 0 && f1 < p.F;
+                const int foff = (kf - p.KF / 2) * p.dil;
+                const bool v0 = u0.exists && u0.f_hi + foff >= 0 && u0.f_lo + foff < p.F;
+                const bool v1 = u1.exists && u1.f_hi + foff >= 0 && u1.f_lo + foff < p.F;
                 if (!(v0 || v1)) continue;
                 for (int ks0 = 0; ks0 < KS; ks0 += p.kps) {
                     const int nk = min(p.kps, KS - ks0);
@@ -275,10 +296,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
                 const UnitInfo u = unit_info(p, 2 * pair + i);
                 if (!u.exists) continue;
                 if (u.b != b_cur) { flush_global(); b_cur = u.b; }
-                const int t = u.t0 + q * 32 + lane;
-                const bool ok = t < p.T;
-                float* po = p.out.p + (long long)u.b * p.out.sb + (long long)(co_base + cbeg) * osc + (long long)u.f * p.T + t;
-                const float* pr = p.R.p + (long long)u.b * p.R.sb + (long long)(co_base + cbeg) * rsc + (long long)u.f * p.T + t;
+                const int o = u.o0 + q * 32 + lane;           // output position in the padded stream of the real rows
+                const int row = o / p.Tp, tp = o - row * p.Tp;
+                const bool ok = tp >= 1 && tp <= p.T && row <= u.f_hi;
+                const long long pix = (long long)row * p.T + (tp - 1);
+                float* po = p.out.p + (long long)u.b * p.out.sb + (long long)(co_base + cbeg) * osc + pix;
+                const float* pr = p.R.p + (long long)u.b * p.R.sb + (long long)(co_base + cbeg) * rsc + pix;
                 const bool hasr = ok && p.R.p != nullptr;
                 const float* gate = p.gate ? p.gate + (long long)u.b * p.gate_bstride + co_base + cbeg : nullptr;
                 const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride + cbeg);
@@ -405,10 +428,10 @@ __device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.f +
 // grid: (ceil(Tp/128), F, B*C/8), block 128: one thread per padded pixel, 8 channels each.
 __global__ void __launch_bounds__(128)
 gn_act_tc_kernel(TV x, const double* __restrict__ stats, double n_per_group, const float* __restrict__ gamma,
-                 const float* __restrict__ affine, long long affine_bstride, int gelu, __half* __restrict__ a_hi,
+                 const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, __half* __restrict__ a_hi,
                  __half* __restrict__ a_lo) {
     const int C8 = x.C >> 3;
-    const int c8 = blockIdx.z % C8, b = blockIdx.z / C8, f = blockIdx.y;
+    const int c8 = blockIdx.z % C8, b = blockIdx.z / C8, fr = blockIdx.y, f = fr - PF;   // fr: row of the padded plane
     const int Tp = x.T + 2;
     const int tp = blockIdx.x * 128 + threadIdx.x;
     __shared__ float s_scale[8];
@@ -430,7 +453,7 @@ gn_act_tc_kernel(TV x, const double* __restrict__ stats, double n_per_group, con
     if (tp >= Tp) return;
     __align__(16) __half hi[8], lo[8];
     const int t = tp - 1;
-    if (t < 0 || t >= x.T) {
+    if (t < 0 || t >= x.T || f < 0 || f >= x.F) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { hi[j] = __float2half_rn(0.f); lo[j] = __float2half_rn(0.f); }
     } else {
@@ -442,21 +465,28 @@ gn_act_tc_kernel(TV x, const double* __restrict__ stats, double n_per_group, con
             split_half(v * TC_A_SCALE, hi[j], lo[j]);
         }
     }
-    const long long o = ((((long long)b * C8 + c8) * x.F + f) * Tp + tp) * 8;
+    const long long o = ((((long long)b * C8 + c8) * (x.F + 2 * PF) + fr) * Tp + tp) * 8;
     *reinterpret_cast<uint4*>(a_hi + o) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(a_lo + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
+// zero rows the tcgen05 kernel needs above and below every [F][T+2] plane (0 in row mode)
+int tc_pad_rows(int T, int KF, int dil) {
+    if (T % 128 == 0) return 0;
+    const int Tp = T + 2;
+    return (KF > 1 ? 2 * dil : 0) + (130 + Tp - 1) / Tp + 1;
+}
+
 void launch_gn_act_tc(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
-                      long long affine_bstride, bool gelu, __half* a_hi, __half* a_lo, cudaStream_t s) {
-    dim3 grid((x.T + 2 + 127) / 128, x.F, x.B * (x.C / 8));
-    gn_act_tc_kernel<<<grid, 128, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, a_hi, a_lo);
+                      long long affine_bstride, bool gelu, int PF, __half* a_hi, __half* a_lo, cudaStream_t s) {
+    dim3 grid((x.T + 2 + 127) / 128, x.F + 2 * PF, x.B * (x.C / 8));
+    gn_act_tc_kernel<<<grid, 128, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, a_hi, a_lo);
     AID_COUNT_LAUNCH(1);
 }
 
 // plain fp32 NCHW -> split-fp16 planar operand (inputs of proj_in / res_conv / qk)
-void launch_to_planar_tc(const TV& x, __half* a_hi, __half* a_lo, cudaStream_t s) {
-    launch_gn_act_tc(x, nullptr, 1, nullptr, nullptr, 0, false, a_hi, a_lo, s);
+void launch_to_planar_tc(const TV& x, int PF, __half* a_hi, __half* a_lo, cudaStream_t s) {
+    launch_gn_act_tc(x, nullptr, 1, nullptr, nullptr, 0, false, PF, a_hi, a_lo, s);
 }
 
 bool conv_tc_supported(int Cin, int Cout, int KF, int KT) {
@@ -464,8 +494,10 @@ bool conv_tc_supported(int Cin, int Cout, int KF, int KT) {
     return k && Cin % 16 == 0 && Cin >= 16 && Cout % 16 == 0 && Cout >= 16 && (Cout <= 256 || Cout % 256 == 0);
 }
 
-void launch_conv_tc(const __half* a_hi, const __half* a_lo, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,
+// a_hi / a_lo: [B][Cin/8][F + 2*PF][T+2][8] with PF >= tc_pad_rows(T, KF, dil)
+void launch_conv_tc(const __half* a_hi, const __half* a_lo, int PF, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,
                     const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s) {
+    if (PF < tc_pad_rows(T, KF, dil)) throw CudaError(cudaErrorInvalidValue, "conv_tc: not enough pad rows", __FILE__, __LINE__);
     if (ep.R2.p) throw CudaError(cudaErrorInvalidValue, "conv_tc: R2 is not supported", __FILE__, __LINE__);
     if (!conv_tc_supported(Cin, out.C, KF, KT)) throw CudaError(cudaErrorInvalidValue, "conv_tc: unsupported shape", __FILE__, __LINE__);
     TcConvArgs p{};
@@ -475,8 +507,11 @@ void launch_conv_tc(const __half* a_hi, const __half* a_lo, const __half* wp, in
     p.F = F; p.T = T; p.Tp = T + 2; p.dil = dil;
     p.KF = KF; p.KT = KT; p.kt_shift = (KT == 1) ? 1 : 0;
     p.kps = (KF == 1) ? min(TC_MAX_KPS, Cin / 16) : 1;
+    p.PF = PF; p.rows_total = F + 2 * PF;
+    p.stream = (T % 128 != 0) ? 1 : 0;
     p.tiles_t = (T + 127) / 128;
-    p.n_units = B * F * p.tiles_t;
+    p.units_per_b = p.stream ? (F * p.Tp + 127) / 128 : F * p.tiles_t;
+    p.n_units = B * p.units_per_b;
     p.n_pairs = (p.n_units + 1) / 2;
     p.n_tiles = p.n_pairs * p.n_ntiles;
     p.b_kstep_bytes = 2 * KT * 2 * p.Ntile * 16;  // (hi, lo) x kt x 2 chunks x Ntile x 16 B

@@ -368,7 +368,7 @@ static void conv(Ctx& c, const TV& a, const ConvW& w, int dil, const TV& out, Co
     if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
-static void conv_tc(Ctx& c, const __half* a_hi, const __half* a_lo, const ConvW& w, int dil, const TV& out, ConvEpilogue ep) {
+static void conv_tc(Ctx& c, const __half* a_hi, const __half* a_lo, int PF, const ConvW& w, int dil, const TV& out, ConvEpilogue ep) {
     if (out.C != w.Cout) throw std::runtime_error("conv_tc: shape mismatch");
     if (c.dry()) return;
     Net& n = *c.n;
@@ -382,7 +382,7 @@ static void conv_tc(Ctx& c, const __half* a_hi, const __half* a_lo, const ConvW&
         rec.bytes = 4.0 * (px * (w.Cin + w.Cout + (ep.R.p ? w.Cout : 0)) + (double)w.Cin * w.Cout * w.KF * w.KT);
         AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
     }
-    launch_conv_tc(a_hi, a_lo, w.wtc, out.B, w.Cin, out.F, out.T, w.KF, w.KT, dil, out, ep, n.num_sms, c.s);
+    launch_conv_tc(a_hi, a_lo, PF, w.wtc, out.B, w.Cin, out.F, out.T, w.KF, w.KT, dil, out, ep, n.num_sms, c.s);
     if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
@@ -394,23 +394,25 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
     const long long n_grp = (long long)(N / 8) * F * T;
     float* xbuf = c.allocf(plane);
     // operand buffer: fp32 [B,N,F,T] for the CUDA-core path, or split-fp16 planar hi|lo [B][N/8][F][T+2][8] each (tcgen05 path)
-    const long long a_halves = (long long)B * N * F * (T + 2);
-    float* abuf = c.allocf(std::max(plane, a_halves));
+    // (hi | lo arrays, each with PF zero rows above and below every plane -- PF depends on the layer's dilation)
+    auto planar_halves = [&](int ch, int pf) { return (long long)B * ch * (F + 2 * pf) * (T + 2); };
+    const int pf_max = tc_pad_rows(T, k.k1x1 ? 1 : 5, k.k1x1 ? 1 : (1 << std::max(0, k.nd - 1)));
+    float* abuf = c.allocf(std::max(plane, planar_halves(N, pf_max)));
     __half* a_hi = reinterpret_cast<__half*>(abuf);
-    __half* a_lo = a_hi + a_halves;
     TV x = make_tv(xbuf, B, N, F, T), a = make_tv(abuf, B, N, F, T);
     // tcgen05 path: the block input is converted once to the split-fp16 planar operand and shared by proj_in and res_conv
     __half* pin_hi = nullptr; __half* pin_lo = nullptr; float* pin_buf = nullptr;
+    const int pf1 = tc_pad_rows(T, 1, 1);
     if (k.proj_in.wtc || k.res_conv.wtc) {
-        const long long in_halves = (long long)B * k.dim * F * (T + 2);
+        const long long in_halves = planar_halves(k.dim, pf1);
         pin_buf = c.allocf(in_halves);
         pin_hi = reinterpret_cast<__half*>(pin_buf); pin_lo = pin_hi + in_halves;
-        RUN(launch_to_planar_tc(in, pin_hi, pin_lo, c.s));
+        RUN(launch_to_planar_tc(in, pf1, pin_hi, pin_lo, c.s));
     }
     TV cur;
     if (k.dim != N) {
         ConvEpilogue ep; ep.stats = x.stats = c.new_slot();
-        if (k.proj_in.wtc) conv_tc(c, pin_hi, pin_lo, k.proj_in, 1, x, ep);
+        if (k.proj_in.wtc) conv_tc(c, pin_hi, pin_lo, pf1, k.proj_in, 1, x, ep);
         else conv(c, in, k.proj_in, 1, x, ep);
         cur = x;
     } else {
@@ -425,11 +427,11 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         TV hflat = make_tv(h.p, B, heads * F, 1, T);
         TV qk = make_tv(c.allocf((long long)B * 2 * heads * F * T), B, 2 * heads * F, 1, T);
         if (k.qk.wtc) {
-            const long long hh = (long long)B * heads * F * (T + 2);
+            const long long hh = (long long)B * heads * F * (1 + 2 * pf1) * (T + 2);
             float* hp = c.allocf(hh);
             __half* h_hi = reinterpret_cast<__half*>(hp);
-            RUN(launch_to_planar_tc(hflat, h_hi, h_hi + hh, c.s));
-            conv_tc(c, h_hi, h_hi + hh, k.qk, 1, qk, ConvEpilogue());
+            RUN(launch_to_planar_tc(hflat, pf1, h_hi, h_hi + hh, c.s));
+            conv_tc(c, h_hi, h_hi + hh, pf1, k.qk, 1, qk, ConvEpilogue());
             c.release(hp);
         } else {
             conv(c, hflat, k.qk, 1, qk, ConvEpilogue());
@@ -451,9 +453,12 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         ep.stats = (i + 1 < k.nd) ? c.new_slot() : nullptr;
         const double* cur_stats = cur.stats;
         if (k.H[i].wtc) {
-            RUN(launch_gn_act_tc(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, a_hi, a_lo, c.s));
+            const int dil = k.k1x1 ? 1 : (1 << i);
+            const int pf = tc_pad_rows(T, k.H[i].KF, dil);
+            __half* a_lo = a_hi + planar_halves(N, pf);
+            RUN(launch_gn_act_tc(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, a_lo, c.s));
             x.stats = ep.stats;
-            conv_tc(c, a_hi, a_lo, k.H[i], k.k1x1 ? 1 : (1 << i), x, ep);
+            conv_tc(c, a_hi, a_lo, pf, k.H[i], dil, x, ep);
         } else {
             RUN(launch_gn_act(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, a, c.s));
             x.stats = ep.stats;
@@ -473,7 +478,7 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         if (accum) throw std::runtime_error("resblock: accum only supported for out blocks");
         if (k.dim != k.dim_out) {
             ConvEpilogue ep; ep.R = cur; ep.alpha = kInvSqrt2; ep.stats = out.stats;
-            if (k.res_conv.wtc) conv_tc(c, pin_hi, pin_lo, k.res_conv, 1, out, ep);
+            if (k.res_conv.wtc) conv_tc(c, pin_hi, pin_lo, pf1, k.res_conv, 1, out, ep);
             else conv(c, in, k.res_conv, 1, out, ep);
         } else {
             RUN(launch_combine(cur, in, kInvSqrt2, kInvSqrt2, out, out.stats, c.s));
@@ -830,7 +835,8 @@ static int op_conv2d_impl(const float* a_dev, const float* w_dev, int B, int Cin
         cudaEvent_t e0, e1;
         AID_CUDA_CHECK(cudaEventCreate(&e0)); AID_CUDA_CHECK(cudaEventCreate(&e1));
         __half *wtc = nullptr, *ah = nullptr;
-        const size_t ahalves = (size_t)B * Cin * F * (T + 2);
+        const int pf = tc_pad_rows(T, KF, dil);
+        const size_t ahalves = (size_t)B * Cin * (F + 2 * pf) * (T + 2);
         int sms = 148, dev = 0;
         if (mode == 1) {
             if (!conv_tc_supported(Cin, Cout, KF, KT) || R2_dev) throw std::invalid_argument("shape not supported by the tcgen05 path");
@@ -839,11 +845,11 @@ static int op_conv2d_impl(const float* a_dev, const float* w_dev, int B, int Cin
             AID_CUDA_CHECK(cudaMalloc(&wtc, 2 * e * sizeof(__half)));
             AID_CUDA_CHECK(cudaMalloc(&ah, 2 * ahalves * sizeof(__half)));
             launch_pack_weight_tc(w_dev, wtc, Cout, Cin, KF, KT, s);
-            launch_to_planar_tc(a, ah, ah + ahalves, s);
+            launch_to_planar_tc(a, pf, ah, ah + ahalves, s);
         } else if (mode != 0 && mode != 2) throw std::invalid_argument("unknown conv mode");
         (void)iters;
         AID_CUDA_CHECK(cudaEventRecord(e0, s));
-        if (mode == 1) launch_conv_tc(ah, ah + ahalves, wtc, B, Cin, F, T, KF, KT, dil, out, ep, sms, s);
+        if (mode == 1) launch_conv_tc(ah, ah + ahalves, pf, wtc, B, Cin, F, T, KF, KT, dil, out, ep, sms, s);
         else if (mode == 2 || !launch_conv_thin(a, wp, KF, KT, dil, out, ep, s)) launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
         AID_CUDA_CHECK(cudaEventRecord(e1, s));
         AID_CUDA_CHECK(cudaGetLastError());

@@ -22,6 +22,8 @@ TC_CASES = [
     (1, 256, 256, 24, 64, 64, True),   # N = 256 (single accumulator buffer), only the centre tap row is in range
     (3, 32, 48, 9, 16, 2, True),       # tiny T, Cin != Cout
     (1, 256, 256, 70, 128, 32, True),  # deep level shape
+    (2, 64, 64, 13, 192, 4, True),     # T not a multiple of 128: stream units straddle rows of 194 padded pixels
+    (1, 32, 32, 50, 4, 8, True),       # T = 4: a unit spans 21 rows
 ]
 
 
