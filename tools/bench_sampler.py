@@ -1,0 +1,83 @@
+"""End-to-end sampling throughput (BASELINE configs 2-5) on the B200 path.
+
+    python tools/bench_sampler.py --config inpaint --batch 32 --gap-ms 300      # config 3
+    python tools/bench_sampler.py --config uncond  --batch 8                    # config 2
+    torchrun --nproc-per-node N ... tools/bench_sampler.py --config inpaint --batch 256 --gap-ms 1500   # config 4 (sharded)
+Prints one JSON line (rank 0): clips/s for the whole 35-step, 69-evaluation run, seconds per run, evals.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.distributed as dist
+import aid_b200
+from aid_b200.dist import ShardedSampler, shard_bounds
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="inpaint", choices=["inpaint", "uncond"])
+ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--len", type=int, default=262144)
+ap.add_argument("--gap-ms", type=float, default=300.0)
+ap.add_argument("--steps", type=int, default=35)
+ap.add_argument("--conv-mode", type=int, default=1)
+a = ap.parse_args()
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+cfg = aid_b200.paper_22k(a.len, conv_mode=a.conv_mode)
+net = aid_b200.Unet_CQT_oct_with_attention(cfg, dev)
+net.load_state_dict(aid_b200.random_state_dict(cfg, seed=1234))
+args = aid_b200.AttrDict.wrap({
+    "tester": {"T": a.steps, "order": 2, "filter_out_cqt_DC_Nyq": True, "posterior_sampling": {"xi": 0, "norm": 2, "smoothl1_beta": 1},
+               "data_consistency": {"use": True, "type": "always", "smooth": True, "hann_size": 50},
+               "diff_params": {"same_as_training": False, "sigma_data": 0.063, "sigma_min": 1e-4, "sigma_max": 1, "ro": 13,
+                               "Schurn": 10, "Snoise": 1.0, "Stmin": 0, "Stmax": 50}},
+    "diff_params": {"sigma_data": 0.063, "sigma_min": 1e-5, "sigma_max": 10, "ro": 13, "Schurn": 5, "Snoise": 1, "Stmin": 0, "Stmax": 50},
+})
+calls = [0]
+orig = net.denoise_fused
+net.denoise_fused = lambda *x, **k: (calls.__setitem__(0, calls[0] + 1), orig(*x, **k))[1]
+smp = ShardedSampler(aid_b200.Sampler(net, aid_b200.EDM(args), args), seed=42)
+B, L = a.batch, a.len
+# MAESTRO-shaped synthetic clips: zero mean, RMS = sigma_data
+y = (torch.randn(B, L, generator=torch.Generator().manual_seed(7)) * 0.063).to(dev)
+gap = int(a.gap_ms * 22050 / 1000)
+mask = torch.ones(1, L, device=dev)
+mask[..., L // 2 - gap // 2: L // 2 - gap // 2 + gap] = 0      # tester_inpainting.py:231-242
+
+def run():
+    if a.config == "inpaint":
+        return smp.predict_inpainting(y * mask, mask)
+    return smp.predict_unconditional((B, L), dev)
+
+net._ensure_weights(dev)
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+t0 = time.perf_counter()
+out = run()
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+dt = time.perf_counter() - t0
+ok = bool(torch.isfinite(out).all()) and tuple(out.shape) == (B, L)
+if a.config == "inpaint":
+    keep = mask[0].bool().clone()
+    keep[L // 2 - gap // 2 - 100: L // 2 + gap // 2 + 100] = False
+    ok = ok and bool(torch.allclose(out[:, keep], (y * mask)[:, keep], atol=1e-5))
+if rank == 0:
+    lo, hi = shard_bounds(B, 0, world)
+    print(json.dumps({"config": a.config, "batch": B, "len": L, "gap_ms": a.gap_ms if a.config == "inpaint" else None, "n_gpus": world,
+                      "sampler_steps": a.steps, "denoiser_evals": calls[0], "seconds": dt, "clips_per_s": B / dt,
+                      "seconds_per_eval": dt / max(calls[0], 1), "clips_per_rank": hi - lo, "output_ok": ok, "conv_mode": a.conv_mode}))
+if world > 1:
+    dist.destroy_process_group()
