@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
         __syncwarp();
         int b_cur = -1;
         auto flush_global = [&]() {
+            __syncwarp();  // lane 0's accumulator updates (flush_group) must be visible to lanes 0..15
             if (p.stats && b_cur >= 0 && lane < 16) {
                 const double v = sst[lane];
                 if (v != 0.0) atomicAdd(p.stats + (long long)b_cur * 16 + lane, v);
