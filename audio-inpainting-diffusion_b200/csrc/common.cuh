@@ -83,16 +83,19 @@ void launch_conv_tc(const __half* a_hi, const __half* a_lo, int PF, const __half
 
 // FFT / CQT
 struct FftPlan {
-    int L = 0, N1 = 0, N2 = 0;
-    const float2* tw = nullptr;  // W_L^k = exp(-2*pi*i*k/L), k in [0, L)
+    int L = 0;                      // transform length (even)
+    int M = 0, N1 = 0, N2 = 0, lgM = 0;  // power-of-two engine: M == L if L is a power of two, else next_pow2(2L) (Bluestein)
+    const float2* tw = nullptr;     // W_M^k = exp(-2*pi*i*k/M), k in [0, M)
+    const float2* chirp = nullptr;  // Bluestein only: exp(-i*pi*n^2/L), n in [0, L)
+    const float2* bfilt = nullptr;  // Bluestein only: FFT_M of the wrapped conj(chirp) filter
 };
-// batched length-L complex FFT via the four-step split L = N1*N2.
-//  in_real != null : input is real [B][in_stride], scaled by in_scale
-//  in_cplx != null : input complex [B][L]
+// batched length-L complex DFT (four-step split M = N1*N2 in shared memory; Bluestein around it when L is not a power of two).
+//  in_real != null : input is real [B][in_stride], scaled by in_scale;   in_cplx != null : input complex [B][L]
 //  out_cplx != null: complex output [B][L] (unscaled)
 //  out_real != null: out_real[b][n] = out_scale * Re(result) + skip_scale * skip[b][n]   (skip may be null)
+//  tmp: [B][M] complex scratch; scratch: second [B][M] buffer, only needed when M != L.
 void launch_fft_big(const FftPlan& plan, int B, bool inverse, const float* in_real, long long in_stride, float in_scale,
-                    const float2* in_cplx, float2* tmp, float2* out_cplx, float* out_real, long long out_stride,
+                    const float2* in_cplx, float2* tmp, float2* scratch, float2* out_cplx, float* out_real, long long out_stride,
                     float out_scale, const float* skip, long long skip_stride, float skip_scale, cudaStream_t s);
 
 struct CqtTables {

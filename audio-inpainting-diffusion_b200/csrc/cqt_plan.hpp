@@ -31,8 +31,8 @@ struct CqtPlanHost {
 
     void build(int nocts_, int bins_, double fs, int L_, int window_kind, double beta) {
         nocts = nocts_; bins = bins_; L = L_; K = nocts * bins;
-        if (L <= 0 || (L & (L - 1)) != 0 || L < 4096)
-            throw std::invalid_argument("audio_len must be a power of two >= 4096 (non-power-of-two lengths such as 184184 are not supported yet)");
+        if (L < 4096 || (L & 1) != 0 || L > (1 << 21))
+            throw std::invalid_argument("audio_len must be even and in [4096, 2097152]");
         if (nocts > 16) throw std::invalid_argument("num_octs > 16");
         const int min_win = 4;
         const double fmax = fs / 2.0 - 1e-6, fmin = fmax / std::pow(2.0, nocts);

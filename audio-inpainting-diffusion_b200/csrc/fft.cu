@@ -102,9 +102,9 @@ fft_rows_kernel(int lg1, int lg2, const float2* __restrict__ tw, bool inverse, c
     }
 }
 
-void launch_fft_big(const FftPlan& plan, int B, bool inverse, const float* in_real, long long in_stride, float in_scale,
-                    const float2* in_cplx, float2* tmp, float2* out_cplx, float* out_real, long long out_stride,
-                    float out_scale, const float* skip, long long skip_stride, float skip_scale, cudaStream_t s) {
+static void fft_pow2(const FftPlan& plan, int B, bool inverse, const float* in_real, long long in_stride, float in_scale,
+                     const float2* in_cplx, float2* tmp, float2* out_cplx, float* out_real, long long out_stride, float out_scale,
+                     const float* skip, long long skip_stride, float skip_scale, cudaStream_t s) {
     int lg1 = 0, lg2 = 0;
     while ((1 << lg1) < plan.N1) ++lg1;
     while ((1 << lg2) < plan.N2) ++lg2;
@@ -117,6 +117,63 @@ void launch_fft_big(const FftPlan& plan, int B, bool inverse, const float* in_re
     fft_rows_kernel<<<dim3(plan.N1 / CW, B), FNT, sm2, s>>>(lg1, lg2, plan.tw, inverse, tmp, out_cplx, out_real, out_stride,
                                                             out_scale, skip, skip_stride, skip_scale);
     AID_COUNT_LAUNCH(1);
+}
+
+// ---- Bluestein (chirp-z) for lengths that are not a power of two (the reference's trained audio_len = 184184) --------
+//   X[k] = w[k] * sum_n (x[n] w[n]) conj(w)[k-n],  w[n] = exp(-i*pi*n^2/L): one circular convolution of power-of-two size M >= 2L-1.
+//   The inverse transform is conj(DFT(conj(x))).
+__global__ void bluestein_pre_kernel(int L, int M, bool inverse, const float* __restrict__ in_real, long long in_stride, float in_scale,
+                                     const float2* __restrict__ in_cplx, const float2* __restrict__ chirp, float2* __restrict__ A) {
+    const int b = blockIdx.y;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < M; n += gridDim.x * blockDim.x) {
+        float2 v = make_float2(0.f, 0.f);
+        if (n < L) {
+            float2 x = in_real ? make_float2(in_real[(long long)b * in_stride + n] * in_scale, 0.f) : in_cplx[(long long)b * L + n];
+            if (inverse) x.y = -x.y;
+            v = cmul(x, __ldg(chirp + n));
+        }
+        A[(long long)b * M + n] = v;
+    }
+}
+__global__ void bluestein_mul_kernel(int M, const float2* __restrict__ bfilt, float2* __restrict__ A) {
+    const int b = blockIdx.y;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < M; n += gridDim.x * blockDim.x)
+        A[(long long)b * M + n] = cmul(A[(long long)b * M + n], __ldg(bfilt + n));
+}
+__global__ void bluestein_post_kernel(int L, int M, bool inverse, const float2* __restrict__ A, const float2* __restrict__ chirp,
+                                      float2* __restrict__ out_cplx, float* __restrict__ out_real, long long out_stride, float out_scale,
+                                      const float* __restrict__ skip, long long skip_stride, float skip_scale) {
+    const int b = blockIdx.y;
+    const float inv = 1.f / (float)M;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
+        float2 v = cmul(A[(long long)b * M + k], __ldg(chirp + k));
+        v.x *= inv; v.y *= inv;
+        if (inverse) v.y = -v.y;
+        if (out_cplx) out_cplx[(long long)b * L + k] = v;
+        if (out_real) {
+            float o = out_scale * v.x;
+            if (skip) o += skip_scale * skip[(long long)b * skip_stride + k];
+            out_real[(long long)b * out_stride + k] = o;
+        }
+    }
+}
+
+void launch_fft_big(const FftPlan& plan, int B, bool inverse, const float* in_real, long long in_stride, float in_scale,
+                    const float2* in_cplx, float2* tmp, float2* scratch, float2* out_cplx, float* out_real, long long out_stride,
+                    float out_scale, const float* skip, long long skip_stride, float skip_scale, cudaStream_t s) {
+    if (plan.M == plan.L) {
+        fft_pow2(plan, B, inverse, in_real, in_stride, in_scale, in_cplx, tmp, out_cplx, out_real, out_stride, out_scale, skip,
+                 skip_stride, skip_scale, s);
+        return;
+    }
+    const dim3 grid(148 * 4, B);
+    bluestein_pre_kernel<<<grid, 256, 0, s>>>(plan.L, plan.M, inverse, in_real, in_stride, in_scale, in_cplx, plan.chirp, scratch);
+    fft_pow2(plan, B, false, nullptr, 0, 0.f, scratch, tmp, scratch, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
+    bluestein_mul_kernel<<<grid, 256, 0, s>>>(plan.M, plan.bfilt, scratch);
+    fft_pow2(plan, B, true, nullptr, 0, 0.f, scratch, tmp, scratch, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
+    bluestein_post_kernel<<<grid, 256, 0, s>>>(plan.L, plan.M, inverse, scratch, plan.chirp, out_cplx, out_real, out_stride, out_scale,
+                                               skip, skip_stride, skip_scale);
+    AID_COUNT_LAUNCH(3);
 }
 
 // ---- CQT analysis: one CTA per (band of the octave, clip) ---------------------------------------------
@@ -158,9 +215,9 @@ cqt_analysis_kernel(CqtTables t, const float2* __restrict__ tw, int lgL, int oct
 
 void launch_cqt_analysis_oct(const CqtTables& t, const FftPlan& fp, int oct, const float2* spec, const TV& C, cudaStream_t s) {
     const int M = t.M[oct];
-    int lgM = 0, lgL = 0;
+    int lgM = 0;
     while ((1 << lgM) < M) ++lgM;
-    while ((1 << lgL) < t.L) ++lgL;
+    const int lgL = fp.lgM;  // log2 of the twiddle table size
     const size_t sm = (size_t)M * sizeof(float2);
     static size_t cfg = 0;
     if (sm > cfg) { AID_CUDA_CHECK(cudaFuncSetAttribute(cqt_analysis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); cfg = sm; }
@@ -185,9 +242,9 @@ cqt_synth_kernel(CqtTables t, const float2* __restrict__ tw, int lgL, int oct, i
 
 void launch_cqt_synth_oct(const CqtTables& t, const FftPlan& fp, int oct, const TV& C, float2* Y, cudaStream_t s) {
     const int M = t.M[oct];
-    int lgM = 0, lgL = 0;
+    int lgM = 0;
     while ((1 << lgM) < M) ++lgM;
-    while ((1 << lgL) < t.L) ++lgL;
+    const int lgL = fp.lgM;  // log2 of the twiddle table size
     const size_t sm = (size_t)M * sizeof(float2);
     static size_t cfg = 0;
     if (sm > cfg) { AID_CUDA_CHECK(cudaFuncSetAttribute(cqt_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); cfg = sm; }
@@ -226,7 +283,7 @@ __global__ void spec_mul_real_kernel(long long n, int L, float2* __restrict__ sp
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const float g = __ldg(h + (i & (L - 1)));
+        const float g = __ldg(h + (i % L));
         float2 v = spec[i];
         spec[i] = make_float2(v.x * g, v.y * g);
     }

@@ -6,6 +6,7 @@
 // Concatenations (unet.py:769-774, 814) and slices (unet.py:821-822) are strided views, never copies.
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -300,20 +301,58 @@ static void upload_tables(Net& n) {
     AID_CUDA_CHECK(cudaSetDevice(n.device));
     const CqtPlanHost& p = n.plan;
     const int L = p.L, K = p.K;
-    std::vector<float2> tw(L);
-    for (int k = 0; k < L; ++k) {
-        const double a = -2.0 * M_PI * (double)k / (double)L;
+    // power-of-two FFT engine size: L itself, or (Bluestein) the next power of two >= 2L
+    const bool pow2 = (L & (L - 1)) == 0;
+    int M = 1; while (M < (pow2 ? L : 2 * L)) M <<= 1;
+    std::vector<float2> tw(M);
+    for (int k = 0; k < M; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)M;
         tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
+    std::vector<float2> chirp, bfilt;
+    if (!pow2) {
+        // w[n] = exp(-i*pi*n^2/L) with n^2 reduced mod 2L exactly; filter b[m] = conj(w[|m|]) wrapped on the circle of size M
+        chirp.resize(L);
+        std::vector<std::complex<double>> wd(L), b(M, 0.0);
+        for (long long i = 0; i < L; ++i) {
+            const double a = -M_PI * (double)((i * i) % (2LL * L)) / (double)L;
+            wd[i] = std::complex<double>(std::cos(a), std::sin(a));
+            chirp[i] = make_float2((float)wd[i].real(), (float)wd[i].imag());
+        }
+        b[0] = std::conj(wd[0]);
+        for (int i = 1; i < L; ++i) { b[i] = std::conj(wd[i]); b[M - i] = std::conj(wd[i]); }
+        // iterative radix-2 FFT in double on the host (once per handle)
+        int lgm = 0; while ((1 << lgm) < M) ++lgm;
+        for (int i = 0; i < M; ++i) {
+            int r = 0; for (int q = 0; q < lgm; ++q) if (i & (1 << q)) r |= 1 << (lgm - 1 - q);
+            if (r > i) std::swap(b[i], b[r]);
+        }
+        for (int len = 2; len <= M; len <<= 1) {
+            const double ang = -2.0 * M_PI / len;
+            const std::complex<double> wl(std::cos(ang), std::sin(ang));
+            for (int i = 0; i < M; i += len) {
+                std::complex<double> w(1.0, 0.0);
+                for (int j = 0; j < len / 2; ++j) {
+                    const std::complex<double> u = b[i + j], v = b[i + j + len / 2] * w;
+                    b[i + j] = u + v; b[i + j + len / 2] = u - v;
+                    w *= wl;
+                }
+            }
+        }
+        bfilt.resize(M);
+        for (int i = 0; i < M; ++i) bfilt[i] = make_float2((float)b[i].real(), (float)b[i].imag());
+    }
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    size_t bytes = al(L * sizeof(float2)) + 3 * al(K * sizeof(int)) + 2 * al(p.win.size() * sizeof(float)) +
-                   2 * al((L / 2 + 1) * sizeof(int)) + al(L * sizeof(float));
+    size_t bytes = al(M * sizeof(float2)) + al(chirp.size() * sizeof(float2)) + al(bfilt.size() * sizeof(float2)) + 3 * al(K * sizeof(int)) +
+                   2 * al(p.win.size() * sizeof(float)) + 2 * al((L / 2 + 1) * sizeof(int)) + al(L * sizeof(float));
     AID_CUDA_CHECK(cudaMalloc(&n.d_tables, bytes));
     char* d = (char*)n.d_tables;
     auto put = [&](const void* src, size_t nb) { void* dst = d; AID_CUDA_CHECK(cudaMemcpy(dst, src, nb, cudaMemcpyHostToDevice)); d += al(nb); return dst; };
-    n.fft.tw = (const float2*)put(tw.data(), L * sizeof(float2));
-    int lg = 0; while ((1 << lg) < L) ++lg;
-    n.fft.L = L; n.fft.N1 = 1 << ((lg + 1) / 2); n.fft.N2 = L / n.fft.N1;
+    n.fft.tw = (const float2*)put(tw.data(), M * sizeof(float2));
+    if (!pow2) {
+        n.fft.chirp = (const float2*)put(chirp.data(), chirp.size() * sizeof(float2));
+        n.fft.bfilt = (const float2*)put(bfilt.data(), bfilt.size() * sizeof(float2));
+    }
     CqtTables& t = n.tabs;
     t.L = L; t.K = K; t.bins = p.bins; t.nocts = p.nocts;
     t.centre = (const int*)put(p.centre.data(), K * sizeof(int));
@@ -328,6 +367,13 @@ static void upload_tables(Net& n) {
 
 static void fill_host_tables(Net& n) {
     const CqtPlanHost& p = n.plan;
+    {
+        const int L = p.L;
+        const bool pow2 = (L & (L - 1)) == 0;
+        int M = 1; while (M < (pow2 ? L : 2 * L)) M <<= 1;
+        int lg = 0; while ((1 << lg) < M) ++lg;
+        n.fft.L = L; n.fft.M = M; n.fft.lgM = lg; n.fft.N1 = 1 << ((lg + 1) / 2); n.fft.N2 = M / n.fft.N1;
+    }
     CqtTables& t = n.tabs;
     t.L = p.L; t.K = p.K; t.bins = p.bins; t.nocts = p.nocts;
     long long yo = 0;
@@ -510,8 +556,9 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
     c.stats_base = (double*)c.ar.alloc(stat_bytes);
     RUN(AID_CUDA_CHECK(cudaMemsetAsync(c.stats_base, 0, stat_bytes, c.s)));
     float2* spec = (float2*)c.ar.alloc((size_t)B * L * sizeof(float2));
-    float2* tmp = (float2*)c.ar.alloc((size_t)B * L * sizeof(float2));
-    RUN(launch_fft_big(n.fft, B, false, x, L, in_scale, nullptr, tmp, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, c.s));
+    float2* tmp = (float2*)c.ar.alloc((size_t)B * n.fft.M * sizeof(float2));
+    float2* fscr = n.fft.M != L ? (float2*)c.ar.alloc((size_t)B * n.fft.M * sizeof(float2)) : nullptr;
+    RUN(launch_fft_big(n.fft, B, false, x, L, in_scale, nullptr, tmp, fscr, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, c.s));
 
     auto Tof = [&](int lvl) { return n.tabs.M[no - 1 - lvl]; };
     std::vector<TV> cat(no);
@@ -591,7 +638,7 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
     }
     c.release(Xout.p);
     RUN(launch_cqt_synth_gather(n.tabs, B, Y, spec, c.s));
-    RUN(launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, nullptr, out, L, out_scale / (float)L,
+    RUN(launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, fscr, nullptr, out, L, out_scale / (float)L,
                        skip_scale != 0.f ? x : nullptr, L, skip_scale, c.s));
     if (!c.dry()) AID_CUDA_CHECK(cudaGetLastError());
 }
@@ -605,7 +652,8 @@ static size_t plan_forward(Net& n, int B, int* slots) {
 
 static size_t cqt_ws_bytes(const Net& n, int B) {
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    return 2 * al((size_t)B * n.cfg.audio_len * sizeof(float2)) + al((size_t)B * n.tabs.ytotal * sizeof(float2)) + 4096;
+    return al((size_t)B * n.cfg.audio_len * sizeof(float2)) + 2 * al((size_t)B * n.fft.M * sizeof(float2)) +
+           al((size_t)B * n.tabs.ytotal * sizeof(float2)) + 4096;
 }
 
 }  // namespace aid
@@ -745,13 +793,14 @@ int aid_cqt_workspace_bytes(const aid_handle* h, int B, size_t* bytes) {
     return AID_OK;
 }
 
-static void cqt_ws_split(Net& n, int B, void* ws, size_t ws_bytes, float2** spec, float2** tmp, float2** Y) {
+static void cqt_ws_split(Net& n, int B, void* ws, size_t ws_bytes, float2** spec, float2** tmp, float2** fscr, float2** Y) {
     upload_tables(n);
     if (ws_bytes < cqt_ws_bytes(n, B)) throw std::runtime_error("workspace too small");
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     char* p = (char*)ws;
     *spec = (float2*)p; p += al((size_t)B * n.cfg.audio_len * sizeof(float2));
-    *tmp = (float2*)p; p += al((size_t)B * n.cfg.audio_len * sizeof(float2));
+    *tmp = (float2*)p; p += al((size_t)B * n.fft.M * sizeof(float2));
+    *fscr = (float2*)p; p += al((size_t)B * n.fft.M * sizeof(float2));
     *Y = (float2*)p;
 }
 
@@ -759,9 +808,9 @@ int aid_cqt_fwd(aid_handle* h, const float* x_dev, float* coef_dev, int B, void*
     if (!h || !x_dev || !coef_dev || !ws) return AID_ERR_INVALID;
     return guarded(h, [&] {
         Net& n = h->net; cudaStream_t s = (cudaStream_t)stream;
-        float2 *spec, *tmp, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &Y);
+        float2 *spec, *tmp, *fscr, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &fscr, &Y);
         const int L = n.cfg.audio_len, bins = n.cfg.bins_per_oct;
-        launch_fft_big(n.fft, B, false, x_dev, L, 1.f, nullptr, tmp, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
+        launch_fft_big(n.fft, B, false, x_dev, L, 1.f, nullptr, tmp, fscr, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
         int64_t off = 0;
         for (int o = 0; o < n.cfg.num_octs; ++o) {
             TV C = make_tv(coef_dev + off, B, 2, bins, n.tabs.M[o]);
@@ -776,7 +825,7 @@ int aid_cqt_bwd(aid_handle* h, const float* coef_dev, float* x_dev, int B, void*
     if (!h || !x_dev || !coef_dev || !ws) return AID_ERR_INVALID;
     return guarded(h, [&] {
         Net& n = h->net; cudaStream_t s = (cudaStream_t)stream;
-        float2 *spec, *tmp, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &Y);
+        float2 *spec, *tmp, *fscr, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &fscr, &Y);
         const int L = n.cfg.audio_len, bins = n.cfg.bins_per_oct;
         int64_t off = 0;
         for (int o = 0; o < n.cfg.num_octs; ++o) {
@@ -785,7 +834,7 @@ int aid_cqt_bwd(aid_handle* h, const float* coef_dev, float* x_dev, int B, void*
             off += (int64_t)B * 2 * bins * n.tabs.M[o];
         }
         launch_cqt_synth_gather(n.tabs, B, Y, spec, s);
-        launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, nullptr, x_dev, L, 1.f / (float)L, nullptr, 0, 0.f, s);
+        launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, fscr, nullptr, x_dev, L, 1.f / (float)L, nullptr, 0, 0.f, s);
         AID_CUDA_CHECK(cudaGetLastError());
     });
 }
@@ -794,11 +843,11 @@ int aid_hpf_dc(aid_handle* h, const float* x_dev, float* out_dev, int B, void* w
     if (!h || !x_dev || !out_dev || !ws) return AID_ERR_INVALID;
     return guarded(h, [&] {
         Net& n = h->net; cudaStream_t s = (cudaStream_t)stream;
-        float2 *spec, *tmp, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &Y);
+        float2 *spec, *tmp, *fscr, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &fscr, &Y);
         const int L = n.cfg.audio_len;
-        launch_fft_big(n.fft, B, false, x_dev, L, 1.f, nullptr, tmp, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
+        launch_fft_big(n.fft, B, false, x_dev, L, 1.f, nullptr, tmp, fscr, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
         launch_spec_mul_real(B, L, spec, n.tabs.hhpf, s);
-        launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, nullptr, out_dev, L, 1.f / (float)L, nullptr, 0, 0.f, s);
+        launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, fscr, nullptr, out_dev, L, 1.f / (float)L, nullptr, 0, 0.f, s);
         AID_CUDA_CHECK(cudaGetLastError());
     });
 }

@@ -21,7 +21,7 @@ def small(aid, cuda):
     return cfg, sd, net, make_oracle(cfg, sd)
 
 
-@pytest.mark.parametrize("L", [16384, 65536])
+@pytest.mark.parametrize("L", [16384, 65536, 184184])
 def test_cqt_fwd_bwd_hpf(aid, cuda, L):
     cfg = aid.small_test(L)
     net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
@@ -187,3 +187,16 @@ def test_full_size_clip_properties(aid, cuda):
     assert rel_l2(net(x, cn), a) < 1e-6
     assert rel_l2(net(x[1:], cn), a[1:]) < 1e-5
     assert rel_l2(net(x, cn - 1.0), a) > 1e-3
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_forward_reference_trained_length_184184(aid, cuda, mode):
+    """audio_len = 184184 (2^3*7*11*13*23, conf/exp/maestro22k_8s.yaml:52): Bluestein FFT, 2048..32 frames per octave."""
+    cfg = aid.NetConfig(audio_len=184184, Ns=[16, 16, 32, 32, 32, 48, 64], num_dils=[1, 2, 2, 3, 3, 3, 2], conv_mode=mode)
+    sd = aid.random_state_dict(cfg, seed=11)
+    net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+    net.load_state_dict(sd)
+    x = seeded((1, 184184), 4, 0.5)
+    cn = torch.tensor([[-0.6]])
+    ref = make_oracle(cfg, sd)(x, cn)
+    assert rel_l2(net(x.to(cuda), cn.to(cuda)), ref) < 1e-4

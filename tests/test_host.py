@@ -35,8 +35,10 @@ def test_config_from_reference_style_args(aid):
 
 
 def test_unsupported_length_is_a_clear_error(aid):
-    with pytest.raises(Exception, match="power of two"):
-        aid.schema_from_lib(aid.NetConfig(audio_len=184184))
+    with pytest.raises(Exception, match="audio_len must be even"):
+        aid.schema_from_lib(aid.NetConfig(audio_len=184185))
+    # the reference's trained length (conf/exp/maestro22k_8s.yaml:52) is supported (Bluestein FFT), T0 = 2048 frames
+    assert len(aid.schema_from_lib(aid.NetConfig(audio_len=184184))) == 662
 
 
 def test_module_surface_and_state_dict_roundtrip(aid):
@@ -80,7 +82,7 @@ def test_workspace_plan_is_host_only_and_grows_with_batch(aid):
         L.aid_destroy(h)
 
 
-@pytest.mark.parametrize("L", [16384, 65536, 262144])
+@pytest.mark.parametrize("L", [16384, 65536, 184184, 262144])
 def test_cqt_band_plan_matches_oracle(aid, L):
     """The C++ band plan (csrc/cqt_plan.hpp) and the oracle's numpy plan are two writings of one definition."""
     import cqt_oracle
