@@ -426,15 +426,16 @@ __device__ __forceinline__ float gelu_erf_tc(float v) { return 0.5f * v * (1.f +
 // Normalise / modulate / GELU (unet.py:159-163, 479, 482) writing the split-fp16 planar operand:
 //   a[b][c/8][f][1+t][c%8] = split(16 * act(x[b,c,f,t] * scale_c)),  pad pixels (index 0 and T+1) = 0
 // With stats == nullptr it is a plain layout/precision conversion (scale_c = 1).
-// grid: (ceil(Tp/128), F, B*C/8), block 128: one thread per padded pixel, 8 channels each.
-__global__ void __launch_bounds__(128)
+// grid: (ceil(rows / rows_per_block), B*C/8), block 256: a block owns a few whole rows of one 8-channel chunk, so the
+// per-(clip, channel) scales are computed once per block and every thread streams several pixels (8 coalesced channel-plane
+// loads, two 16-byte stores each).
+__global__ void __launch_bounds__(256)
 gn_act_tc_kernel(TV x, const double* __restrict__ stats, double n_per_group, const float* __restrict__ gamma,
-                 const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, __half* __restrict__ a_hi,
-                 __half* __restrict__ a_lo) {
+                 const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, int rows_per_block,
+                 __half* __restrict__ a_hi, __half* __restrict__ a_lo) {
     const int C8 = x.C >> 3;
-    const int c8 = blockIdx.z % C8, b = blockIdx.z / C8, fr = blockIdx.y, f = fr - PF;   // fr: row of the padded plane
-    const int Tp = x.T + 2;
-    const int tp = blockIdx.x * 128 + threadIdx.x;
+    const int c8 = blockIdx.y % C8, b = blockIdx.y / C8;
+    const int Tp = x.T + 2, rows_total = x.F + 2 * PF;
     __shared__ float s_scale[8];
     if (threadIdx.x < 8) {
         float sc = 1.f;
@@ -451,24 +452,38 @@ gn_act_tc_kernel(TV x, const double* __restrict__ stats, double n_per_group, con
         s_scale[threadIdx.x] = sc;
     }
     __syncthreads();
-    if (tp >= Tp) return;
-    __align__(16) __half hi[8], lo[8];
-    const int t = tp - 1;
-    if (t < 0 || t >= x.T || f < 0 || f >= x.F) {
+    float sc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { hi[j] = __float2half_rn(0.f); lo[j] = __float2half_rn(0.f); }
-    } else {
-        const float* src = x.p + (long long)b * x.sb + (long long)(c8 * 8) * x.sc + (long long)f * x.T + t;
+    for (int j = 0; j < 8; ++j) sc[j] = s_scale[j];
+    const float* xb = x.p + (long long)b * x.sb + (long long)(c8 * 8) * x.sc;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(rows_total, r0 + rows_per_block);
+    for (int fr = r0; fr < r1; ++fr) {
+        const int f = fr - PF;
+        const bool rowok = f >= 0 && f < x.F;
+        const float* src = xb + (long long)(rowok ? f : 0) * x.T;
+        const long long obase = (((long long)b * C8 + c8) * rows_total + fr) * Tp;
+#pragma unroll 2
+        for (int tp = threadIdx.x; tp < Tp; tp += 256) {
+            __align__(16) __half hi[8], lo[8];
+            const int t = tp - 1;
+            if (!rowok || t < 0 || t >= x.T) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float v = __ldg(src + (long long)j * x.sc) * s_scale[j];
-            if (gelu) v = gelu_erf_tc(v);
-            split_half(v * TC_A_SCALE, hi[j], lo[j]);
+                for (int j = 0; j < 8; ++j) { hi[j] = __float2half_rn(0.f); lo[j] = __float2half_rn(0.f); }
+            } else {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (long long)j * x.sc + t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float w = v[j] * sc[j];
+                    if (gelu) w = gelu_erf_tc(w);
+                    split_half(w * TC_A_SCALE, hi[j], lo[j]);
+                }
+            }
+            *reinterpret_cast<uint4*>(a_hi + (obase + tp) * 8) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(a_lo + (obase + tp) * 8) = *reinterpret_cast<const uint4*>(lo);
         }
     }
-    const long long o = ((((long long)b * C8 + c8) * (x.F + 2 * PF) + fr) * Tp + tp) * 8;
-    *reinterpret_cast<uint4*>(a_hi + o) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(a_lo + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // zero rows the tcgen05 kernel needs above and below every [F][T+2] plane (0 in row mode)
@@ -480,8 +495,12 @@ int tc_pad_rows(int T, int KF, int dil) {
 
 void launch_gn_act_tc(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
                       long long affine_bstride, bool gelu, int PF, __half* a_hi, __half* a_lo, cudaStream_t s) {
-    dim3 grid((x.T + 2 + 127) / 128, x.F + 2 * PF, x.B * (x.C / 8));
-    gn_act_tc_kernel<<<grid, 128, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, a_hi, a_lo);
+    const int rows_total = x.F + 2 * PF, Tp = x.T + 2;
+    int rpb = max(1, 4096 / Tp);
+    // keep at least ~4 blocks per SM in flight
+    while (rpb > 1 && (long long)((rows_total + rpb - 1) / rpb) * x.B * (x.C / 8) < 148 * 4) rpb >>= 1;
+    dim3 grid((rows_total + rpb - 1) / rpb, x.B * (x.C / 8));
+    gn_act_tc_kernel<<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, rpb, a_hi, a_lo);
     AID_COUNT_LAUNCH(1);
 }
 

@@ -136,11 +136,25 @@ __global__ void __launch_bounds__(kThreads) combine_kernel(TV a, TV bb, float al
     const long long start = (long long)blockIdx.x * kElemsPerCta;
     const long long end = min(P, start + kElemsPerCta);
     float s = 0.f, q = 0.f;
-    for (long long e = start + threadIdx.x; e < end; e += kThreads) {
-        float v = alpha * pa[e];
-        if (pb) v += beta * pb[e];
-        po[e] = v;
-        s += v; q += v * v;
+    if ((P & 3) == 0 && aligned16(pa) && aligned16(po) && (!pb || aligned16(pb))) {
+        for (long long e = (start >> 2) + threadIdx.x; e < (end >> 2); e += kThreads) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(pa) + e);
+            v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+            if (pb) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(pb) + e);
+                v.x += beta * w.x; v.y += beta * w.y; v.z += beta * w.z; v.w += beta * w.w;
+            }
+            reinterpret_cast<float4*>(po)[e] = v;
+            s += (v.x + v.y) + (v.z + v.w);
+            q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        }
+    } else {
+        for (long long e = start + threadIdx.x; e < end; e += kThreads) {
+            float v = alpha * pa[e];
+            if (pb) v += beta * pb[e];
+            po[e] = v;
+            s += v; q += v * v;
+        }
     }
     if (stats) {
         double ds = s, dq = q;
@@ -169,7 +183,7 @@ __device__ __forceinline__ int reflect(int n, int T) {
     return n >= T ? 2 * (T - 1) - n : n;
 }
 
-// y[to] = sum_j k[j] * x[reflect(2*to + j - 3)]          grid: (ceil(F*To/256), C, B)
+// y[to] = sum_j k[j] * x[reflect(2*to + j - 3)]          grid: (ceil(F*To/256), C, B)   (scalar fallback)
 __global__ void __launch_bounds__(kThreads) resample_down_kernel(TV x, TV out) {
     const int c = blockIdx.y, b = blockIdx.z;
     const int To = out.T;
@@ -181,6 +195,35 @@ __global__ void __launch_bounds__(kThreads) resample_down_kernel(TV x, TV out) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc += c_cubic[j] * __ldg(row + reflect(2 * to + j - 3, x.T));
     out.p[(long long)b * out.sb + (long long)c * out.sc + e] = acc;
+}
+
+// 4 outputs per thread: 16 aligned inputs (four float4 loads) in the interior, reflected scalar loads at the row ends.
+// grid: (ceil(F*To/4 / 256), C, B); requires To % 4 == 0 and 16-byte aligned rows.
+__global__ void __launch_bounds__(kThreads) resample_down4_kernel(TV x, TV out) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int To = out.T, T = x.T, tq = To >> 2;
+    const int q = blockIdx.x * kThreads + threadIdx.x;
+    if (q >= out.F * tq) return;
+    const int f = q / tq, to = (q - f * tq) << 2;
+    const float* row = x.p + (long long)b * x.sb + (long long)c * x.sc + (long long)f * T;
+    float w[16];  // x[2*to - 4 .. 2*to + 11]
+    if (to > 0 && to + 4 < To) {
+        const float4* r4 = reinterpret_cast<const float4*>(row + 2 * to - 4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float4 v = __ldg(r4 + i); w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = __ldg(row + reflect(2 * to - 4 + i, T));
+    }
+    float y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += c_cubic[j] * w[2 * i + j + 1];  // x[2*(to+i) + j - 3] = w[2i + j + 1]
+        y[i] = acc;
+    }
+    *reinterpret_cast<float4*>(out.p + (long long)b * out.sb + (long long)c * out.sc + (long long)f * To + to) = make_float4(y[0], y[1], y[2], y[3]);
 }
 
 // conv_transpose1d(reflect_pad(x, 2), k, stride 2, padding 7):
@@ -202,14 +245,48 @@ __global__ void __launch_bounds__(kThreads) resample_up_kernel(TV x, TV out) {
     out.p[(long long)b * out.sb + (long long)c * out.sc + e] = acc;
 }
 
+// 4 outputs (m = 4v .. 4v+3) per thread from the 6 inputs x[2v-2 .. 2v+3]; one float4 store.  Requires To % 4 == 0.
+__global__ void __launch_bounds__(kThreads) resample_up4_kernel(TV x, TV out) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int To = out.T, T = x.T, tq = To >> 2;
+    const int qd = blockIdx.x * kThreads + threadIdx.x;
+    if (qd >= out.F * tq) return;
+    const int f = qd / tq, v = qd - f * tq;
+    const float* row = x.p + (long long)b * x.sb + (long long)c * x.sc + (long long)f * T;
+    float w[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) w[i] = __ldg(row + reflect(2 * v - 2 + i, T));
+    float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        y[0] += c_cubic[7 - 2 * q] * w[q];       // u = 2v   (even):  x[u+q-2] = w[q]
+        y[1] += c_cubic[6 - 2 * q] * w[q + 1];   // u = 2v   (odd) :  x[u+q-1] = w[q+1]
+        y[2] += c_cubic[7 - 2 * q] * w[q + 1];   // u = 2v+1 (even):  x[u+q-2] = w[q+1]
+        y[3] += c_cubic[6 - 2 * q] * w[q + 2];   // u = 2v+1 (odd) :  x[u+q-1] = w[q+2]
+    }
+    *reinterpret_cast<float4*>(out.p + (long long)b * out.sb + (long long)c * out.sc + (long long)f * To + 4 * v) = make_float4(y[0], y[1], y[2], y[3]);
+}
+
+static bool tv_vec4(const TV& v) { return ((reinterpret_cast<uintptr_t>(v.p) & 15) == 0) && (v.sb & 3) == 0 && (v.sc & 3) == 0 && (v.T & 3) == 0; }
+
 void launch_resample_down(const TV& x, const TV& out, cudaStream_t s) {
-    dim3 grid((unsigned)(((long long)out.F * out.T + kThreads - 1) / kThreads), out.C, out.B);
-    resample_down_kernel<<<grid, kThreads, 0, s>>>(x, out);
+    if (tv_vec4(out) && tv_vec4(x) && out.T >= 8) {
+        dim3 grid((unsigned)(((long long)out.F * (out.T / 4) + kThreads - 1) / kThreads), out.C, out.B);
+        resample_down4_kernel<<<grid, kThreads, 0, s>>>(x, out);
+    } else {
+        dim3 grid((unsigned)(((long long)out.F * out.T + kThreads - 1) / kThreads), out.C, out.B);
+        resample_down_kernel<<<grid, kThreads, 0, s>>>(x, out);
+    }
     AID_COUNT_LAUNCH(1);
 }
 void launch_resample_up(const TV& x, const TV& out, cudaStream_t s) {
-    dim3 grid((unsigned)(((long long)out.F * out.T + kThreads - 1) / kThreads), out.C, out.B);
-    resample_up_kernel<<<grid, kThreads, 0, s>>>(x, out);
+    if (tv_vec4(out) && x.T >= 4) {
+        dim3 grid((unsigned)(((long long)out.F * (out.T / 4) + kThreads - 1) / kThreads), out.C, out.B);
+        resample_up4_kernel<<<grid, kThreads, 0, s>>>(x, out);
+    } else {
+        dim3 grid((unsigned)(((long long)out.F * out.T + kThreads - 1) / kThreads), out.C, out.B);
+        resample_up_kernel<<<grid, kThreads, 0, s>>>(x, out);
+    }
     AID_COUNT_LAUNCH(1);
 }
 

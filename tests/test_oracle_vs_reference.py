@@ -80,3 +80,20 @@ def test_sampler_mirror_equals_reference_sampler(aid, ref):
         assert torch.equal(got_u, want_u)
     s = aid.Sampler(net, aid.EDM(args), args)
     assert torch.equal(s.prepare_smooth_mask(mask.expand(3, -1), 50), RefSampler(net, RefEDM(args), args).prepare_smooth_mask(mask.expand(3, -1), 50))
+
+
+def test_reference_checkpoint_loader_works_on_our_module(aid, ref):
+    """tester_inpainting.py:195-202 -> utils/training_utils.py:214-382 load_state_dict(state_dict, ema=network): the
+    reference's own multi-strategy loader drives our nn.Module unchanged (strict, then shape-matched partial load)."""
+    import utils.training_utils as t_utils
+    cfg = aid.small_test(16384)
+    sd = aid.random_state_dict(cfg, seed=21)
+    net = aid.Unet_CQT_oct_with_attention(cfg.to_args(), "cpu")
+    assert t_utils.load_state_dict({"it": 5, "ema": sd}, ema=net, log=False) is True
+    assert torch.equal(net.state_dict()["ups.3.1.H.2.weight"], sd["ups.3.1.H.2.weight"])
+    # attempt 3: a checkpoint with one wrongly shaped tensor still loads everything else
+    bad = dict(sd)
+    bad["downs.0.1.weight"] = torch.zeros(3, 3)
+    net2 = aid.Unet_CQT_oct_with_attention(cfg.to_args(), "cpu")
+    assert t_utils.load_state_dict({"ema": bad, "network": bad}, network=net2, ema=net2, log=False) is True
+    assert torch.equal(net2.state_dict()["middle.0.1.qk.weight" if False else "middle.0.1.attn_block.qk.weight"], sd["middle.0.1.attn_block.qk.weight"])
