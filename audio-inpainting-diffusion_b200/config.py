@@ -56,7 +56,7 @@ class NetConfig:
     attention_layers: List[int] = field(default_factory=lambda: [0, 0, 0, 0, 1, 1, 1, 1])
     num_heads: int = 8
     num_bottleneck_layers: int = 1
-    conv_mode: int = 0  # 0 = exact fp32 CUDA cores, 1 = tcgen05 split-fp16 tensor cores for the 5x3 layers
+    conv_mode: int = 0  # 0 = exact fp32 CUDA cores; 1 = tcgen05 with split-fp16 operands (fp32-grade, 3 MMAs per tap); 2 = tcgen05, single fp16 operands
 
     @staticmethod
     def from_args(args, conv_mode=None):

@@ -73,13 +73,23 @@ void launch_mod_vectors(const float* emb, int n_sigma, const float* W, const flo
 // tcgen05 path for the dilated 5x3 convolutions (conv_tc.cu).  Operands are split-fp16 planar: [B][C/8][F][T+2][8].
 
 bool conv_tc_supported(int Cin, int Cout, int KF, int KT);
-void launch_pack_weight_tc(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s);
+void launch_pack_weight_tc(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, int parts, cudaStream_t s);
 int tc_pad_rows(int T, int KF, int dil);  // zero rows needed above/below each operand plane (0 when T % 128 == 0)
 void launch_gn_act_tc(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
                       long long affine_bstride, bool gelu, int PF, __half* a_hi, __half* a_lo, cudaStream_t s);
 void launch_to_planar_tc(const TV& x, int PF, __half* a_hi, __half* a_lo, cudaStream_t s);
 void launch_conv_tc(const __half* a_hi, const __half* a_lo, int PF, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,
                     const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s);
+
+// second-generation tcgen05 path (conv_tc2.cu, conv_mode 2): single fp16 operands, channels-last [B][ceil(C/64)][F+2PF][T+2][64]
+size_t tc2_weight_halves(int Cout, int Cin, int KF, int KT);
+size_t tc2_act_halves(int B, int C, int F, int T, int PF);
+void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s);
+void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
+                       long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s);
+void launch_to_planar_tc2(const TV& x, int PF, __half* a, cudaStream_t s);
+void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,
+                     const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s);
 
 // FFT / CQT
 struct FftPlan {

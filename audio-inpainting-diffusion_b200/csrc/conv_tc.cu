@@ -23,12 +23,13 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace aid {
 
 static constexpr int TC_THREADS = 576;        // producer warp, MMA warp, 16 epilogue warps
 static constexpr int TC_PLANE = 130 * 16;     // bytes of one (16 B chunk) x (130 pixel) plane of A in smem
-static constexpr int TC_MAX_KPS = 2;          // 16-channel k-steps per pipeline stage (1 for 5x3, 2 for 1x1)
+static constexpr int TC_MAX_KPS = 4;          // most 16-channel k-steps per pipeline stage
 static constexpr float TC_A_SCALE = 16.f, TC_W_SCALE = 1024.f, TC_OUT_SCALE = 1.f / (16.f * 1024.f);
 
 struct TcConvArgs {
@@ -39,65 +40,11 @@ struct TcConvArgs {
     int B, Cin, Ntot, Ntile, n_ntiles, F, T, Tp, dil;
     int PF, rows_total, stream, units_per_b;   // zero pad rows above/below each plane; stream mode: units tile the padded pixel stream
     int KF, KT, kt_shift, kps;                 // taps along F / T, first tap's pixel shift inside the window, k-steps per stage
+    int parts;                                 // 2: split fp16 (hi, lo) operands, 3 MMAs per tap;  1: single fp16 operands, 1 MMA per tap
     int tiles_t, n_units, n_pairs, n_tiles, nstages, acc_bufs, ncol_stride;
     int b_kstep_bytes, a_bytes, stage_bytes;
     int dbg;  // AID_TC_DEBUG bits (tuning only): 1 skip epilogue body, 2 skip MMAs, 4 skip A loads, 8 skip B loads
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // A unit = 128 consecutive output positions of one clip.
 //   row mode    (T % 128 == 0): 128 pixels of one frequency row (PF = 0, taps outside [0,F) are skipped exactly);
@@ -133,8 +80,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* bar_base = smem + (size_t)p.nstages * p.stage_bytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);
-    uint64_t* empty = full + 8;
-    uint64_t* tmem_full = empty + 8;
+    uint64_t* empty = full + 12;
+    uint64_t* tmem_full = empty + 12;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -162,9 +109,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
         int stage = 0; uint32_t phase = 0;
         // lane l >= 1: A copy of unit ai, k-step akk of the stage, (hi|lo), 16-byte chunk ac
         const int aidx = lane - 1;
-        const int ai = aidx / (p.kps * 4), arem = aidx % (p.kps * 4);
-        const int akk = arem >> 2, ahl = (arem >> 1) & 1, ac = arem & 1;
-        const bool a_lane = lane >= 1 && aidx < 2 * p.kps * 4;
+        const int per_unit = p.kps * p.parts * 2;
+        const int ai = aidx / per_unit, arem = aidx % per_unit;
+        const int akk = arem / (p.parts * 2), ahl = (arem / 2) % p.parts, ac = arem & 1;
+        const bool a_lane = lane >= 1 && aidx < 2 * per_unit;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int pair = tile % p.n_pairs, nt = tile / p.n_pairs;
             const UnitInfo u0 = unit_info(p, 2 * pair), u1 = unit_info(p, 2 * pair + 1);
@@ -180,7 +128,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
                     if (lane == 0) {
                         const uint32_t bb = (uint32_t)(p.b_kstep_bytes * nk);
                         uint32_t bytes = (p.dbg & 8) ? 0u : bb;
-                        if (!(p.dbg & 4)) bytes += (uint32_t)nk * ((v0 ? 4u * u0.seg_px * 16u : 0u) + (v1 ? 4u * u1.seg_px * 16u : 0u));
+                        if (!(p.dbg & 4)) bytes += (uint32_t)(nk * p.parts) * ((v0 ? 2u * u0.seg_px * 16u : 0u) + (v1 ? 2u * u1.seg_px * 16u : 0u));
                         mbar_expect_tx(full + stage, bytes);
                         if (!(p.dbg & 8))
                             bulk_g2s(sb, p.w + ((size_t)(nt * p.KF + kf) * KS + ks0) * (p.b_kstep_bytes >> 1), bb, full + stage);
@@ -191,7 +139,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
                         if (ai ? v1 : v0) {
                             const size_t off = (((size_t)u.b * c8_total + (2 * (ks0 + akk) + ac)) * p.rows_total * p.Tp +
                                                 (size_t)(u.win_start + foff * p.Tp)) * 8;
-                            bulk_g2s(sb + b_bytes_full + (((ai * p.kps + akk) * 2 + ahl) * 2 + ac) * TC_PLANE, (ahl ? p.a_lo : p.a_hi) + off,
+                            bulk_g2s(sb + b_bytes_full + (((ai * p.kps + akk) * p.parts + ahl) * 2 + ac) * TC_PLANE, (ahl ? p.a_lo : p.a_hi) + off,
                                      (uint32_t)u.seg_px * 16u, full + stage);
                         }
                     }
@@ -227,18 +175,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(TcConvArgs p) {
                                 if (!(i ? v1 : v0)) continue;
                                 const uint32_t d = tmem_base + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride);
                                 for (int kk = 0; kk < nk; ++kk) {
-                                    const uint32_t a0 = sa + (uint32_t)(((i * p.kps + kk) * 2) * 2) * TC_PLANE;
+                                    const uint32_t a0 = sa + (uint32_t)(((i * p.kps + kk) * p.parts) * 2) * TC_PLANE;
                                     const uint32_t b0 = sb + (uint32_t)(kk * p.b_kstep_bytes);
                                     for (int kt = 0; kt < p.KT; ++kt) {
                                         const uint32_t sh = (uint32_t)(kt + p.kt_shift) * 16u;
                                         const uint64_t a_hi = make_desc(a0 + sh, TC_PLANE, 128);
-                                        const uint64_t a_lo = make_desc(a0 + 2 * TC_PLANE + sh, TC_PLANE, 128);
                                         const uint64_t b_hi = make_desc(b0 + (uint32_t)((0 * p.KT + kt) * 2) * b_lbo, b_lbo, 128);
-                                        const uint64_t b_lo = make_desc(b0 + (uint32_t)((1 * p.KT + kt) * 2) * b_lbo, b_lbo, 128);
                                         tc_mma_f16(d, a_hi, b_hi, idesc, started[i]);
                                         started[i] = 1u;
-                                        tc_mma_f16(d, a_lo, b_hi, idesc, 1u);
-                                        tc_mma_f16(d, a_hi, b_lo, idesc, 1u);
+                                        if (p.parts == 2) {
+                                            const uint64_t a_lo = make_desc(a0 + 2 * TC_PLANE + sh, TC_PLANE, 128);
+                                            const uint64_t b_lo = make_desc(b0 + (uint32_t)((1 * p.KT + kt) * 2) * b_lbo, b_lbo, 128);
+                                            tc_mma_f16(d, a_lo, b_hi, idesc, 1u);
+                                            tc_mma_f16(d, a_hi, b_lo, idesc, 1u);
+                                        }
                                     }
                                 }
                             }
@@ -390,8 +340,8 @@ static int tc_ntile(int Cout) {
     return Cout <= 256 ? Cout : 256;
 }
 
-// w[co][ci][kf][kt] (fp32) -> [n-tile][kf][Cin/16][hi|lo][kt][2][Ntile][8] fp16, scaled by 2^10
-__global__ void pack_weight_tc_kernel(const float* __restrict__ w, __half* __restrict__ wp, int Ntot, int Ntile, int Cin, int KF, int KT) {
+// w[co][ci][kf][kt] (fp32) -> [n-tile][kf][Cin/16][parts: hi|lo][kt][2][Ntile][8] fp16, scaled by 2^10
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, __half* __restrict__ wp, int Ntot, int Ntile, int Cin, int KF, int KT, int parts) {
     const int KS = Cin >> 4;
     const long long total = (long long)Ntot * Cin * KF * KT;  // one (hi, lo) pair per weight
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -408,16 +358,16 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, __half* __res
         __half hi, lo;
         split_half(v, hi, lo);
         const long long half_blk = (long long)KT * 2 * Ntile * 8;                       // one of (hi | lo) of a k-step block
-        const long long blk = (((long long)nt * KF + kf) * KS + ks) * (2 * half_blk);
+        const long long blk = (((long long)nt * KF + kf) * KS + ks) * (parts * half_blk);
         const long long in_blk = (((long long)kt * 2 + c) * Ntile + n) * 8 + e;
         wp[blk + in_blk] = hi;
-        wp[blk + half_blk + in_blk] = lo;
+        if (parts == 2) wp[blk + half_blk + in_blk] = lo;
     }
 }
 
-void launch_pack_weight_tc(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s) {
+void launch_pack_weight_tc(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, int parts, cudaStream_t s) {
     const long long total = (long long)Cout * Cin * KF * KT;
-    pack_weight_tc_kernel<<<(int)min((long long)8192, (total + 255) / 256), 256, 0, s>>>(w, wp, Cout, tc_ntile(Cout), Cin, KF, KT);
+    pack_weight_tc_kernel<<<(int)min((long long)8192, (total + 255) / 256), 256, 0, s>>>(w, wp, Cout, tc_ntile(Cout), Cin, KF, KT, parts);
     AID_COUNT_LAUNCH(1);
 }
 
@@ -481,7 +431,7 @@ gn_act_tc_kernel(TV x, const double* __restrict__ stats, double n_per_group, con
                 }
             }
             *reinterpret_cast<uint4*>(a_hi + (obase + tp) * 8) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(a_lo + (obase + tp) * 8) = *reinterpret_cast<const uint4*>(lo);
+            if (a_lo) *reinterpret_cast<uint4*>(a_lo + (obase + tp) * 8) = *reinterpret_cast<const uint4*>(lo);
         }
     }
 }
@@ -514,19 +464,24 @@ bool conv_tc_supported(int Cin, int Cout, int KF, int KT) {
     return k && Cin % 16 == 0 && Cin >= 16 && Cout % 16 == 0 && Cout >= 16 && (Cout <= 256 || Cout % 256 == 0);
 }
 
-// a_hi / a_lo: [B][Cin/8][F + 2*PF][T+2][8] with PF >= tc_pad_rows(T, KF, dil)
+// a_hi / a_lo: [B][Cin/8][F + 2*PF][T+2][8] with PF >= tc_pad_rows(T, KF, dil); a_lo == nullptr selects the single-fp16 scheme
+// (weights packed with parts = 1)
 void launch_conv_tc(const __half* a_hi, const __half* a_lo, int PF, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,
                     const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s) {
     if (PF < tc_pad_rows(T, KF, dil)) throw CudaError(cudaErrorInvalidValue, "conv_tc: not enough pad rows", __FILE__, __LINE__);
     if (ep.R2.p) throw CudaError(cudaErrorInvalidValue, "conv_tc: R2 is not supported", __FILE__, __LINE__);
     if (!conv_tc_supported(Cin, out.C, KF, KT)) throw CudaError(cudaErrorInvalidValue, "conv_tc: unsupported shape", __FILE__, __LINE__);
     TcConvArgs p{};
-    p.a_hi = a_hi; p.a_lo = a_lo; p.w = wp; p.out = out; p.R = ep.R; p.gate = ep.gate; p.gate_bstride = ep.gate_bstride;
+    p.a_hi = a_hi; p.a_lo = a_lo; p.w = wp; p.parts = a_lo ? 2 : 1; p.out = out; p.R = ep.R; p.gate = ep.gate; p.gate_bstride = ep.gate_bstride;
     p.alpha = ep.alpha; p.stats = ep.stats;
     p.B = B; p.Cin = Cin; p.Ntot = out.C; p.Ntile = tc_ntile(out.C); p.n_ntiles = out.C / p.Ntile;
     p.F = F; p.T = T; p.Tp = T + 2; p.dil = dil;
     p.KF = KF; p.KT = KT; p.kt_shift = (KT == 1) ? 1 : 0;
-    p.kps = (KF == 1) ? min(TC_MAX_KPS, Cin / 16) : 1;
+    static const int env_kps5 = getenv("AID_TC_KPS5") ? atoi(getenv("AID_TC_KPS5")) : 1;
+    static const int env_kps1 = getenv("AID_TC_KPS1") ? atoi(getenv("AID_TC_KPS1")) : 2;
+    static const int env_stages = getenv("AID_TC_STAGES") ? atoi(getenv("AID_TC_STAGES")) : 6;
+    p.kps = min(min(TC_MAX_KPS, Cin / 16), (KF == 1) ? env_kps1 : env_kps5);
+    while (2 * p.kps * p.parts * 2 > 31) --p.kps;   // one producer lane per A plane copy
     p.PF = PF; p.rows_total = F + 2 * PF;
     p.stream = (T % 128 != 0) ? 1 : 0;
     p.tiles_t = (T + 127) / 128;
@@ -534,10 +489,10 @@ void launch_conv_tc(const __half* a_hi, const __half* a_lo, int PF, const __half
     p.n_units = B * p.units_per_b;
     p.n_pairs = (p.n_units + 1) / 2;
     p.n_tiles = p.n_pairs * p.n_ntiles;
-    p.b_kstep_bytes = 2 * KT * 2 * p.Ntile * 16;  // (hi, lo) x kt x 2 chunks x Ntile x 16 B
-    p.a_bytes = 2 * p.kps * 4 * TC_PLANE;         // 2 units x kps x (hi, lo) x 2 chunks
+    p.b_kstep_bytes = p.parts * KT * 2 * p.Ntile * 16;  // (hi, lo) x kt x 2 chunks x Ntile x 16 B
+    p.a_bytes = 2 * p.kps * p.parts * 2 * TC_PLANE;     // 2 units x kps x (hi, lo) x 2 chunks
     p.stage_bytes = p.b_kstep_bytes * p.kps + p.a_bytes;
-    p.nstages = min(6, (224 * 1024) / p.stage_bytes);
+    p.nstages = min(min(12, env_stages), (224 * 1024) / p.stage_bytes);
     p.ncol_stride = p.Ntile <= 64 ? 64 : (p.Ntile <= 128 ? 128 : 256);
     p.acc_bufs = p.ncol_stride <= 128 ? 2 : 1;
     const size_t smem = (size_t)p.nstages * p.stage_bytes + 256 + 16 * 16 * sizeof(double);  // stages + barriers + per-warp statistics

@@ -1,0 +1,509 @@
+// tcgen05 implicit-GEMM convolution, second generation (conv_mode 2): single-fp16 operands, channels-last operand
+// layout, large bulk copies, separate activation / weight rings, 32-column epilogue batches.
+//
+// Same GEMM view, unit definition and fused epilogue as conv_tc.cu (out = alpha*(acc*gate + R), group statistics):
+//     D[128 px, Ntile couts] += A[128 px, 16 ch] * B[Ntile, 16 ch]^T     for every (kf, kt, 16-channel step)
+// What changed, and why (measured with tools/bench_bulk.cu on B200: every cp.async.bulk costs ~75-150 cycles of
+// issue/processing regardless of its size, every mbarrier operation ~100 cycles, L2 -> shared tops out near 70 B/clk/SM):
+//   * activations in HBM : [B][G = ceil(C/64)][rows][T+2][64] fp16, 128-byte pixel rows whose eight 16-byte chunks are
+//     stored XOR-swizzled by (flattened padded pixel index & 7).  A unit's 130-pixel window of one 64-channel group is ONE
+//     contiguous 16.6 KB run: a single bulk copy lands it in shared memory, already in the K-major SWIZZLE_128B UMMA
+//     layout (the copy starts at row (pixel index & 7) of a 1024-byte aligned slot so that shared-memory row phase ==
+//     global pixel phase).  The kt taps are the same window with the descriptor start advanced by one 128-byte row, the
+//     four 16-channel k-steps of a group advance it by 32 bytes.  (conv_tc.cu needs eight 2 KB copies for the same data.)
+//   * weights in HBM     : [n-tile][kf][G][kt][Ntile][64] fp16 (x 2^10), chunks swizzled by (n & 7): one copy per
+//     (kf, group, kt-chunk).
+//   * two producer warps (activations, weights) with their own rings, so a stage costs one wait + one expect + 1-2 copies;
+//   * epilogue: 8 warps, each thread owns one pixel and walks its warp's column range 32 columns at a time with all 32
+//     residual loads in flight before the accumulator is read (the old 8-column batches left the LSU latency bound).
+#include <cuda_fp16.h>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace aid {
+
+static constexpr int T2_THREADS = 384;          // A producer, B producer, MMA issuer, spare, 8 epilogue warps
+static constexpr int T2_EPI_WARP0 = 4, T2_EPI_WARPS = 8;
+static constexpr int T2_ASLOT_UNIT = 18 * 1024; // one unit's window: (130 + 7) rows x 128 B, rounded to 1 KB
+static constexpr float T2_A_SCALE = 16.f, T2_W_SCALE = 1024.f, T2_OUT_SCALE = 1.f / (16.f * 1024.f);
+
+struct Tc2Args {
+    const __half* a; const __half* w;
+    TV out, R;
+    const float* gate; long long gate_bstride;
+    float alpha; double* stats;
+    int B, Cin, G, Ntot, Ntile, n_ntiles, F, T, Tp, dil;
+    int PF, rows_total, stream, units_per_b;
+    int KF, KT, kt_shift, ktb;                 // ktb: kt taps per weight slot
+    int tiles_t, n_units, n_pairs, n_tiles;
+    int nA, nB, b_slot_bytes, acc_bufs, ncol_stride;
+    int dbg;  // AID_TC_DEBUG bits (tuning only): 1 skip epilogue body, 2 skip MMAs, 4 skip A loads, 8 skip B loads
+};
+
+struct Unit2 { int exists, b, f_lo, f_hi, win_start, o0; };
+
+__device__ __forceinline__ Unit2 unit2_info(const Tc2Args& p, int u) {
+    Unit2 i;
+    i.exists = u < p.n_units;
+    if (p.stream) {
+        const int k = u % p.units_per_b;
+        i.b = u / p.units_per_b;
+        i.o0 = k * 128;                               // first output position in the padded stream of the real rows
+        i.f_lo = i.o0 / p.Tp;
+        i.f_hi = min(p.F - 1, (i.o0 + 127) / p.Tp);
+        i.win_start = p.PF * p.Tp + i.o0 - 1;         // window = positions [o0-1, o0+129) of the padded plane
+    } else {
+        const int tt = u % p.tiles_t, r = u / p.tiles_t;
+        const int f = r % p.F, t0 = tt * 128;
+        i.b = r / p.F; i.f_lo = i.f_hi = f;
+        i.o0 = f * p.Tp + t0 + 1;
+        i.win_start = f * p.Tp + t0;
+    }
+    return i;
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a_slot_bytes = 2 * T2_ASLOT_UNIT;
+    uint8_t* ringA = smem;
+    uint8_t* ringB = smem + (size_t)p.nA * a_slot_bytes;
+    uint8_t* bar_base = ringB + (size_t)p.nB * p.b_slot_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* a_empty = a_full + 4;
+    uint64_t* b_full = a_empty + 4;
+    uint64_t* b_empty = b_full + 8;
+    uint64_t* tmem_full = b_empty + 8;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    if (warp == 2) {
+        if (lane == 0) {
+            for (int s = 0; s < p.nA; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
+            for (int s = 0; s < p.nB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+            for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, T2_EPI_WARPS * 32); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nktb = (p.KT + p.ktb - 1) / p.ktb;   // weight slots per (kf, group)
+
+    if (warp == 0) {
+        // ===================== activation producer: one 16.6 KB bulk copy per (unit, kf, 64-channel group) =====================
+        int slot = 0; uint32_t phase = 0;
+        const size_t gstride = (size_t)p.rows_total * p.Tp * 64;   // halves per (clip, group) plane
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int pair = tile % p.n_pairs;
+            const Unit2 u0 = unit2_info(p, 2 * pair), u1 = unit2_info(p, 2 * pair + 1);
+            for (int kf = 0; kf < p.KF; ++kf) {
+                const int foff = (kf - p.KF / 2) * p.dil;
+                const bool v0 = u0.exists && u0.f_hi + foff >= 0 && u0.f_lo + foff < p.F;
+                const bool v1 = u1.exists && u1.f_hi + foff >= 0 && u1.f_lo + foff < p.F;
+                if (!(v0 || v1)) continue;
+                const int s0 = u0.win_start + foff * p.Tp, s1 = u1.win_start + foff * p.Tp;
+                for (int g = 0; g < p.G; ++g) {
+                    mbar_wait(a_empty + slot, phase ^ 1);
+                    if (lane == 0) {
+                        uint8_t* sa = ringA + (size_t)slot * a_slot_bytes;
+                        const uint32_t bytes = (p.dbg & 4) ? 0u : ((v0 ? 130u * 128u : 0u) + (v1 ? 130u * 128u : 0u));
+                        mbar_expect_tx(a_full + slot, bytes);
+                        if (!(p.dbg & 4)) {
+                            if (v0) bulk_g2s(sa + (s0 & 7) * 128, p.a + ((size_t)u0.b * p.G + g) * gstride + (size_t)s0 * 64, 130u * 128u, a_full + slot);
+                            if (v1) bulk_g2s(sa + T2_ASLOT_UNIT + (s1 & 7) * 128, p.a + ((size_t)u1.b * p.G + g) * gstride + (size_t)s1 * 64, 130u * 128u, a_full + slot);
+                        }
+                    }
+                    __syncwarp();
+                    if (++slot == p.nA) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== weight producer: one bulk copy per (kf, group, kt chunk) =====================
+        int slot = 0; uint32_t phase = 0;
+        const size_t kt_halves = (size_t)p.Ntile * 64;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int pair = tile % p.n_pairs, nt = tile / p.n_pairs;
+            const Unit2 u0 = unit2_info(p, 2 * pair), u1 = unit2_info(p, 2 * pair + 1);
+            for (int kf = 0; kf < p.KF; ++kf) {
+                const int foff = (kf - p.KF / 2) * p.dil;
+                const bool v0 = u0.exists && u0.f_hi + foff >= 0 && u0.f_lo + foff < p.F;
+                const bool v1 = u1.exists && u1.f_hi + foff >= 0 && u1.f_lo + foff < p.F;
+                if (!(v0 || v1)) continue;
+                for (int g = 0; g < p.G; ++g) {
+                    const __half* wg = p.w + (((size_t)nt * p.KF + kf) * p.G + g) * p.KT * kt_halves;
+                    for (int c = 0; c < nktb; ++c) {
+                        const int nkt = min(p.ktb, p.KT - c * p.ktb);
+                        mbar_wait(b_empty + slot, phase ^ 1);
+                        if (lane == 0) {
+                            const uint32_t bytes = (uint32_t)(nkt * kt_halves * 2);
+                            mbar_expect_tx(b_full + slot, (p.dbg & 8) ? 0u : bytes);
+                            if (!(p.dbg & 8)) bulk_g2s(ringB + (size_t)slot * p.b_slot_bytes, wg + (size_t)c * p.ktb * kt_halves, bytes, b_full + slot);
+                        }
+                        __syncwarp();
+                        if (++slot == p.nB) { slot = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== MMA issuer (whole warp loops, lane 0 issues) =====================
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Ntile >> 3) << 17) | ((128u >> 4) << 24);  // F16 x F16 -> F32, K-major A/B
+        const uint32_t kt_bytes = (uint32_t)p.Ntile * 128u;
+        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int ab = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int pair = tile % p.n_pairs;
+            const Unit2 u0 = unit2_info(p, 2 * pair), u1 = unit2_info(p, 2 * pair + 1);
+            mbar_wait(tmem_empty + ab, aphase ^ 1);
+            tc_fence_after();
+            uint32_t started0 = 0u, started1 = 0u;
+            const uint32_t d0 = tmem_base + (uint32_t)(ab * 2 * p.ncol_stride), d1 = d0 + (uint32_t)p.ncol_stride;
+            for (int kf = 0; kf < p.KF; ++kf) {
+                const int foff = (kf - p.KF / 2) * p.dil;
+                const bool v0 = u0.exists && u0.f_hi + foff >= 0 && u0.f_lo + foff < p.F;
+                const bool v1 = u1.exists && u1.f_hi + foff >= 0 && u1.f_lo + foff < p.F;
+                if (!(v0 || v1)) continue;
+                const uint32_t r0 = (uint32_t)((u0.win_start + foff * p.Tp) & 7), r1 = (uint32_t)((u1.win_start + foff * p.Tp) & 7);
+                for (int g = 0; g < p.G; ++g) {
+                    const int nk = min(4, (p.Cin - g * 64) >> 4);     // 16-channel k-steps in this group
+                    mbar_wait(a_full + sa, pha);
+                    const uint32_t abase = smem_u32(ringA + (size_t)sa * a_slot_bytes);
+                    for (int c = 0; c < nktb; ++c) {
+                        const int nkt = min(p.ktb, p.KT - c * p.ktb);
+                        mbar_wait(b_full + sb, phb);
+                        tc_fence_after();
+                        if (p.dbg & 32) __nanosleep(5000);
+                        if (p.dbg & 128) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        if (lane == 0) {
+                            const uint32_t bbase = smem_u32(ringB + (size_t)sb * p.b_slot_bytes);
+                            if (!(p.dbg & 2)) {
+                                for (int k = 0; k < nkt; ++k) {
+                                    const uint32_t kt = (uint32_t)(c * p.ktb + k + p.kt_shift);
+                                    for (int j = 0; j < nk; ++j) {
+                                        const uint64_t bd = make_desc_sw128(bbase + (uint32_t)k * kt_bytes + (uint32_t)j * 32u, 1024);
+                                        if (v0) { tc_mma_f16(d0, make_desc_sw128(abase + (r0 + kt) * 128u + (uint32_t)j * 32u, 1024, (p.dbg & 16) ? r0 + kt : 0u), bd, idesc, started0); started0 = 1u; }
+                                        if (v1) { tc_mma_f16(d1, make_desc_sw128(abase + T2_ASLOT_UNIT + (r1 + kt) * 128u + (uint32_t)j * 32u, 1024, (p.dbg & 16) ? r1 + kt : 0u), bd, idesc, started1); started1 = 1u; }
+                                    }
+                                }
+                            }
+                            tc_commit(b_empty + sb);
+                            if (c == nktb - 1) tc_commit(a_empty + sa);
+                        }
+                        __syncwarp();
+                        if (++sb == p.nB) { sb = 0; phb ^= 1; }
+                    }
+                    if (++sa == p.nA) { sa = 0; pha ^= 1; }
+                }
+            }
+            if (lane == 0) tc_commit(tmem_full + ab);
+            __syncwarp();
+            if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
+        }
+    } else if (warp >= T2_EPI_WARP0) {
+        // ===================== epilogue: TMEM -> registers -> out = alpha*(acc*gate + R), statistics =====================
+        const int e = warp - T2_EPI_WARP0;
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+        const int cw = e >> 2;                  // column half
+        const int ncols = p.Ntile / 2;          // multiple of 8
+        const int cbeg = cw * ncols;
+        int ab = 0; uint32_t aphase = 0;
+        const int gcn = p.Ntot / 8;
+        const float al = p.alpha, gs = T2_OUT_SCALE * p.alpha;
+        const long long osc = p.out.sc, rsc = p.R.sc;
+        double* sst = reinterpret_cast<double*>(bar_base + 256) + e * 16;  // this warp's (group, {sum, sumsq}) accumulators
+        if (lane < 16) sst[lane] = 0.0;
+        __syncwarp();
+        int b_cur = -1;
+        auto flush_global = [&]() {
+            __syncwarp();
+            if (p.stats && b_cur >= 0 && lane < 16) {
+                const double v = sst[lane];
+                if (v != 0.0) atomicAdd(p.stats + (long long)b_cur * 16 + lane, v);
+                sst[lane] = 0.0;
+            }
+            __syncwarp();
+        };
+        auto flush_group = [&](float s, float qq, int g) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
+            if (lane == 0) { sst[g * 2 + 0] += (double)s; sst[g * 2 + 1] += (double)qq; }
+        };
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int pair = tile % p.n_pairs, nt = tile / p.n_pairs;
+            const int co_base = nt * p.Ntile;
+            mbar_wait(tmem_full + ab, aphase);
+            tc_fence_after();
+            if (p.dbg & 64) __nanosleep(20000);
+#pragma unroll 1
+            for (int i = 0; i < 2 && !(p.dbg & 1); ++i) {
+                const Unit2 u = unit2_info(p, 2 * pair + i);
+                if (!u.exists) continue;
+                if (u.b != b_cur) { flush_global(); b_cur = u.b; }
+                const int o = u.o0 + q * 32 + lane;           // output position in the padded stream of the real rows
+                const int row = o / p.Tp, tp = o - row * p.Tp;
+                const bool ok = tp >= 1 && tp <= p.T && row <= u.f_hi;
+                const long long pix = (long long)row * p.T + (tp - 1);
+                float* po = p.out.p + (long long)u.b * p.out.sb + (long long)(co_base + cbeg) * osc + pix;
+                const float* pr = p.R.p + (long long)u.b * p.R.sb + (long long)(co_base + cbeg) * rsc + pix;
+                const bool hasr = ok && p.R.p != nullptr;
+                const float* gate = p.gate ? p.gate + (long long)u.b * p.gate_bstride + co_base + cbeg : nullptr;
+                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride + cbeg);
+                int grp = (co_base + cbeg) / gcn;
+                int left = (grp + 1) * gcn - (co_base + cbeg);  // columns left in the current statistics group
+                float ssum = 0.f, ssq = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    const int nb = min(32, ncols - c0);       // 8, 16, 24 or 32 columns in this batch
+                    float rr[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) rr[j] = (hasr && j < nb) ? pr[(long long)(c0 + j) * rsc] : 0.f;
+                    uint32_t acc[32];
+                    if (nb == 32) tmem_ld32_nowait(tcol + c0, acc);
+                    else {
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) if (j8 * 8 < nb) tmem_ld8p_nowait(tcol + c0 + j8 * 8, acc + j8 * 8);
+                    }
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        if (j8 * 8 < nb) {
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int c = c0 + j8 * 8 + j;
+                                const float g = gate ? __ldg(gate + c) * gs : gs;
+                                v[j] = fmaf(__uint_as_float(acc[j8 * 8 + j]), g, rr[j8 * 8 + j] * al);
+                            }
+                            if (ok) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) po[(long long)(c0 + j8 * 8 + j) * osc] = v[j];
+                            }
+                            if (p.stats) {
+                                if (gcn >= 8) {
+                                    // at most one group boundary inside the 8-column chunk, at column `left`
+                                    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float w = ok ? v[j] : 0.f;
+                                        if (j < left) { a0 += w; a1 = fmaf(w, w, a1); } else { b0 += w; b1 = fmaf(w, w, b1); }
+                                    }
+                                    ssum += a0; ssq += a1;
+                                    left -= 8;
+                                    if (left <= 0) { flush_group(ssum, ssq, grp); ++grp; ssum = b0; ssq = b1; left += gcn; }
+                                } else {
+#pragma unroll 1
+                                    for (int j = 0; j < 8; ++j) {
+                                        const float w = ok ? v[j] : 0.f;
+                                        ssum += w; ssq = fmaf(w, w, ssq);
+                                        if (--left == 0) { flush_group(ssum, ssq, grp); ++grp; ssum = 0.f; ssq = 0.f; left = gcn; }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (p.stats) flush_group(ssum, ssq, min(grp, 7));
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty + ab);
+            if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
+        }
+        flush_global();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- operand preparation ---------------------------------------------------------------------------------
+static int tc2_ntile(int Cout) { return Cout <= 256 ? Cout : 256; }
+
+size_t tc2_weight_halves(int Cout, int Cin, int KF, int KT) { return (size_t)Cout * KF * KT * ((Cin + 63) / 64) * 64; }
+
+// w[co][ci][kf][kt] (fp32) -> [n-tile][kf][G][kt][Ntile][64] fp16 (x 2^10), 16-byte chunks swizzled by (n & 7); channels past Cin = 0
+__global__ void pack_weight_tc2_kernel(const float* __restrict__ w, __half* __restrict__ wp, int Ntot, int Ntile, int Cin, int KF, int KT) {
+    const int G = (Cin + 63) / 64;
+    const long long total = (long long)Ntot * KF * KT * G * 64;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int pos = (int)(r % 64); r /= 64;       // physical position inside the 128-byte row
+        const int n = (int)(r % Ntile); r /= Ntile;
+        const int kt = (int)(r % KT); r /= KT;
+        const int g = (int)(r % G); r /= G;
+        const int kf = (int)(r % KF); r /= KF;
+        const int nt = (int)r;
+        const int chunk = (pos >> 3) ^ (n & 7);       // logical chunk stored at this position
+        const int ci = g * 64 + chunk * 8 + (pos & 7), co = nt * Ntile + n;
+        float v = 0.f;
+        if (ci < Cin) v = w[(((long long)co * Cin + ci) * KF + kf) * KT + kt] * T2_W_SCALE;
+        v = fminf(fmaxf(v, -60000.f), 60000.f);
+        wp[i] = __float2half_rn(v);
+    }
+}
+
+void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s) {
+    const long long total = (long long)tc2_weight_halves(Cout, Cin, KF, KT);
+    pack_weight_tc2_kernel<<<(int)min((long long)8192, (total + 255) / 256), 256, 0, s>>>(w, wp, Cout, tc2_ntile(Cout), Cin, KF, KT);
+    AID_COUNT_LAUNCH(1);
+}
+
+__device__ __forceinline__ float gelu_erf_tc2(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+
+// Normalise / modulate / GELU (unet.py:159-163, 479, 482) writing the channels-last fp16 operand:
+//   a[b][g][r][tp][chunk ^ ((r*Tp + tp) & 7)][8] = fp16(16 * act(x[b, 64g + 8 chunk + j, r - PF, tp - 1] * scale_c)),
+//   pad pixels (tp = 0, T+1), pad rows and channels past C = 0.  stats == nullptr: plain layout/precision conversion.
+// grid: (B * G * rows_total, segment chunks), block 256 = 8 warps: warp w converts channels [8w, 8w+8) of the group for 64
+// pixels per iteration (coalesced channel-plane loads), the 64 x 128 B tile is transposed through shared memory (the
+// swizzle makes the 16-byte stores conflict free) and written out as one contiguous 8 KB run.
+__global__ void __launch_bounds__(256)
+gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, const float* __restrict__ gamma,
+                  const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, int G, __half* __restrict__ a) {
+    const int Tp = x.T + 2, rows_total = x.F + 2 * PF;
+    int bid = blockIdx.x;
+    const int fr = bid % rows_total; bid /= rows_total;
+    const int g = bid % G, b = bid / G;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ float s_scale[64];
+    __shared__ __align__(16) uint8_t tile[64 * 128];
+    if (threadIdx.x < 64) {
+        float sc = 0.f;
+        const int c = g * 64 + threadIdx.x;
+        if (c < x.C) {
+            sc = 1.f;
+            if (stats) {
+                const int grp = c / (x.C / 8);
+                const double s1 = stats[((long long)b * 8 + grp) * 2 + 0], s2 = stats[((long long)b * 8 + grp) * 2 + 1];
+                double var = (s2 - s1 * s1 / n_per_group) / (n_per_group - 1.0);
+                var = var > 0.0 ? var : 0.0;
+                const float stdv = (float)sqrt(var);
+                const float mod = affine ? (1.f + affine[b * affine_bstride + c]) : 1.f;
+                sc = gamma[c] * mod / (stdv + 1e-7f);
+            }
+        }
+        s_scale[threadIdx.x] = sc;
+    }
+    __syncthreads();
+    float sc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[j] = s_scale[w * 8 + j];
+    const int f = fr - PF;
+    const bool rowok = f >= 0 && f < x.F;
+    const bool chok = g * 64 + w * 8 < x.C;      // C is a multiple of 8: a chunk is either all real or all padding
+    const float* src = x.p + (long long)b * x.sb + (long long)(g * 64 + w * 8) * x.sc + (long long)(rowok ? f : 0) * x.T;
+    __half* dst_row = a + ((((long long)b * G + g) * rows_total + fr) * Tp) * 64;
+    const long long gp_row = (long long)fr * Tp;
+    const int nseg = (Tp + 63) / 64;
+    for (int seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
+        const int tp0 = seg * 64;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int pl = h * 32 + lane, tp = tp0 + pl, t = tp - 1;
+            __align__(16) __half hv[8];
+            if (rowok && chok && t >= 0 && t < x.T) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (long long)j * x.sc + t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float y = v[j] * sc[j];
+                    if (gelu) y = gelu_erf_tc2(y);
+                    y = fminf(fmaxf(y * T2_A_SCALE, -60000.f), 60000.f);
+                    hv[j] = __float2half_rn(y);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(0.f);
+            }
+            const int phase = (int)((gp_row + tp) & 7);
+            *reinterpret_cast<uint4*>(tile + pl * 128 + ((w ^ phase) << 4)) = *reinterpret_cast<const uint4*>(hv);
+        }
+        __syncthreads();
+        const int npx = min(64, Tp - tp0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int idx = threadIdx.x + k * 256;        // 16-byte unit of the 8 KB tile
+            if ((idx >> 3) < npx)
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst_row + (long long)tp0 * 64) + idx * 16) =
+                    *reinterpret_cast<const uint4*>(tile + idx * 16);
+        }
+        __syncthreads();
+    }
+}
+
+size_t tc2_act_halves(int B, int C, int F, int T, int PF) { return (size_t)B * ((C + 63) / 64) * 64 * (F + 2 * PF) * (T + 2); }
+
+void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
+                       long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s) {
+    const int rows_total = x.F + 2 * PF, Tp = x.T + 2, G = (x.C + 63) / 64;
+    const int nseg = (Tp + 63) / 64;
+    const long long rows = (long long)x.B * G * rows_total;
+    // enough blocks to fill the machine, but several segments per block when rows are long
+    int ychunks = 1;
+    while (ychunks < nseg && rows * ychunks < 148 * 16) ychunks <<= 1;
+    ychunks = min(ychunks, nseg);
+    dim3 grid((unsigned)rows, ychunks);
+    gn_act_tc2_kernel<<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
+    AID_COUNT_LAUNCH(1);
+}
+
+void launch_to_planar_tc2(const TV& x, int PF, __half* a, cudaStream_t s) {
+    launch_gn_act_tc2(x, nullptr, 1, nullptr, nullptr, 0, false, PF, a, s);
+}
+
+// a: [B][ceil(Cin/64)][F + 2*PF][T+2][64] with PF >= tc_pad_rows(T, KF, dil); wp from launch_pack_weight_tc2
+void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,
+                     const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s) {
+    if (PF < tc_pad_rows(T, KF, dil)) throw CudaError(cudaErrorInvalidValue, "conv_tc2: not enough pad rows", __FILE__, __LINE__);
+    if (ep.R2.p) throw CudaError(cudaErrorInvalidValue, "conv_tc2: R2 is not supported", __FILE__, __LINE__);
+    if (!conv_tc_supported(Cin, out.C, KF, KT)) throw CudaError(cudaErrorInvalidValue, "conv_tc2: unsupported shape", __FILE__, __LINE__);
+    Tc2Args p{};
+    p.a = a; p.w = wp; p.out = out; p.R = ep.R; p.gate = ep.gate; p.gate_bstride = ep.gate_bstride;
+    p.alpha = ep.alpha; p.stats = ep.stats;
+    p.B = B; p.Cin = Cin; p.G = (Cin + 63) / 64; p.Ntot = out.C; p.Ntile = tc2_ntile(out.C); p.n_ntiles = out.C / p.Ntile;
+    p.F = F; p.T = T; p.Tp = T + 2; p.dil = dil;
+    p.KF = KF; p.KT = KT; p.kt_shift = (KT == 1) ? 1 : 0;
+    p.PF = PF; p.rows_total = F + 2 * PF;
+    p.stream = (T % 128 != 0) ? 1 : 0;
+    p.tiles_t = (T + 127) / 128;
+    p.units_per_b = p.stream ? (F * p.Tp + 127) / 128 : F * p.tiles_t;
+    p.n_units = B * p.units_per_b;
+    p.n_pairs = (p.n_units + 1) / 2;
+    p.n_tiles = p.n_pairs * p.n_ntiles;
+    static const int env_ktb = getenv("AID_TC2_KTB") ? atoi(getenv("AID_TC2_KTB")) : 0;
+    static const int env_nA = getenv("AID_TC2_NA") ? atoi(getenv("AID_TC2_NA")) : 3;
+    const int kt_bytes = p.Ntile * 128;
+    p.ktb = env_ktb > 0 ? min(env_ktb, KT) : (kt_bytes * KT <= 48 * 1024 ? KT : 1);
+    p.b_slot_bytes = p.ktb * kt_bytes;
+    p.nA = max(2, min(4, env_nA));
+    const int budget = 224 * 1024 - 1024 - 256 - T2_EPI_WARPS * 16 * (int)sizeof(double);
+    while (p.nA > 2 && budget - p.nA * 2 * T2_ASLOT_UNIT < 2 * p.b_slot_bytes) --p.nA;
+    p.nB = min(8, (budget - p.nA * 2 * T2_ASLOT_UNIT) / p.b_slot_bytes);
+    if (p.nB < 2) throw CudaError(cudaErrorInvalidValue, "conv_tc2: shared memory budget", __FILE__, __LINE__);
+    p.ncol_stride = p.Ntile <= 64 ? 64 : (p.Ntile <= 128 ? 128 : 256);
+    p.acc_bufs = p.ncol_stride <= 128 ? 2 : 1;
+    const size_t smem = 1024 + (size_t)p.nA * 2 * T2_ASLOT_UNIT + (size_t)p.nB * p.b_slot_bytes + 256 + T2_EPI_WARPS * 16 * sizeof(double);
+    static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
+    p.dbg = dbg;
+    static size_t configured = 0;
+    if (smem > configured) {
+        AID_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int grid = min(p.n_tiles, num_sms);
+    conv_tc2_kernel<<<grid, T2_THREADS, smem, s>>>(p);
+    AID_COUNT_LAUNCH(1);
+}
+
+}  // namespace aid

@@ -98,6 +98,7 @@ struct Net {
     void* d_tables = nullptr;
     int n_stat_slots = 0;
     int num_sms = 148;
+    int tc_parts() const { return cfg.conv_mode == 1 ? 2 : 1; }  // fp16 parts per tensor-core operand (conv_mode 1: hi + lo)
     __half* dweights_tc = nullptr;  // split-fp16 packed weights of the tcgen05 convolutions (conv_mode 1)
     std::map<std::string, float*> probes;  // debug: name -> caller buffer that receives a contiguous copy
     // optional per-launch timing of the convolution kernels (bench.py roofline): CUDA events on the launching stream
@@ -170,7 +171,7 @@ static void build_net(Net& n) {
     if (c.emb_dim != 256) throw std::invalid_argument("emb_dim must be 256");
     if (c.num_bottleneck_layers != 1) throw std::invalid_argument("num_bottleneck_layers must be 1");
     if (c.num_heads < 1) throw std::invalid_argument("num_heads must be >= 1");
-    if (c.conv_mode != 0 && c.conv_mode != 1) throw std::invalid_argument("conv_mode must be 0 (fp32 CUDA cores) or 1 (tcgen05 split-fp16)");
+    if (c.conv_mode < 0 || c.conv_mode > 2) throw std::invalid_argument("conv_mode must be 0 (fp32 CUDA cores), 1 (tcgen05 split-fp16, 3 MMAs) or 2 (tcgen05 single fp16)");
     const int no = c.num_octs, bins = c.bins_per_oct;
     n.emb_idx[0] = add_weight(n, "embedding.RFF_freq", {1, 32});
     const int dims[4] = {64, 128, 256, 256};
@@ -254,10 +255,14 @@ static void finalize_net(Net& n) {
         AID_CUDA_CHECK(cudaDeviceSynchronize());
         off += al(e);
     }
-    if (n.cfg.conv_mode == 1) {
+    if (n.cfg.conv_mode >= 1) {
+        const int parts = n.tc_parts();
         AID_CUDA_CHECK(cudaDeviceGetAttribute(&n.num_sms, cudaDevAttrMultiProcessorCount, n.device));
         size_t tc_total = 0;
-        for (auto* c : convs) if (conv_tc_supported(c->Cin, c->Cout, c->KF, c->KT)) tc_total += al(2 * n.weights[c->widx].numel());
+        auto tc_halves = [&](const ConvW* c) {
+            return n.cfg.conv_mode == 2 ? tc2_weight_halves(c->Cout, c->Cin, c->KF, c->KT) : (size_t)parts * n.weights[c->widx].numel();
+        };
+        for (auto* c : convs) if (conv_tc_supported(c->Cin, c->Cout, c->KF, c->KT)) tc_total += al(tc_halves(c));
         if (tc_total) AID_CUDA_CHECK(cudaMalloc(&n.dweights_tc, tc_total * sizeof(__half)));
         size_t toff = 0;
         for (auto* c : convs) {
@@ -265,10 +270,11 @@ static void finalize_net(Net& n) {
             Weight& w = n.weights[c->widx];
             AID_CUDA_CHECK(cudaMemcpy(stage, w.host.data(), w.numel() * sizeof(float), cudaMemcpyHostToDevice));
             c->wtc = n.dweights_tc + toff;
-            launch_pack_weight_tc(stage, c->wtc, c->Cout, c->Cin, c->KF, c->KT, 0);
+            if (n.cfg.conv_mode == 2) launch_pack_weight_tc2(stage, c->wtc, c->Cout, c->Cin, c->KF, c->KT, 0);
+            else launch_pack_weight_tc(stage, c->wtc, c->Cout, c->Cin, c->KF, c->KT, parts, 0);
             AID_CUDA_CHECK(cudaGetLastError());
             AID_CUDA_CHECK(cudaDeviceSynchronize());
-            toff += al(2 * w.numel());
+            toff += al(tc_halves(c));
         }
     }
     AID_CUDA_CHECK(cudaFree(stage));
@@ -428,7 +434,8 @@ static void conv_tc(Ctx& c, const __half* a_hi, const __half* a_lo, int PF, cons
         rec.bytes = 4.0 * (px * (w.Cin + w.Cout + (ep.R.p ? w.Cout : 0)) + (double)w.Cin * w.Cout * w.KF * w.KT);
         AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
     }
-    launch_conv_tc(a_hi, a_lo, PF, w.wtc, out.B, w.Cin, out.F, out.T, w.KF, w.KT, dil, out, ep, n.num_sms, c.s);
+    if (n.cfg.conv_mode == 2) launch_conv_tc2(a_hi, PF, w.wtc, out.B, w.Cin, out.F, out.T, w.KF, w.KT, dil, out, ep, n.num_sms, c.s);
+    else launch_conv_tc(a_hi, a_lo, PF, w.wtc, out.B, w.Cin, out.F, out.T, w.KF, w.KT, dil, out, ep, n.num_sms, c.s);
     if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
@@ -442,18 +449,28 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
     // operand buffer: fp32 [B,N,F,T] for the CUDA-core path, or split-fp16 planar hi|lo [B][N/8][F][T+2][8] each (tcgen05 path)
     // (hi | lo arrays, each with PF zero rows above and below every plane -- PF depends on the layer's dilation)
     auto planar_halves = [&](int ch, int pf) { return (long long)B * ch * (F + 2 * pf) * (T + 2); };
+    const int cmode = c.n->cfg.conv_mode;
+    const int parts = c.n->tc_parts();
+    // fp32 elements of an operand buffer for `ch` channels: conv_mode 1 = (hi | lo) planar arrays, conv_mode 2 = channels-last fp16
+    auto operand_floats = [&](int ch, int pf, int Fd) {
+        if (cmode == 2) return (long long)((tc2_act_halves(B, ch, Fd, T, pf) + 1) / 2);
+        return ((long long)B * ch * (Fd + 2 * pf) * (T + 2) * parts + 1) / 2;
+    };
+    auto to_operand = [&](const TV& v, int pf, __half* hi, __half* lo) {
+        if (cmode == 2) launch_to_planar_tc2(v, pf, hi, c.s); else launch_to_planar_tc(v, pf, hi, lo, c.s);
+    };
     const int pf_max = tc_pad_rows(T, k.k1x1 ? 1 : 5, k.k1x1 ? 1 : (1 << std::max(0, k.nd - 1)));
-    float* abuf = c.allocf(std::max(plane, planar_halves(N, pf_max)));
+    float* abuf = c.allocf(std::max(plane, operand_floats(N, pf_max, F)));
     __half* a_hi = reinterpret_cast<__half*>(abuf);
     TV x = make_tv(xbuf, B, N, F, T), a = make_tv(abuf, B, N, F, T);
-    // tcgen05 path: the block input is converted once to the split-fp16 planar operand and shared by proj_in and res_conv
+    // tcgen05 path: the block input is converted once to the fp16 operand layout and shared by proj_in and res_conv
     __half* pin_hi = nullptr; __half* pin_lo = nullptr; float* pin_buf = nullptr;
     const int pf1 = tc_pad_rows(T, 1, 1);
     if (k.proj_in.wtc || k.res_conv.wtc) {
-        const long long in_halves = planar_halves(k.dim, pf1);
-        pin_buf = c.allocf(in_halves);
-        pin_hi = reinterpret_cast<__half*>(pin_buf); pin_lo = pin_hi + in_halves;
-        RUN(launch_to_planar_tc(in, pf1, pin_hi, pin_lo, c.s));
+        pin_buf = c.allocf(operand_floats(k.dim, pf1, F));
+        pin_hi = reinterpret_cast<__half*>(pin_buf);
+        pin_lo = parts == 2 ? pin_hi + planar_halves(k.dim, pf1) : nullptr;
+        RUN(to_operand(in, pf1, pin_hi, pin_lo));
     }
     TV cur;
     if (k.dim != N) {
@@ -474,10 +491,11 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         TV qk = make_tv(c.allocf((long long)B * 2 * heads * F * T), B, 2 * heads * F, 1, T);
         if (k.qk.wtc) {
             const long long hh = (long long)B * heads * F * (1 + 2 * pf1) * (T + 2);
-            float* hp = c.allocf(hh);
+            float* hp = c.allocf(operand_floats(heads * F, pf1, 1));
             __half* h_hi = reinterpret_cast<__half*>(hp);
-            RUN(launch_to_planar_tc(hflat, pf1, h_hi, h_hi + hh, c.s));
-            conv_tc(c, h_hi, h_hi + hh, pf1, k.qk, 1, qk, ConvEpilogue());
+            __half* h_lo = parts == 2 ? h_hi + hh : nullptr;
+            RUN(to_operand(hflat, pf1, h_hi, h_lo));
+            conv_tc(c, h_hi, h_lo, pf1, k.qk, 1, qk, ConvEpilogue());
             c.release(hp);
         } else {
             conv(c, hflat, k.qk, 1, qk, ConvEpilogue());
@@ -501,8 +519,9 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         if (k.H[i].wtc) {
             const int dil = k.k1x1 ? 1 : (1 << i);
             const int pf = tc_pad_rows(T, k.H[i].KF, dil);
-            __half* a_lo = a_hi + planar_halves(N, pf);
-            RUN(launch_gn_act_tc(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, a_lo, c.s));
+            __half* a_lo = parts == 2 ? a_hi + planar_halves(N, pf) : nullptr;
+            if (cmode == 2) RUN(launch_gn_act_tc2(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s));
+            else RUN(launch_gn_act_tc(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, a_lo, c.s));
             x.stats = ep.stats;
             conv_tc(c, a_hi, a_lo, pf, k.H[i], dil, x, ep);
         } else {
@@ -887,18 +906,26 @@ static int op_conv2d_impl(const float* a_dev, const float* w_dev, int B, int Cin
         const int pf = tc_pad_rows(T, KF, dil);
         const size_t ahalves = (size_t)B * Cin * (F + 2 * pf) * (T + 2);
         int sms = 148, dev = 0;
-        if (mode == 1) {
+        if (mode == 1 || mode == 3) {
             if (!conv_tc_supported(Cin, Cout, KF, KT) || R2_dev) throw std::invalid_argument("shape not supported by the tcgen05 path");
             AID_CUDA_CHECK(cudaGetDevice(&dev));
             AID_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            AID_CUDA_CHECK(cudaMalloc(&wtc, 2 * e * sizeof(__half)));
-            AID_CUDA_CHECK(cudaMalloc(&ah, 2 * ahalves * sizeof(__half)));
-            launch_pack_weight_tc(w_dev, wtc, Cout, Cin, KF, KT, s);
-            launch_to_planar_tc(a, pf, ah, ah + ahalves, s);
+            if (mode == 3) {
+                AID_CUDA_CHECK(cudaMalloc(&wtc, tc2_weight_halves(Cout, Cin, KF, KT) * sizeof(__half)));
+                AID_CUDA_CHECK(cudaMalloc(&ah, tc2_act_halves(B, Cin, F, T, pf) * sizeof(__half)));
+                launch_pack_weight_tc2(w_dev, wtc, Cout, Cin, KF, KT, s);
+                launch_to_planar_tc2(a, pf, ah, s);
+            } else {
+                AID_CUDA_CHECK(cudaMalloc(&wtc, 2 * e * sizeof(__half)));
+                AID_CUDA_CHECK(cudaMalloc(&ah, 2 * ahalves * sizeof(__half)));
+                launch_pack_weight_tc(w_dev, wtc, Cout, Cin, KF, KT, 2, s);
+                launch_to_planar_tc(a, pf, ah, ah + ahalves, s);
+            }
         } else if (mode != 0 && mode != 2) throw std::invalid_argument("unknown conv mode");
         (void)iters;
         AID_CUDA_CHECK(cudaEventRecord(e0, s));
-        if (mode == 1) launch_conv_tc(ah, ah + ahalves, pf, wtc, B, Cin, F, T, KF, KT, dil, out, ep, sms, s);
+        if (mode == 3) launch_conv_tc2(ah, pf, wtc, B, Cin, F, T, KF, KT, dil, out, ep, sms, s);
+        else if (mode == 1) launch_conv_tc(ah, ah + ahalves, pf, wtc, B, Cin, F, T, KF, KT, dil, out, ep, sms, s);
         else if (mode == 2 || !launch_conv_thin(a, wp, KF, KT, dil, out, ep, s)) launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
         AID_CUDA_CHECK(cudaEventRecord(e1, s));
         AID_CUDA_CHECK(cudaGetLastError());
@@ -930,6 +957,20 @@ int aid_debug_time_conv2d(const float* a_dev, const float* w_dev, int B, int Cin
     if (rc != AID_OK) return rc;
     return op_conv2d_impl(a_dev, w_dev, B, Cin, Cout, F, T, KF, KT, dil, gate_dev, R_dev, nullptr, alpha, 0.f, out_dev, stats_dev, mode,
                           nullptr, 1, ms_out);
+}
+
+/* debug / layout parity: the conv_mode 2 operand layouts.  a_out: tc2_act_halves fp16, w_out: tc2_weight_halves fp16 (either may be NULL) */
+int aid_debug_tc2_operands(const float* x_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int PF,
+                           void* a_out_dev, void* w_out_dev, uint64_t* a_halves, uint64_t* w_halves) {
+    if (a_halves) *a_halves = tc2_act_halves(B, Cin, F, T, PF);
+    if (w_halves) *w_halves = tc2_weight_halves(Cout, Cin, KF, KT);
+    try {
+        if (a_out_dev && x_dev) launch_to_planar_tc2(make_tv(const_cast<float*>(x_dev), B, Cin, F, T), PF, (__half*)a_out_dev, nullptr);
+        if (w_out_dev && w_dev) launch_pack_weight_tc2(w_dev, (__half*)w_out_dev, Cout, Cin, KF, KT, nullptr);
+        AID_CUDA_CHECK(cudaGetLastError());
+        AID_CUDA_CHECK(cudaDeviceSynchronize());
+        return AID_OK;
+    } catch (const CudaError& e) { fprintf(stderr, "aid_debug_tc2_operands: CUDA error %s\n", cudaGetErrorString(e.code)); return AID_ERR_CUDA; }
 }
 
 int aid_op_groupnorm_act(const float* x_dev, const float* gamma_dev, const float* affine_dev, int B, int C, int F, int T, int gelu,

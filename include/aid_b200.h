@@ -46,7 +46,7 @@ typedef struct aid_config {
     int32_t num_dils[AID_MAX_OCTS];
     int32_t attention_layers[AID_MAX_OCTS + 1]; /* num_octs entries + bottleneck */
     int32_t num_bottleneck_layers; /* must be 1 */
-    int32_t conv_mode;            /* 0 = exact fp32 CUDA cores; 1 = tcgen05 split-fp16 tensor cores for the 5x3 layers */
+    int32_t conv_mode;            /* 0 = exact fp32 CUDA cores; 1 = tcgen05, split-fp16 operands (fp32-grade); 2 = tcgen05, single fp16 operands */
 } aid_config;
 
 typedef struct aid_handle aid_handle;
@@ -102,7 +102,8 @@ int aid_edm_step(const float* xin_dev, const float* xhat_dev, const float* y_dev
 /* F.conv2d(a[B,Cin,F,T], w[Cout,Cin,KF,KT], padding="same", dilation=(dil,1)) with the fused epilogue
  * out = alpha*(conv*gate[c] + R) + beta*R2; gate/R/R2 may be NULL.  stats_dev (may be NULL): [B][8][2] doubles
  * accumulated with (sum, sumsq) of out per channel group.  mode: 0 = fp32 CUDA cores (thin-channel kernels where they apply),
- * 1 = tcgen05 split-fp16, 2 = force the general fp32 CUDA-core kernel.                       unet.py:79-88, 482 */
+ * 1 = tcgen05 split-fp16 (3 MMAs per tap), 2 = force the general fp32 CUDA-core kernel, 3 = tcgen05 single fp16 (1 MMA per tap).
+ *                                                                                            unet.py:79-88, 482 */
 int aid_op_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
                   const float* gate_dev, const float* R_dev, const float* R2_dev, float alpha, float beta,
                   float* out_dev, double* stats_dev, int mode, void* stream);
@@ -121,6 +122,11 @@ int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float
 int aid_debug_time_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
                           const float* gate_dev, const float* R_dev, float alpha, float* out_dev, double* stats_dev, int mode,
                           float* ms_out);
+
+/* Debug / layout parity (not part of the drop-in surface): writes the conv_mode 2 tensor-core operand layouts of an
+ * activation x[B,Cin,F,T] (channels-last fp16, swizzled, PF pad rows) and of a weight w[Cout,Cin,KF,KT]; sizes in halves. */
+int aid_debug_tc2_operands(const float* x_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int PF,
+                           void* a_out_dev, void* w_out_dev, uint64_t* a_halves, uint64_t* w_halves);
 
 /* Per-launch timing of the convolution kernels with CUDA events on the launching stream (bench.py's roofline).
  * aid_profile(h, 1) clears and starts recording, aid_profile(h, 0) stops; aid_profile_read sums the recorded launches
