@@ -20,6 +20,10 @@ struct TV {
 static inline TV make_tv(float* p, int B, int C, int F, int T) {
     TV v; v.p = p; v.B = B; v.C = C; v.F = F; v.T = T; v.sc = (long long)F * T; v.sb = v.sc * C; return v;
 }
+// channels-last [B][F][T][C] tensor described by a TV (sb = F*T*C, channel stride 1; only conv_tc2 / gn_act_tc2_cl take these)
+static inline TV make_tv_cl(float* p, int B, int C, int F, int T) {
+    TV v; v.p = p; v.B = B; v.C = C; v.F = F; v.T = T; v.sc = 1; v.sb = (long long)C * F * T; return v;
+}
 // rows [f0, f0+nf) of v
 static inline TV slice_f(const TV& v, int f0, int nf) {
     TV r = v; r.p = v.p + (long long)f0 * v.T; r.F = nf; r.stats = nullptr; return r;
@@ -37,6 +41,8 @@ struct ConvEpilogue {
     TV R2;                        // R2.p == nullptr => none
     float alpha = 1.f, beta = 0.f;
     double* stats = nullptr;      // accumulate (sum, sumsq) of `out` per (b, group of Cout/8 channels)
+    // conv_mode 2 only: R / out are channels-last [B][F][T][C] tensors (TV with sb = F*T*C; see make_tv_cl)
+    bool R_cl = false, out_cl = false;
 };
 
 #define AID_CUDA_CHECK(expr)                                                         \
@@ -88,6 +94,8 @@ void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int K
 void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
                        long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s);
 void launch_to_planar_tc2(const TV& x, int PF, __half* a, cudaStream_t s);
+void launch_gn_act_tc2_cl(const float* x_cl, int B, int C, int F, int T, const double* stats, long long n_per_group, const float* gamma,
+                          const float* affine, long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s);
 void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,
                      const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s);
 

@@ -24,8 +24,10 @@
 
 namespace aid {
 
-static constexpr int T2_THREADS = 384;          // A producer, B producer, MMA issuer, spare, 8 epilogue warps
-static constexpr int T2_EPI_WARP0 = 4, T2_EPI_WARPS = 8;
+// warps 0-7: epilogue, 8: activation producer, 9: weight producer, 10: spare, 11: MMA issuer.  The SM's warp arbiter favours
+// the highest warp id of a sub-partition, and the MMA issuer is the one serial, latency-critical instruction stream.
+static constexpr int T2_THREADS = 384;
+static constexpr int T2_EPI_WARP0 = 0, T2_EPI_WARPS = 8, T2_WARP_A = 8, T2_WARP_B = 9, T2_WARP_MMA = 11;
 static constexpr int T2_ASLOT_UNIT = 18 * 1024; // one unit's window: (130 + 7) rows x 128 B, rounded to 1 KB
 static constexpr float T2_A_SCALE = 16.f, T2_W_SCALE = 1024.f, T2_OUT_SCALE = 1.f / (16.f * 1024.f);
 
@@ -39,6 +41,7 @@ struct Tc2Args {
     int KF, KT, kt_shift, ktb;                 // ktb: kt taps per weight slot
     int tiles_t, n_units, n_pairs, n_tiles;
     int nA, nB, b_slot_bytes, acc_bufs, ncol_stride;
+    int out_cl, r_cl;   // 1: that tensor is channels-last [B][F][T][C] (C = its TV's channel count), else NCHW
     int dbg;  // AID_TC_DEBUG bits (tuning only): 1 skip epilogue body, 2 skip MMAs, 4 skip A loads, 8 skip B loads
 };
 
@@ -80,11 +83,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    if (warp == 2) {
+    if (warp == T2_WARP_MMA) {
         if (lane == 0) {
             for (int s = 0; s < p.nA; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
             for (int s = 0; s < p.nB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
-            for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, T2_EPI_WARPS * 32); }
+            for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, T2_EPI_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
     const uint32_t tmem_base = *tmem_slot;
     const int nktb = (p.KT + p.ktb - 1) / p.ktb;   // weight slots per (kf, group)
 
-    if (warp == 0) {
+    if (warp == T2_WARP_A) {
         // ===================== activation producer: one 16.6 KB bulk copy per (unit, kf, 64-channel group) =====================
         int slot = 0; uint32_t phase = 0;
         const size_t gstride = (size_t)p.rows_total * p.Tp * 64;   // halves per (clip, group) plane
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == T2_WARP_B) {
         // ===================== weight producer: one bulk copy per (kf, group, kt chunk) =====================
         int slot = 0; uint32_t phase = 0;
         const size_t kt_halves = (size_t)p.Ntile * 64;
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                 }
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == T2_WARP_MMA) {
         // ===================== MMA issuer (whole warp loops, lane 0 issues) =====================
         const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Ntile >> 3) << 17) | ((128u >> 4) << 24);  // F16 x F16 -> F32, K-major A/B
         const uint32_t kt_bytes = (uint32_t)p.Ntile * 128u;
@@ -182,15 +185,21 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                         tc_fence_after();
                         if (p.dbg & 32) __nanosleep(5000);
                         if (p.dbg & 128) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        if (lane == 0) {
+                        if (elect_one_sync()) {
                             const uint32_t bbase = smem_u32(ringB + (size_t)sb * p.b_slot_bytes);
                             if (!(p.dbg & 2)) {
                                 for (int k = 0; k < nkt; ++k) {
                                     const uint32_t kt = (uint32_t)(c * p.ktb + k + p.kt_shift);
-                                    for (int j = 0; j < nk; ++j) {
-                                        const uint64_t bd = make_desc_sw128(bbase + (uint32_t)k * kt_bytes + (uint32_t)j * 32u, 1024);
-                                        if (v0) { tc_mma_f16(d0, make_desc_sw128(abase + (r0 + kt) * 128u + (uint32_t)j * 32u, 1024, (p.dbg & 16) ? r0 + kt : 0u), bd, idesc, started0); started0 = 1u; }
-                                        if (v1) { tc_mma_f16(d1, make_desc_sw128(abase + T2_ASLOT_UNIT + (r1 + kt) * 128u + (uint32_t)j * 32u, 1024, (p.dbg & 16) ? r1 + kt : 0u), bd, idesc, started1); started1 = 1u; }
+                                    const uint32_t blo = desc_lo_sw128(bbase + (uint32_t)k * kt_bytes);
+                                    const uint32_t alo0 = desc_lo_sw128(abase + (r0 + kt) * 128u);
+                                    const uint32_t alo1 = desc_lo_sw128(abase + T2_ASLOT_UNIT + (r1 + kt) * 128u);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        if (j < nk) {
+                                            const uint64_t bd = ((uint64_t)DESC_HI_SW128 << 32) | (blo + 2u * j);
+                                            if (v0) { tc_mma_f16(d0, ((uint64_t)DESC_HI_SW128 << 32) | (alo0 + 2u * j), bd, idesc, started0); started0 = 1u; }
+                                            if (v1) { tc_mma_f16(d1, ((uint64_t)DESC_HI_SW128 << 32) | (alo1 + 2u * j), bd, idesc, started1); started1 = 1u; }
+                                        }
                                     }
                                 }
                             }
@@ -203,125 +212,207 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                     if (++sa == p.nA) { sa = 0; pha ^= 1; }
                 }
             }
-            if (lane == 0) tc_commit(tmem_full + ab);
+            if (elect_one_sync()) tc_commit(tmem_full + ab);
             __syncwarp();
             if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
         }
-    } else if (warp >= T2_EPI_WARP0) {
+    } else if (warp < T2_EPI_WARP0 + T2_EPI_WARPS) {
         // ===================== epilogue: TMEM -> registers -> out = alpha*(acc*gate + R), statistics =====================
+        // 8 warps: warp e reads TMEM lane quadrant (e & 3) (one pixel per thread) and column half (e >> 2).  The work is a flat
+        // sequence of 32-column batches (tile -> unit -> batch); the residual loads of batch k+1 are issued before batch k is
+        // processed, so one batch of loads is always in flight, also across the wait for the next tile's accumulator.
         const int e = warp - T2_EPI_WARP0;
-        const int q = warp & 3;                 // TMEM lane quadrant this warp may read
-        const int cw = e >> 2;                  // column half
-        const int ncols = p.Ntile / 2;          // multiple of 8
+        const int q = warp & 3;
+        const int cw = e >> 2;
+        const int ncols = p.Ntile / 2;          // multiple of 8; equals 4 statistics groups when Ntile == Ntot
         const int cbeg = cw * ncols;
-        int ab = 0; uint32_t aphase = 0;
         const int gcn = p.Ntot / 8;
         const float al = p.alpha, gs = T2_OUT_SCALE * p.alpha;
-        const long long osc = p.out.sc, rsc = p.R.sc;
-        double* sst = reinterpret_cast<double*>(bar_base + 256) + e * 16;  // this warp's (group, {sum, sumsq}) accumulators
-        if (lane < 16) sst[lane] = 0.0;
-        __syncwarp();
-        int b_cur = -1;
-        auto flush_global = [&]() {
-            __syncwarp();
-            if (p.stats && b_cur >= 0 && lane < 16) {
-                const double v = sst[lane];
-                if (v != 0.0) atomicAdd(p.stats + (long long)b_cur * 16 + lane, v);
-                sst[lane] = 0.0;
-            }
-            __syncwarp();
-        };
-        auto flush_group = [&](float s, float qq, int g) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
-            if (lane == 0) { sst[g * 2 + 0] += (double)s; sst[g * 2 + 1] += (double)qq; }
-        };
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int pair = tile % p.n_pairs, nt = tile / p.n_pairs;
-            const int co_base = nt * p.Ntile;
-            mbar_wait(tmem_full + ab, aphase);
-            tc_fence_after();
-            if (p.dbg & 64) __nanosleep(20000);
-#pragma unroll 1
-            for (int i = 0; i < 2 && !(p.dbg & 1); ++i) {
-                const Unit2 u = unit2_info(p, 2 * pair + i);
-                if (!u.exists) continue;
-                if (u.b != b_cur) { flush_global(); b_cur = u.b; }
+        const int osc = (int)p.out.sc, rsc = (int)p.R.sc;   // plane strides (< 2^31 elements)
+        const bool has_r = p.R.p != nullptr, has_gate = p.gate != nullptr, do_stats = p.stats != nullptr;
+        const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
+
+        // gate[c] * 2^-14 * alpha of this warp's columns, private copy in shared memory (refreshed when the clip changes)
+        float* gsm = reinterpret_cast<float*>(bar_base + 256) + e * 128;
+        int gate_b = -2;
+
+        // batch descriptor (plain scalars: a struct passed through lambdas ends up in local memory)
+        float* c_po = nullptr; uint32_t c_tcol = 0; int c_ui = 0, c_c0 = 0, c_b = 0, c_ab = 0, c_nt = 0;
+        uint32_t c_aphase = 0; bool c_ok = false, c_last = false;
+        const float* n_pr = nullptr; float* n_po = nullptr; uint32_t n_tcol = 0; int n_ui = 0, n_c0 = 0, n_b = 0, n_ab = 0, n_nt = 0;
+        uint32_t n_aphase = 0; bool n_ok = false, n_valid = false, n_last = false;
+        // iterator state of the next batch to set up; per-unit values are recomputed only at the first batch of a unit
+        int it_tile = blockIdx.x, it_ui = 0, it_c0 = 0, it_ab = 0; uint32_t it_aphase = 0;
+        const float* u_pr = nullptr; float* u_po = nullptr; int u_b = 0, u_nt = 0; bool u_ok = false;
+        auto setup_next = [&]() {
+            n_valid = it_tile < p.n_tiles;
+            if (!n_valid) return;
+            const int pair = it_tile % p.n_pairs;
+            if (it_c0 == 0) {
+                u_nt = it_tile / p.n_pairs;
+                const int co0 = u_nt * p.Ntile + cbeg;
+                const Unit2 u = unit2_info(p, 2 * pair + it_ui);
                 const int o = u.o0 + q * 32 + lane;           // output position in the padded stream of the real rows
                 const int row = o / p.Tp, tp = o - row * p.Tp;
-                const bool ok = tp >= 1 && tp <= p.T && row <= u.f_hi;
+                u_ok = tp >= 1 && tp <= p.T && row <= u.f_hi;
                 const long long pix = (long long)row * p.T + (tp - 1);
-                float* po = p.out.p + (long long)u.b * p.out.sb + (long long)(co_base + cbeg) * osc + pix;
-                const float* pr = p.R.p + (long long)u.b * p.R.sb + (long long)(co_base + cbeg) * rsc + pix;
-                const bool hasr = ok && p.R.p != nullptr;
-                const float* gate = p.gate ? p.gate + (long long)u.b * p.gate_bstride + co_base + cbeg : nullptr;
-                const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 2 * p.ncol_stride + i * p.ncol_stride + cbeg);
-                int grp = (co_base + cbeg) / gcn;
-                int left = (grp + 1) * gcn - (co_base + cbeg);  // columns left in the current statistics group
-                float ssum = 0.f, ssq = 0.f;
-#pragma unroll 1
-                for (int c0 = 0; c0 < ncols; c0 += 32) {
-                    const int nb = min(32, ncols - c0);       // 8, 16, 24 or 32 columns in this batch
-                    float rr[32];
+                u_po = p.out_cl ? p.out.p + (long long)u.b * p.out.sb + pix * p.out.C + co0
+                                : p.out.p + (long long)u.b * p.out.sb + (long long)co0 * osc + pix;
+                u_pr = p.r_cl ? p.R.p + (long long)u.b * p.R.sb + pix * p.R.C + co0
+                              : p.R.p + (long long)u.b * p.R.sb + (long long)co0 * rsc + pix;
+                u_b = u.b;
+            }
+            n_po = u_po + (p.out_cl ? (long long)it_c0 : (long long)it_c0 * osc);
+            n_pr = u_pr + (p.r_cl ? (long long)it_c0 : (long long)it_c0 * rsc);
+            n_tcol = tq + (uint32_t)(it_ab * 2 * p.ncol_stride + it_ui * p.ncol_stride + it_c0);
+            n_ui = it_ui; n_c0 = it_c0; n_b = u_b; n_nt = u_nt; n_ab = it_ab; n_aphase = it_aphase; n_ok = u_ok;
+            n_last = false;
+            it_c0 += 32;
+            if (it_c0 >= ncols) {
+                it_c0 = 0;
+                if (it_ui == 1 || 2 * pair + 1 >= p.n_units) {
+                    n_last = true;
+                    it_ui = 0; it_tile += gridDim.x;
+                    if (++it_ab == p.acc_bufs) { it_ab = 0; it_aphase ^= 1; }
+                } else it_ui = 1;
+            }
+        };
+        float rr[32], rn[32];
+        auto load_next = [&]() {
+            if (n_valid && n_ok && has_r && !(p.dbg & 1)) {
+                const int nb = ncols - n_c0;      // >= 8, multiple of 8; columns past it are not loaded
+                if (p.r_cl) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) rr[j] = (hasr && j < nb) ? pr[(long long)(c0 + j) * rsc] : 0.f;
-                    uint32_t acc[32];
-                    if (nb == 32) tmem_ld32_nowait(tcol + c0, acc);
-                    else {
-#pragma unroll
-                        for (int j8 = 0; j8 < 4; ++j8) if (j8 * 8 < nb) tmem_ld8p_nowait(tcol + c0 + j8 * 8, acc + j8 * 8);
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (j4 * 4 < nb) t4 = __ldg(reinterpret_cast<const float4*>(n_pr) + j4);
+                        rn[j4 * 4 + 0] = t4.x; rn[j4 * 4 + 1] = t4.y; rn[j4 * 4 + 2] = t4.z; rn[j4 * 4 + 3] = t4.w;
                     }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) rn[j] = (j < nb) ? n_pr[(long long)j * rsc] : 0.f;   // may alias out: plain loads
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) rn[j] = 0.f;
+            }
+        };
+        // per-thread statistics of the current clip: (sum, sumsq) of the 4 groups this warp's columns cover
+        float S0 = 0.f, S1 = 0.f, S2 = 0.f, S3 = 0.f, Q0 = 0.f, Q1 = 0.f, Q2 = 0.f, Q3 = 0.f;
+        int b_cur = -1, gk = 0, gpos = 0;
+        auto flush_stats = [&]() {
+            if (do_stats && b_cur >= 0) {
+                float v[8] = {S0, Q0, S1, Q1, S2, Q2, S3, Q3};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+                }
+                if (lane == 0) {
+                    const int g0 = cbeg / gcn;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (g0 + (k >> 1) < 8) atomicAdd(p.stats + (long long)b_cur * 16 + (g0 + (k >> 1)) * 2 + (k & 1), (double)v[k]);
+                }
+            }
+            S0 = S1 = S2 = S3 = Q0 = Q1 = Q2 = Q3 = 0.f;
+        };
+        auto add_group = [&](float s, float qq) {
+            if (gk == 0) { S0 += s; Q0 += qq; } else if (gk == 1) { S1 += s; Q1 += qq; } else if (gk == 2) { S2 += s; Q2 += qq; } else { S3 += s; Q3 += qq; }
+        };
+
+        setup_next();
+        load_next();
+        while (n_valid) {
+            // the prefetched batch becomes the current one
+            c_po = n_po; c_tcol = n_tcol; c_ui = n_ui; c_c0 = n_c0; c_b = n_b; c_ab = n_ab; c_nt = n_nt; c_aphase = n_aphase;
+            c_ok = n_ok; c_last = n_last;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rr[j] = rn[j];
+            setup_next();
+            load_next();
+            if (c_ui == 0 && c_c0 == 0) { mbar_wait(tmem_full + c_ab, c_aphase); tc_fence_after(); }
+            if (c_c0 == 0) {
+                gk = 0; gpos = 0;
+                if (c_b != b_cur) { flush_stats(); b_cur = c_b; }
+                const int gkey = p.gate_bstride ? c_b * p.n_ntiles + c_nt : c_nt;
+                if (gkey != gate_b) {
+                    gate_b = gkey;
+                    __syncwarp();
+                    for (int k = lane; k < ncols; k += 32)
+                        gsm[k] = has_gate ? __ldg(p.gate + (long long)c_b * p.gate_bstride + c_nt * p.Ntile + cbeg + k) * gs : gs;
+                    __syncwarp();
+                }
+            }
+            if (!(p.dbg & 1)) {
+                uint32_t acc[32];
+                if (!(p.dbg & 512)) {
+                    tmem_ld32_nowait(c_tcol, acc);     // columns past this warp's range are read but never used
                     tmem_wait_ld();
+                } else {
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        if (j8 * 8 < nb) {
-                            float v[8];
+                    for (int j = 0; j < 32; ++j) acc[j] = 0x3f800000u;
+                }
+                const int nb = ncols - c_c0;
+                const float* gq = gsm + c_c0;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int c = c0 + j8 * 8 + j;
-                                const float g = gate ? __ldg(gate + c) * gs : gs;
-                                v[j] = fmaf(__uint_as_float(acc[j8 * 8 + j]), g, rr[j8 * 8 + j] * al);
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    if (j8 * 8 < nb) {
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(acc[j8 * 8 + j]), gq[j8 * 8 + j], rr[j8 * 8 + j] * al);
+                        if (c_ok && !(p.dbg & 256)) {
+                            if (p.out_cl) {
+                                float4* o4 = reinterpret_cast<float4*>(c_po + j8 * 8);
+                                o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) c_po[(long long)(j8 * 8 + j) * osc] = v[j];
                             }
-                            if (ok) {
+                        }
+                        if (do_stats) {
+                            const float m = c_ok ? 1.f : 0.f;
+                            if (gpos + 8 <= gcn) {
+                                float s = 0.f, qq = 0.f;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) po[(long long)(c0 + j8 * 8 + j) * osc] = v[j];
-                            }
-                            if (p.stats) {
-                                if (gcn >= 8) {
-                                    // at most one group boundary inside the 8-column chunk, at column `left`
-                                    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                                for (int j = 0; j < 8; ++j) { s += v[j]; qq = fmaf(v[j], v[j], qq); }
+                                add_group(s * m, qq * m);
+                                gpos += 8;
+                                if (gpos == gcn) { gpos = 0; ++gk; }
+                            } else if (gcn >= 8) {
+                                // one group boundary inside the chunk (group widths that are not multiples of 8, e.g. 12 for 96 channels)
+                                const int first = gcn - gpos;       // columns [0, first) finish the current group
+                                float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float w = ok ? v[j] : 0.f;
-                                        if (j < left) { a0 += w; a1 = fmaf(w, w, a1); } else { b0 += w; b1 = fmaf(w, w, b1); }
-                                    }
-                                    ssum += a0; ssq += a1;
-                                    left -= 8;
-                                    if (left <= 0) { flush_group(ssum, ssq, grp); ++grp; ssum = b0; ssq = b1; left += gcn; }
-                                } else {
+                                for (int j = 0; j < 8; ++j) {
+                                    if (j < first) { s0 += v[j]; q0 = fmaf(v[j], v[j], q0); } else { s1 += v[j]; q1 = fmaf(v[j], v[j], q1); }
+                                }
+                                add_group(s0 * m, q0 * m); ++gk;
+                                add_group(s1 * m, q1 * m); gpos = 8 - first;
+                            } else {
 #pragma unroll 1
-                                    for (int j = 0; j < 8; ++j) {
-                                        const float w = ok ? v[j] : 0.f;
-                                        ssum += w; ssq = fmaf(w, w, ssq);
-                                        if (--left == 0) { flush_group(ssum, ssq, grp); ++grp; ssum = 0.f; ssq = 0.f; left = gcn; }
-                                    }
+                                for (int j = 0; j < 8; ++j) {     // narrow test networks only (groups of 2, 4 or 6 channels)
+                                    add_group(v[j] * m, v[j] * v[j] * m);
+                                    if (++gpos == gcn) { gpos = 0; ++gk; }
                                 }
                             }
                         }
                     }
                 }
-                if (p.stats) flush_group(ssum, ssq, min(grp, 7));
             }
-            tc_fence_before();
-            mbar_arrive(tmem_empty + ab);
-            if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
+            if (c_last) {      // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory pipe
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty + c_ab);
+            }
         }
-        flush_global();
+        flush_stats();
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == T2_WARP_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -442,6 +533,69 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
     }
 }
 
+// Same operand, from a channels-last input x[B][F][T][C] (the residual stream inside a conv_mode 2 residual block).  Pure
+// streaming: 8 consecutive lanes read one pixel's 64-channel group (256 contiguous bytes), each thread converts one 8-channel
+// chunk and writes its 16 bytes at the swizzled position of the same pixel row.  grid: (B * G * rows_total, segment chunks)
+__global__ void __launch_bounds__(256)
+gn_act_tc2_cl_kernel(const float* __restrict__ x, int B, int C, int F, int T, const double* __restrict__ stats, double n_per_group,
+                     const float* __restrict__ gamma, const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, int G,
+                     __half* __restrict__ a) {
+    const int Tp = T + 2, rows_total = F + 2 * PF;
+    int bid = blockIdx.x;
+    const int fr = bid % rows_total; bid /= rows_total;
+    const int g = bid % G, b = bid / G;
+    __shared__ float s_scale[64];
+    if (threadIdx.x < 64) {
+        float sc = 0.f;
+        const int c = g * 64 + threadIdx.x;
+        if (c < C) {
+            sc = 1.f;
+            if (stats) {
+                const int grp = c / (C / 8);
+                const double s1 = stats[((long long)b * 8 + grp) * 2 + 0], s2 = stats[((long long)b * 8 + grp) * 2 + 1];
+                double var = (s2 - s1 * s1 / n_per_group) / (n_per_group - 1.0);
+                var = var > 0.0 ? var : 0.0;
+                const float stdv = (float)sqrt(var);
+                const float mod = affine ? (1.f + affine[b * affine_bstride + c]) : 1.f;
+                sc = gamma[c] * mod / (stdv + 1e-7f);
+            }
+        }
+        s_scale[threadIdx.x] = sc;
+    }
+    __syncthreads();
+    const int chunk = threadIdx.x & 7, psub = threadIdx.x >> 3;   // 32 pixels per pass
+    float sc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[j] = s_scale[chunk * 8 + j];
+    const int f = fr - PF;
+    const bool rowok = f >= 0 && f < F;
+    const bool chok = g * 64 + chunk * 8 < C;
+    const float* src = x + (((long long)b * F + (rowok ? f : 0)) * T) * C + g * 64 + chunk * 8;
+    uint8_t* dst_row = reinterpret_cast<uint8_t*>(a + ((((long long)b * G + g) * rows_total + fr) * Tp) * 64);
+    const long long gp_row = (long long)fr * Tp;
+    for (int tp = blockIdx.y * 32 + psub; tp < Tp; tp += gridDim.y * 32) {
+        const int t = tp - 1;
+        __align__(16) __half hv[8];
+        if (rowok && chok && t >= 0 && t < T) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (long long)t * C));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (long long)t * C) + 1);
+            const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float y = v[j] * sc[j];
+                if (gelu) y = gelu_erf_tc2(y);
+                y = fminf(fmaxf(y * T2_A_SCALE, -60000.f), 60000.f);
+                hv[j] = __float2half_rn(y);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(0.f);
+        }
+        const int phase = (int)((gp_row + tp) & 7);
+        *reinterpret_cast<uint4*>(dst_row + (long long)tp * 128 + ((chunk ^ phase) << 4)) = *reinterpret_cast<const uint4*>(hv);
+    }
+}
+
 size_t tc2_act_halves(int B, int C, int F, int T, int PF) { return (size_t)B * ((C + 63) / 64) * 64 * (F + 2 * PF) * (T + 2); }
 
 void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
@@ -458,6 +612,20 @@ void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, 
     AID_COUNT_LAUNCH(1);
 }
 
+// x_cl: channels-last fp32 [B][F][T][C]
+void launch_gn_act_tc2_cl(const float* x_cl, int B, int C, int F, int T, const double* stats, long long n_per_group, const float* gamma,
+                          const float* affine, long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s) {
+    const int rows_total = F + 2 * PF, Tp = T + 2, G = (C + 63) / 64;
+    const int npass = (Tp + 31) / 32;
+    const long long rows = (long long)B * G * rows_total;
+    int ychunks = 1;
+    while (ychunks < npass && rows * ychunks < 148 * 16) ychunks <<= 1;
+    ychunks = min(ychunks, npass);
+    dim3 grid((unsigned)rows, ychunks);
+    gn_act_tc2_cl_kernel<<<grid, 256, 0, s>>>(x_cl, B, C, F, T, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
+    AID_COUNT_LAUNCH(1);
+}
+
 void launch_to_planar_tc2(const TV& x, int PF, __half* a, cudaStream_t s) {
     launch_gn_act_tc2(x, nullptr, 1, nullptr, nullptr, 0, false, PF, a, s);
 }
@@ -470,7 +638,7 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     if (!conv_tc_supported(Cin, out.C, KF, KT)) throw CudaError(cudaErrorInvalidValue, "conv_tc2: unsupported shape", __FILE__, __LINE__);
     Tc2Args p{};
     p.a = a; p.w = wp; p.out = out; p.R = ep.R; p.gate = ep.gate; p.gate_bstride = ep.gate_bstride;
-    p.alpha = ep.alpha; p.stats = ep.stats;
+    p.alpha = ep.alpha; p.stats = ep.stats; p.out_cl = ep.out_cl ? 1 : 0; p.r_cl = ep.R_cl ? 1 : 0;
     p.B = B; p.Cin = Cin; p.G = (Cin + 63) / 64; p.Ntot = out.C; p.Ntile = tc2_ntile(out.C); p.n_ntiles = out.C / p.Ntile;
     p.F = F; p.T = T; p.Tp = T + 2; p.dil = dil;
     p.KF = KF; p.KT = KT; p.kt_shift = (KT == 1) ? 1 : 0;
@@ -487,13 +655,14 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     p.ktb = env_ktb > 0 ? min(env_ktb, KT) : (kt_bytes * KT <= 48 * 1024 ? KT : 1);
     p.b_slot_bytes = p.ktb * kt_bytes;
     p.nA = max(2, min(4, env_nA));
-    const int budget = 224 * 1024 - 1024 - 256 - T2_EPI_WARPS * 16 * (int)sizeof(double);
+    const int budget = 224 * 1024 - 1024 - 256 - T2_EPI_WARPS * 128 * (int)sizeof(float);
     while (p.nA > 2 && budget - p.nA * 2 * T2_ASLOT_UNIT < 2 * p.b_slot_bytes) --p.nA;
     p.nB = min(8, (budget - p.nA * 2 * T2_ASLOT_UNIT) / p.b_slot_bytes);
     if (p.nB < 2) throw CudaError(cudaErrorInvalidValue, "conv_tc2: shared memory budget", __FILE__, __LINE__);
     p.ncol_stride = p.Ntile <= 64 ? 64 : (p.Ntile <= 128 ? 128 : 256);
     p.acc_bufs = p.ncol_stride <= 128 ? 2 : 1;
-    const size_t smem = 1024 + (size_t)p.nA * 2 * T2_ASLOT_UNIT + (size_t)p.nB * p.b_slot_bytes + 256 + T2_EPI_WARPS * 16 * sizeof(double);
+    if (ep.stats && p.n_ntiles != 1) throw CudaError(cudaErrorInvalidValue, "conv_tc2: statistics need a single n-tile", __FILE__, __LINE__);
+    const size_t smem = 1024 + (size_t)p.nA * 2 * T2_ASLOT_UNIT + (size_t)p.nB * p.b_slot_bytes + 256 + T2_EPI_WARPS * 128 * sizeof(float);
     static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
     p.dbg = dbg;
     static size_t configured = 0;

@@ -510,6 +510,15 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         c.release(h.p); c.release(qk.p); c.release(o.p);
         cur = x;
     }
+    // conv_mode 2, dilated blocks: between the layers the residual stream lives channels-last ([B][F][T][N] fp32), so that a
+    // unit's 128 x N output tile and residual tile are contiguous in HBM (the NCHW planes give 512-byte fragments 1 MB apart,
+    // which the DRAM serves at a fraction of its streaming rate).  Layer 0 reads NCHW, the last layer writes NCHW.
+    static const bool env_cl = getenv("AID_TC2_CL") && atoi(getenv("AID_TC2_CL")) != 0;   // measured slower than NCHW so far: off by default
+    bool use_cl = env_cl && cmode == 2 && !k.k1x1 && k.nd >= 2;
+    for (auto& h : k.H) use_cl = use_cl && h.wtc != nullptr;
+    float* xcl = use_cl ? c.allocf(plane) : nullptr;
+    TV xc = make_tv_cl(xcl, B, N, F, T);
+    bool cur_is_cl = false;
     for (int i = 0; i < k.nd; ++i) {
         ConvEpilogue ep;
         ep.gate = c.mod + k.gate[i].off; ep.gate_bstride = c.modstride();
@@ -520,10 +529,20 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
             const int dil = k.k1x1 ? 1 : (1 << i);
             const int pf = tc_pad_rows(T, k.H[i].KF, dil);
             __half* a_lo = parts == 2 ? a_hi + planar_halves(N, pf) : nullptr;
-            if (cmode == 2) RUN(launch_gn_act_tc2(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s));
-            else RUN(launch_gn_act_tc(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, a_lo, c.s));
-            x.stats = ep.stats;
-            conv_tc(c, a_hi, a_lo, pf, k.H[i], dil, x, ep);
+            if (cmode == 2) {
+                if (cur_is_cl) RUN(launch_gn_act_tc2_cl(xcl, B, N, F, T, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s));
+                else RUN(launch_gn_act_tc2(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s));
+                const bool out_is_cl = use_cl && i + 1 < k.nd;
+                if (cur_is_cl) ep.R = xc;
+                ep.R_cl = cur_is_cl; ep.out_cl = out_is_cl;
+                x.stats = ep.stats;
+                conv_tc(c, a_hi, nullptr, pf, k.H[i], dil, out_is_cl ? xc : x, ep);
+                cur_is_cl = out_is_cl;
+            } else {
+                RUN(launch_gn_act_tc(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, a_lo, c.s));
+                x.stats = ep.stats;
+                conv_tc(c, a_hi, a_lo, pf, k.H[i], dil, x, ep);
+            }
         } else {
             RUN(launch_gn_act(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, a, c.s));
             x.stats = ep.stats;
@@ -531,6 +550,7 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         }
         cur = x;
     }
+    if (xcl) c.release(xcl);
     if (k.after && N != k.dim_out) {
         TV t = make_tv(c.allocf((long long)B * k.dim_out * F * T), B, k.dim_out, F, T);
         conv(c, cur, k.proj_out, 1, t, ConvEpilogue());
@@ -906,15 +926,20 @@ static int op_conv2d_impl(const float* a_dev, const float* w_dev, int B, int Cin
         const int pf = tc_pad_rows(T, KF, dil);
         const size_t ahalves = (size_t)B * Cin * (F + 2 * pf) * (T + 2);
         int sms = 148, dev = 0;
-        if (mode == 1 || mode == 3) {
+        if (mode == 1 || mode == 3 || mode == 4) {
             if (!conv_tc_supported(Cin, Cout, KF, KT) || R2_dev) throw std::invalid_argument("shape not supported by the tcgen05 path");
             AID_CUDA_CHECK(cudaGetDevice(&dev));
             AID_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            if (mode == 3) {
+            if (mode == 3 || mode == 4) {
                 AID_CUDA_CHECK(cudaMalloc(&wtc, tc2_weight_halves(Cout, Cin, KF, KT) * sizeof(__half)));
                 AID_CUDA_CHECK(cudaMalloc(&ah, tc2_act_halves(B, Cin, F, T, pf) * sizeof(__half)));
                 launch_pack_weight_tc2(w_dev, wtc, Cout, Cin, KF, KT, s);
-                launch_to_planar_tc2(a, pf, ah, s);
+                if (mode == 4) {   // a, R and out are channels-last [B][F][T][C]
+                    launch_gn_act_tc2_cl(a_dev, B, Cin, F, T, nullptr, 1, nullptr, nullptr, 0, false, pf, ah, s);
+                    out = make_tv_cl(out_dev, B, Cout, F, T);
+                    if (R_dev) ep.R = make_tv_cl(const_cast<float*>(R_dev), B, Cout, F, T);
+                    ep.R_cl = R_dev != nullptr; ep.out_cl = true;
+                } else launch_to_planar_tc2(a, pf, ah, s);
             } else {
                 AID_CUDA_CHECK(cudaMalloc(&wtc, 2 * e * sizeof(__half)));
                 AID_CUDA_CHECK(cudaMalloc(&ah, 2 * ahalves * sizeof(__half)));
@@ -924,7 +949,7 @@ static int op_conv2d_impl(const float* a_dev, const float* w_dev, int B, int Cin
         } else if (mode != 0 && mode != 2) throw std::invalid_argument("unknown conv mode");
         (void)iters;
         AID_CUDA_CHECK(cudaEventRecord(e0, s));
-        if (mode == 3) launch_conv_tc2(ah, pf, wtc, B, Cin, F, T, KF, KT, dil, out, ep, sms, s);
+        if (mode == 3 || mode == 4) launch_conv_tc2(ah, pf, wtc, B, Cin, F, T, KF, KT, dil, out, ep, sms, s);
         else if (mode == 1) launch_conv_tc(ah, ah + ahalves, pf, wtc, B, Cin, F, T, KF, KT, dil, out, ep, sms, s);
         else if (mode == 2 || !launch_conv_thin(a, wp, KF, KT, dil, out, ep, s)) launch_conv_simt(a, wp, KF, KT, dil, out, ep, s);
         AID_CUDA_CHECK(cudaEventRecord(e1, s));

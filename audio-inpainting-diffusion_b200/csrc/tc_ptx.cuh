@@ -67,6 +67,21 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t sbo
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
            ((uint64_t)(base_offset & 7) << 49) | (2ull << 61);
 }
+// one elected lane of a fully active warp (the compiler then knows the guarded region runs on a single thread and can keep
+// descriptors in uniform registers instead of emitting a per-lane R2UR loop around every tcgen05.mma)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
+// low / high words of a K-major SWIZZLE_128B descriptor with SBO = 1024 (see make_desc_sw128)
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+static constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"

@@ -102,7 +102,8 @@ int aid_edm_step(const float* xin_dev, const float* xhat_dev, const float* y_dev
 /* F.conv2d(a[B,Cin,F,T], w[Cout,Cin,KF,KT], padding="same", dilation=(dil,1)) with the fused epilogue
  * out = alpha*(conv*gate[c] + R) + beta*R2; gate/R/R2 may be NULL.  stats_dev (may be NULL): [B][8][2] doubles
  * accumulated with (sum, sumsq) of out per channel group.  mode: 0 = fp32 CUDA cores (thin-channel kernels where they apply),
- * 1 = tcgen05 split-fp16 (3 MMAs per tap), 2 = force the general fp32 CUDA-core kernel, 3 = tcgen05 single fp16 (1 MMA per tap).
+ * 1 = tcgen05 split-fp16 (3 MMAs per tap), 2 = force the general fp32 CUDA-core kernel, 3 = tcgen05 single fp16 (1 MMA per tap),
+ * 4 = like 3 with a, R and out given channels-last ([B,F,T,C], the layout the residual stream has inside a conv_mode 2 block).
  *                                                                                            unet.py:79-88, 482 */
 int aid_op_conv2d(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
                   const float* gate_dev, const float* R_dev, const float* R2_dev, float alpha, float beta,

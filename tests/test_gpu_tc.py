@@ -73,6 +73,33 @@ def test_conv_tc_single_fp16(cuda, case):
         assert torch.allclose(stats[:, :, 1].cpu(), (g * g).sum(-1), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_single_fp16_channels_last(cuda, case):
+    """op mode 4: the same kernel with the activation, the residual and the output channels-last (inside-block layout)."""
+    B, Cin, Cout, Fd, T, dil, use_stats = case
+    L = _lib()
+    a = seeded((B, Cin, Fd, T), 1)
+    w = seeded((Cout, Cin, 5, 3), 2, 1.0 / math.sqrt(Cin * 15))
+    gate, R = seeded((Cout,), 3), seeded((B, Cout, Fd, T), 4)
+    alpha = 0.70710678
+    ar, wr = _round_operands(a, w)
+    ref16 = conv_ref(ar, wr, dil, gate, R, None, alpha)
+    cl = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    ad, wd, gd, Rd = cl(a).to(cuda), w.to(cuda), gate.to(cuda), cl(R).to(cuda)
+    out = torch.full((B, Fd, T, Cout), float("nan"), device=cuda)
+    stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=cuda) if use_stats else None
+    L.check(L.lib().aid_op_conv2d(L.ptr(ad), L.ptr(wd), B, Cin, Cout, Fd, T, 5, 3, dil, L.ptr(gd), L.ptr(Rd), None,
+                                  alpha, 0.0, L.ptr(out), L.ptr(stats), 4, None))
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2).cpu().double()
+    assert torch.isfinite(got).all()
+    assert rel_l2(got - alpha * R.double(), ref16 - alpha * R.double()) < 1e-5
+    if use_stats:
+        g = ref16.reshape(B, 8, -1)
+        assert torch.allclose(stats[:, :, 0].cpu(), g.sum(-1), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(stats[:, :, 1].cpu(), (g * g).sum(-1), rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize("case", TC_1x1_CASES)
 def test_conv_tc_1x1(cuda, case):
     B, Cin, Cout, Fd, T, use_stats = case

@@ -10,7 +10,8 @@ shapes = [  # B, C, F, T, dil   (levels of the paper network at B=8)
     (8, 64, 64, 4096, 2), (8, 96, 128, 2048, 4), (8, 128, 256, 512, 16), (8, 128, 320, 256, 32), (8, 256, 384, 128, 64), (8, 256, 448, 64, 8)]
 def run(B, Ci, Co, Fd, T, K, dil, useR=True):
     KF, KT = (5, 3) if K == 5 else (1, 1)
-    a = torch.randn(B, Ci, Fd, T, device=dev); w = torch.randn(Co, Ci, KF, KT, device=dev) * 0.03
+    a = torch.randn(B, Ci, Fd, T, device=dev)  # mode 4 reads the same buffers as channels-last: timing only
+    w = torch.randn(Co, Ci, KF, KT, device=dev) * 0.03
     g = torch.randn(Co, device=dev); R = torch.randn(B, Co, Fd, T, device=dev) if useR else None; out = torch.empty(B, Co, Fd, T, device=dev)
     st = torch.zeros(B * 16, dtype=torch.float64, device=dev) if os.environ.get('NOSTATS') is None else None
     ms = C.c_float()
@@ -20,6 +21,11 @@ def run(B, Ci, Co, Fd, T, K, dil, useR=True):
     print(f"mode {mode} dbg {os.environ.get('AID_TC_DEBUG','0')} nt {os.environ.get('AID_TC_NTILE','0')} nostats {int(os.environ.get('NOSTATS') is not None)} {K}x B{B} Ci{Ci} Co{Co} F{Fd} T{T} d{dil} R{int(useR)}: {ms.value:8.3f} ms  {fl/ms.value/1e9:8.1f} TFLOP/s  {gb/ms.value*1e3:7.0f} GB/s (algorithmic)", flush=True)
 
 which = sys.argv[2] if len(sys.argv) > 2 else "all"
+if os.environ.get("TC_SHAPES"):   # "B,C,F,T,dil;B,C,F,T,dil;..."  (5x3 layers)
+    for sh in os.environ["TC_SHAPES"].split(";"):
+        B, Cn, Fd, T, dil = (int(v) for v in sh.split(","))
+        run(B, Cn, Cn, Fd, T, 5, dil, useR=os.environ.get('NOR') is None)
+    sys.exit(0)
 if which in ("all", "5x3"):
     for B, Cn, Fd, T, dil in shapes:
         run(B, Cn, Cn, Fd, T, 5, dil)
