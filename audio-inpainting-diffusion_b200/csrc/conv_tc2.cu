@@ -41,26 +41,36 @@ struct Tc2Args {
     int KF, KT, kt_shift, ktb;                 // ktb: kt taps per weight slot
     int tiles_t, n_units, n_pairs, n_tiles;
     int nA, nB, b_slot_bytes, acc_bufs, ncol_stride;
+    uint32_t mg_pairs, mg_upb, mg_Tp, mg_tt, mg_F;   // division magics (fast_divmod) of n_pairs, units_per_b, Tp, tiles_t, F
     int out_cl, r_cl;   // 1: that tensor is channels-last [B][F][T][C] (C = its TV's channel count), else NCHW
     int dbg;  // AID_TC_DEBUG bits (tuning only): 1 skip epilogue body, 2 skip MMAs, 4 skip A loads, 8 skip B loads
 };
 
 struct Unit2 { int exists, b, f_lo, f_hi, win_start, o0; };
 
+// n / d and n % d with a host-computed magic = floor(2^32 / d) (0xffffffff for d == 1): the estimate is low by at most one
+__device__ __forceinline__ uint2 fast_divmod(uint32_t n, uint32_t d, uint32_t magic) {
+    uint32_t q = __umulhi(n, magic), r = n - q * d;
+    if (r >= d) { ++q; r -= d; }
+    return make_uint2(q, r);
+}
+static uint32_t div_magic(uint32_t d) { return d <= 1 ? 0xffffffffu : (uint32_t)(0x100000000ull / d); }
+
 __device__ __forceinline__ Unit2 unit2_info(const Tc2Args& p, int u) {
     Unit2 i;
     i.exists = u < p.n_units;
     if (p.stream) {
-        const int k = u % p.units_per_b;
-        i.b = u / p.units_per_b;
-        i.o0 = k * 128;                               // first output position in the padded stream of the real rows
-        i.f_lo = i.o0 / p.Tp;
-        i.f_hi = min(p.F - 1, (i.o0 + 127) / p.Tp);
+        const uint2 bk = fast_divmod((uint32_t)u, (uint32_t)p.units_per_b, p.mg_upb);
+        i.b = (int)bk.x;
+        i.o0 = (int)bk.y * 128;                       // first output position in the padded stream of the real rows
+        i.f_lo = (int)fast_divmod((uint32_t)i.o0, (uint32_t)p.Tp, p.mg_Tp).x;
+        i.f_hi = min(p.F - 1, (int)fast_divmod((uint32_t)(i.o0 + 127), (uint32_t)p.Tp, p.mg_Tp).x);
         i.win_start = p.PF * p.Tp + i.o0 - 1;         // window = positions [o0-1, o0+129) of the padded plane
     } else {
-        const int tt = u % p.tiles_t, r = u / p.tiles_t;
-        const int f = r % p.F, t0 = tt * 128;
-        i.b = r / p.F; i.f_lo = i.f_hi = f;
+        const uint2 rt = fast_divmod((uint32_t)u, (uint32_t)p.tiles_t, p.mg_tt);
+        const uint2 bf = fast_divmod(rt.x, (uint32_t)p.F, p.mg_F);
+        const int f = (int)bf.y, t0 = (int)rt.y * 128;
+        i.b = (int)bf.x; i.f_lo = i.f_hi = f;
         i.o0 = f * p.Tp + t0 + 1;
         i.win_start = f * p.Tp + t0;
     }
@@ -69,7 +79,7 @@ __device__ __forceinline__ Unit2 unit2_info(const Tc2Args& p, int u) {
 
 __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer for the compiler
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a_slot_bytes = 2 * T2_ASLOT_UNIT;
     uint8_t* ringA = smem;
@@ -105,7 +115,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         int slot = 0; uint32_t phase = 0;
         const size_t gstride = (size_t)p.rows_total * p.Tp * 64;   // halves per (clip, group) plane
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int pair = tile % p.n_pairs;
+            const int pair = (int)fast_divmod((uint32_t)tile, (uint32_t)p.n_pairs, p.mg_pairs).y;
             const Unit2 u0 = unit2_info(p, 2 * pair), u1 = unit2_info(p, 2 * pair + 1);
             for (int kf = 0; kf < p.KF; ++kf) {
                 const int foff = (kf - p.KF / 2) * p.dil;
@@ -134,7 +144,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         int slot = 0; uint32_t phase = 0;
         const size_t kt_halves = (size_t)p.Ntile * 64;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int pair = tile % p.n_pairs, nt = tile / p.n_pairs;
+            const uint2 tdm = fast_divmod((uint32_t)tile, (uint32_t)p.n_pairs, p.mg_pairs);
+            const int pair = (int)tdm.y, nt = (int)tdm.x;
             const Unit2 u0 = unit2_info(p, 2 * pair), u1 = unit2_info(p, 2 * pair + 1);
             for (int kf = 0; kf < p.KF; ++kf) {
                 const int foff = (kf - p.KF / 2) * p.dil;
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         const uint32_t kt_bytes = (uint32_t)p.Ntile * 128u;
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int ab = 0; uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int pair = tile % p.n_pairs;
+            const int pair = (int)fast_divmod((uint32_t)tile, (uint32_t)p.n_pairs, p.mg_pairs).y;
             const Unit2 u0 = unit2_info(p, 2 * pair), u1 = unit2_info(p, 2 * pair + 1);
             mbar_wait(tmem_empty + ab, aphase ^ 1);
             tc_fence_after();
@@ -234,43 +245,49 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
 
         // gate[c] * 2^-14 * alpha of this warp's columns, private copy in shared memory (refreshed when the clip changes)
         float* gsm = reinterpret_cast<float*>(bar_base + 256) + e * 128;
-        int gate_b = -2;
+        int gate_key = -2;
+        const uint32_t gsm_addr = smem_u32(gsm);
+        const int pofs = q * 32 + lane;           // this thread's pixel inside a unit
 
-        // batch descriptor (plain scalars: a struct passed through lambdas ends up in local memory)
-        float* c_po = nullptr; uint32_t c_tcol = 0; int c_ui = 0, c_c0 = 0, c_b = 0, c_ab = 0, c_nt = 0;
+        // batch descriptors as plain scalars (a struct passed through lambdas ends up in local memory)
+        float* c_po = nullptr; uint32_t c_oo = 0; uint32_t c_tcol = 0; int c_ui = 0, c_c0 = 0, c_b = 0, c_ab = 0, c_nt = 0;
         uint32_t c_aphase = 0; bool c_ok = false, c_last = false;
-        const float* n_pr = nullptr; float* n_po = nullptr; uint32_t n_tcol = 0; int n_ui = 0, n_c0 = 0, n_b = 0, n_ab = 0, n_nt = 0;
+        const float* n_pr = nullptr; float* n_po = nullptr; uint32_t n_ro = 0, n_oo = 0; uint32_t n_tcol = 0; int n_ui = 0, n_c0 = 0, n_b = 0, n_ab = 0, n_nt = 0;
         uint32_t n_aphase = 0; bool n_ok = false, n_valid = false, n_last = false;
         // iterator state of the next batch to set up; per-unit values are recomputed only at the first batch of a unit
         int it_tile = blockIdx.x, it_ui = 0, it_c0 = 0, it_ab = 0; uint32_t it_aphase = 0;
-        const float* u_pr = nullptr; float* u_po = nullptr; int u_b = 0, u_nt = 0; bool u_ok = false;
+        const float* u_pr = nullptr; float* u_po = nullptr; uint32_t u_ro = 0, u_oo = 0; int u_b = 0, u_nt = 0; bool u_ok = false, u_has1 = false;
         auto setup_next = [&]() {
             n_valid = it_tile < p.n_tiles;
             if (!n_valid) return;
-            const int pair = it_tile % p.n_pairs;
             if (it_c0 == 0) {
-                u_nt = it_tile / p.n_pairs;
+                uint32_t pair = (uint32_t)it_tile; u_nt = 0;
+                if (p.n_ntiles > 1) { const uint2 dm = fast_divmod((uint32_t)it_tile, (uint32_t)p.n_pairs, p.mg_pairs); u_nt = (int)dm.x; pair = dm.y; }
+                u_has1 = 2 * (int)pair + 1 < p.n_units;
                 const int co0 = u_nt * p.Ntile + cbeg;
-                const Unit2 u = unit2_info(p, 2 * pair + it_ui);
-                const int o = u.o0 + q * 32 + lane;           // output position in the padded stream of the real rows
-                const int row = o / p.Tp, tp = o - row * p.Tp;
+                const Unit2 u = unit2_info(p, 2 * (int)pair + it_ui);
+                const int o = u.o0 + pofs;                // output position in the padded stream of the real rows
+                const int row = (int)fast_divmod((uint32_t)o, (uint32_t)p.Tp, p.mg_Tp).x, tp = o - row * p.Tp;
                 u_ok = tp >= 1 && tp <= p.T && row <= u.f_hi;
-                const long long pix = (long long)row * p.T + (tp - 1);
-                u_po = p.out_cl ? p.out.p + (long long)u.b * p.out.sb + pix * p.out.C + co0
-                                : p.out.p + (long long)u.b * p.out.sb + (long long)co0 * osc + pix;
-                u_pr = p.r_cl ? p.R.p + (long long)u.b * p.R.sb + pix * p.R.C + co0
-                              : p.R.p + (long long)u.b * p.R.sb + (long long)co0 * rsc + pix;
+                // lanes that own no real pixel read (never write) pixel 0 of their clip: the loads need no predicate
+                const long long pix = u_ok ? (long long)row * p.T + (tp - 1) : 0;
+                // warp-uniform clip base pointers + 32-bit per-thread element offsets (a clip's tensor has < 2^31 elements)
+                u_po = p.out.p + (long long)u.b * p.out.sb;
+                u_pr = p.R.p + (long long)u.b * p.R.sb;
+                u_oo = p.out_cl ? (uint32_t)pix * (uint32_t)p.out.C + (uint32_t)co0 : (uint32_t)co0 * (uint32_t)osc + (uint32_t)pix;
+                u_ro = p.r_cl ? (uint32_t)pix * (uint32_t)p.R.C + (uint32_t)co0 : (uint32_t)co0 * (uint32_t)rsc + (uint32_t)pix;
                 u_b = u.b;
             }
-            n_po = u_po + (p.out_cl ? (long long)it_c0 : (long long)it_c0 * osc);
-            n_pr = u_pr + (p.r_cl ? (long long)it_c0 : (long long)it_c0 * rsc);
+            n_po = u_po; n_pr = u_pr;
+            n_oo = u_oo + (p.out_cl ? (uint32_t)it_c0 : (uint32_t)it_c0 * (uint32_t)osc);
+            n_ro = u_ro + (p.r_cl ? (uint32_t)it_c0 : (uint32_t)it_c0 * (uint32_t)rsc);
             n_tcol = tq + (uint32_t)(it_ab * 2 * p.ncol_stride + it_ui * p.ncol_stride + it_c0);
             n_ui = it_ui; n_c0 = it_c0; n_b = u_b; n_nt = u_nt; n_ab = it_ab; n_aphase = it_aphase; n_ok = u_ok;
             n_last = false;
             it_c0 += 32;
             if (it_c0 >= ncols) {
                 it_c0 = 0;
-                if (it_ui == 1 || 2 * pair + 1 >= p.n_units) {
+                if (it_ui == 1 || !u_has1) {
                     n_last = true;
                     it_ui = 0; it_tile += gridDim.x;
                     if (++it_ab == p.acc_bufs) { it_ab = 0; it_aphase ^= 1; }
@@ -279,18 +296,21 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         };
         float rr[32], rn[32];
         auto load_next = [&]() {
-            if (n_valid && n_ok && has_r && !(p.dbg & 1)) {
+            if (n_valid && has_r && !(p.dbg & 1)) {
                 const int nb = ncols - n_c0;      // >= 8, multiple of 8; columns past it are not loaded
                 if (p.r_cl) {
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (j4 * 4 < nb) t4 = __ldg(reinterpret_cast<const float4*>(n_pr) + j4);
+                        if (j4 * 4 < nb) t4 = __ldg(reinterpret_cast<const float4*>(n_pr + n_ro) + j4);
                         rn[j4 * 4 + 0] = t4.x; rn[j4 * 4 + 1] = t4.y; rn[j4 * 4 + 2] = t4.z; rn[j4 * 4 + 3] = t4.w;
                     }
+                } else if (nb >= 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) rn[j] = n_pr[n_ro + (uint32_t)j * (uint32_t)rsc];   // may alias out: plain loads
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) rn[j] = (j < nb) ? n_pr[(long long)j * rsc] : 0.f;   // may alias out: plain loads
+                    for (int j = 0; j < 32; ++j) rn[j] = (j < nb) ? n_pr[n_ro + (uint32_t)j * (uint32_t)rsc] : 0.f;
                 }
             } else {
 #pragma unroll
@@ -320,12 +340,58 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         auto add_group = [&](float s, float qq) {
             if (gk == 0) { S0 += s; Q0 += qq; } else if (gk == 1) { S1 += s; Q1 += qq; } else if (gk == 2) { S2 += s; Q2 += qq; } else { S3 += s; Q3 += qq; }
         };
+        // one 8-column chunk: out = acc*gate' + R*alpha, store, statistics
+        auto chunk = [&](const uint32_t* acc8, const float* r8, uint32_t g8, uint32_t oo8) {
+            float g[8];
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g[0]), "=f"(g[1]), "=f"(g[2]), "=f"(g[3]) : "r"(g8));
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(g[4]), "=f"(g[5]), "=f"(g[6]), "=f"(g[7]) : "r"(g8));
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(acc8[j]), g[j], r8[j] * al);
+            if (c_ok && !(p.dbg & 256)) {
+                if (p.out_cl) {
+                    float4* o4 = reinterpret_cast<float4*>(c_po + oo8);
+                    o4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    o4[1] = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) c_po[oo8 + (uint32_t)j * (uint32_t)osc] = v[j];
+                }
+            }
+            if (do_stats) {
+                const float m = c_ok ? 1.f : 0.f;
+                if (gpos + 8 <= gcn) {
+                    float s = 0.f, qq = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s += v[j]; qq = fmaf(v[j], v[j], qq); }
+                    add_group(s * m, qq * m);
+                    gpos += 8;
+                    if (gpos == gcn) { gpos = 0; ++gk; }
+                } else if (gcn >= 8) {
+                    // one group boundary inside the chunk (group widths that are not multiples of 8, e.g. 12 for 96 channels)
+                    const int first = gcn - gpos;       // columns [0, first) finish the current group
+                    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < first) { s0 += v[j]; q0 = fmaf(v[j], v[j], q0); } else { s1 += v[j]; q1 = fmaf(v[j], v[j], q1); }
+                    }
+                    add_group(s0 * m, q0 * m); ++gk;
+                    add_group(s1 * m, q1 * m); gpos = 8 - first;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {     // narrow test networks only (groups of 2, 4 or 6 channels)
+                        add_group(v[j] * m, v[j] * v[j] * m);
+                        if (++gpos == gcn) { gpos = 0; ++gk; }
+                    }
+                }
+            }
+        };
 
         setup_next();
         load_next();
         while (n_valid) {
             // the prefetched batch becomes the current one
-            c_po = n_po; c_tcol = n_tcol; c_ui = n_ui; c_c0 = n_c0; c_b = n_b; c_ab = n_ab; c_nt = n_nt; c_aphase = n_aphase;
+            c_po = n_po; c_oo = n_oo; c_tcol = n_tcol; c_ui = n_ui; c_c0 = n_c0; c_b = n_b; c_ab = n_ab; c_nt = n_nt; c_aphase = n_aphase;
             c_ok = n_ok; c_last = n_last;
 #pragma unroll
             for (int j = 0; j < 32; ++j) rr[j] = rn[j];
@@ -336,8 +402,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                 gk = 0; gpos = 0;
                 if (c_b != b_cur) { flush_stats(); b_cur = c_b; }
                 const int gkey = p.gate_bstride ? c_b * p.n_ntiles + c_nt : c_nt;
-                if (gkey != gate_b) {
-                    gate_b = gkey;
+                if (gkey != gate_key) {
+                    gate_key = gkey;
                     __syncwarp();
                     for (int k = lane; k < ncols; k += 32)
                         gsm[k] = has_gate ? __ldg(p.gate + (long long)c_b * p.gate_bstride + c_nt * p.Ntile + cbeg + k) * gs : gs;
@@ -354,51 +420,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                     for (int j = 0; j < 32; ++j) acc[j] = 0x3f800000u;
                 }
                 const int nb = ncols - c_c0;
-                const float* gq = gsm + c_c0;
+                const uint32_t gq = gsm_addr + (uint32_t)c_c0 * 4u;
+                if (nb >= 32) {
 #pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {
-                    if (j8 * 8 < nb) {
-                        float v[8];
+                    for (int j8 = 0; j8 < 4; ++j8) chunk(acc + j8 * 8, rr + j8 * 8, gq + j8 * 32, c_oo + (p.out_cl ? (uint32_t)(j8 * 8) : (uint32_t)(j8 * 8) * (uint32_t)osc));
+                } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(acc[j8 * 8 + j]), gq[j8 * 8 + j], rr[j8 * 8 + j] * al);
-                        if (c_ok && !(p.dbg & 256)) {
-                            if (p.out_cl) {
-                                float4* o4 = reinterpret_cast<float4*>(c_po + j8 * 8);
-                                o4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                                o4[1] = make_float4(v[4], v[5], v[6], v[7]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) c_po[(long long)(j8 * 8 + j) * osc] = v[j];
-                            }
-                        }
-                        if (do_stats) {
-                            const float m = c_ok ? 1.f : 0.f;
-                            if (gpos + 8 <= gcn) {
-                                float s = 0.f, qq = 0.f;
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) { s += v[j]; qq = fmaf(v[j], v[j], qq); }
-                                add_group(s * m, qq * m);
-                                gpos += 8;
-                                if (gpos == gcn) { gpos = 0; ++gk; }
-                            } else if (gcn >= 8) {
-                                // one group boundary inside the chunk (group widths that are not multiples of 8, e.g. 12 for 96 channels)
-                                const int first = gcn - gpos;       // columns [0, first) finish the current group
-                                float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    if (j < first) { s0 += v[j]; q0 = fmaf(v[j], v[j], q0); } else { s1 += v[j]; q1 = fmaf(v[j], v[j], q1); }
-                                }
-                                add_group(s0 * m, q0 * m); ++gk;
-                                add_group(s1 * m, q1 * m); gpos = 8 - first;
-                            } else {
-#pragma unroll 1
-                                for (int j = 0; j < 8; ++j) {     // narrow test networks only (groups of 2, 4 or 6 channels)
-                                    add_group(v[j] * m, v[j] * v[j] * m);
-                                    if (++gpos == gcn) { gpos = 0; ++gk; }
-                                }
-                            }
-                        }
-                    }
+                    for (int j8 = 0; j8 < 3; ++j8)
+                        if (j8 * 8 < nb) chunk(acc + j8 * 8, rr + j8 * 8, gq + j8 * 32, c_oo + (p.out_cl ? (uint32_t)(j8 * 8) : (uint32_t)(j8 * 8) * (uint32_t)osc));
                 }
             }
             if (c_last) {      // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory pipe
@@ -450,7 +479,31 @@ void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int K
     AID_COUNT_LAUNCH(1);
 }
 
-__device__ __forceinline__ float gelu_erf_tc2(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+// 16 * GELU(v) with the exact-erf definition to ~5e-7 absolute (Abramowitz & Stegun 7.1.26, MUFU rcp / ex2): erff() costs
+// about twice the instructions, and this HBM-streaming pass was instruction bound; the result is rounded to fp16 (2^-11
+// relative) right after, so the approximation error is invisible.  The operand scale (x16) is folded into the last FMA.
+__device__ __forceinline__ float gelu16_tc2(float v) {
+    const float ax = fabsf(v) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
+    float pl = fmaf(t, 1.061405429f, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    pl *= t;
+    const float z = v * 0.84932180028801904272f;          // sqrt(log2(e) / 2): exp(-v^2 / 2) = 2^(-z^2)
+    float ex;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z));
+    const float erf_abs = fmaf(-pl, ex, 1.f);
+    const float h = 8.f * v;
+    return fmaf(h, copysignf(erf_abs, v), h);
+}
+// two operand values (already x16) -> packed fp16x2, saturating to the finite range
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
 // Normalise / modulate / GELU (unet.py:159-163, 479, 482) writing the channels-last fp16 operand:
 //   a[b][g][r][tp][chunk ^ ((r*Tp + tp) & 7)][8] = fp16(16 * act(x[b, 64g + 8 chunk + j, r - PF, tp - 1] * scale_c)),
@@ -458,16 +511,18 @@ __device__ __forceinline__ float gelu_erf_tc2(float v) { return 0.5f * v * (1.f 
 // grid: (B * G * rows_total, segment chunks), block 256 = 8 warps: warp w converts channels [8w, 8w+8) of the group for 64
 // pixels per iteration (coalesced channel-plane loads), the 64 x 128 B tile is transposed through shared memory (the
 // swizzle makes the 16-byte stores conflict free) and written out as one contiguous 8 KB run.
+template <int NH>   // NH * 32 pixels per iteration: NH * 128 contiguous bytes per channel plane and iteration (DRAM page locality)
 __global__ void __launch_bounds__(256)
 gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, const float* __restrict__ gamma,
                   const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, int G, __half* __restrict__ a) {
+    constexpr int PXI = NH * 32;
     const int Tp = x.T + 2, rows_total = x.F + 2 * PF;
     int bid = blockIdx.x;
     const int fr = bid % rows_total; bid /= rows_total;
     const int g = bid % G, b = bid / G;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ float s_scale[64];
-    __shared__ __align__(16) uint8_t tile[64 * 128];
+    extern __shared__ __align__(16) uint8_t tile[];   // [PXI][128 B]
     if (threadIdx.x < 64) {
         float sc = 0.f;
         const int c = g * 64 + threadIdx.x;
@@ -495,36 +550,39 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
     const float* src = x.p + (long long)b * x.sb + (long long)(g * 64 + w * 8) * x.sc + (long long)(rowok ? f : 0) * x.T;
     __half* dst_row = a + ((((long long)b * G + g) * rows_total + fr) * Tp) * 64;
     const long long gp_row = (long long)fr * Tp;
-    const int nseg = (Tp + 63) / 64;
+    const int nseg = (Tp + PXI - 1) / PXI;
     for (int seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
-        const int tp0 = seg * 64;
+        const int tp0 = seg * PXI;
+        float v[NH][8];
+        // all loads of the iteration first: NH consecutive 128-byte lines of each of this warp's 8 channel planes
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NH; ++h) {
+            const int t = tp0 + h * 32 + lane - 1;
+            const bool ld = rowok && chok && t >= 0 && t < x.T;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[h][j] = ld ? __ldg(src + (long long)j * x.sc + t) : 0.f;
+        }
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
             const int pl = h * 32 + lane, tp = tp0 + pl, t = tp - 1;
-            __align__(16) __half hv[8];
+            uint4 hv = make_uint4(0u, 0u, 0u, 0u);
             if (rowok && chok && t >= 0 && t < x.T) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __ldg(src + (long long)j * x.sc + t);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    float y = v[j] * sc[j];
-                    if (gelu) y = gelu_erf_tc2(y);
-                    y = fminf(fmaxf(y * T2_A_SCALE, -60000.f), 60000.f);
-                    hv[j] = __float2half_rn(y);
+                    v[h][j] *= sc[j];
+                    v[h][j] = gelu ? gelu16_tc2(v[h][j]) : v[h][j] * T2_A_SCALE;
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(0.f);
+                hv = make_uint4(pack_half2_sat(v[h][0], v[h][1]), pack_half2_sat(v[h][2], v[h][3]), pack_half2_sat(v[h][4], v[h][5]),
+                                pack_half2_sat(v[h][6], v[h][7]));
             }
             const int phase = (int)((gp_row + tp) & 7);
-            *reinterpret_cast<uint4*>(tile + pl * 128 + ((w ^ phase) << 4)) = *reinterpret_cast<const uint4*>(hv);
+            *reinterpret_cast<uint4*>(tile + pl * 128 + ((w ^ phase) << 4)) = hv;
         }
         __syncthreads();
-        const int npx = min(64, Tp - tp0);
+        const int npx = min(PXI, Tp - tp0);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int idx = threadIdx.x + k * 256;        // 16-byte unit of the 8 KB tile
+        for (int k = 0; k < NH; ++k) {
+            const int idx = threadIdx.x + k * 256;        // 16-byte unit of the tile
             if ((idx >> 3) < npx)
                 *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst_row + (long long)tp0 * 64) + idx * 16) =
                     *reinterpret_cast<const uint4*>(tile + idx * 16);
@@ -575,24 +633,20 @@ gn_act_tc2_cl_kernel(const float* __restrict__ x, int B, int C, int F, int T, co
     const long long gp_row = (long long)fr * Tp;
     for (int tp = blockIdx.y * 32 + psub; tp < Tp; tp += gridDim.y * 32) {
         const int t = tp - 1;
-        __align__(16) __half hv[8];
+        uint4 hv = make_uint4(0u, 0u, 0u, 0u);
         if (rowok && chok && t >= 0 && t < T) {
             const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + (long long)t * C));
             const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + (long long)t * C) + 1);
-            const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float y = v[j] * sc[j];
-                if (gelu) y = gelu_erf_tc2(y);
-                y = fminf(fmaxf(y * T2_A_SCALE, -60000.f), 60000.f);
-                hv[j] = __float2half_rn(y);
+                v[j] *= sc[j];
+                v[j] = gelu ? gelu16_tc2(v[j]) : v[j] * T2_A_SCALE;
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) hv[j] = __float2half_rn(0.f);
+            hv = make_uint4(pack_half2_sat(v[0], v[1]), pack_half2_sat(v[2], v[3]), pack_half2_sat(v[4], v[5]), pack_half2_sat(v[6], v[7]));
         }
         const int phase = (int)((gp_row + tp) & 7);
-        *reinterpret_cast<uint4*>(dst_row + (long long)tp * 128 + ((chunk ^ phase) << 4)) = *reinterpret_cast<const uint4*>(hv);
+        *reinterpret_cast<uint4*>(dst_row + (long long)tp * 128 + ((chunk ^ phase) << 4)) = hv;
     }
 }
 
@@ -601,14 +655,19 @@ size_t tc2_act_halves(int B, int C, int F, int T, int PF) { return (size_t)B * (
 void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
                        long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s) {
     const int rows_total = x.F + 2 * PF, Tp = x.T + 2, G = (x.C + 63) / 64;
-    const int nseg = (Tp + 63) / 64;
+    static const int env_nh = getenv("AID_GN_NH") ? atoi(getenv("AID_GN_NH")) : 4;
+    const int nh = (Tp >= 256 && env_nh >= 8) ? 8 : (Tp >= 128 && env_nh >= 4 ? 4 : 2);
+    const int nseg = (Tp + nh * 32 - 1) / (nh * 32);
     const long long rows = (long long)x.B * G * rows_total;
     // enough blocks to fill the machine, but several segments per block when rows are long
     int ychunks = 1;
     while (ychunks < nseg && rows * ychunks < 148 * 16) ychunks <<= 1;
     ychunks = min(ychunks, nseg);
     dim3 grid((unsigned)rows, ychunks);
-    gn_act_tc2_kernel<<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
+    const double npg = (double)n_per_group;
+    if (nh == 8) gn_act_tc2_kernel<8><<<grid, 256, 8 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
+    else if (nh == 4) gn_act_tc2_kernel<4><<<grid, 256, 4 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
+    else gn_act_tc2_kernel<2><<<grid, 256, 2 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
     AID_COUNT_LAUNCH(1);
 }
 
@@ -649,6 +708,7 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     p.n_units = B * p.units_per_b;
     p.n_pairs = (p.n_units + 1) / 2;
     p.n_tiles = p.n_pairs * p.n_ntiles;
+    p.mg_pairs = div_magic(p.n_pairs); p.mg_upb = div_magic(p.units_per_b); p.mg_Tp = div_magic(p.Tp); p.mg_tt = div_magic(p.tiles_t); p.mg_F = div_magic(p.F);
     static const int env_ktb = getenv("AID_TC2_KTB") ? atoi(getenv("AID_TC2_KTB")) : 0;
     static const int env_nA = getenv("AID_TC2_NA") ? atoi(getenv("AID_TC2_NA")) : 3;
     const int kt_bytes = p.Ntile * 128;

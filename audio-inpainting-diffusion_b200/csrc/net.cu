@@ -998,6 +998,30 @@ int aid_debug_tc2_operands(const float* x_dev, const float* w_dev, int B, int Ci
     } catch (const CudaError& e) { fprintf(stderr, "aid_debug_tc2_operands: CUDA error %s\n", cudaGetErrorString(e.code)); return AID_ERR_CUDA; }
 }
 
+/* debug / tuning: device time (ms per launch, averaged over iters) of the conv_mode 2 normalise + GELU + operand-layout pass */
+int aid_debug_time_gn_tc2(const float* x_dev, int B, int C, int F, int T, int PF, int iters, float* ms_out) {
+    try {
+        TV x = make_tv(const_cast<float*>(x_dev), B, C, F, T);
+        double* st = nullptr; float *gamma = nullptr, *aff = nullptr; __half* a = nullptr;
+        AID_CUDA_CHECK(cudaMalloc(&st, (size_t)B * 16 * sizeof(double)));
+        AID_CUDA_CHECK(cudaMalloc(&gamma, C * sizeof(float))); AID_CUDA_CHECK(cudaMalloc(&aff, C * sizeof(float)));
+        AID_CUDA_CHECK(cudaMemset(gamma, 0, C * sizeof(float))); AID_CUDA_CHECK(cudaMemset(aff, 0, C * sizeof(float)));
+        AID_CUDA_CHECK(cudaMalloc(&a, tc2_act_halves(B, C, F, T, PF) * sizeof(__half)));
+        AID_CUDA_CHECK(cudaMemset(st, 0, (size_t)B * 16 * sizeof(double)));
+        launch_group_stats(x, st, nullptr);
+        cudaEvent_t e0, e1; AID_CUDA_CHECK(cudaEventCreate(&e0)); AID_CUDA_CHECK(cudaEventCreate(&e1));
+        launch_gn_act_tc2(x, st, (long long)(C / 8) * F * T, gamma, aff, 0, true, PF, a, nullptr);
+        AID_CUDA_CHECK(cudaEventRecord(e0, nullptr));
+        for (int i = 0; i < iters; ++i) launch_gn_act_tc2(x, st, (long long)(C / 8) * F * T, gamma, aff, 0, true, PF, a, nullptr);
+        AID_CUDA_CHECK(cudaEventRecord(e1, nullptr));
+        AID_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f; AID_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_out) *ms_out = ms / iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(st); cudaFree(gamma); cudaFree(aff); cudaFree(a);
+        return AID_OK;
+    } catch (const CudaError& e) { fprintf(stderr, "aid_debug_time_gn_tc2: CUDA error %s\n", cudaGetErrorString(e.code)); return AID_ERR_CUDA; }
+}
+
 int aid_op_groupnorm_act(const float* x_dev, const float* gamma_dev, const float* affine_dev, int B, int C, int F, int T, int gelu,
                          float* out_dev, double* stats_scratch_dev, void* stream) {
     if (!x_dev || !gamma_dev || !out_dev || !stats_scratch_dev || C % 8 != 0) return AID_ERR_INVALID;

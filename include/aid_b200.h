@@ -129,6 +129,9 @@ int aid_debug_time_conv2d(const float* a_dev, const float* w_dev, int B, int Cin
 int aid_debug_tc2_operands(const float* x_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int PF,
                            void* a_out_dev, void* w_out_dev, uint64_t* a_halves, uint64_t* w_halves);
 
+/* Debug / tuning: ms per launch of the conv_mode 2 normalise + GELU + operand-layout pass on x[B,C,F,T]. */
+int aid_debug_time_gn_tc2(const float* x_dev, int B, int C, int F, int T, int PF, int iters, float* ms_out);
+
 /* Per-launch timing of the convolution kernels with CUDA events on the launching stream (bench.py's roofline).
  * aid_profile(h, 1) clears and starts recording, aid_profile(h, 0) stops; aid_profile_read sums the recorded launches
  * of one kind (0 = dilated 5x3 residual-layer convolutions, 1 = all other convolutions): count, device ms, algorithmic
