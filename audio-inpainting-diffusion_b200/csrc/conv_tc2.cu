@@ -656,7 +656,10 @@ void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, 
                        long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s) {
     const int rows_total = x.F + 2 * PF, Tp = x.T + 2, G = (x.C + 63) / 64;
     static const int env_nh = getenv("AID_GN_NH") ? atoi(getenv("AID_GN_NH")) : 4;
-    const int nh = (Tp >= 256 && env_nh >= 8) ? 8 : (Tp >= 128 && env_nh >= 4 ? 4 : 2);
+    // whole short rows in one iteration (T = 64 -> 96 pixels, T = 128 -> 160), otherwise 128 pixels per iteration
+    int nh = (Tp >= 256 && env_nh >= 8) ? 8 : (Tp >= 128 && env_nh >= 4 ? 4 : 2);
+    if (Tp > 64 && Tp <= 96) nh = 3;
+    else if (Tp > 128 && Tp <= 160) nh = 5;
     const int nseg = (Tp + nh * 32 - 1) / (nh * 32);
     const long long rows = (long long)x.B * G * rows_total;
     // enough blocks to fill the machine, but several segments per block when rows are long
@@ -666,6 +669,8 @@ void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, 
     dim3 grid((unsigned)rows, ychunks);
     const double npg = (double)n_per_group;
     if (nh == 8) gn_act_tc2_kernel<8><<<grid, 256, 8 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
+    else if (nh == 5) gn_act_tc2_kernel<5><<<grid, 256, 5 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
+    else if (nh == 3) gn_act_tc2_kernel<3><<<grid, 256, 3 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
     else if (nh == 4) gn_act_tc2_kernel<4><<<grid, 256, 4 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
     else gn_act_tc2_kernel<2><<<grid, 256, 2 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
     AID_COUNT_LAUNCH(1);

@@ -131,7 +131,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--len", type=int, default=262144)
-    ap.add_argument("--conv-mode", type=int, default=int(os.environ.get("AID_CONV_MODE", "1")))
+    ap.add_argument("--conv-mode", type=int, default=int(os.environ.get("AID_CONV_MODE", "2")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -225,7 +225,7 @@ def main():
         line = {
             "metric": "denoiser-fwd clips/s at 22.05 kHz, 262144-len, batch 32", "value": world * B / (ms / 1e3), "unit": "clips/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.conv_mode == 0 else "f16x3-split (fp32 accumulate)",
+            "scaling": "weak", "vs_baseline": None, "dtype": {0: "f32", 1: "f16x3-split (fp32 accumulate)", 2: "f16 (fp32 accumulate)"}[args.conv_mode],
             "data": "synthetic",
             "config": {"workload": f"denoiser forward, paper_1912 CQT-octave U-Net (186.3M params, random init), batch {B} x {L} samples per GPU, shared sigma",
                        "batch_per_gpu": B, "audio_len": L, "conv_mode": args.conv_mode,
@@ -234,9 +234,12 @@ def main():
             "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * L * 4},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "tensor", "kernel": "dilated 5x3 conv residual layers (conv_simt_kernel<5,3,8>)" if args.conv_mode == 0 else "dilated 5x3 conv (tcgen05)",
+            "roofline": {"bound": "tensor", "kernel": {0: "dilated 5x3 conv residual layers (conv_simt_kernel<5,3,8>)", 1: "dilated 5x3 conv (tcgen05, conv_tc_kernel, 3 MMAs per tap)",
+                                    2: "dilated 5x3 conv (tcgen05, conv_tc2_kernel, 1 fp16 MMA per tap)"}[args.conv_mode],
                          "achieved": conv_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": conv_tflops / pk["tensor"],
                          "peak_source": f"{pk['src']} bf16 dense GEMM, sustained", "traffic": traffic,
+                         "algorithmic_gbs": (by.value / 1e9) / (t_ms.value / 1e3) if t_ms.value > 0 else 0.0,
+                         "frac_of_hbm_peak": ((by.value / 1e9) / (t_ms.value / 1e3) / pk["hbm"]) if t_ms.value > 0 else 0.0,
                          "launches_timed": int(n_l.value), "kernel_ms_per_step": t_ms.value / args.steps,
                          "kernel_share_of_step": (t_ms.value / args.steps) / ms,
                          "whole_forward": {"tflops": B * GFLOP_PER_CLIP.get(L, 0) / 1e3 / (ms / 1e3),

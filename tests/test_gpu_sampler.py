@@ -84,3 +84,25 @@ def test_sampler_fused_equals_generic_path(aid, cuda, setup):
     torch.manual_seed(1)
     plain = s2.predict_inpainting(y * mask, mask)
     assert rel_l2(fused, plain) < 1e-4
+
+
+def test_sampler_single_fp16_path_vs_reference_golden(aid, cuda):
+    """conv_mode 2 (one fp16 MMA per tap) through the whole sampler: every denoiser call is within 1e-3 of the reference
+    (tests/test_gpu_tc.py); six Heun steps chain 11 calls, the trajectory is held to 3e-3 against the reference's own run."""
+    cfg = aid.small_test(16384, conv_mode=2)
+    net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+    net.load_state_dict(aid.random_state_dict(cfg, seed=1234))
+    g = np.load(GOLD)
+    args = _tester_args(aid, T=6)
+    s = aid.Sampler(net, aid.EDM(args), args)
+    torch.manual_seed(42)
+    xu = s.predict_unconditional((2, cfg.audio_len), cuda)
+    eu = rel_l2(xu, torch.from_numpy(g["small_sample_uncond_T6"]))
+    y = seeded((2, cfg.audio_len), 7, 0.063)
+    mask = torch.ones(1, cfg.audio_len)
+    mask[..., cfg.audio_len // 2 - 750: cfg.audio_len // 2 + 750] = 0
+    torch.manual_seed(43)
+    xi = s.predict_inpainting((y * mask).to(cuda), mask.to(cuda))
+    ei = rel_l2(xi, torch.from_numpy(g["small_sample_inpaint_T6"]))
+    print(f"conv_mode 2 sampler trajectories vs reference golden: unconditional {eu:.3e}, inpainting {ei:.3e}")
+    assert eu < 3e-3 and ei < 3e-3

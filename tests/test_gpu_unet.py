@@ -189,7 +189,7 @@ def test_full_size_clip_properties(aid, cuda):
     assert rel_l2(net(x, cn - 1.0), a) > 1e-3
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_forward_reference_trained_length_184184(aid, cuda, mode):
     """audio_len = 184184 (2^3*7*11*13*23, conf/exp/maestro22k_8s.yaml:52): Bluestein FFT, 2048..32 frames per octave."""
     cfg = aid.NetConfig(audio_len=184184, Ns=[16, 16, 32, 32, 32, 48, 64], num_dils=[1, 2, 2, 3, 3, 3, 2], conv_mode=mode)
@@ -199,4 +199,4 @@ def test_forward_reference_trained_length_184184(aid, cuda, mode):
     x = seeded((1, 184184), 4, 0.5)
     cn = torch.tensor([[-0.6]])
     ref = make_oracle(cfg, sd)(x, cn)
-    assert rel_l2(net(x.to(cuda), cn.to(cuda)), ref) < 1e-4
+    assert rel_l2(net(x.to(cuda), cn.to(cuda)), ref) < (1e-3 if mode == 2 else 1e-4)
