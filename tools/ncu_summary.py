@@ -1,0 +1,19 @@
+"""Key metrics of every kernel in an .ncu-rep as JSON: python tools/ncu_summary.py report.ncu-rep out.json"""
+import csv, json, subprocess, sys
+WANT = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__grid_size", "launch__block_size",
+        "smsp__cycles_active.avg", "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "launch__shared_mem_per_block_dynamic"]
+raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+out = []
+for r in rows[2:]:
+    d = {"kernel": r[hdr.index("Kernel Name")]}
+    for w in WANT:
+        if w in hdr:
+            d[w] = [r[hdr.index(w)], units[hdr.index(w)]]
+    out.append(d)
+json.dump(out, open(sys.argv[2], "w"), indent=1)
+print(f"{len(out)} kernels -> {sys.argv[2]}")
