@@ -514,28 +514,33 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
 template <int NH>   // NH * 32 pixels per iteration: NH * 128 contiguous bytes per channel plane and iteration (DRAM page locality)
 __global__ void __launch_bounds__(256)
 gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, const float* __restrict__ gamma,
-                  const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, int G, __half* __restrict__ a) {
+                  const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, int G, int rpb, __half* __restrict__ a) {
     constexpr int PXI = NH * 32;
     const int Tp = x.T + 2, rows_total = x.F + 2 * PF;
+    const int nrb = (rows_total + rpb - 1) / rpb;     // row blocks per (clip, group)
     int bid = blockIdx.x;
-    const int fr = bid % rows_total; bid /= rows_total;
+    const int rb = bid % nrb; bid /= nrb;
     const int g = bid % G, b = bid / G;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ float s_scale[64];
+    __shared__ float s_inv[8];
     extern __shared__ __align__(16) uint8_t tile[];   // [PXI][128 B]
+    // 1 / (unbiased std + eps) of the 8 statistics groups in double (8 threads), then the 64 per-channel scales of this group
+    if (threadIdx.x < 8 && stats) {
+        const double s1 = stats[((long long)b * 8 + threadIdx.x) * 2 + 0], s2 = stats[((long long)b * 8 + threadIdx.x) * 2 + 1];
+        double var = (s2 - s1 * s1 / n_per_group) / (n_per_group - 1.0);
+        var = var > 0.0 ? var : 0.0;
+        s_inv[threadIdx.x] = 1.f / ((float)sqrt(var) + 1e-7f);
+    }
+    __syncthreads();
     if (threadIdx.x < 64) {
         float sc = 0.f;
         const int c = g * 64 + threadIdx.x;
         if (c < x.C) {
             sc = 1.f;
             if (stats) {
-                const int grp = c / (x.C / 8);
-                const double s1 = stats[((long long)b * 8 + grp) * 2 + 0], s2 = stats[((long long)b * 8 + grp) * 2 + 1];
-                double var = (s2 - s1 * s1 / n_per_group) / (n_per_group - 1.0);
-                var = var > 0.0 ? var : 0.0;
-                const float stdv = (float)sqrt(var);
                 const float mod = affine ? (1.f + affine[b * affine_bstride + c]) : 1.f;
-                sc = gamma[c] * mod / (stdv + 1e-7f);
+                sc = gamma[c] * mod * s_inv[c / (x.C / 8)];
             }
         }
         s_scale[threadIdx.x] = sc;
@@ -544,50 +549,53 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
     float sc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sc[j] = s_scale[w * 8 + j];
-    const int f = fr - PF;
-    const bool rowok = f >= 0 && f < x.F;
     const bool chok = g * 64 + w * 8 < x.C;      // C is a multiple of 8: a chunk is either all real or all padding
-    const float* src = x.p + (long long)b * x.sb + (long long)(g * 64 + w * 8) * x.sc + (long long)(rowok ? f : 0) * x.T;
-    __half* dst_row = a + ((((long long)b * G + g) * rows_total + fr) * Tp) * 64;
-    const long long gp_row = (long long)fr * Tp;
     const int nseg = (Tp + PXI - 1) / PXI;
-    for (int seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
-        const int tp0 = seg * PXI;
-        float v[NH][8];
-        // all loads of the iteration first: NH consecutive 128-byte lines of each of this warp's 8 channel planes
+    const int fr_end = min(rows_total, (rb + 1) * rpb);
+    for (int fr = rb * rpb; fr < fr_end; ++fr) {
+        const int f = fr - PF;
+        const bool rowok = f >= 0 && f < x.F;
+        const float* src = x.p + (long long)b * x.sb + (long long)(g * 64 + w * 8) * x.sc + (long long)(rowok ? f : 0) * x.T;
+        __half* dst_row = a + ((((long long)b * G + g) * rows_total + fr) * Tp) * 64;
+        const long long gp_row = (long long)fr * Tp;
+        for (int seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
+            const int tp0 = seg * PXI;
+            float v[NH][8];
+            // all loads of the iteration first: NH consecutive 128-byte lines of each of this warp's 8 channel planes
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            const int t = tp0 + h * 32 + lane - 1;
-            const bool ld = rowok && chok && t >= 0 && t < x.T;
+            for (int h = 0; h < NH; ++h) {
+                const int t = tp0 + h * 32 + lane - 1;
+                const bool ld = rowok && chok && t >= 0 && t < x.T;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[h][j] = ld ? __ldg(src + (long long)j * x.sc + t) : 0.f;
-        }
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            const int pl = h * 32 + lane, tp = tp0 + pl, t = tp - 1;
-            uint4 hv = make_uint4(0u, 0u, 0u, 0u);
-            if (rowok && chok && t >= 0 && t < x.T) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[h][j] *= sc[j];
-                    v[h][j] = gelu ? gelu16_tc2(v[h][j]) : v[h][j] * T2_A_SCALE;
-                }
-                hv = make_uint4(pack_half2_sat(v[h][0], v[h][1]), pack_half2_sat(v[h][2], v[h][3]), pack_half2_sat(v[h][4], v[h][5]),
-                                pack_half2_sat(v[h][6], v[h][7]));
+                for (int j = 0; j < 8; ++j) v[h][j] = ld ? __ldg(src + (long long)j * x.sc + t) : 0.f;
             }
-            const int phase = (int)((gp_row + tp) & 7);
-            *reinterpret_cast<uint4*>(tile + pl * 128 + ((w ^ phase) << 4)) = hv;
-        }
-        __syncthreads();
-        const int npx = min(PXI, Tp - tp0);
 #pragma unroll
-        for (int k = 0; k < NH; ++k) {
-            const int idx = threadIdx.x + k * 256;        // 16-byte unit of the tile
-            if ((idx >> 3) < npx)
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst_row + (long long)tp0 * 64) + idx * 16) =
-                    *reinterpret_cast<const uint4*>(tile + idx * 16);
+            for (int h = 0; h < NH; ++h) {
+                const int pl = h * 32 + lane, tp = tp0 + pl, t = tp - 1;
+                uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+                if (rowok && chok && t >= 0 && t < x.T) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[h][j] *= sc[j];
+                        v[h][j] = gelu ? gelu16_tc2(v[h][j]) : v[h][j] * T2_A_SCALE;
+                    }
+                    hv = make_uint4(pack_half2_sat(v[h][0], v[h][1]), pack_half2_sat(v[h][2], v[h][3]), pack_half2_sat(v[h][4], v[h][5]),
+                                    pack_half2_sat(v[h][6], v[h][7]));
+                }
+                const int phase = (int)((gp_row + tp) & 7);
+                *reinterpret_cast<uint4*>(tile + pl * 128 + ((w ^ phase) << 4)) = hv;
+            }
+            __syncthreads();
+            const int npx = min(PXI, Tp - tp0);
+#pragma unroll
+            for (int k = 0; k < NH; ++k) {
+                const int idx = threadIdx.x + k * 256;        // 16-byte unit of the tile
+                if ((idx >> 3) < npx)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst_row + (long long)tp0 * 64) + idx * 16) =
+                        *reinterpret_cast<const uint4*>(tile + idx * 16);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -661,18 +669,21 @@ void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, 
     if (Tp > 64 && Tp <= 96) nh = 3;
     else if (Tp > 128 && Tp <= 160) nh = 5;
     const int nseg = (Tp + nh * 32 - 1) / (nh * 32);
-    const long long rows = (long long)x.B * G * rows_total;
-    // enough blocks to fill the machine, but several segments per block when rows are long
+    // a block converts `rpb` whole rows when rows are short (amortises the per-block scale set-up), or a share of the
+    // segments of one long row; either way ~16 blocks per SM stay available
+    int rpb = 1;
+    while (rpb < 16 && rpb * Tp < 512 && (long long)x.B * G * ((rows_total + 2 * rpb - 1) / (2 * rpb)) >= 148 * 16) rpb <<= 1;
+    const long long rows = (long long)x.B * G * ((rows_total + rpb - 1) / rpb);
     int ychunks = 1;
     while (ychunks < nseg && rows * ychunks < 148 * 16) ychunks <<= 1;
     ychunks = min(ychunks, nseg);
     dim3 grid((unsigned)rows, ychunks);
     const double npg = (double)n_per_group;
-    if (nh == 8) gn_act_tc2_kernel<8><<<grid, 256, 8 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
-    else if (nh == 5) gn_act_tc2_kernel<5><<<grid, 256, 5 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
-    else if (nh == 3) gn_act_tc2_kernel<3><<<grid, 256, 3 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
-    else if (nh == 4) gn_act_tc2_kernel<4><<<grid, 256, 4 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
-    else gn_act_tc2_kernel<2><<<grid, 256, 2 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
+    if (nh == 8) gn_act_tc2_kernel<8><<<grid, 256, 8 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, rpb, a);
+    else if (nh == 5) gn_act_tc2_kernel<5><<<grid, 256, 5 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, rpb, a);
+    else if (nh == 3) gn_act_tc2_kernel<3><<<grid, 256, 3 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, rpb, a);
+    else if (nh == 4) gn_act_tc2_kernel<4><<<grid, 256, 4 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, rpb, a);
+    else gn_act_tc2_kernel<2><<<grid, 256, 2 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, rpb, a);
     AID_COUNT_LAUNCH(1);
 }
 

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(TH) conv_thin_out_kernel(TV a, const float* __
     for (int co = 0; co < COUT; ++co)
 #pragma unroll
         for (int px = 0; px < 4; ++px) acc[co][px] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int ci = 0; ci < Cin; ++ci) {
         const float4 x = __ldg(reinterpret_cast<const float4*>(pa + (long long)ci * a.sc));
 #pragma unroll
