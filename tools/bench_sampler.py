@@ -24,7 +24,7 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--len", type=int, default=262144)
 ap.add_argument("--gap-ms", type=float, default=300.0)
 ap.add_argument("--steps", type=int, default=35)
-ap.add_argument("--conv-mode", type=int, default=1)
+ap.add_argument("--conv-mode", type=int, default=2)
 a = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

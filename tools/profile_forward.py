@@ -16,7 +16,7 @@ import aid_b200
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--len", type=int, default=262144)
-ap.add_argument("--conv-mode", type=int, default=0)
+ap.add_argument("--conv-mode", type=int, default=2)
 ap.add_argument("--warm", type=int, default=1)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
