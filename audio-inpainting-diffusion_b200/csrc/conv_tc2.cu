@@ -42,6 +42,8 @@ struct Tc2Args {
     int tiles_t, n_units, n_pairs, n_tiles;
     int nA, nB, b_slot_bytes, acc_bufs, ncol_stride;
     uint32_t mg_pairs, mg_upb, mg_Tp, mg_tt, mg_F;   // division magics (fast_divmod) of n_pairs, units_per_b, Tp, tiles_t, F
+    int pair;           // 1: the two units of a tile live in the two CTAs of a cluster that share the weight ring by multicast
+    int a_slot_bytes;   // activation ring slot: 2 unit windows, or 1 in pair mode
     int out_cl, r_cl;   // 1: that tensor is channels-last [B][F][T][C] (C = its TV's channel count), else NCHW
     int dbg;  // AID_TC_DEBUG bits (tuning only): 1 skip epilogue body, 2 skip MMAs, 4 skip A loads, 8 skip B loads
 };
@@ -81,7 +83,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer for the compiler
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_slot_bytes = 2 * T2_ASLOT_UNIT;
+    const int a_slot_bytes = p.a_slot_bytes;
+    uint32_t crank = 0;
+    if (p.pair) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    // pair mode: a tile is shared by the 2 CTAs of a cluster (one unit each); tiles advance by cluster
+    const int tile0 = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstep = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int uown = p.pair ? (int)crank : 0, upeer = p.pair ? (int)(crank ^ 1u) : 1;
     uint8_t* ringA = smem;
     uint8_t* ringB = smem + (size_t)p.nA * a_slot_bytes;
     uint8_t* bar_base = ringB + (size_t)p.nB * p.b_slot_bytes;
@@ -96,7 +103,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
     if (warp == T2_WARP_MMA) {
         if (lane == 0) {
             for (int s = 0; s < p.nA; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
-            for (int s = 0; s < p.nB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); }
+            for (int s = 0; s < p.nB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, p.pair ? 2u : 1u); }
             for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, T2_EPI_WARPS); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -107,6 +114,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (p.pair) {   // the peer's barriers must be initialised before our multicast copies / commits can signal them
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     const uint32_t tmem_base = *tmem_slot;
     const int nktb = (p.KT + p.ktb - 1) / p.ktb;   // weight slots per (kf, group)
 
@@ -114,9 +125,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         // ===================== activation producer: one 16.6 KB bulk copy per (unit, kf, 64-channel group) =====================
         int slot = 0; uint32_t phase = 0;
         const size_t gstride = (size_t)p.rows_total * p.Tp * 64;   // halves per (clip, group) plane
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
             const int pair = (int)fast_divmod((uint32_t)tile, (uint32_t)p.n_pairs, p.mg_pairs).y;
-            const Unit2 u0 = unit2_info(p, 2 * pair), u1 = unit2_info(p, 2 * pair + 1);
+            const Unit2 u0 = unit2_info(p, 2 * pair + uown), u1 = unit2_info(p, 2 * pair + upeer);
             for (int kf = 0; kf < p.KF; ++kf) {
                 const int foff = (kf - p.KF / 2) * p.dil;
                 const bool v0 = u0.exists && u0.f_hi + foff >= 0 && u0.f_lo + foff < p.F;
@@ -127,11 +138,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                     mbar_wait(a_empty + slot, phase ^ 1);
                     if (lane == 0) {
                         uint8_t* sa = ringA + (size_t)slot * a_slot_bytes;
-                        const uint32_t bytes = (p.dbg & 4) ? 0u : ((v0 ? 130u * 128u : 0u) + (v1 ? 130u * 128u : 0u));
+                        const bool l1 = v1 && !p.pair;     // the peer CTA loads its own unit
+                        const uint32_t bytes = (p.dbg & 4) ? 0u : ((v0 ? 130u * 128u : 0u) + (l1 ? 130u * 128u : 0u));
                         mbar_expect_tx(a_full + slot, bytes);
                         if (!(p.dbg & 4)) {
                             if (v0) bulk_g2s(sa + (s0 & 7) * 128, p.a + ((size_t)u0.b * p.G + g) * gstride + (size_t)s0 * 64, 130u * 128u, a_full + slot);
-                            if (v1) bulk_g2s(sa + T2_ASLOT_UNIT + (s1 & 7) * 128, p.a + ((size_t)u1.b * p.G + g) * gstride + (size_t)s1 * 64, 130u * 128u, a_full + slot);
+                            if (l1) bulk_g2s(sa + T2_ASLOT_UNIT + (s1 & 7) * 128, p.a + ((size_t)u1.b * p.G + g) * gstride + (size_t)s1 * 64, 130u * 128u, a_full + slot);
                         }
                     }
                     __syncwarp();
@@ -143,10 +155,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         // ===================== weight producer: one bulk copy per (kf, group, kt chunk) =====================
         int slot = 0; uint32_t phase = 0;
         const size_t kt_halves = (size_t)p.Ntile * 64;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
             const uint2 tdm = fast_divmod((uint32_t)tile, (uint32_t)p.n_pairs, p.mg_pairs);
             const int pair = (int)tdm.y, nt = (int)tdm.x;
-            const Unit2 u0 = unit2_info(p, 2 * pair), u1 = unit2_info(p, 2 * pair + 1);
+            const Unit2 u0 = unit2_info(p, 2 * pair + uown), u1 = unit2_info(p, 2 * pair + upeer);
             for (int kf = 0; kf < p.KF; ++kf) {
                 const int foff = (kf - p.KF / 2) * p.dil;
                 const bool v0 = u0.exists && u0.f_hi + foff >= 0 && u0.f_lo + foff < p.F;
@@ -160,7 +172,17 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                         if (lane == 0) {
                             const uint32_t bytes = (uint32_t)(nkt * kt_halves * 2);
                             mbar_expect_tx(b_full + slot, (p.dbg & 8) ? 0u : bytes);
-                            if (!(p.dbg & 8)) bulk_g2s(ringB + (size_t)slot * p.b_slot_bytes, wg + (size_t)c * p.ktb * kt_halves, bytes, b_full + slot);
+                            if (!(p.dbg & 8)) {
+                                if (!p.pair) bulk_g2s(ringB + (size_t)slot * p.b_slot_bytes, wg + (size_t)c * p.ktb * kt_halves, bytes, b_full + slot);
+                                else {
+                                    // each CTA fetches half of the rows of every kt sub-tile and multicasts it into both CTAs' rings;
+                                    // both full barriers expect the whole slot
+                                    const uint32_t half = (uint32_t)(kt_halves);     // bytes of half a sub-tile (kt_halves halves * 2 B / 2)
+                                    for (int k = 0; k < nkt; ++k)
+                                        bulk_g2s_mc2(ringB + (size_t)slot * p.b_slot_bytes + (size_t)k * kt_halves * 2 + crank * half,
+                                                     reinterpret_cast<const uint8_t*>(wg + ((size_t)c * p.ktb + k) * kt_halves) + crank * half, half, b_full + slot);
+                                }
+                            }
                         }
                         __syncwarp();
                         if (++slot == p.nB) { slot = 0; phase ^= 1; }
@@ -173,13 +195,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Ntile >> 3) << 17) | ((128u >> 4) << 24);  // F16 x F16 -> F32, K-major A/B
         const uint32_t kt_bytes = (uint32_t)p.Ntile * 128u;
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int ab = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
             const int pair = (int)fast_divmod((uint32_t)tile, (uint32_t)p.n_pairs, p.mg_pairs).y;
-            const Unit2 u0 = unit2_info(p, 2 * pair), u1 = unit2_info(p, 2 * pair + 1);
+            const Unit2 u0 = unit2_info(p, 2 * pair + uown), u1 = unit2_info(p, 2 * pair + upeer);
             mbar_wait(tmem_empty + ab, aphase ^ 1);
             tc_fence_after();
             uint32_t started0 = 0u, started1 = 0u;
-            const uint32_t d0 = tmem_base + (uint32_t)(ab * 2 * p.ncol_stride), d1 = d0 + (uint32_t)p.ncol_stride;
+            const uint32_t d0 = tmem_base + (uint32_t)(ab * (p.pair ? 1 : 2) * p.ncol_stride), d1 = d0 + (uint32_t)p.ncol_stride;
             for (int kf = 0; kf < p.KF; ++kf) {
                 const int foff = (kf - p.KF / 2) * p.dil;
                 const bool v0 = u0.exists && u0.f_hi + foff >= 0 && u0.f_lo + foff < p.F;
@@ -209,12 +231,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                                         if (j < nk) {
                                             const uint64_t bd = ((uint64_t)DESC_HI_SW128 << 32) | (blo + 2u * j);
                                             if (v0) { tc_mma_f16(d0, ((uint64_t)DESC_HI_SW128 << 32) | (alo0 + 2u * j), bd, idesc, started0); started0 = 1u; }
-                                            if (v1) { tc_mma_f16(d1, ((uint64_t)DESC_HI_SW128 << 32) | (alo1 + 2u * j), bd, idesc, started1); started1 = 1u; }
+                                            if (v1 && !p.pair) { tc_mma_f16(d1, ((uint64_t)DESC_HI_SW128 << 32) | (alo1 + 2u * j), bd, idesc, started1); started1 = 1u; }
                                         }
                                     }
                                 }
                             }
-                            tc_commit(b_empty + sb);
+                            if (p.pair) tc_commit_mc2(b_empty + sb); else tc_commit(b_empty + sb);
                             if (c == nktb - 1) tc_commit(a_empty + sa);
                         }
                         __syncwarp();
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         const float* n_pr = nullptr; float* n_po = nullptr; uint32_t n_ro = 0, n_oo = 0; uint32_t n_tcol = 0; int n_ui = 0, n_c0 = 0, n_b = 0, n_ab = 0, n_nt = 0;
         uint32_t n_aphase = 0; bool n_ok = false, n_valid = false, n_last = false;
         // iterator state of the next batch to set up; per-unit values are recomputed only at the first batch of a unit
-        int it_tile = blockIdx.x, it_ui = 0, it_c0 = 0, it_ab = 0; uint32_t it_aphase = 0;
+        int it_tile = tile0, it_ui = 0, it_c0 = 0, it_ab = 0; uint32_t it_aphase = 0;
         const float* u_pr = nullptr; float* u_po = nullptr; uint32_t u_ro = 0, u_oo = 0; int u_b = 0, u_nt = 0; bool u_ok = false, u_has1 = false;
         auto setup_next = [&]() {
             n_valid = it_tile < p.n_tiles;
@@ -263,12 +285,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
             if (it_c0 == 0) {
                 uint32_t pair = (uint32_t)it_tile; u_nt = 0;
                 if (p.n_ntiles > 1) { const uint2 dm = fast_divmod((uint32_t)it_tile, (uint32_t)p.n_pairs, p.mg_pairs); u_nt = (int)dm.x; pair = dm.y; }
-                u_has1 = 2 * (int)pair + 1 < p.n_units;
+                u_has1 = !p.pair && 2 * (int)pair + 1 < p.n_units;
                 const int co0 = u_nt * p.Ntile + cbeg;
-                const Unit2 u = unit2_info(p, 2 * (int)pair + it_ui);
+                Unit2 u = unit2_info(p, 2 * (int)pair + (p.pair ? uown : it_ui));
+                if (!u.exists) u.b = 0;                   // pair mode, odd unit count: this CTA only keeps the handshakes going
                 const int o = u.o0 + pofs;                // output position in the padded stream of the real rows
                 const int row = (int)fast_divmod((uint32_t)o, (uint32_t)p.Tp, p.mg_Tp).x, tp = o - row * p.Tp;
-                u_ok = tp >= 1 && tp <= p.T && row <= u.f_hi;
+                u_ok = u.exists && tp >= 1 && tp <= p.T && row <= u.f_hi;
                 // lanes that own no real pixel read (never write) pixel 0 of their clip: the loads need no predicate
                 const long long pix = u_ok ? (long long)row * p.T + (tp - 1) : 0;
                 // warp-uniform clip base pointers + 32-bit per-thread element offsets (a clip's tensor has < 2^31 elements)
@@ -281,7 +304,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
             n_po = u_po; n_pr = u_pr;
             n_oo = u_oo + (p.out_cl ? (uint32_t)it_c0 : (uint32_t)it_c0 * (uint32_t)osc);
             n_ro = u_ro + (p.r_cl ? (uint32_t)it_c0 : (uint32_t)it_c0 * (uint32_t)rsc);
-            n_tcol = tq + (uint32_t)(it_ab * 2 * p.ncol_stride + it_ui * p.ncol_stride + it_c0);
+            n_tcol = tq + (uint32_t)(it_ab * (p.pair ? 1 : 2) * p.ncol_stride + it_ui * p.ncol_stride + it_c0);
             n_ui = it_ui; n_c0 = it_c0; n_b = u_b; n_nt = u_nt; n_ab = it_ab; n_aphase = it_aphase; n_ok = u_ok;
             n_last = false;
             it_c0 += 32;
@@ -289,7 +312,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                 it_c0 = 0;
                 if (it_ui == 1 || !u_has1) {
                     n_last = true;
-                    it_ui = 0; it_tile += gridDim.x;
+                    it_ui = 0; it_tile += tstep;
                     if (++it_ab == p.acc_bufs) { it_ab = 0; it_aphase ^= 1; }
                 } else it_ui = 1;
             }
@@ -441,6 +464,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
 
     tc_fence_before();
     __syncthreads();
+    if (p.pair) {   // the peer may still multicast into this CTA's ring or signal its barriers until it is done too
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     if (warp == T2_WARP_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -731,14 +758,23 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     p.ktb = env_ktb > 0 ? min(env_ktb, KT) : (kt_bytes * KT <= 48 * 1024 ? KT : 1);
     p.b_slot_bytes = p.ktb * kt_bytes;
     p.nA = max(2, min(4, env_nA));
+    // pair mode (N = 256 only, AID_TC2_PAIR=1, off by default): a 2 x 256-column tile fills the TMEM, so the epilogue cannot
+    // overlap the next tile's MMAs; with the tile's two units in the two CTAs of a cluster each CTA holds 256 columns per tile
+    // (double buffered) and the weight slots are still fetched once per unit pair: each CTA loads half of a slot and
+    // multicasts it to both rings.  Measured on B200: results identical, the epilogue does overlap, but the weight ring now
+    // needs a cross-CTA round trip per 512 MMA cycles and the main loop drops from 1600 to 1110 TFLOP/s (0.72 vs 0.60 ms on
+    // the level-5 layers), so it stays off until the ring is deepened (cta_group::2 halves the slot size).
+    const int env_pair = getenv("AID_TC2_PAIR") ? atoi(getenv("AID_TC2_PAIR")) : 0;
+    p.pair = (env_pair && p.Ntile == 256 && p.ktb == 1 && num_sms % 2 == 0) ? 1 : 0;
+    p.a_slot_bytes = (p.pair ? 1 : 2) * T2_ASLOT_UNIT;
     const int budget = 224 * 1024 - 1024 - 256 - T2_EPI_WARPS * 128 * (int)sizeof(float);
-    while (p.nA > 2 && budget - p.nA * 2 * T2_ASLOT_UNIT < 2 * p.b_slot_bytes) --p.nA;
-    p.nB = min(8, (budget - p.nA * 2 * T2_ASLOT_UNIT) / p.b_slot_bytes);
+    while (p.nA > 2 && budget - p.nA * p.a_slot_bytes < 2 * p.b_slot_bytes) --p.nA;
+    p.nB = min(8, (budget - p.nA * p.a_slot_bytes) / p.b_slot_bytes);
     if (p.nB < 2) throw CudaError(cudaErrorInvalidValue, "conv_tc2: shared memory budget", __FILE__, __LINE__);
     p.ncol_stride = p.Ntile <= 64 ? 64 : (p.Ntile <= 128 ? 128 : 256);
-    p.acc_bufs = p.ncol_stride <= 128 ? 2 : 1;
+    p.acc_bufs = (p.ncol_stride <= 128 || p.pair) ? 2 : 1;
     if (ep.stats && p.n_ntiles != 1) throw CudaError(cudaErrorInvalidValue, "conv_tc2: statistics need a single n-tile", __FILE__, __LINE__);
-    const size_t smem = 1024 + (size_t)p.nA * 2 * T2_ASLOT_UNIT + (size_t)p.nB * p.b_slot_bytes + 256 + T2_EPI_WARPS * 128 * sizeof(float);
+    const size_t smem = 1024 + (size_t)p.nA * p.a_slot_bytes + (size_t)p.nB * p.b_slot_bytes + 256 + T2_EPI_WARPS * 128 * sizeof(float);
     static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
     p.dbg = dbg;
     static size_t configured = 0;
@@ -746,8 +782,17 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
         AID_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int grid = min(p.n_tiles, num_sms);
-    conv_tc2_kernel<<<grid, T2_THREADS, smem, s>>>(p);
+    if (p.pair) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * min(p.n_tiles, num_sms / 2)); cfg.blockDim = dim3(T2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        AID_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc2_kernel, p));
+    } else {
+        const int grid = min(p.n_tiles, num_sms);
+        conv_tc2_kernel<<<grid, T2_THREADS, smem, s>>>(p);
+    }
     AID_COUNT_LAUNCH(1);
 }
 

@@ -234,3 +234,11 @@ def test_forward_single_fp16_paper_network_matches_reference_golden(aid, cuda):
     e1 = rel_l2(e.denoiser(x * 0.05, net, torch.tensor([0.05], device=cuda)), torch.from_numpy(g["paper_denoise_1"]))
     print(f"conv_mode 2 paper network vs reference golden: {e0:.3e} {e1:.3e}")
     assert e0 < 1e-3 and e1 < 1e-3
+
+
+def test_conv_tc2_cluster_pair_mode(cuda, monkeypatch):
+    """AID_TC2_PAIR=1: the two units of an N = 256 tile in the two CTAs of a cluster, weight ring shared by multicast."""
+    monkeypatch.setenv("AID_TC2_PAIR", "1")
+    for case in [(1, 256, 256, 24, 64, 64, True), (2, 256, 256, 9, 128, 2, True), (1, 64, 256, 7, 256, 1, True)]:
+        test_conv_tc_single_fp16(cuda, case)
+    test_conv_tc_single_fp16(cuda, (1, 512, 768, 1, 256, 0, False))     # 3 n-tiles, 1x1
