@@ -17,6 +17,8 @@
 //   * epilogue: 8 warps, each thread owns one pixel and walks its warp's column range 32 columns at a time with all 32
 //     residual loads in flight before the accumulator is read (the old 8-column batches left the LSU latency bound).
 #include <cuda_fp16.h>
+#include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -523,7 +525,25 @@ __device__ __forceinline__ float gelu16_tc2(float v) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z));
     const float erf_abs = fmaf(-pl, ex, 1.f);
     const float h = 8.f * v;
-    return fmaf(h, copysignf(erf_abs, v), h);
+    return fmaf(fabsf(h), erf_abs, h);                    // h * (1 + sign(v) * erf(|v| / sqrt 2))
+}
+// The same value for v = x * s with the per-channel scale folded into two constants, cu = |s| * sqrt(log2(e) / 2) and
+// ch = 8 s: u = |x| cu serves both the exponent (2^(-u^2)) and the rational argument (|v| / sqrt 2 = u / sqrt(log2 e)),
+// 14 instructions per element instead of 16.
+__device__ __forceinline__ float gelu16_tc2_folded(float x, float cu, float ch) {
+    const float u = fabsf(x) * cu;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.83255461115769775635f, u, 1.f)));
+    float pl = fmaf(t, 1.061405429f, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    pl *= t;
+    float ex;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-u * u));
+    const float erf_abs = fmaf(-pl, ex, 1.f);
+    const float h = x * ch;
+    return fmaf(fabsf(h), erf_abs, h);
 }
 // two operand values (already x16) -> packed fp16x2, saturating to the finite range
 __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
@@ -535,23 +555,24 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
 // Normalise / modulate / GELU (unet.py:159-163, 479, 482) writing the channels-last fp16 operand:
 //   a[b][g][r][tp][chunk ^ ((r*Tp + tp) & 7)][8] = fp16(16 * act(x[b, 64g + 8 chunk + j, r - PF, tp - 1] * scale_c)),
 //   pad pixels (tp = 0, T+1), pad rows and channels past C = 0.  stats == nullptr: plain layout/precision conversion.
-// grid: (B * G * rows_total, segment chunks), block 256 = 8 warps: warp w converts channels [8w, 8w+8) of the group for 64
-// pixels per iteration (coalesced channel-plane loads), the 64 x 128 B tile is transposed through shared memory (the
-// swizzle makes the 16-byte stores conflict free) and written out as one contiguous 8 KB run.
-template <int NH>   // NH * 32 pixels per iteration: NH * 128 contiguous bytes per channel plane and iteration (DRAM page locality)
-__global__ void __launch_bounds__(256)
+// The pass is instruction-issue bound, not HBM bound (17 instructions of GELU per element), so the layout work around it is
+// kept to a few instructions per element: the source plane [F][T] of a channel is a flat run (rows are contiguous), a block
+// converts 128 consecutive source pixels per iteration whatever the row length, thread (warp w, lane) loads 4 consecutive
+// pixels of the channels [8w, 8w+8) of the group with 8 x LDG.128 and leaves four 16-byte chunks in a shared tile whose
+// private layout (chunk slot = (chunk + pixel / 4) & 7) is conflict free for both sides; the way out applies the operand
+// swizzle, writes 128 contiguous bytes per pixel and the zero pad pixels next to the first / last pixel of a row.
+// grid: (B * G, chunk shares), block 256.  vec == 0 (T or the view not 16-byte aligned): scalar loads, same mapping.
+__global__ void __launch_bounds__(256, 3)
 gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, const float* __restrict__ gamma,
-                  const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, int G, int rpb, __half* __restrict__ a) {
-    constexpr int PXI = NH * 32;
-    const int Tp = x.T + 2, rows_total = x.F + 2 * PF;
-    const int nrb = (rows_total + rpb - 1) / rpb;     // row blocks per (clip, group)
-    int bid = blockIdx.x;
-    const int rb = bid % nrb; bid /= nrb;
-    const int g = bid % G, b = bid / G;
+                  const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, int G, int vec, uint32_t mg_T,
+                  __half* __restrict__ a) {
+    const int T = x.T, Tp = T + 2, rows_total = x.F + 2 * PF;
+    const int n_src = x.F * T;                        // source pixels of one channel plane
+    const int g = blockIdx.x % G, b = blockIdx.x / G;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ float s_scale[64];
     __shared__ float s_inv[8];
-    extern __shared__ __align__(16) uint8_t tile[];   // [PXI][128 B]
+    __shared__ __align__(16) uint8_t tile[128 * 128];   // [pixel][slot][16 B]
     // 1 / (unbiased std + eps) of the 8 statistics groups in double (8 threads), then the 64 per-channel scales of this group
     if (threadIdx.x < 8 && stats) {
         const double s1 = stats[((long long)b * 8 + threadIdx.x) * 2 + 0], s2 = stats[((long long)b * 8 + threadIdx.x) * 2 + 1];
@@ -573,56 +594,92 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
         s_scale[threadIdx.x] = sc;
     }
     __syncthreads();
-    float sc[8];
+    float cu[8], chh[8];                         // gelu: |scale| sqrt(log2(e) / 2) and 8 scale; otherwise chh = 16 scale
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sc[j] = s_scale[w * 8 + j];
+    for (int j = 0; j < 8; ++j) {
+        const float sj = s_scale[w * 8 + j];
+        cu[j] = fabsf(sj) * 0.84932180028801904272f;
+        chh[j] = gelu ? 8.f * sj : T2_A_SCALE * sj;
+    }
     const bool chok = g * 64 + w * 8 < x.C;      // C is a multiple of 8: a chunk is either all real or all padding
-    const int nseg = (Tp + PXI - 1) / PXI;
-    const int fr_end = min(rows_total, (rb + 1) * rpb);
-    for (int fr = rb * rpb; fr < fr_end; ++fr) {
-        const int f = fr - PF;
-        const bool rowok = f >= 0 && f < x.F;
-        const float* src = x.p + (long long)b * x.sb + (long long)(g * 64 + w * 8) * x.sc + (long long)(rowok ? f : 0) * x.T;
-        __half* dst_row = a + ((((long long)b * G + g) * rows_total + fr) * Tp) * 64;
-        const long long gp_row = (long long)fr * Tp;
-        for (int seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
-            const int tp0 = seg * PXI;
-            float v[NH][8];
-            // all loads of the iteration first: NH consecutive 128-byte lines of each of this warp's 8 channel planes
+    uint8_t* dst = reinterpret_cast<uint8_t*>(a + ((long long)b * G + g) * rows_total * Tp * 64);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    if (PF > 0) {                                // zero rows above and below the plane, shared by the blocks of the plane
+        uint4* top = reinterpret_cast<uint4*>(dst);
+        uint4* bot = reinterpret_cast<uint4*>(dst + (long long)(x.F + PF) * Tp * 128);
+        const int n16 = PF * Tp * 8;
+        for (int i = blockIdx.y * 256 + threadIdx.x; i < n16; i += gridDim.y * 256) { top[i] = zero4; bot[i] = zero4; }
+    }
+    const float* src = x.p + (long long)b * x.sb + (long long)(g * 64 + w * 8) * x.sc + 4 * lane;
+    const int nchunk = (n_src + 127) >> 7;
+    const int slot_w = ((w + lane) & 7) << 4;    // this thread's pixels are 4 lane + i: pixel / 4 == lane
+    const int cp = threadIdx.x & 7;              // way out: 16-byte position inside the 128-byte pixel row
+    uint8_t* dst_cp = dst + cp * 16;
+    for (int ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
+        const int s0 = ch << 7, st = s0 + 4 * lane;
+        float v[8][4];
+        if (chok) {
+            if (vec) {
+                const bool ld = st < n_src;      // n_src is a multiple of 4 here
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {
-                const int t = tp0 + h * 32 + lane - 1;
-                const bool ld = rowok && chok && t >= 0 && t < x.T;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[h][j] = ld ? __ldg(src + (long long)j * x.sc + t) : 0.f;
-            }
-#pragma unroll
-            for (int h = 0; h < NH; ++h) {
-                const int pl = h * 32 + lane, tp = tp0 + pl, t = tp - 1;
-                uint4 hv = make_uint4(0u, 0u, 0u, 0u);
-                if (rowok && chok && t >= 0 && t < x.T) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        v[h][j] *= sc[j];
-                        v[h][j] = gelu ? gelu16_tc2(v[h][j]) : v[h][j] * T2_A_SCALE;
-                    }
-                    hv = make_uint4(pack_half2_sat(v[h][0], v[h][1]), pack_half2_sat(v[h][2], v[h][3]), pack_half2_sat(v[h][4], v[h][5]),
-                                    pack_half2_sat(v[h][6], v[h][7]));
+                for (int j = 0; j < 8; ++j) {
+                    const float4 q = ld ? __ldg(reinterpret_cast<const float4*>(src + (long long)j * x.sc + s0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[j][0] = q.x; v[j][1] = q.y; v[j][2] = q.z; v[j][3] = q.w;
                 }
-                const int phase = (int)((gp_row + tp) & 7);
-                *reinterpret_cast<uint4*>(tile + pl * 128 + ((w ^ phase) << 4)) = hv;
-            }
-            __syncthreads();
-            const int npx = min(PXI, Tp - tp0);
+            } else {
 #pragma unroll
-            for (int k = 0; k < NH; ++k) {
-                const int idx = threadIdx.x + k * 256;        // 16-byte unit of the tile
-                if ((idx >> 3) < npx)
-                    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(dst_row + (long long)tp0 * 64) + idx * 16) =
-                        *reinterpret_cast<const uint4*>(tile + idx * 16);
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[j][i] = st + i < n_src ? __ldg(src + (long long)j * x.sc + s0 + i) : 0.f;
             }
-            __syncthreads();
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 hv = zero4;
+            if (chok) {
+                float r[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = gelu ? gelu16_tc2_folded(v[j][i], cu[j], chh[j]) : v[j][i] * chh[j];
+                hv = make_uint4(pack_half2_sat(r[0], r[1]), pack_half2_sat(r[2], r[3]), pack_half2_sat(r[4], r[5]), pack_half2_sat(r[6], r[7]));
+            }
+            *reinterpret_cast<uint4*>(tile + (4 * lane + i) * 128 + slot_w) = hv;
+        }
+        __syncthreads();
+        const int p0 = threadIdx.x >> 3;
+        if (T % 32 == 0) {
+            // the 32 pixels of a pass share a row; row / column of the first pass once, then incrementally (block-uniform)
+            const uint2 ft = fast_divmod((uint32_t)s0, (uint32_t)T, mg_T);
+            int tk = (int)ft.y, qk = ((int)ft.x + PF) * Tp + tk + 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (s0 + 32 * k < n_src) {                              // n_src is a multiple of 32: a pass is all in or all out
+                    const int p = p0 + 32 * k, q = qk + p0;
+                    const int c = cp ^ (q & 7);                         // the chunk that lives at position cp of that pixel row
+                    uint8_t* o = dst_cp + (long long)q * 128;
+                    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(tile + p * 128 + (((c + (p >> 2)) & 7) << 4));
+                    if (tk == 0 && p0 == 0) *reinterpret_cast<uint4*>(o - 128) = zero4;
+                    if (tk + 32 == T && p0 == 31) *reinterpret_cast<uint4*>(o + 128) = zero4;
+                }
+                tk += 32; qk += 32;
+                if (tk == T) { tk = 0; qk += 2; }                       // next row: two pad pixels in between
+            }
+        } else {
+            int p = p0;
+            const uint2 ft = fast_divmod((uint32_t)(s0 + p), (uint32_t)T, mg_T);
+            int t = (int)ft.y, q = ((int)ft.x + PF) * Tp + t + 1;      // column, flattened padded pixel index
+            for (int k = 0; k < 4; ++k) {
+                if (s0 + p < n_src) {
+                    const int c = cp ^ (q & 7);
+                    uint8_t* o = dst_cp + (long long)q * 128;
+                    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(tile + p * 128 + (((c + (p >> 2)) & 7) << 4));
+                    if (t == 0) *reinterpret_cast<uint4*>(o - 128) = zero4;
+                    if (t == T - 1) *reinterpret_cast<uint4*>(o + 128) = zero4;
+                }
+                p += 32; t += 32; q += 32;
+                while (t >= T) { t -= T; q += 2; }                      // next row: two pad pixels in between
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -690,27 +747,17 @@ size_t tc2_act_halves(int B, int C, int F, int T, int PF) { return (size_t)B * (
 void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
                        long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s) {
     const int rows_total = x.F + 2 * PF, Tp = x.T + 2, G = (x.C + 63) / 64;
-    static const int env_nh = getenv("AID_GN_NH") ? atoi(getenv("AID_GN_NH")) : 4;
-    // whole short rows in one iteration (T = 64 -> 96 pixels, T = 128 -> 160), otherwise 128 pixels per iteration
-    int nh = (Tp >= 256 && env_nh >= 8) ? 8 : (Tp >= 128 && env_nh >= 4 ? 4 : 2);
-    if (Tp > 64 && Tp <= 96) nh = 3;
-    else if (Tp > 128 && Tp <= 160) nh = 5;
-    const int nseg = (Tp + nh * 32 - 1) / (nh * 32);
-    // a block converts `rpb` whole rows when rows are short (amortises the per-block scale set-up), or a share of the
-    // segments of one long row; either way ~16 blocks per SM stay available
-    int rpb = 1;
-    while (rpb < 16 && rpb * Tp < 512 && (long long)x.B * G * ((rows_total + 2 * rpb - 1) / (2 * rpb)) >= 148 * 16) rpb <<= 1;
-    const long long rows = (long long)x.B * G * ((rows_total + rpb - 1) / rpb);
-    int ychunks = 1;
-    while (ychunks < nseg && rows * ychunks < 148 * 16) ychunks <<= 1;
-    ychunks = min(ychunks, nseg);
-    dim3 grid((unsigned)rows, ychunks);
-    const double npg = (double)n_per_group;
-    if (nh == 8) gn_act_tc2_kernel<8><<<grid, 256, 8 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, rpb, a);
-    else if (nh == 5) gn_act_tc2_kernel<5><<<grid, 256, 5 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, rpb, a);
-    else if (nh == 3) gn_act_tc2_kernel<3><<<grid, 256, 3 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, rpb, a);
-    else if (nh == 4) gn_act_tc2_kernel<4><<<grid, 256, 4 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, rpb, a);
-    else gn_act_tc2_kernel<2><<<grid, 256, 2 * 32 * 128, s>>>(x, stats, npg, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, rpb, a);
+    static const int env_bps = getenv("AID_GN_BPS") ? atoi(getenv("AID_GN_BPS")) : 16;
+    if ((long long)rows_total * Tp >= (1ll << 31) / 128)
+        throw CudaError(cudaErrorInvalidValue, "gn_act_tc2: plane too large for 32-bit pixel indices", __FILE__, __LINE__);
+    const int nchunk = (x.F * x.T + 127) / 128;
+    // 3 blocks per SM are resident; env_bps blocks per SM stride over the chunks of their plane (finer shares balance better)
+    const long long planes = (long long)x.B * G;
+    const int shares = (int)std::min<long long>(nchunk, std::max<long long>(1, (148ll * env_bps + planes - 1) / planes));
+    const int vec = (x.T % 4 == 0 && x.sb % 4 == 0 && x.sc % 4 == 0 && (reinterpret_cast<uintptr_t>(x.p) & 15) == 0) ? 1 : 0;
+    dim3 grid((unsigned)planes, shares);
+    gn_act_tc2_kernel<<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, vec,
+                                           div_magic((uint32_t)x.T), a);
     AID_COUNT_LAUNCH(1);
 }
 

@@ -106,3 +106,48 @@ def test_sampler_single_fp16_path_vs_reference_golden(aid, cuda):
     ei = rel_l2(xi, torch.from_numpy(g["small_sample_inpaint_T6"]))
     print(f"conv_mode 2 sampler trajectories vs reference golden: unconditional {eu:.3e}, inpainting {ei:.3e}")
     assert eu < 3e-3 and ei < 3e-3
+
+
+GAPS_MS = {25: 551, 50: 1102, 100: 2205, 300: 6615, 371: 8180, 743: 16383, 1486: 32766, 1500: 33075}
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_inpainting_gap_sweep_vs_oracle(aid, cuda, mode):
+    """BASELINE config 5 as a correctness sweep: the reference's gap lengths (inpainting_tester.yaml:71,75;
+    tester_inpainting.py:355-357) in samples at 22.05 kHz, centred like prepare_mask, three Heun steps (5 denoiser calls) on a
+    65536-sample clip.  Each gap is compared with the oracle sampler driving the oracle network on the same noise; outside
+    the gap and its 50-sample ramps the known samples must come back exactly."""
+    import unet_oracle
+    L = 65536
+    cfg = aid.small_test(L, conv_mode=mode)
+    sd = aid.random_state_dict(cfg, seed=1234)
+    net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+    net.load_state_dict(sd)
+    oracle = make_oracle(cfg, sd)
+    args = _tester_args(aid, T=3)
+    s = aid.Sampler(net, aid.EDM(args), args)
+    y = seeded((1, L), 7, 0.063)
+    tol = 1e-3 if mode == 0 else 3e-3           # 5 chained calls; the per-call bars are 1e-4 / 1e-3
+
+    def stream():
+        while True:
+            yield torch.randn(1, L)
+
+    worst = 0.0
+    for ms, gap in GAPS_MS.items():
+        mask = torch.ones(1, L)
+        a = L // 2 - gap // 2
+        mask[..., a:a + gap] = 0
+        torch.manual_seed(100 + ms)
+        got = s.predict_inpainting((y * mask).to(cuda), mask.to(cuda)).cpu()
+        torch.manual_seed(100 + ms)
+        want = unet_oracle.sample_oracle(oracle, unet_oracle.EDMOracle(), (1, L), stream(), nb_steps=3, y=y * mask,
+                                         mask_s=unet_oracle.smooth_mask(mask, 50))
+        e = rel_l2(got, want)
+        worst = max(worst, e)
+        assert e < tol, (ms, gap, e)
+        keep = torch.ones(L, dtype=torch.bool)
+        keep[a - 50:a + gap + 50] = False
+        assert torch.allclose(got[:, keep], y[:, keep], atol=1e-6), ms
+        assert got[:, a:a + gap].abs().max() > 0
+    print(f"conv_mode {mode}: worst gap-sweep rel-L2 vs oracle sampler {worst:.3e}")

@@ -45,7 +45,8 @@ def weight_layout_ref(w):
 
 
 @pytest.mark.parametrize("case", [(1, 16, 16, 3, 128, 1, 1, 0), (2, 64, 32, 5, 20, 5, 3, 4), (1, 96, 96, 4, 256, 5, 3, 0),
-                                   (1, 320, 512, 1, 64, 1, 1, 3), (1, 128, 256, 6, 64, 5, 3, 7)])
+                                   (1, 320, 512, 1, 64, 1, 1, 3), (1, 128, 256, 6, 64, 5, 3, 7),
+                                   (2, 80, 16, 7, 10, 1, 1, 2), (1, 64, 64, 40, 4, 5, 3, 9), (1, 16, 16, 5, 300, 1, 1, 0)])
 def test_tc2_operand_layouts(cuda, case):
     B, Ci, Co, Fd, T, KF, KT, PF = case
     L = _lib()
