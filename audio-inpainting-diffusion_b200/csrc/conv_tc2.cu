@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         };
         // per-thread statistics of the current clip: (sum, sumsq) of the 4 groups this warp's columns cover
         float S0 = 0.f, S1 = 0.f, S2 = 0.f, S3 = 0.f, Q0 = 0.f, Q1 = 0.f, Q2 = 0.f, Q3 = 0.f;
-        int b_cur = -1, gk = 0, gpos = 0;
+        int b_cur = -1, nt_cur = 0, gk = 0, gpos = 0;
         auto flush_stats = [&]() {
             if (do_stats && b_cur >= 0) {
                 float v[8] = {S0, Q0, S1, Q1, S2, Q2, S3, Q3};
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
                 }
                 if (lane == 0) {
-                    const int g0 = cbeg / gcn;
+                    const int g0 = (nt_cur * p.Ntile + cbeg) / gcn;
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         if (g0 + (k >> 1) < 8) atomicAdd(p.stats + (long long)b_cur * 16 + (g0 + (k >> 1)) * 2 + (k & 1), (double)v[k]);
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
             if (c_ui == 0 && c_c0 == 0) { mbar_wait(tmem_full + c_ab, c_aphase); tc_fence_after(); }
             if (c_c0 == 0) {
                 gk = 0; gpos = 0;
-                if (c_b != b_cur) { flush_stats(); b_cur = c_b; }
+                if (c_b != b_cur || c_nt != nt_cur) { flush_stats(); b_cur = c_b; nt_cur = c_nt; }
                 const int gkey = p.gate_bstride ? c_b * p.n_ntiles + c_nt : c_nt;
                 if (gkey != gate_key) {
                     gate_key = gkey;
@@ -477,7 +477,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
 }
 
 // ---- operand preparation ---------------------------------------------------------------------------------
-static int tc2_ntile(int Cout) { return Cout <= 256 ? Cout : 256; }
+// Couts per tile.  256-wide tiles fill TMEM with one accumulator (2 units x 256 columns), so their epilogue cannot overlap the
+// next tile's MMAs; multi-tap convolutions with 256 couts run as two 128-wide n-tiles with double-buffered accumulators
+// instead (AID_TC2_SPLIT256=0 restores the single tile).  1x1 convolutions are HBM bound and keep the widest tile.
+static int tc2_ntile(int Cout, int taps) {
+    static const int split256 = getenv("AID_TC2_SPLIT256") ? atoi(getenv("AID_TC2_SPLIT256")) : 1;
+    if (Cout == 256 && taps > 1 && split256) return 128;
+    return Cout <= 256 ? Cout : 256;
+}
 
 size_t tc2_weight_halves(int Cout, int Cin, int KF, int KT) { return (size_t)Cout * KF * KT * ((Cin + 63) / 64) * 64; }
 
@@ -504,7 +511,7 @@ __global__ void pack_weight_tc2_kernel(const float* __restrict__ w, __half* __re
 
 void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s) {
     const long long total = (long long)tc2_weight_halves(Cout, Cin, KF, KT);
-    pack_weight_tc2_kernel<<<(int)min((long long)8192, (total + 255) / 256), 256, 0, s>>>(w, wp, Cout, tc2_ntile(Cout), Cin, KF, KT);
+    pack_weight_tc2_kernel<<<(int)min((long long)8192, (total + 255) / 256), 256, 0, s>>>(w, wp, Cout, tc2_ntile(Cout, KF * KT), Cin, KF, KT);
     AID_COUNT_LAUNCH(1);
 }
 
@@ -788,7 +795,7 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     Tc2Args p{};
     p.a = a; p.w = wp; p.out = out; p.R = ep.R; p.gate = ep.gate; p.gate_bstride = ep.gate_bstride;
     p.alpha = ep.alpha; p.stats = ep.stats; p.out_cl = ep.out_cl ? 1 : 0; p.r_cl = ep.R_cl ? 1 : 0;
-    p.B = B; p.Cin = Cin; p.G = (Cin + 63) / 64; p.Ntot = out.C; p.Ntile = tc2_ntile(out.C); p.n_ntiles = out.C / p.Ntile;
+    p.B = B; p.Cin = Cin; p.G = (Cin + 63) / 64; p.Ntot = out.C; p.Ntile = tc2_ntile(out.C, KF * KT); p.n_ntiles = out.C / p.Ntile;
     p.F = F; p.T = T; p.Tp = T + 2; p.dil = dil;
     p.KF = KF; p.KT = KT; p.kt_shift = (KT == 1) ? 1 : 0;
     p.PF = PF; p.rows_total = F + 2 * PF;
@@ -820,7 +827,9 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     if (p.nB < 2) throw CudaError(cudaErrorInvalidValue, "conv_tc2: shared memory budget", __FILE__, __LINE__);
     p.ncol_stride = p.Ntile <= 64 ? 64 : (p.Ntile <= 128 ? 128 : 256);
     p.acc_bufs = (p.ncol_stride <= 128 || p.pair) ? 2 : 1;
-    if (ep.stats && p.n_ntiles != 1) throw CudaError(cudaErrorInvalidValue, "conv_tc2: statistics need a single n-tile", __FILE__, __LINE__);
+    // an epilogue warp owns Ntile / 2 columns: they must be whole statistics groups, at most four of them
+    if (ep.stats && p.n_ntiles != 1 && ((p.Ntile / 2) % (p.Ntot / 8) != 0 || p.Ntile / 2 > 4 * (p.Ntot / 8)))
+        throw CudaError(cudaErrorInvalidValue, "conv_tc2: statistics groups do not align with the n-tiles", __FILE__, __LINE__);
     const size_t smem = 1024 + (size_t)p.nA * p.a_slot_bytes + (size_t)p.nB * p.b_slot_bytes + 256 + T2_EPI_WARPS * 128 * sizeof(float);
     static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
     p.dbg = dbg;

@@ -38,6 +38,7 @@ TC_1x1_CASES = [
     (2, 320, 512, 1, 64, False),      # qk-like: [B, 8F, 1, T] -> 2 n-tiles of 256
     (1, 512, 768, 1, 256, False),     # 3 n-tiles, 2 units per pair
     (1, 16, 16, 3, 8, True),          # smallest
+    (1, 64, 256, 6, 128, True),       # 256-wide tile (single accumulator buffer) with statistics
 ]
 
 

@@ -33,7 +33,8 @@ def act_layout_ref(x, PF):
 
 def weight_layout_ref(w):
     Co, Ci, KF, KT = w.shape
-    G, Nt = (Ci + 63) // 64, min(Co, 256)
+    G = (Ci + 63) // 64
+    Nt = 128 if (Co == 256 and KF * KT > 1) else min(Co, 256)   # multi-tap 256-cout layers run as two 128-wide n-tiles
     ws = (w.numpy() * 1024).astype(np.float16)
     out = np.zeros((Co // Nt, KF, G, KT, Nt, 8, 8), dtype=np.float16)
     for n in range(Co):
