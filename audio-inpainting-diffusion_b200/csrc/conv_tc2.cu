@@ -46,6 +46,7 @@ struct Tc2Args {
     uint32_t mg_pairs, mg_upb, mg_Tp, mg_tt, mg_F;   // division magics (fast_divmod) of n_pairs, units_per_b, Tp, tiles_t, F
     int pair;           // 1: the two units of a tile live in the two CTAs of a cluster that share the weight ring by multicast
     int a_slot_bytes;   // activation ring slot: 2 unit windows, or 1 in pair mode
+    int nt_minor;       // 1: tile = 2 * pair + n-tile (two n-tiles), else tile = n-tile * n_pairs + pair
     int out_cl, r_cl;   // 1: that tensor is channels-last [B][F][T][C] (C = its TV's channel count), else NCHW
     int dbg;  // AID_TC_DEBUG bits (tuning only): 1 skip epilogue body, 2 skip MMAs, 4 skip A loads, 8 skip B loads
 };
@@ -79,6 +80,13 @@ __device__ __forceinline__ Unit2 unit2_info(const Tc2Args& p, int u) {
         i.win_start = f * p.Tp + t0;
     }
     return i;
+}
+
+// tile -> (n-tile, unit pair).  nt_minor (two n-tiles): neighbouring CTAs work on the two n-tiles of the same unit pair at the
+// same time, so the second read of the activation windows hits L2, and with an even grid a CTA keeps one half of the weights.
+__device__ __forceinline__ uint2 tile_decode(const Tc2Args& p, int tile) {
+    if (p.nt_minor) return make_uint2((uint32_t)tile & 1u, (uint32_t)tile >> 1);
+    return fast_divmod((uint32_t)tile, (uint32_t)p.n_pairs, p.mg_pairs);
 }
 
 __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         int slot = 0; uint32_t phase = 0;
         const size_t gstride = (size_t)p.rows_total * p.Tp * 64;   // halves per (clip, group) plane
         for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
-            const int pair = (int)fast_divmod((uint32_t)tile, (uint32_t)p.n_pairs, p.mg_pairs).y;
+            const int pair = (int)tile_decode(p, tile).y;
             const Unit2 u0 = unit2_info(p, 2 * pair + uown), u1 = unit2_info(p, 2 * pair + upeer);
             for (int kf = 0; kf < p.KF; ++kf) {
                 const int foff = (kf - p.KF / 2) * p.dil;
@@ -158,7 +166,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         int slot = 0; uint32_t phase = 0;
         const size_t kt_halves = (size_t)p.Ntile * 64;
         for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
-            const uint2 tdm = fast_divmod((uint32_t)tile, (uint32_t)p.n_pairs, p.mg_pairs);
+            const uint2 tdm = tile_decode(p, tile);
             const int pair = (int)tdm.y, nt = (int)tdm.x;
             const Unit2 u0 = unit2_info(p, 2 * pair + uown), u1 = unit2_info(p, 2 * pair + upeer);
             for (int kf = 0; kf < p.KF; ++kf) {
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
         const uint32_t kt_bytes = (uint32_t)p.Ntile * 128u;
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int ab = 0; uint32_t aphase = 0;
         for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
-            const int pair = (int)fast_divmod((uint32_t)tile, (uint32_t)p.n_pairs, p.mg_pairs).y;
+            const int pair = (int)tile_decode(p, tile).y;
             const Unit2 u0 = unit2_info(p, 2 * pair + uown), u1 = unit2_info(p, 2 * pair + upeer);
             mbar_wait(tmem_empty + ab, aphase ^ 1);
             tc_fence_after();
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
             if (!n_valid) return;
             if (it_c0 == 0) {
                 uint32_t pair = (uint32_t)it_tile; u_nt = 0;
-                if (p.n_ntiles > 1) { const uint2 dm = fast_divmod((uint32_t)it_tile, (uint32_t)p.n_pairs, p.mg_pairs); u_nt = (int)dm.x; pair = dm.y; }
+                if (p.n_ntiles > 1) { const uint2 dm = tile_decode(p, it_tile); u_nt = (int)dm.x; pair = dm.y; }
                 u_has1 = !p.pair && 2 * (int)pair + 1 < p.n_units;
                 const int co0 = u_nt * p.Ntile + cbeg;
                 Unit2 u = unit2_info(p, 2 * (int)pair + (p.pair ? uown : it_ui));
@@ -805,6 +813,8 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     p.n_units = B * p.units_per_b;
     p.n_pairs = (p.n_units + 1) / 2;
     p.n_tiles = p.n_pairs * p.n_ntiles;
+    static const int env_ntm = getenv("AID_TC2_NT_MINOR") ? atoi(getenv("AID_TC2_NT_MINOR")) : 1;
+    p.nt_minor = (p.n_ntiles == 2 && env_ntm) ? 1 : 0;
     p.mg_pairs = div_magic(p.n_pairs); p.mg_upb = div_magic(p.units_per_b); p.mg_Tp = div_magic(p.Tp); p.mg_tt = div_magic(p.tiles_t); p.mg_F = div_magic(p.F);
     static const int env_ktb = getenv("AID_TC2_KTB") ? atoi(getenv("AID_TC2_KTB")) : 0;
     static const int env_nA = getenv("AID_TC2_NA") ? atoi(getenv("AID_TC2_NA")) : 3;
