@@ -39,14 +39,15 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms.  The process is started before the warm-up (its start-up takes
+    a few hundred ms); only the samples that arrive between mark_start() and mark_end() -- the timed region -- are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -55,7 +56,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.monotonic()
+
+    def mark_end(self):
+        self.t1 = time.monotonic()
 
     def stop(self):
         if self.proc is None:
@@ -67,7 +74,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in list(self.rows):
+            if (self.t0 is not None and ts < self.t0) or (self.t1 is not None and ts > self.t1):
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -171,19 +180,23 @@ def main():
     def step():
         net.denoise_fused(x, cn, out=out)
 
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
     lib.aid_profile(net._handle, 1)
     launches0 = lib.aid_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if clocks:
+        clocks.mark_start()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    if clocks:
+        clocks.mark_end()
     ms = e0.elapsed_time(e1) / args.steps
     launches = lib.aid_launch_count() - launches0
     n_l, t_ms, fl, by = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
