@@ -44,6 +44,7 @@ _SIGS = {
     "aid_cqt_workspace_bytes": (C.c_int, [_P, C.c_int, C.POINTER(C.c_size_t)]),
     "aid_edm_add_noise": (C.c_int, [_P, _P, C.c_float, C.c_int64, _P]),
     "aid_edm_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_int, _P, _P, _P, _P, _P]),
+    "aid_spectral_mask": (C.c_int, [_P, _P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, _P]),
     "aid_op_conv2d": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 _P, _P, _P, C.c_float, C.c_float, _P, _P, C.c_int, _P]),
     "aid_op_groupnorm_act": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

@@ -91,6 +91,9 @@ void launch_conv_tc(const __half* a_hi, const __half* a_lo, int PF, const __half
 size_t tc2_weight_halves(int Cout, int Cin, int KF, int KT);
 size_t tc2_act_halves(int B, int C, int F, int T, int PF);
 void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s);
+// stft.cu: out = y ? y + x - S(x) : S(x), S = crop(istft(mask * stft(zero-pad(x))))  (sampler.py:271-290, 361); frames: [B][n_frames][n_fft] scratch
+void launch_spectral_mask(const float* x, const float* y, const float* mask, int B, int L, int n_fft, int hop, int n_frames,
+                          float* frames, float* out, cudaStream_t s);
 void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
                        long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s);
 void launch_to_planar_tc2(const TV& x, int PF, __half* a, cudaStream_t s);

@@ -905,6 +905,21 @@ int aid_edm_step(const float* xin, const float* xhat, const float* y, const floa
     return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
 }
 
+int aid_spectral_mask(const float* x, const float* y, const float* mask, int B, int64_t L, int n_fft, int hop, int n_frames, float* frames,
+                      size_t frames_bytes, float* out, void* stream) {
+    if (!x || !mask || !frames || !out || B <= 0 || L <= 0 || L > (1ll << 30) || n_fft < 4 || n_fft > 4096 || (n_fft & (n_fft - 1)) != 0 ||
+        hop <= 0 || hop > n_fft)
+        return AID_ERR_INVALID;
+    const int64_t Lp = L + (n_fft - L % n_fft);
+    if (n_frames != 1 + Lp / hop || frames_bytes < (size_t)B * n_frames * n_fft * sizeof(float)) return AID_ERR_INVALID;
+    try {
+        launch_spectral_mask(x, y, mask, B, (int)L, n_fft, hop, n_frames, frames, out, (cudaStream_t)stream);
+    } catch (const CudaError&) {
+        return AID_ERR_CUDA;
+    }
+    return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
 // ---- single-operator entry points -----------------------------------------------------------------------
 static int op_conv2d_impl(const float* a_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
                           const float* gate_dev, const float* R_dev, const float* R2_dev, float alpha, float beta, float* out_dev,

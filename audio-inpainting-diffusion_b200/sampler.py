@@ -14,6 +14,9 @@ Differences that are deliberate and documented:
   * Reconstruction guidance (xi > 0, sampler.py:57-113) needs autograd through the denoiser and crashes for
     batch > 1 in the reference itself; it raises NotImplementedError here.  Use xi = 0 (replacement method).
   * `prepare_smooth_mask` is vectorised (the reference loops over L samples in Python, sampler.py:311-324).
+  * Spectrogram inpainting (sampler.py:271-290, 348-364): on CUDA tensors the STFT -> mask -> inverse STFT degradation and the
+    projection `y + x - S(x)` are hand-written kernels (csrc/stft.cu, aid_spectral_mask); on CPU tensors (host-logic tests
+    only) the reference's torch.stft / torch.istft calls are used.
 """
 import torch
 
@@ -41,6 +44,8 @@ class Sampler:
         self.noise_source = None  # optional iterator of pre-drawn N(0,1) tensors (prior first), for parity tests
         self.y = self.mask = self.degradation = None
         self._smooth_mask = None
+        self._spectral = False      # True while the projection is the spectrogram one (predict_spectrogram_inpainting)
+        self._frames = None         # scratch of the CUDA STFT, reused across evaluations
 
     def update_diff_params(self):
         """sampler.py:43-53"""
@@ -64,6 +69,44 @@ class Sampler:
         if mask is None:
             mask = self.mask
         return mask * x
+
+    def _stft_params(self):
+        st = "tester.spectrogram_inpainting.stft."
+        if cfg_get(self.args, st + "window") != "hann":
+            raise NotImplementedError("Only hann window is implemented for now")     # sampler.py:276
+        n_fft, hop, win = (int(cfg_get(self.args, st + k)) for k in ("n_fft", "hop_length", "win_length"))
+        return n_fft, hop, win
+
+    def apply_spectral_mask(self, x, y=None):
+        """sampler.py:271-290: S(x) = crop(istft(mask * stft(zero-pad(x)))) with self.mask [n_fft/2+1, frames].
+        With `y` the projection of the spectrogram mode, y + x - S(x) (sampler.py:361), comes out of the same kernel."""
+        n_fft, hop, win = self._stft_params()
+        L = x.shape[-1]
+        if not x.is_cuda:
+            window = torch.hann_window(win).to(x.device)
+            xp = torch.nn.functional.pad(x, (0, n_fft - L % n_fft), mode="constant", value=0)
+            X = torch.stft(xp, n_fft, hop, win, window, return_complex=True) * self.mask.unsqueeze(0)
+            s = torch.istft(X, n_fft, hop, win, window, return_complex=False)[..., 0:L]
+            return s if y is None else y + x - s
+        if win != n_fft:
+            raise NotImplementedError("the CUDA STFT needs win_length == n_fft (the reference's configuration: 1024 / 1024)")
+        shape = x.shape
+        x2 = x.reshape(-1, L).contiguous().float()
+        B = x2.shape[0]
+        n_frames = 1 + (L + n_fft - L % n_fft) // hop
+        mask = self.mask.to(x.device, torch.float32).contiguous()
+        if tuple(mask.shape) != (n_fft // 2 + 1, n_frames):
+            raise ValueError(f"spectral mask has shape {tuple(mask.shape)}, the STFT of this input has {(n_fft // 2 + 1, n_frames)}")
+        need = B * n_frames * n_fft
+        if self._frames is None or self._frames.numel() < need or self._frames.device != x.device:
+            self._frames = torch.empty(need, device=x.device, dtype=torch.float32)
+        y2 = None if y is None else y.reshape(-1, L).contiguous().float()
+        out = torch.empty_like(x2)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().aid_spectral_mask(_lib.ptr(x2), _lib.ptr(y2), _lib.ptr(mask), B, L, n_fft, hop, n_frames,
+                                                    _lib.ptr(self._frames), self._frames.numel() * 4, _lib.ptr(out),
+                                                    torch.cuda.current_stream(x.device).cuda_stream))
+        return out.reshape(shape)
 
     def prepare_smooth_mask(self, mask, size=10):
         """sampler.py:302-325: half-Hann ramps of `size` samples around every gap of mask[0], broadcast to B rows."""
@@ -105,12 +148,14 @@ class Sampler:
         self.y = None
         self.degradation = None
         self._smooth_mask = None
+        self._spectral = False
         return self.predict(shape, device)
 
     def predict_resample(self, y, shape, degradation):
         """sampler.py:164-173"""
         self.degradation = degradation
         self.y = y
+        self._spectral = False
         return self.predict(shape, y.device)
 
     def predict_inpainting(self, y_masked, mask):
@@ -119,6 +164,7 @@ class Sampler:
         self.y = y_masked
         self.degradation = lambda x: self.apply_mask(x)
         self._smooth_mask = None
+        self._spectral = False
         if self.data_consistency or self.data_consistency_end:
             if self.smooth:
                 smooth_mask = self.prepare_smooth_mask(mask, cfg_get(self.args, "tester.data_consistency.hann_size"))
@@ -130,7 +176,16 @@ class Sampler:
         return self.predict(self.y.shape, self.y.device)
 
     def predict_spectrogram_inpainting(self, y_masked, mask):
-        raise NotImplementedError("spectrogram inpainting (sampler.py:348-364) is a 'next' row of SURVEY.md section 8f")
+        """sampler.py:348-364: mask is the real [n_fft/2+1, frames] spectrogram mask, y_masked = apply_spectral_mask(y)."""
+        self.mask = mask.to(y_masked.device)
+        self.y = y_masked
+        self.degradation = lambda x: self.apply_spectral_mask(x)
+        self._smooth_mask = None
+        self._spectral = False
+        if self.data_consistency or self.data_consistency_end:
+            self._spectral = True
+            self.proj_convex_set = lambda x: self.apply_spectral_mask(x, self.y)     # y + x - S(x)
+        return self.predict(self.y.shape, self.y.device)
 
     # ---- the hot loop ---------------------------------------------------------------------------------
     def predict(self, shape, device):
@@ -150,7 +205,7 @@ class Sampler:
         if conditional and not use_proj and not hasattr(self, "proj_convex_set"):
             raise AttributeError("'Sampler' object has no attribute 'proj_convex_set'")  # sampler.py:145 with consistency off
         hpf = (not conditional) and bool(cfg_get(self.args, "tester.filter_out_cqt_DC_Nyq"))
-        fused = dev.type == "cuda" and hasattr(self.model, "denoise_fused") and (not conditional or self._smooth_mask is not None)
+        fused = dev.type == "cuda" and hasattr(self.model, "denoise_fused") and (not conditional or self._smooth_mask is not None or self._spectral)
         ops = _CudaOps(self, dev) if fused else _TorchOps(self)
 
         for i in range(self.nb_steps):
@@ -211,6 +266,7 @@ class _CudaOps:
         self.s, self.dev = s, dev
         self.L = _lib.lib()
         self.mask = None
+        self.y = None
         if s._smooth_mask is not None and s.y is not None:  # the projection closes over the y it was built with
             m = s._smooth_mask
             m = m[0] if (m.dim() == 2 and (m.stride(0) == 0 or m.shape[0] == 1)) else m
@@ -240,6 +296,8 @@ class _CudaOps:
         d_out = torch.empty_like(xin) if mode == 0 else None
         mask = self.mask if conditional else None
         y = self.y if conditional else None
+        if conditional and self.s._spectral:      # xhat <- y + xhat - S(xhat) (stft.cu), then the plain step
+            xhat, mask, y = self.s.apply_spectral_mask(xhat, self.s.y), None, None
         with torch.cuda.device(self.dev):
             _lib.check(self.L.aid_edm_step(_lib.ptr(xin), _lib.ptr(xhat), _lib.ptr(y), _lib.ptr(mask),
                                            0 if mask is None else mask.numel(), xin.numel(), float(sigma), float(h), mode,

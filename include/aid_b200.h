@@ -98,6 +98,14 @@ int aid_edm_step(const float* xin_dev, const float* xhat_dev, const float* y_dev
                  int64_t n, float sigma, float h, int mode, const float* d_prev_dev, const float* xbase_dev,
                  float* d_out_dev, float* x_out_dev, void* stream);
 
+/* Spectrogram-inpainting degradation S(x) = crop(istft(mask * stft(zero-pad(x)))) with a periodic Hann window of n_fft samples,
+ * centre = True / reflect padding, as Sampler.apply_spectral_mask does with torch.stft / torch.istft   sampler.py:271-290
+ * y_dev == NULL: out = S(x);  else out = y + x - S(x), the projection of the spectrogram mode          sampler.py:361
+ * mask_dev: float [n_fft/2 + 1][n_frames], n_frames = 1 + (L + n_fft - L % n_fft) / hop;  n_fft a power of two <= 4096;
+ * frames_dev: scratch of B * n_frames * n_fft floats.  x, y, out: [B, L]; out may alias neither x nor y. */
+int aid_spectral_mask(const float* x_dev, const float* y_dev, const float* mask_dev, int B, int64_t L, int n_fft, int hop,
+                      int n_frames, float* frames_dev, size_t frames_bytes, float* out_dev, void* stream);
+
 /* ---- single-operator entry points (unit parity tests; same kernels the forward uses) ---------------- */
 /* F.conv2d(a[B,Cin,F,T], w[Cout,Cin,KF,KT], padding="same", dilation=(dil,1)) with the fused epilogue
  * out = alpha*(conv*gate[c] + R) + beta*R2; gate/R/R2 may be NULL.  stats_dev (may be NULL): [B][8][2] doubles

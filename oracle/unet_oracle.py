@@ -216,8 +216,26 @@ def smooth_mask(mask, size):
     return new.unsqueeze(0).expand(mask.shape[0], -1)
 
 
-def sample_oracle(net, edm, shape, noises, nb_steps=35, order=2, y=None, mask_s=None, hpf=None):
+def spectral_mask(x, mask, n_fft=1024, hop=256, win_length=1024):
+    """sampler.py:271-290 (= tester_inpainting.py:298-322): zero-pad to a multiple of n_fft (a whole n_fft when it already is
+    one), torch.stft with a periodic Hann window (centre = True, reflect), multiply by the real [n_fft/2+1, frames] mask,
+    torch.istft, crop to the input length."""
+    window = torch.hann_window(win_length)
+    L = x.shape[-1]
+    xp = F.pad(x, (0, n_fft - L % n_fft), mode="constant", value=0)
+    X = torch.stft(xp, n_fft, hop, win_length, window, return_complex=True)
+    X = X * mask.unsqueeze(0)
+    return torch.istft(X, n_fft, hop, win_length, window, return_complex=False)[..., 0:L]
+
+
+def spectral_projection(y, mask, **stft):
+    """sampler.py:361: proj_convex_set of the spectrogram-inpainting mode, x -> y + x - S(x)."""
+    return lambda x: y + x - spectral_mask(x, mask, **stft)
+
+
+def sample_oracle(net, edm, shape, noises, nb_steps=35, order=2, y=None, mask_s=None, hpf=None, project=None):
     """sampler.py:178-262 with the xi=0 replacement branch (141-147) or the unconditional branch (116-125).
+    `project` (a callable) replaces the time-domain projection `mask_s*y + (1-mask_s)*x` by another proj_convex_set.
 
     `noises` is an iterator of pre-drawn standard normal tensors consumed in the reference's order:
     first the prior (edm.py:94), then one per stochastic step (sampler.py:212).
@@ -229,7 +247,9 @@ def sample_oracle(net, edm, shape, noises, nb_steps=35, order=2, y=None, mask_s=
 
     def score(x, ti):
         xh = edm.denoiser(x, net, ti.reshape(1, 1))
-        if y is not None:
+        if project is not None:
+            xh = project(xh)
+        elif y is not None:
             xh = mask_s * y + (1 - mask_s) * xh
         elif hpf is not None:
             xh = hpf(xh)

@@ -34,6 +34,8 @@ TESTER = {
         "T": 35, "order": 2, "filter_out_cqt_DC_Nyq": True,
         "posterior_sampling": {"xi": 0, "norm": 2, "smoothl1_beta": 1},
         "data_consistency": {"use": True, "type": "always", "smooth": True, "hann_size": 50},
+        "spectrogram_inpainting": {"stft": {"window": "hann", "n_fft": 1024, "hop_length": 256, "win_length": 1024},
+                                   "time_mask_length": 2000, "time_start_idx": "None", "min_masked_freq": 300, "max_masked_freq": 2000},
         "diff_params": {"same_as_training": False, "sigma_data": 0.063, "sigma_min": 1e-4, "sigma_max": 1, "P_mean": -1.2,
                         "P_std": 1.2, "ro": 13, "ro_train": 13, "Schurn": 10, "Snoise": 1.0, "Stmin": 0, "Stmax": 50},
     },

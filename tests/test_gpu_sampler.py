@@ -151,3 +151,76 @@ def test_inpainting_gap_sweep_vs_oracle(aid, cuda, mode):
         assert torch.allclose(got[:, keep], y[:, keep], atol=1e-6), ms
         assert got[:, a:a + gap].abs().max() > 0
     print(f"conv_mode {mode}: worst gap-sweep rel-L2 vs oracle sampler {worst:.3e}")
+
+
+@pytest.mark.parametrize("name", ["ragged", "multiple", "small_random"])
+def test_spectral_mask_kernels_vs_reference_golden(aid, cuda, name):
+    """csrc/stft.cu through aid_spectral_mask against the output of the reference's own Sampler.apply_spectral_mask
+    (tests/golden/golden_spectral.npz): the degradation S(x) and the projection y + x - S(x).  fp32 FFTs: 1e-5."""
+    from util import spectral_case
+    x, mask, n_fft, hop = spectral_case(name)
+    want = torch.from_numpy(np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_spectral.npz"))[name])
+    args = _tester_args(aid)
+    args["tester"]["spectrogram_inpainting"]["stft"].update({"n_fft": n_fft, "hop_length": hop, "win_length": n_fft})
+    s = aid.Sampler(torch.nn.Identity(), aid.EDM(args), args)
+    s.mask = mask.to(cuda)
+    got = s.apply_spectral_mask(x.to(cuda))
+    assert got.is_cuda and got.shape == x.shape
+    assert rel_l2(got, want) < 1e-5
+    y = seeded(tuple(x.shape), 12, 0.063)
+    proj = s.apply_spectral_mask(x.to(cuda), y.to(cuda))
+    assert rel_l2(proj, y + x - want) < 1e-5
+    with pytest.raises(ValueError, match="spectral mask"):
+        s.mask = mask[:, :-1].to(cuda)
+        s.apply_spectral_mask(x.to(cuda))
+
+
+def test_spectral_mask_full_size_vs_oracle(aid, cuda):
+    """BASELINE-size clips (4 x 262144, the reference's 1024 / 256 STFT and its 2 s x 300-2000 Hz mask) against the oracle."""
+    import unet_oracle
+    from util import spectral_mask_rect
+    L = 262144
+    x = seeded((4, L), 3, 0.063)
+    mask = spectral_mask_rect(L)
+    args = _tester_args(aid)
+    s = aid.Sampler(torch.nn.Identity(), aid.EDM(args), args)
+    s.mask = mask.to(cuda)
+    got = s.apply_spectral_mask(x.to(cuda))
+    want = unet_oracle.spectral_mask(x, mask)
+    assert rel_l2(got, want) < 1e-5
+    assert rel_l2(x.to(cuda) - got, x - want) < 1e-4        # the removed band itself (small difference of large numbers)
+    ones = torch.ones_like(mask).to(cuda)                    # an all-pass mask reconstructs the input
+    s.mask = ones
+    assert rel_l2(s.apply_spectral_mask(x.to(cuda)), x) < 1e-5
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_spectrogram_inpainting_sampler_vs_oracle(aid, cuda, mode):
+    """predict_spectrogram_inpainting (sampler.py:348-364) on the CUDA path -- fused denoiser, STFT projection kernels, fused
+    step -- against the oracle sampler driving the oracle network with the same noise: 3 Heun steps, 65536-sample clips."""
+    import unet_oracle
+    from util import spectral_mask_rect
+    L = 65536
+    cfg = aid.small_test(L, conv_mode=mode)
+    sd = aid.random_state_dict(cfg, seed=1234)
+    net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+    net.load_state_dict(sd)
+    oracle = make_oracle(cfg, sd)
+    args = _tester_args(aid, T=3)
+    s = aid.Sampler(net, aid.EDM(args), args)
+    y = seeded((2, L), 7, 0.063)
+    mask = spectral_mask_rect(L, gap_ms=500)
+    y_masked = unet_oracle.spectral_mask(y, mask)
+
+    def stream():
+        while True:
+            yield torch.randn(2, L)
+
+    torch.manual_seed(77)
+    got = s.predict_spectrogram_inpainting(y_masked.to(cuda), mask.to(cuda))
+    torch.manual_seed(77)
+    want = unet_oracle.sample_oracle(oracle, unet_oracle.EDMOracle(), (2, L), stream(), nb_steps=3, y=y_masked,
+                                     project=unet_oracle.spectral_projection(y_masked, mask))
+    e = rel_l2(got, want)
+    print(f"conv_mode {mode}: spectrogram-inpainting trajectory vs oracle {e:.3e}")
+    assert got.is_cuda and e < (1e-3 if mode == 0 else 3e-3)

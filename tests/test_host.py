@@ -131,6 +131,9 @@ def _tester_args(aid, T=35, order=2):
     a = aid.AttrDict.wrap({
         "tester": {"T": T, "order": order, "filter_out_cqt_DC_Nyq": True, "posterior_sampling": {"xi": 0, "norm": 2, "smoothl1_beta": 1},
                    "data_consistency": {"use": True, "type": "always", "smooth": True, "hann_size": 50},
+                   "spectrogram_inpainting": {"stft": {"window": "hann", "n_fft": 1024, "hop_length": 256, "win_length": 1024},
+                                              "time_mask_length": 2000, "time_start_idx": "None", "min_masked_freq": 300,
+                                              "max_masked_freq": 2000},
                    "diff_params": {"same_as_training": False, "sigma_data": 0.063, "sigma_min": 1e-4, "sigma_max": 1, "ro": 13,
                                    "Schurn": 10, "Snoise": 1.0, "Stmin": 0, "Stmax": 50}},
         "diff_params": {"sigma_data": 0.063, "sigma_min": 1e-5, "sigma_max": 10, "ro": 13, "Schurn": 5, "Snoise": 1, "Stmin": 0, "Stmax": 50},
@@ -197,3 +200,42 @@ def test_smooth_mask_matches_the_reference_loop(aid):
                 new[i:i + size] = hann[:size]
         prev = m[i]
     assert torch.equal(s.prepare_smooth_mask(mask, size), new.unsqueeze(0).expand(2, -1))
+
+
+def test_spectrogram_inpainting_host_logic(aid):
+    """sampler.py:271-290, 348-364 on CPU tensors: the degradation equals the reference's golden output bit for bit, and the
+    sampling loop with the projection y + x - S(x) equals the oracle loop."""
+    import numpy as np
+    import unet_oracle
+    from util import spectral_case, spectral_mask_rect
+    args = _tester_args(aid, T=5)
+    s = aid.Sampler(_FakeNet(), aid.EDM(args), args)
+    x, mask, n_fft, hop = spectral_case("ragged")
+    s.mask = mask
+    want = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "golden_spectral.npz"))["ragged"])
+    assert torch.equal(s.apply_spectral_mask(x), want)
+    L = 8192
+    y = seeded((2, L), 2, 0.063)
+    m = spectral_mask_rect(L, gap_ms=100)
+    s.mask = m
+    y_masked = s.apply_spectral_mask(y)
+
+    def stream(shape):
+        while True:
+            yield torch.randn(shape)
+
+    torch.manual_seed(21)
+    got = s.predict_spectrogram_inpainting(y_masked, m)
+    torch.manual_seed(21)
+    want = unet_oracle.sample_oracle(_FakeNet(), unet_oracle.EDMOracle(), (2, L), stream((2, L)), nb_steps=5, y=y_masked,
+                                     project=unet_oracle.spectral_projection(y_masked, m))
+    assert rel_l2(got, want) < 1e-6
+    # (no consistency property is asserted: masking an STFT is not idempotent, S(S(x)) != S(x), so y + x - S(x) is not an
+    #  exact projection -- the reference's own comment at sampler.py:361 says as much)
+    # another mode afterwards does not inherit the spectral projection
+    tm = torch.ones(1, L); tm[..., 4000:4300] = 0
+    torch.manual_seed(22)
+    a = s.predict_inpainting(y * tm, tm)
+    torch.manual_seed(22)
+    b = aid.Sampler(_FakeNet(), aid.EDM(args), args).predict_inpainting(y * tm, tm)
+    assert torch.equal(a, b)

@@ -137,3 +137,48 @@ def test_resampler_oracle_facts():
     imp[..., 8] = 1
     d = unet_oracle.down_t(imp)[0, 0, 0]
     assert torch.allclose(d[2:6], torch.tensor([-0.01171875, 0.11328125, 0.43359375, -0.03515625]), atol=1e-7)
+
+
+def _stft_kernel_definition(x, mask, n_fft, hop):
+    """What csrc/stft.cu computes, stated with numpy FFTs (frame grid, reflect / zero-extension indices, mask on both halves of
+    the full spectrum, synthesis window, gather overlap-add with the squared-window envelope)."""
+    import numpy as np
+    B, L = x.shape
+    N = n_fft
+    Lp = L + (N - L % N)
+    n_frames = 1 + Lp // hop
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(N) / N)
+    xs = x.numpy().astype(np.float64)
+    frames = np.zeros((B, n_frames, N))
+    kk = np.minimum(np.arange(N), N - np.arange(N))
+    for t in range(n_frames):
+        i = t * hop - N // 2 + np.arange(N)
+        i = np.where(i < 0, -i, np.where(i >= Lp, 2 * (Lp - 1) - i, i))
+        v = np.where(i < L, xs[:, np.minimum(i, L - 1)], 0.0)
+        X = np.fft.fft(w * v, axis=-1) * mask.numpy()[kk, t]
+        frames[:, t] = w * np.fft.ifft(X, axis=-1).real
+    out = np.zeros((B, L))
+    for n in range(L):
+        p = n + N // 2
+        t_lo = (p - N) // hop + 1 if p >= N else 0
+        t_hi = min(p // hop, n_frames - 1)
+        ts = np.arange(t_lo, t_hi + 1)
+        j = p - ts * hop
+        out[:, n] = frames[:, ts, j].sum(-1) / (w[j] ** 2).sum()
+    return torch.from_numpy(out).float()
+
+
+@pytest.mark.parametrize("name", ["ragged", "multiple", "small_random"])
+def test_spectral_mask_oracle_and_kernel_definition_match_reference_golden(name):
+    """oracle.spectral_mask (sampler.py:271-290 restated with the same torch calls) is bit-identical to what the reference's own
+    Sampler.apply_spectral_mask produced (tests/golden/make_golden_spectral.py); the formula the CUDA kernels implement agrees
+    with it to fp32 rounding."""
+    import numpy as np
+    import unet_oracle
+    from util import spectral_case
+    x, mask, n_fft, hop = spectral_case(name)
+    want = torch.from_numpy(np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_spectral.npz"))[name])
+    got = unet_oracle.spectral_mask(x, mask, n_fft, hop, n_fft)
+    assert torch.equal(got, want)
+    if name != "ragged":                      # the per-sample python loop: keep the CPU suite short
+        assert rel_l2(_stft_kernel_definition(x, mask, n_fft, hop), want) < 1e-6

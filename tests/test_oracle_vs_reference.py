@@ -97,3 +97,25 @@ def test_reference_checkpoint_loader_works_on_our_module(aid, ref):
     net2 = aid.Unet_CQT_oct_with_attention(cfg.to_args(), "cpu")
     assert t_utils.load_state_dict({"ema": bad, "network": bad}, network=net2, ema=net2, log=False) is True
     assert torch.equal(net2.state_dict()["middle.0.1.qk.weight" if False else "middle.0.1.attn_block.qk.weight"], sd["middle.0.1.attn_block.qk.weight"])
+
+
+def test_spectrogram_inpainting_mirror_equals_reference_sampler(aid, ref):
+    """predict_spectrogram_inpainting / apply_spectral_mask (sampler.py:271-290, 348-364), CPU tensors, same fake denoiser."""
+    from test_host import _FakeNet
+    from util import spectral_mask_rect
+    _, RefEDM, RefSampler = ref
+    cfg = aid.small_test(16384)
+    args = _args(aid, cfg, 6)
+    net = _FakeNet()
+    L = 8192
+    y = seeded((2, L), 2, 0.063)
+    m = spectral_mask_rect(L, gap_ms=100)
+    rs, s = RefSampler(net, RefEDM(args), args), aid.Sampler(net, aid.EDM(args), args)
+    rs.mask = s.mask = m
+    ym = rs.apply_spectral_mask(y)
+    assert torch.equal(s.apply_spectral_mask(y), ym)
+    torch.manual_seed(8)
+    want = rs.predict_spectrogram_inpainting(ym, m)
+    torch.manual_seed(8)
+    got = s.predict_spectrogram_inpainting(ym, m)
+    assert torch.equal(got, want)
