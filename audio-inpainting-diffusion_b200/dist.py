@@ -78,6 +78,18 @@ class ShardedSampler:
             self.sampler.noise_source = None
         return gather_clips(x, B, self.group)
 
+    def predict_spectrogram_inpainting(self, y_masked, mask):
+        """y_masked [B, L] (the whole batch, identical on every rank), mask [n_fft/2+1, frames] shared by all clips."""
+        rank, world = self._rank_world()
+        B, L = y_masked.shape
+        lo, hi = shard_bounds(B, rank, world)
+        self.sampler.noise_source = ClipNoise(self.seed, lo, hi, L)
+        try:
+            x = self.sampler.predict_spectrogram_inpainting(y_masked[lo:hi], mask) if hi > lo else y_masked[lo:hi]
+        finally:
+            self.sampler.noise_source = None
+        return gather_clips(x, B, self.group)
+
     def predict_unconditional(self, shape, device):
         rank, world = self._rank_world()
         B, L = shape

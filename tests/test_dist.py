@@ -10,6 +10,13 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _spectral_inputs(sampler, y):
+    from util import spectral_mask_rect
+    smask = spectral_mask_rect(y.shape[-1], gap_ms=30)
+    sampler.mask = smask
+    return smask, sampler.apply_spectral_mask(y)
+
+
 def _worker(rank, world, port, ret):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -25,12 +32,14 @@ def _worker(rank, world, port, ret):
     mask[..., 900:1100] = 0
     s = ShardedSampler(aid_b200.Sampler(_FakeNet(), aid_b200.EDM(args), args), seed=7)
     out = s.predict_inpainting(y * mask, mask)
+    smask, ym = _spectral_inputs(s.sampler, y)
+    out_s = s.predict_spectrogram_inpainting(ym, smask)
     lo, hi = shard_bounds(B, rank, world)
     g = gather_clips(torch.full((hi - lo, 4), float(rank)), B)
     if rank == 0:
-        ret["out"], ret["g"] = out, g
+        ret["out"], ret["g"], ret["out_s"] = out, g, out_s
     else:
-        ret["out1"] = out
+        ret["out1"], ret["out_s1"] = out, out_s
     dist.destroy_process_group()
 
 
@@ -54,3 +63,8 @@ def test_sharded_sampling_is_independent_of_world_size(aid):
     mask[..., 900:1100] = 0
     out1 = ShardedSampler(aid.Sampler(_FakeNet(), aid.EDM(args), args), seed=7).predict_inpainting(y * mask, mask)
     assert out1.shape == (B, L) and torch.equal(out1, out2)
+    # spectrogram mode: shared [513, frames] mask, clips sharded the same way
+    assert torch.equal(ret["out_s"], ret["out_s1"])
+    sh = ShardedSampler(aid.Sampler(_FakeNet(), aid.EDM(args), args), seed=7)
+    smask, ym = _spectral_inputs(sh.sampler, y)
+    assert torch.equal(sh.predict_spectrogram_inpainting(ym, smask), ret["out_s"])
