@@ -13,6 +13,8 @@
 //     four 16-channel k-steps of a group advance it by 32 bytes.  (conv_tc.cu needs eight 2 KB copies for the same data.)
 //   * weights in HBM     : [n-tile][kf][G][kt][Ntile][64] fp16 (x 2^10), chunks swizzled by (n & 7): one copy per
 //     (kf, group, kt-chunk).
+//   * couts per tile: min(Cout, 256), except multi-tap layers with 256 couts, which run as two 128-wide n-tiles so that the
+//     accumulators stay double buffered (tc2_ntile); tiles are numbered n-tile-minor then.
 //   * two producer warps (activations, weights) with their own rings, so a stage costs one wait + one expect + 1-2 copies;
 //   * epilogue: 8 warps, each thread owns one pixel and walks its warp's column range 32 columns at a time with all 32
 //     residual loads in flight before the accumulator is read (the old 8-column batches left the LSU latency bound).

@@ -11,4 +11,4 @@ for B, Cn, Fd, T in [(8, 64, 64, 4096), (8, 96, 128, 2048), (8, 96, 192, 1024), 
     pf = 0 if T % 128 == 0 else 8
     _lib.check(L.aid_debug_time_gn_tc2(_lib.ptr(x), B, Cn, Fd, T, pf, 10, C.byref(ms)))
     gb = B * Cn * Fd * T * 6 / 1e9
-    print(f"nh {os.environ.get('AID_GN_NH', '8')} B{B} C{Cn} F{Fd} T{T}: {ms.value:7.3f} ms  {gb / ms.value * 1e3:7.0f} GB/s (4 B read + 2 B written per element)", flush=True)
+    print(f"bps {os.environ.get('AID_GN_BPS', '16')} B{B} C{Cn} F{Fd} T{T}: {ms.value:7.3f} ms  {gb / ms.value * 1e3:7.0f} GB/s (4 B read + 2 B written per element)", flush=True)
