@@ -26,6 +26,10 @@ if os.environ.get("TC_SHAPES"):   # "B,C,F,T,dil;B,C,F,T,dil;..."  (5x3 layers)
         B, Cn, Fd, T, dil = (int(v) for v in sh.split(","))
         run(B, Cn, Cn, Fd, T, 5, dil, useR=os.environ.get('NOR') is None)
     sys.exit(0)
+if which == "thin":   # the 2 -> N pyramid convolutions (5x3) of the seven levels, CUDA-core thin-channel kernel (mode 0)
+    for B, Co, Fd, T in [(8, 64, 64, 4096), (8, 96, 128, 2048), (8, 96, 192, 1024), (8, 128, 256, 512), (8, 128, 320, 256), (8, 256, 384, 128), (8, 256, 448, 64)]:
+        run(B, 2, Co, Fd, T, 5, 1)
+    sys.exit(0)
 if which in ("all", "5x3"):
     for B, Cn, Fd, T, dil in shapes:
         run(B, Cn, Cn, Fd, T, 5, dil)
