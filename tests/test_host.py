@@ -239,3 +239,22 @@ def test_spectrogram_inpainting_host_logic(aid):
     torch.manual_seed(22)
     b = aid.Sampler(_FakeNet(), aid.EDM(args), args).predict_inpainting(y * tm, tm)
     assert torch.equal(a, b)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver runs it next to our arm): one JSON line with the contract's keys, produced by the
+    CPU oracle without touching CUDA; under torchrun only rank 0 prints, the other ranks exit 0 without work."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--len", "16384", "--steps", "1", "--warmup", "0"]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["gpu_launches"] == 0 and line["config"]["audio_len"] == 16384
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=600)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
