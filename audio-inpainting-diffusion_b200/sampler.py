@@ -11,8 +11,11 @@ Differences that are deliberate and documented:
   * On CUDA tensors each step's element-wise work is one fused kernel (aid_edm_step) and the denoiser call is the
     fused EDM-preconditioned forward; on CPU tensors (only reachable with a non-product denoiser, e.g. the
     host-logic tests) the same updates are written with torch ops in the reference's order.
-  * Reconstruction guidance (xi > 0, sampler.py:57-113) needs autograd through the denoiser and crashes for
-    batch > 1 in the reference itself; it raises NotImplementedError here.  Use xi = 0 (replacement method).
+  * Reconstruction guidance (xi > 0, sampler.py:55-113) needs the denoiser's vector-Jacobian product.  The branch is
+    mirrored for any denoiser torch can differentiate (host logic, torch ops); the CUDA denoiser of this package is
+    forward-only, so with it xi > 0 raises NotImplementedError -- use xi = 0 (replacement method) there.  The reference
+    itself fails for batch > 1 (autograd.grad of a vector norm, sampler.py:78): here the per-clip norms are summed and the
+    step size is normalised per clip, which is the reference's arithmetic at batch 1.
   * `prepare_smooth_mask` is vectorised (the reference loops over L samples in Python, sampler.py:311-324).
   * Spectrogram inpainting (sampler.py:271-290, 348-364): on CUDA tensors the STFT -> mask -> inverse STFT degradation and the
     projection `y + x - S(x)` are hand-written kernels (csrc/stft.cu, aid_spectral_mask); on CPU tensors (host-logic tests
@@ -134,13 +137,50 @@ class Sampler:
                     x_hat = self.model.CQTransform.apply_hpf_DC(x_hat)
                 return (x_hat - x) / t_i ** 2
         if self.xi > 0:
-            raise NotImplementedError(
-                "reconstruction guidance (xi > 0) needs the denoiser's VJP, which this forward-only path does not "
-                "provide (the reference's own implementation fails for batch > 1, sampler.py:78); set xi = 0")
+            return self.get_score_rec_guidance(x, y, t_i, degradation)
         with torch.no_grad():
             x_hat = self.diff_params.denoiser(x, self.model, t_i.unsqueeze(-1))
             x_hat = self.proj_convex_set(x_hat.detach())
             return (x_hat.detach() - x) / t_i ** 2
+
+    def _refuse_guidance_on_forward_only_model(self):
+        if hasattr(self.model, "denoise_fused"):
+            raise NotImplementedError(
+                "reconstruction guidance (xi > 0) needs the denoiser's VJP, which this forward-only CUDA denoiser does not "
+                "provide; set tester.posterior_sampling.xi = 0 (replacement method)")
+
+    def get_score_rec_guidance(self, x, y, t_i, degradation):
+        """sampler.py:55-113: denoise with autograd on, measure ||y - degradation(x_hat)||, step x_hat against its gradient
+        w.r.t. x with size t_i * xi / (rms of the gradient), then the optional projection."""
+        self._refuse_guidance_on_forward_only_model()
+        x = x.detach().requires_grad_()
+        with torch.enable_grad():
+            x_hat = self.diff_params.denoiser(x, self.model, t_i.unsqueeze(-1))
+            if cfg_get(self.args, "tester.filter_out_cqt_DC_Nyq"):
+                x_hat = self.model.CQTransform.apply_hpf_DC(x_hat)
+            den_rec = degradation(x_hat)
+            dim = (1, 2) if y.dim() == 3 else 1
+            kind = cfg_get(self.args, "tester.posterior_sampling.norm")
+            if kind == "smoothl1":
+                norm = torch.nn.functional.smooth_l1_loss(y, den_rec, reduction="sum",
+                                                          beta=cfg_get(self.args, "tester.posterior_sampling.smoothl1_beta"))
+            else:
+                norm = torch.linalg.norm(y - den_rec, dim=dim, ord=kind)
+            rec_grads = torch.autograd.grad(outputs=norm.sum(), inputs=x)[0]     # clips are independent: per-clip gradients
+        audio_len = cfg_get(self.args, "exp.audio_len")
+        gdim = tuple(range(1, rec_grads.dim()))
+        normguide = torch.linalg.norm(rec_grads.reshape(rec_grads.shape[0], -1), dim=1).reshape((-1,) + (1,) * len(gdim)) / audio_len ** 0.5
+        s = t_i * self.xi / (normguide + 1e-6)
+        x_hat = x_hat.detach()
+        x_hat_old = x_hat.clone() if self.rid else None
+        x_hat = x_hat - s * rec_grads
+        x_hat_old_2 = x_hat.clone() if self.rid else None
+        if self.data_consistency:
+            x_hat = self.proj_convex_set(x_hat.detach())
+        score = (x_hat.detach() - x.detach()) / t_i ** 2
+        if self.rid:
+            return score, x_hat_old, s * rec_grads, x_hat_old_2, x_hat
+        return score
 
     # ---- entry points ---------------------------------------------------------------------------------
     def predict_unconditional(self, shape, device):
@@ -190,6 +230,9 @@ class Sampler:
     # ---- the hot loop ---------------------------------------------------------------------------------
     def predict(self, shape, device):
         """sampler.py:178-262: stochastic 2nd-order EDM sampler; 69 denoiser evaluations for T = 35."""
+        conditional = self.y is not None
+        if conditional and self.xi > 0:
+            return self._predict_guided(shape, device)
         if self.rid:
             raise NotImplementedError("rid=True logging is only defined on the guidance branch of the reference")
         dp = self.diff_params
@@ -198,9 +241,6 @@ class Sampler:
         t = dp.create_schedule(self.nb_steps)        # host, fp32
         gamma = dp.get_gamma(t)
         x = self._randn(shape, dev) * t[0].to(dev)
-        conditional = self.y is not None
-        if conditional and self.xi > 0:
-            self.get_score(x, self.y, t[0], self.degradation)  # raises
         use_proj = conditional and self.data_consistency
         if conditional and not use_proj and not hasattr(self, "proj_convex_set"):
             raise AttributeError("'Sampler' object has no attribute 'proj_convex_set'")  # sampler.py:145 with consistency off
@@ -227,6 +267,48 @@ class Sampler:
                 x = x_next
         if self.data_consistency_end:
             x = self.proj_convex_set(x)
+        return x.detach()
+
+
+    def _predict_guided(self, shape, device):
+        """sampler.py:178-262 on the guidance branch (xi > 0): the reference's loop with torch ops, scores from get_score."""
+        self._refuse_guidance_on_forward_only_model()
+        dp = self.diff_params
+        shape = tuple(shape)
+        dev = torch.device(device)
+        n = self.nb_steps
+        if self.rid:
+            rid_xt, rid_grads, rid_denoised, rid_grad_update, rid_pocs, rid_xt2 = (torch.zeros((n,) + shape[:2]) for _ in range(6))
+        t = dp.create_schedule(n).to(dev)
+        x = self._randn(shape, dev) * t[0]
+        gamma = dp.get_gamma(t).to(dev)
+        for i in range(n):
+            if gamma[i] == 0:
+                t_hat = t[i]
+            else:
+                t_hat = t[i] + gamma[i] * t[i]
+                x = x + ((t_hat ** 2 - t[i] ** 2) ** (1 / 2)) * (self._randn(shape, dev) * dp.Snoise)
+            if self.rid:
+                rid_xt[i] = x
+            score = self.get_score(x, self.y, t_hat, self.degradation)
+            if self.rid:
+                score, rid_denoised[i], rid_grads[i], rid_grad_update[i], rid_pocs[i] = score
+            d = -t_hat * score
+            h = t[i + 1] - t_hat
+            if t[i + 1] != 0 and self.order == 2:
+                score = self.get_score(x + h * d, self.y, t[i + 1], self.degradation)
+                if self.rid:
+                    score = score[0]
+                x = x + h * ((1 / 2) * d + (1 / 2) * (-t[i + 1] * score))
+            else:
+                x = x + h * d
+            if self.rid:
+                rid_xt2[i] = x
+        if self.data_consistency_end:
+            x = self.proj_convex_set(x)
+        if self.rid:
+            return (x.detach(), rid_denoised.detach(), rid_grads.detach(), rid_grad_update.detach(), rid_pocs.detach(),
+                    rid_xt.detach(), rid_xt2.detach(), t.detach())
         return x.detach()
 
 

@@ -233,9 +233,25 @@ def spectral_projection(y, mask, **stft):
     return lambda x: y + x - spectral_mask(x, mask, **stft)
 
 
-def sample_oracle(net, edm, shape, noises, nb_steps=35, order=2, y=None, mask_s=None, hpf=None, project=None):
+def guided_estimate(net, edm, x, ti, y, degradation, xi, audio_len, norm_ord=2, hpf=None):
+    """sampler.py:55-95 (reconstruction guidance, batch 1 as in the reference -- its autograd.grad call needs a scalar):
+    x_hat - s * d||y - degradation(x_hat)|| / dx with s = t_i * xi / (||grad|| / sqrt(audio_len) + 1e-6)."""
+    x = x.detach().requires_grad_()
+    with torch.enable_grad():
+        xh = edm.denoiser(x, net, ti.reshape(1, 1))
+        if hpf is not None:
+            xh = hpf(xh)
+        norm = torch.linalg.norm(y - degradation(xh), dim=1, ord=norm_ord)
+        g = torch.autograd.grad(outputs=norm, inputs=x)[0]
+    s = ti * xi / (torch.linalg.norm(g) / audio_len ** 0.5 + 1e-6)
+    return xh.detach() - s * g
+
+
+def sample_oracle(net, edm, shape, noises, nb_steps=35, order=2, y=None, mask_s=None, hpf=None, project=None, guidance=None):
     """sampler.py:178-262 with the xi=0 replacement branch (141-147) or the unconditional branch (116-125).
     `project` (a callable) replaces the time-domain projection `mask_s*y + (1-mask_s)*x` by another proj_convex_set.
+    `guidance` = dict(xi, degradation, audio_len[, norm_ord]) selects the xi > 0 branch (sampler.py:133-135, 55-113): the
+    guided estimate first, then the projection if one is given (data_consistency).
 
     `noises` is an iterator of pre-drawn standard normal tensors consumed in the reference's order:
     first the prior (edm.py:94), then one per stochastic step (sampler.py:212).
@@ -246,6 +262,14 @@ def sample_oracle(net, edm, shape, noises, nb_steps=35, order=2, y=None, mask_s=
     x = next(noises) * t[0]
 
     def score(x, ti):
+        if guidance is not None:
+            xh = guided_estimate(net, edm, x, ti, y, guidance["degradation"], guidance["xi"], guidance["audio_len"],
+                                 guidance.get("norm_ord", 2), hpf)
+            if project is not None:
+                xh = project(xh)
+            elif mask_s is not None:
+                xh = mask_s * y + (1 - mask_s) * xh
+            return (xh - x) / ti ** 2
         xh = edm.denoiser(x, net, ti.reshape(1, 1))
         if project is not None:
             xh = project(xh)

@@ -137,6 +137,7 @@ def _tester_args(aid, T=35, order=2):
                    "diff_params": {"same_as_training": False, "sigma_data": 0.063, "sigma_min": 1e-4, "sigma_max": 1, "ro": 13,
                                    "Schurn": 10, "Snoise": 1.0, "Stmin": 0, "Stmax": 50}},
         "diff_params": {"sigma_data": 0.063, "sigma_min": 1e-5, "sigma_max": 10, "ro": 13, "Schurn": 5, "Snoise": 1, "Stmin": 0, "Stmax": 50},
+        "exp": {"audio_len": 8192, "sample_rate": 22050},
     })
     return a
 
@@ -174,12 +175,63 @@ def test_sampler_host_logic_against_oracle(aid):
     assert rel_l2(got_u, want_u) < 1e-6
 
 
-def test_sampler_guidance_is_refused(aid):
+def test_sampler_guidance_is_refused_on_the_forward_only_denoiser(aid):
+    """xi > 0 needs the denoiser's VJP: a model exposing the CUDA path's `denoise_fused` is refused before any work."""
+    class ForwardOnly(_FakeNet):
+        def denoise_fused(self, *a, **k):
+            raise AssertionError("must not be reached")
+
     args = _tester_args(aid)
     args["tester"]["posterior_sampling"]["xi"] = 0.25
-    s = aid.Sampler(_FakeNet(), aid.EDM(args), args)
+    s = aid.Sampler(ForwardOnly(), aid.EDM(args), args)
     with pytest.raises(NotImplementedError, match="xi"):
         s.predict_inpainting(torch.zeros(1, 4096), torch.ones(1, 4096))
+
+
+@pytest.mark.parametrize("consistency", [True, False])
+def test_sampler_guidance_host_logic(aid, consistency):
+    """sampler.py:55-113 with a differentiable stand-in denoiser: equals the oracle loop at batch 1 (the reference's only
+    working batch size); at batch 2 every clip gets what it gets alone (per-clip norm and step size)."""
+    import unet_oracle
+    L = 8192
+    args = _tester_args(aid, T=6)
+    args["tester"]["posterior_sampling"]["xi"] = 0.25
+    args["tester"]["data_consistency"]["use"] = consistency
+    net = _FakeNet()
+    y = seeded((2, L), 1, 0.063)
+    mask = torch.ones(1, L)
+    mask[..., 4000:4600] = 0
+    outs = []
+    for b in range(2):
+        yb = y[b:b + 1] * mask
+
+        def stream():
+            g = torch.Generator().manual_seed(50 + b)
+            while True:
+                yield torch.randn(1, L, generator=g)
+
+        s = aid.Sampler(net, aid.EDM(args), args)
+        s.noise_source = stream()
+        got = s.predict_inpainting(yb, mask)
+        want = unet_oracle.sample_oracle(net, unet_oracle.EDMOracle(), (1, L), stream(), nb_steps=6, y=yb,
+                                         mask_s=unet_oracle.smooth_mask(mask, 50) if consistency else None,
+                                         hpf=net.CQTransform.apply_hpf_DC,       # filter_out_cqt_DC_Nyq acts on this branch (sampler.py:62)
+                                         guidance={"xi": 0.25, "degradation": lambda x: mask * x, "audio_len": 8192})
+        assert rel_l2(got, want) < 1e-5
+        outs.append(got)
+
+    def both():
+        gens = [torch.Generator().manual_seed(50 + b) for b in range(2)]
+        while True:
+            yield torch.cat([torch.randn(1, L, generator=g) for g in gens])
+
+    s = aid.Sampler(net, aid.EDM(args), args)
+    s.noise_source = both()
+    got2 = s.predict_inpainting(y * mask, mask)
+    assert rel_l2(got2, torch.cat(outs)) < 1e-5
+    s.rid, s.noise_source = True, both()
+    rid = s.predict_inpainting(y * mask, mask)
+    assert len(rid) == 8 and torch.equal(rid[0], got2) and rid[1].shape == (6, 2, L) and rid[7].shape == (7,)
 
 
 def test_smooth_mask_matches_the_reference_loop(aid):

@@ -119,3 +119,31 @@ def test_spectrogram_inpainting_mirror_equals_reference_sampler(aid, ref):
     torch.manual_seed(8)
     got = s.predict_spectrogram_inpainting(ym, m)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("consistency", [True, False])
+def test_guidance_branch_mirror_equals_reference_sampler(aid, ref, consistency):
+    """xi = 0.25 (sampler.py:55-113), batch 1 -- the only batch size the reference's autograd.grad call accepts -- with and
+    without the projection, plus the rid=True diagnostics."""
+    from test_host import _FakeNet
+    _, RefEDM, RefSampler = ref
+    cfg = aid.small_test(16384)
+    args = _args(aid, cfg, 6)
+    args["tester"]["posterior_sampling"]["xi"] = 0.25
+    args["tester"]["data_consistency"]["use"] = consistency
+    net = _FakeNet()
+    L = 4096
+    y = seeded((1, L), 1, 0.063)
+    mask = torch.ones(1, L)
+    mask[..., 1000:1400] = 0
+    for rid in (False, True):
+        torch.manual_seed(5)
+        want = RefSampler(net, RefEDM(args), args, rid).predict_inpainting(y * mask, mask)
+        torch.manual_seed(5)
+        got = aid.Sampler(net, aid.EDM(args), args, rid).predict_inpainting(y * mask, mask)
+        if rid:
+            assert len(got) == len(want) == 8
+            for g, w in zip(got, want):
+                assert rel_l2(g, w) < 1e-6
+        else:
+            assert rel_l2(got, want) < 1e-6
