@@ -9,6 +9,7 @@ from .config import NetConfig, AttrDict, paper_22k, small_test
 from .unet import Unet_CQT_oct_with_attention, random_state_dict, schema_from_lib
 from .edm import EDM
 from .sampler import Sampler
+from .masks import prepare_mask, prepare_spectral_mask
 
 __all__ = ["NetConfig", "AttrDict", "paper_22k", "small_test", "Unet_CQT_oct_with_attention", "random_state_dict",
-           "schema_from_lib", "EDM", "Sampler"]
+           "schema_from_lib", "EDM", "Sampler", "prepare_mask", "prepare_spectral_mask"]

@@ -310,3 +310,30 @@ def test_bench_reference_arm_contract():
     assert line["e2e"] == {"value": line["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     r1 = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=600)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_mask_builders(aid):
+    """tester_inpainting.py:231-296 restated: centred / placed long gap, random short gaps, the spectrogram rectangle."""
+    from util import spectral_mask_rect
+    a = _tester_args(aid)
+    a["exp"] = aid.AttrDict.wrap({"audio_len": 65536, "sample_rate": 22050})
+    a["tester"]["inpainting"] = aid.AttrDict.wrap({"mask_mode": "long", "long": {"gap_length": 300, "start_gap_idx": "None"},
+                                                   "short": {"num_gaps": 4, "gap_length": 25, "start_gap_idx": "None"}})
+    m = aid.prepare_mask(a)
+    assert m.shape == (1, 65536) and int((m == 0).sum()) == 6615 and m[0, 32768 - 3307] == 0 and m[0, 32768 - 3308] == 1
+    a["tester"]["inpainting"]["long"]["start_gap_idx"] = 100
+    assert int(torch.nonzero(aid.prepare_mask(a)[0] == 0)[0]) == 2205
+    a["tester"]["inpainting"]["mask_mode"] = "short"
+    torch.manual_seed(3)
+    ms = aid.prepare_mask(a)
+    torch.manual_seed(3)
+    starts = torch.randint(0, 65536 - 551, (4,))
+    want = torch.ones(1, 65536)
+    for st in starts:
+        want[..., st:st + 551] = 0
+    assert torch.equal(ms, want)
+    sm = aid.prepare_spectral_mask(a)
+    assert torch.equal(sm, spectral_mask_rect(65536)) and sm.shape == (513, 1 + (65536 + 1024) // 256)
+    s = aid.Sampler(_FakeNet(), aid.EDM(a), a)      # the mask fits the sampler's STFT of a clip of that length
+    s.mask = sm
+    assert s.apply_spectral_mask(torch.zeros(1, 65536)).shape == (1, 65536)

@@ -147,3 +147,36 @@ def test_guidance_branch_mirror_equals_reference_sampler(aid, ref, consistency):
                 assert rel_l2(g, w) < 1e-6
         else:
             assert rel_l2(got, want) < 1e-6
+
+
+def test_mask_builders_equal_the_reference_tester(aid, ref):
+    """prepare_mask / prepare_spectral_mask against testing.tester_inpainting.Tester's methods, called unbound on a namespace
+    that carries what they read (args, device)."""
+    import importlib
+    import types
+    from unittest import mock
+    Tester = None
+    for _ in range(30):     # the tester imports plotting / logging packages that are not installed here: stub what is missing
+        try:
+            Tester = importlib.import_module("testing.tester_inpainting").Tester
+            break
+        except ModuleNotFoundError as e:
+            sys.modules[e.name] = mock.MagicMock()
+    assert Tester is not None
+    for L in (65536, 184184):
+        a = _args(aid, aid.small_test(16384), 6)
+        a["exp"]["audio_len"] = L
+        a["tester"]["inpainting"] = aid.AttrDict.wrap({"mask_mode": "long", "long": {"gap_length": 1500, "start_gap_idx": "None"},
+                                                       "short": {"num_gaps": 4, "gap_length": 25, "start_gap_idx": "None"}})
+        ns = types.SimpleNamespace(args=a, device="cpu")
+        assert torch.equal(aid.prepare_mask(a), Tester.prepare_mask(ns))
+        a["tester"]["inpainting"]["long"]["start_gap_idx"] = 250
+        assert torch.equal(aid.prepare_mask(a), Tester.prepare_mask(ns))
+        a["tester"]["inpainting"]["mask_mode"] = "short"
+        torch.manual_seed(1)
+        want = Tester.prepare_mask(ns)
+        torch.manual_seed(1)
+        assert torch.equal(aid.prepare_mask(a), want)
+        assert torch.equal(aid.prepare_spectral_mask(a), Tester.prepare_spectral_mask(ns))
+        a["tester"]["spectrogram_inpainting"]["time_start_idx"] = 1000
+        assert torch.equal(aid.prepare_spectral_mask(a), Tester.prepare_spectral_mask(ns))
