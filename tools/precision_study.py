@@ -11,6 +11,8 @@ Schemes (a = activation operand, w = weight; h() = round to fp16, b() = bf16, q(
     f16x3   a_hi*w_hi + a_lo*w_hi + a_hi*w_lo              3 MMAs   (current conv_mode 1)
     f16+f8  a_hi*w_hi + q(a_lo)*q(w) + q(a)*q(w_lo)        1 fp16 + 2 fp8 MMAs = 2 fp16-equivalents
     bf16x1  b(a)*b(w)
+A second table measures the GELU of the operand pass: f16x1 with the exact erf replaced by the Abramowitz-Stegun rational
+approximations 7.1.26 (5 coefficients, what gn_act_tc2_kernel evaluates) and 7.1.25 (3 coefficients, 2 FMAs fewer per element).
 """
 import os
 import sys
@@ -73,6 +75,21 @@ def make_conv(scheme):
     return conv
 
 
+def gelu_as(order):
+    """x * Phi(x) with erf from A&S 7.1.26 (order 5) or 7.1.25 (order 3), evaluated in fp32 like the kernel does."""
+    def g(v):
+        ax = v.abs() * 0.7071067811865476
+        if order == 5:
+            t = 1.0 / (1.0 + 0.3275911 * ax)
+            pl = ((((1.061405429 * t - 1.453152027) * t + 1.421413741) * t - 0.284496736) * t + 0.254829592) * t
+        else:
+            t = 1.0 / (1.0 + 0.47047 * ax)
+            pl = ((0.7478556 * t - 0.0958798) * t + 0.3480242) * t
+        erf_abs = 1.0 - pl * torch.exp(-ax * ax)
+        return 0.5 * v * (1.0 + torch.sign(v) * erf_abs)
+    return g
+
+
 def main():
     L = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     test_mode = bool(int(sys.argv[2])) if len(sys.argv) > 2 else True
@@ -91,6 +108,16 @@ def main():
             unet_oracle.conv = make_conv(scheme)
             out = orc(cin * x, cn)
             print(f"L={L} test_mode={int(test_mode)} sigma={sigma:<5} {scheme:7s} rel-L2 = {rel_l2(out, ref):.3e}", flush=True)
+        orig_gelu = F.gelu
+        try:
+            for scheme in ("fp32", "f16x1"):       # the approximation alone, then together with the operand rounding
+                unet_oracle.conv = make_conv(scheme)
+                for name, order in (("A&S 7.1.26", 5), ("A&S 7.1.25", 3)):
+                    unet_oracle.F.gelu = lambda v, _g=gelu_as(order): _g(v)
+                    out = orc(cin * x, cn)
+                    print(f"L={L} test_mode={int(test_mode)} sigma={sigma:<5} {scheme:7s} + GELU {name} rel-L2 = {rel_l2(out, ref):.3e}", flush=True)
+        finally:
+            unet_oracle.F.gelu = orig_gelu
     unet_oracle.conv = orig
 
 
