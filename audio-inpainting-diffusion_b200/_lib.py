@@ -59,6 +59,7 @@ _SIGS = {
     "aid_profile": (C.c_int, [_P, C.c_int]),
     "aid_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "aid_debug_probe": (C.c_int, [_P, C.c_char_p, _P]),
+    "aid_debug_saturation": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "aid_launch_count": (C.c_uint64, []),
 }
 EXPORTS = tuple(_SIGS)

@@ -148,11 +148,8 @@ void launch_attention(const TV& h, const float* qk, const TV& out, cudaStream_t 
     const int F = h.F, T = h.T;
     const size_t smem = ((size_t)F * TQ + (((size_t)TQ * (T + 1) + 3) & ~(size_t)3) + (size_t)T * TQ + (size_t)T * FCH + (size_t)(ANT / 32) * FCH * TQ) * sizeof(float);
     if (smem > 227 * 1024) throw CudaError(cudaErrorInvalidValue, "attention tile exceeds shared memory", __FILE__, __LINE__);
-    static size_t configured = 0;
-    if (smem > configured) {
-        AID_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemConfig configured;
+    ensure_dyn_smem(attention_kernel, smem, configured);
     dim3 grid((T + TQ - 1) / TQ, h.C, h.B);
     attention_kernel<<<grid, ANT, smem, s>>>(h, qk, out, 1.0f / sqrtf((float)F));
     AID_COUNT_LAUNCH(1);

@@ -59,6 +59,31 @@ struct CudaError {
 extern unsigned long long g_launch_count;  // kernels launched by this library (bench.py's gpu_launches)
 #define AID_COUNT_LAUNCH(n) (aid::g_launch_count += (n))
 
+// Per-device bookkeeping.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only, so the size a
+// kernel was configured with is remembered per device (a second handle on another GPU of the same process configures again).
+static constexpr int kMaxDevices = 64;
+struct SmemConfig { size_t bytes[kMaxDevices] = {0}; };
+template <class Kernel>
+inline void ensure_dyn_smem(Kernel kernel, size_t bytes, SmemConfig& cfg, size_t preset = 0) {
+    int dev = 0;
+    AID_CUDA_CHECK(cudaGetDevice(&dev));
+    const int slot = dev < kMaxDevices ? dev : kMaxDevices - 1;
+    if (dev < kMaxDevices && bytes <= (cfg.bytes[slot] ? cfg.bytes[slot] : preset)) return;
+    AID_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cfg.bytes[slot] = bytes;
+}
+// multiprocessor count of the current device (cached per device); launch heuristics size their grids from it
+int device_sm_count();
+// RAII: make `device` current, restore the caller's device on scope exit (torch's current device is left alone)
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        AID_CUDA_CHECK(cudaGetDevice(&prev));
+        if (prev != device) AID_CUDA_CHECK(cudaSetDevice(device)); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // ---- launchers (defined in the .cu files) ---------------------------------------------------------
 void launch_group_stats(const TV& x, double* stats, cudaStream_t s);
 void launch_gn_act(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
@@ -90,13 +115,13 @@ void launch_conv_tc(const __half* a_hi, const __half* a_lo, int PF, const __half
 // second-generation tcgen05 path (conv_tc2.cu, conv_mode 2): single fp16 operands, channels-last [B][ceil(C/64)][F+2PF][T+2][64]
 size_t tc2_weight_halves(int Cout, int Cin, int KF, int KT);
 size_t tc2_act_halves(int B, int C, int F, int T, int PF);
-void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s);
+void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s, unsigned long long* sat = nullptr);
 // stft.cu: out = y ? y + x - S(x) : S(x), S = crop(istft(mask * stft(zero-pad(x))))  (sampler.py:271-290, 361); frames: [B][n_frames][n_fft] scratch
 void launch_spectral_mask(const float* x, const float* y, const float* mask, int B, int L, int n_fft, int hop, int n_frames,
                           float* frames, float* out, cudaStream_t s);
 void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
-                       long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s);
-void launch_to_planar_tc2(const TV& x, int PF, __half* a, cudaStream_t s);
+                       long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s, unsigned long long* sat = nullptr);
+void launch_to_planar_tc2(const TV& x, int PF, __half* a, cudaStream_t s, unsigned long long* sat = nullptr);
 void launch_gn_act_tc2_cl(const float* x_cl, int B, int C, int F, int T, const double* stats, long long n_per_group, const float* gamma,
                           const float* affine, long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s);
 void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,

@@ -145,12 +145,8 @@ template <int KF, int KT, int CI_CHUNK>
 static void launch_t(const TV& a, const float* wp, int dil, const TV& out, const ConvEpilogue& ep, cudaStream_t s) {
     constexpr int KC = CI_CHUNK * KF * KT;
     const size_t smem = (size_t)KC * (BM + BN) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        AID_CUDA_CHECK(cudaFuncSetAttribute(conv_simt_kernel<KF, KT, CI_CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-        configured = true;
-    }
+    static SmemConfig configured;
+    ensure_dyn_smem(conv_simt_kernel<KF, KT, CI_CHUNK>, smem, configured);
     int pt_t = 8, lg = 3;
     while (pt_t < BM && pt_t < a.T) { pt_t <<= 1; ++lg; }
     const int pt_f = BM / pt_t;

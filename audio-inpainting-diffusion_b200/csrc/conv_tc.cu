@@ -448,7 +448,7 @@ void launch_gn_act_tc(const TV& x, const double* stats, long long n_per_group, c
     const int rows_total = x.F + 2 * PF, Tp = x.T + 2;
     int rpb = max(1, 4096 / Tp);
     // keep at least ~4 blocks per SM in flight
-    while (rpb > 1 && (long long)((rows_total + rpb - 1) / rpb) * x.B * (x.C / 8) < 148 * 4) rpb >>= 1;
+    while (rpb > 1 && (long long)((rows_total + rpb - 1) / rpb) * x.B * (x.C / 8) < device_sm_count() * 4) rpb >>= 1;
     dim3 grid((rows_total + rpb - 1) / rpb, x.B * (x.C / 8));
     gn_act_tc_kernel<<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, rpb, a_hi, a_lo);
     AID_COUNT_LAUNCH(1);
@@ -498,11 +498,8 @@ void launch_conv_tc(const __half* a_hi, const __half* a_lo, int PF, const __half
     const size_t smem = (size_t)p.nstages * p.stage_bytes + 256 + 16 * 16 * sizeof(double);  // stages + barriers + per-warp statistics
     static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
     p.dbg = dbg;
-    static size_t configured = 0;
-    if (smem > configured) {
-        AID_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemConfig configured;
+    ensure_dyn_smem(conv_tc_kernel, smem, configured);
     const int grid = min(p.n_tiles, num_sms);
     conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(p);
     AID_COUNT_LAUNCH(1);

@@ -499,7 +499,8 @@ static int tc2_ntile(int Cout, int taps) {
 size_t tc2_weight_halves(int Cout, int Cin, int KF, int KT) { return (size_t)Cout * KF * KT * ((Cin + 63) / 64) * 64; }
 
 // w[co][ci][kf][kt] (fp32) -> [n-tile][kf][G][kt][Ntile][64] fp16 (x 2^10), 16-byte chunks swizzled by (n & 7); channels past Cin = 0
-__global__ void pack_weight_tc2_kernel(const float* __restrict__ w, __half* __restrict__ wp, int Ntot, int Ntile, int Cin, int KF, int KT) {
+__global__ void pack_weight_tc2_kernel(const float* __restrict__ w, __half* __restrict__ wp, int Ntot, int Ntile, int Cin, int KF, int KT,
+                                       unsigned long long* __restrict__ sat) {
     const int G = (Cin + 63) / 64;
     const long long total = (long long)Ntot * KF * KT * G * 64;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -514,14 +515,15 @@ __global__ void pack_weight_tc2_kernel(const float* __restrict__ w, __half* __re
         const int ci = g * 64 + chunk * 8 + (pos & 7), co = nt * Ntile + n;
         float v = 0.f;
         if (ci < Cin) v = w[(((long long)co * Cin + ci) * KF + kf) * KT + kt] * T2_W_SCALE;
+        if (sat && fabsf(v) > 60000.f) atomicAdd(sat, 1ull);
         v = fminf(fmaxf(v, -60000.f), 60000.f);
         wp[i] = __float2half_rn(v);
     }
 }
 
-void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s) {
+void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s, unsigned long long* sat) {
     const long long total = (long long)tc2_weight_halves(Cout, Cin, KF, KT);
-    pack_weight_tc2_kernel<<<(int)min((long long)8192, (total + 255) / 256), 256, 0, s>>>(w, wp, Cout, tc2_ntile(Cout, KF * KT), Cin, KF, KT);
+    pack_weight_tc2_kernel<<<(int)min((long long)8192, (total + 255) / 256), 256, 0, s>>>(w, wp, Cout, tc2_ntile(Cout, KF * KT), Cin, KF, KT, sat);
     AID_COUNT_LAUNCH(1);
 }
 
@@ -562,6 +564,7 @@ __device__ __forceinline__ float gelu16_tc2_folded(float x, float cu, float ch) 
     const float h = x * ch;
     return fmaf(fabsf(h), erf_abs, h);
 }
+__device__ __forceinline__ bool ld_ok(int i, int n) { return i < n; }
 // two operand values (already x16) -> packed fp16x2, saturating to the finite range
 __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
     uint32_t r;
@@ -579,10 +582,12 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
 // private layout (chunk slot = (chunk + pixel / 4) & 7) is conflict free for both sides; the way out applies the operand
 // swizzle, writes 128 contiguous bytes per pixel and the zero pad pixels next to the first / last pixel of a row.
 // grid: (B * G, chunk shares), block 256.  vec == 0 (T or the view not 16-byte aligned): scalar loads, same mapping.
+template <bool COUNT>
 __global__ void __launch_bounds__(256, 3)
 gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, const float* __restrict__ gamma,
                   const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, int G, int vec, uint32_t mg_T,
-                  __half* __restrict__ a) {
+                  __half* __restrict__ a, unsigned long long* __restrict__ sat) {
+    unsigned int nsat = 0;   // COUNT: values this thread clamped to the finite fp16 range (aid_debug_saturation)
     const int T = x.T, Tp = T + 2, rows_total = x.F + 2 * PF;
     const int n_src = x.F * T;                        // source pixels of one channel plane
     const int g = blockIdx.x % G, b = blockIdx.x / G;
@@ -657,6 +662,10 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
                 float r[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) r[j] = gelu ? gelu16_tc2_folded(v[j][i], cu[j], chh[j]) : v[j][i] * chh[j];
+                if (COUNT) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) nsat += (!(fabsf(r[j]) <= 65504.f) && (ld_ok(st + i, n_src))) ? 1u : 0u;
+                }
                 hv = make_uint4(pack_half2_sat(r[0], r[1]), pack_half2_sat(r[2], r[3]), pack_half2_sat(r[4], r[5]), pack_half2_sat(r[6], r[7]));
             }
             *reinterpret_cast<uint4*>(tile + (4 * lane + i) * 128 + slot_w) = hv;
@@ -698,6 +707,7 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
         }
         __syncthreads();
     }
+    if (COUNT && nsat) atomicAdd(sat, (unsigned long long)nsat);
 }
 
 // Same operand, from a channels-last input x[B][F][T][C] (the residual stream inside a conv_mode 2 residual block).  Pure
@@ -762,7 +772,7 @@ gn_act_tc2_cl_kernel(const float* __restrict__ x, int B, int C, int F, int T, co
 size_t tc2_act_halves(int B, int C, int F, int T, int PF) { return (size_t)B * ((C + 63) / 64) * 64 * (F + 2 * PF) * (T + 2); }
 
 void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
-                       long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s) {
+                       long long affine_bstride, bool gelu, int PF, __half* a, cudaStream_t s, unsigned long long* sat) {
     const int rows_total = x.F + 2 * PF, Tp = x.T + 2, G = (x.C + 63) / 64;
     static const int env_bps = getenv("AID_GN_BPS") ? atoi(getenv("AID_GN_BPS")) : 16;
     if ((long long)rows_total * Tp >= (1ll << 31) / 128)
@@ -770,11 +780,13 @@ void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, 
     const int nchunk = (x.F * x.T + 127) / 128;
     // 3 blocks per SM are resident; env_bps blocks per SM stride over the chunks of their plane (finer shares balance better)
     const long long planes = (long long)x.B * G;
-    const int shares = (int)std::min<long long>(nchunk, std::max<long long>(1, (148ll * env_bps + planes - 1) / planes));
+    const int shares = (int)std::min<long long>(nchunk, std::max<long long>(1, ((long long)device_sm_count() * env_bps + planes - 1) / planes));
     const int vec = (x.T % 4 == 0 && x.sb % 4 == 0 && x.sc % 4 == 0 && (reinterpret_cast<uintptr_t>(x.p) & 15) == 0) ? 1 : 0;
     dim3 grid((unsigned)planes, shares);
-    gn_act_tc2_kernel<<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, vec,
-                                           div_magic((uint32_t)x.T), a);
+    if (sat) gn_act_tc2_kernel<true><<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, vec,
+                                                       div_magic((uint32_t)x.T), a, sat);
+    else gn_act_tc2_kernel<false><<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, vec,
+                                                       div_magic((uint32_t)x.T), a, nullptr);
     AID_COUNT_LAUNCH(1);
 }
 
@@ -785,15 +797,15 @@ void launch_gn_act_tc2_cl(const float* x_cl, int B, int C, int F, int T, const d
     const int npass = (Tp + 31) / 32;
     const long long rows = (long long)B * G * rows_total;
     int ychunks = 1;
-    while (ychunks < npass && rows * ychunks < 148 * 16) ychunks <<= 1;
+    while (ychunks < npass && rows * ychunks < device_sm_count() * 16) ychunks <<= 1;
     ychunks = min(ychunks, npass);
     dim3 grid((unsigned)rows, ychunks);
     gn_act_tc2_cl_kernel<<<grid, 256, 0, s>>>(x_cl, B, C, F, T, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, a);
     AID_COUNT_LAUNCH(1);
 }
 
-void launch_to_planar_tc2(const TV& x, int PF, __half* a, cudaStream_t s) {
-    launch_gn_act_tc2(x, nullptr, 1, nullptr, nullptr, 0, false, PF, a, s);
+void launch_to_planar_tc2(const TV& x, int PF, __half* a, cudaStream_t s, unsigned long long* sat) {
+    launch_gn_act_tc2(x, nullptr, 1, nullptr, nullptr, 0, false, PF, a, s, sat);
 }
 
 // a: [B][ceil(Cin/64)][F + 2*PF][T+2][64] with PF >= tc_pad_rows(T, KF, dil); wp from launch_pack_weight_tc2
@@ -845,11 +857,8 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     const size_t smem = 1024 + (size_t)p.nA * p.a_slot_bytes + (size_t)p.nB * p.b_slot_bytes + 256 + T2_EPI_WARPS * 128 * sizeof(float);
     static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
     p.dbg = dbg;
-    static size_t configured = 0;
-    if (smem > configured) {
-        AID_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemConfig configured;
+    ensure_dyn_smem(conv_tc2_kernel, smem, configured);
     if (p.pair) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(2 * min(p.n_tiles, num_sms / 2)); cfg.blockDim = dim3(T2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;

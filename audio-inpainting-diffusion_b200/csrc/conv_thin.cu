@@ -163,11 +163,8 @@ static bool aligned16(const TV& v) {
 template <int KF, int KT, int CIN, int PX>
 static void launch_thin_in(const TV& a, const float* wp, int dil, const TV& out, const ConvEpilogue& ep, cudaStream_t s) {
     const size_t smem = (size_t)CIN * KF * KT * out.C * sizeof(float);
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        AID_CUDA_CHECK(cudaFuncSetAttribute(conv_thin_in_kernel<KF, KT, CIN, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemConfig configured;
+    ensure_dyn_smem(conv_thin_in_kernel<KF, KT, CIN, PX>, smem, configured, 48 * 1024);
     const long long n = (long long)a.F * (a.T / PX);
     conv_thin_in_kernel<KF, KT, CIN, PX><<<dim3((unsigned)((n + TH - 1) / TH), 1, a.B), TH, smem, s>>>(a, wp, dil, out, ep);
     AID_COUNT_LAUNCH(1);

@@ -166,7 +166,7 @@ void launch_fft_big(const FftPlan& plan, int B, bool inverse, const float* in_re
                  skip_stride, skip_scale, s);
         return;
     }
-    const dim3 grid(148 * 4, B);
+    const dim3 grid(device_sm_count() * 4, B);
     bluestein_pre_kernel<<<grid, 256, 0, s>>>(plan.L, plan.M, inverse, in_real, in_stride, in_scale, in_cplx, plan.chirp, scratch);
     fft_pow2(plan, B, false, nullptr, 0, 0.f, scratch, tmp, scratch, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
     bluestein_mul_kernel<<<grid, 256, 0, s>>>(plan.M, plan.bfilt, scratch);
@@ -290,7 +290,7 @@ __global__ void spec_mul_real_kernel(long long n, int L, float2* __restrict__ sp
 }
 void launch_spec_mul_real(int B, int L, float2* spec, const float* h, cudaStream_t s) {
     const long long n = (long long)B * L;
-    const int blocks = (int)min((long long)148 * 8, (n + 255) / 256);
+    const int blocks = (int)min((long long)device_sm_count() * 8, (n + 255) / 256);
     spec_mul_real_kernel<<<blocks, 256, 0, s>>>(n, L, spec, h);
     AID_COUNT_LAUNCH(1);
 }

@@ -363,7 +363,7 @@ __global__ void axpy_noise_kernel(float* __restrict__ x, const float* __restrict
     for (; i < n; i += stride) x[i] += scale * eps[i];
 }
 void launch_axpy_noise(float* x, const float* eps, float scale, long long n, cudaStream_t s) {
-    const int blocks = (int)min((long long)148 * 8, (n + 255) / 256);
+    const int blocks = (int)min((long long)device_sm_count() * 8, (n + 255) / 256);
     axpy_noise_kernel<<<blocks, 256, 0, s>>>(x, eps, scale, n);
     AID_COUNT_LAUNCH(1);
 }
@@ -399,7 +399,7 @@ __global__ void edm_step_kernel(const float* __restrict__ xin, const float* __re
 void launch_edm_step(const float* xin, const float* xhat, const float* y, const float* mask, long long mask_n, long long n,
                      float sigma, float h, int mode, const float* d_prev, const float* xbase, float* d_out, float* x_out,
                      cudaStream_t s) {
-    const int blocks = (int)min((long long)148 * 8, (n + 255) / 256);
+    const int blocks = (int)min((long long)device_sm_count() * 8, (n + 255) / 256);
     edm_step_kernel<<<blocks, 256, 0, s>>>(xin, xhat, y, mask, mask_n, n, sigma, h, mode, d_prev, xbase, d_out, x_out);
     AID_COUNT_LAUNCH(1);
 }

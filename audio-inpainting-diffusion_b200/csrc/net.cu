@@ -22,6 +22,18 @@ namespace aid {
 
 unsigned long long g_launch_count = 0;
 
+int device_sm_count() {
+    static int sms[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        sms[dev] = v;
+    }
+    return sms[dev];
+}
+
 static const float kInvSqrt2 = 0.70710678118654752440f;
 
 // ---- weights --------------------------------------------------------------------------------------
@@ -97,7 +109,7 @@ struct Net {
     FftPlan fft;
     void* d_tables = nullptr;
     int n_stat_slots = 0;
-    int num_sms = 148;
+    int num_sms = 0;   // multiprocessors of `device`, read at finalize
     int tc_parts() const { return cfg.conv_mode == 1 ? 2 : 1; }  // fp16 parts per tensor-core operand (conv_mode 1: hi + lo)
     __half* dweights_tc = nullptr;  // split-fp16 packed weights of the tcgen05 convolutions (conv_mode 1)
     std::map<std::string, float*> probes;  // debug: name -> caller buffer that receives a contiguous copy
@@ -106,6 +118,12 @@ struct Net {
     bool prof = false;
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
+    // conv_mode 2 saturation accounting (aid_debug_saturation): fp16 operands are x16 / x1024 scaled and converted with
+    // satfinite; d_sat[0] counts activation values clamped by the operand passes while counting is enabled, weight_sat the
+    // weight values clamped at finalize
+    unsigned long long* d_sat = nullptr;
+    bool count_sat = false;
+    unsigned long long weight_sat = 0;
 };
 
 static int add_weight(Net& n, const std::string& name, std::vector<int64_t> shape, bool ignored = false) {
@@ -222,7 +240,8 @@ static void upload_tables(Net& n);
 static void finalize_net(Net& n) {
     for (auto& w : n.weights)
         if (!w.loaded && !w.ignored) throw std::runtime_error("missing weight: " + w.name);
-    AID_CUDA_CHECK(cudaSetDevice(n.device));
+    DeviceGuard guard(n.device);
+    AID_CUDA_CHECK(cudaDeviceGetAttribute(&n.num_sms, cudaDevAttrMultiProcessorCount, n.device));
     size_t total = 0, max_conv = 0;
     auto al = [](size_t v) { return (v + 63) & ~(size_t)63; };
     std::vector<ConvW*> convs;
@@ -257,20 +276,21 @@ static void finalize_net(Net& n) {
     }
     if (n.cfg.conv_mode >= 1) {
         const int parts = n.tc_parts();
-        AID_CUDA_CHECK(cudaDeviceGetAttribute(&n.num_sms, cudaDevAttrMultiProcessorCount, n.device));
         size_t tc_total = 0;
         auto tc_halves = [&](const ConvW* c) {
             return n.cfg.conv_mode == 2 ? tc2_weight_halves(c->Cout, c->Cin, c->KF, c->KT) : (size_t)parts * n.weights[c->widx].numel();
         };
         for (auto* c : convs) if (conv_tc_supported(c->Cin, c->Cout, c->KF, c->KT)) tc_total += al(tc_halves(c));
         if (tc_total) AID_CUDA_CHECK(cudaMalloc(&n.dweights_tc, tc_total * sizeof(__half)));
+        AID_CUDA_CHECK(cudaMalloc(&n.d_sat, 2 * sizeof(unsigned long long)));
+        AID_CUDA_CHECK(cudaMemset(n.d_sat, 0, 2 * sizeof(unsigned long long)));
         size_t toff = 0;
         for (auto* c : convs) {
             if (!conv_tc_supported(c->Cin, c->Cout, c->KF, c->KT)) continue;
             Weight& w = n.weights[c->widx];
             AID_CUDA_CHECK(cudaMemcpy(stage, w.host.data(), w.numel() * sizeof(float), cudaMemcpyHostToDevice));
             c->wtc = n.dweights_tc + toff;
-            if (n.cfg.conv_mode == 2) launch_pack_weight_tc2(stage, c->wtc, c->Cout, c->Cin, c->KF, c->KT, 0);
+            if (n.cfg.conv_mode == 2) launch_pack_weight_tc2(stage, c->wtc, c->Cout, c->Cin, c->KF, c->KT, 0, n.d_sat + 1);
             else launch_pack_weight_tc(stage, c->wtc, c->Cout, c->Cin, c->KF, c->KT, parts, 0);
             AID_CUDA_CHECK(cudaGetLastError());
             AID_CUDA_CHECK(cudaDeviceSynchronize());
@@ -278,6 +298,7 @@ static void finalize_net(Net& n) {
         }
     }
     AID_CUDA_CHECK(cudaFree(stage));
+    if (n.d_sat) AID_CUDA_CHECK(cudaMemcpy(&n.weight_sat, n.d_sat + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     for (auto* nr : norms) {
         Weight& w = n.weights[nr->widx];
         nr->gamma = n.dweights + off;
@@ -304,7 +325,7 @@ static void finalize_net(Net& n) {
 // CQT tables + FFT twiddles live in one device allocation made at create time (no weights needed).
 static void upload_tables(Net& n) {
     if (n.d_tables) return;
-    AID_CUDA_CHECK(cudaSetDevice(n.device));
+    DeviceGuard guard(n.device);
     const CqtPlanHost& p = n.plan;
     const int L = p.L, K = p.K;
     // power-of-two FFT engine size: L itself, or (Bluestein) the next power of two >= 2L
@@ -456,8 +477,9 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         if (cmode == 2) return (long long)((tc2_act_halves(B, ch, Fd, T, pf) + 1) / 2);
         return ((long long)B * ch * (Fd + 2 * pf) * (T + 2) * parts + 1) / 2;
     };
+    unsigned long long* sat = c.n->count_sat ? c.n->d_sat : nullptr;
     auto to_operand = [&](const TV& v, int pf, __half* hi, __half* lo) {
-        if (cmode == 2) launch_to_planar_tc2(v, pf, hi, c.s); else launch_to_planar_tc(v, pf, hi, lo, c.s);
+        if (cmode == 2) launch_to_planar_tc2(v, pf, hi, c.s, sat); else launch_to_planar_tc(v, pf, hi, lo, c.s);
     };
     const int pf_max = tc_pad_rows(T, k.k1x1 ? 1 : 5, k.k1x1 ? 1 : (1 << std::max(0, k.nd - 1)));
     float* abuf = c.allocf(std::max(plane, operand_floats(N, pf_max, F)));
@@ -531,7 +553,7 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
             __half* a_lo = parts == 2 ? a_hi + planar_halves(N, pf) : nullptr;
             if (cmode == 2) {
                 if (cur_is_cl) RUN(launch_gn_act_tc2_cl(xcl, B, N, F, T, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s));
-                else RUN(launch_gn_act_tc2(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s));
+                else RUN(launch_gn_act_tc2(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s, sat));
                 const bool out_is_cl = use_cl && i + 1 < k.nd;
                 if (cur_is_cl) ep.R = xc;
                 ep.R_cl = cur_is_cl; ep.out_cl = out_is_cl;
@@ -740,10 +762,16 @@ int aid_create(const aid_config* cfg, int device, aid_handle** out) {
 
 void aid_destroy(aid_handle* h) {
     if (!h) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
     cudaSetDevice(h->net.device);
     if (h->net.dweights) cudaFree(h->net.dweights);
     if (h->net.dweights_tc) cudaFree(h->net.dweights_tc);
     if (h->net.d_tables) cudaFree(h->net.d_tables);
+    if (h->net.d_sat) cudaFree(h->net.d_sat);
+    for (auto& r : h->net.prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto& e : h->net.prof_pool) cudaEventDestroy(e);
+    if (prev >= 0) cudaSetDevice(prev);
     delete h;
 }
 
@@ -1096,6 +1124,28 @@ int aid_profile_read(aid_handle* h, int kind, uint64_t* launches, double* ms, do
         if (ms) *ms = t;
         if (flops) *flops = f;
         if (bytes) *bytes = b;
+    });
+}
+
+/* debug: conv_mode 2 converts its operands to fp16 with saturation (activations x16, weights x1024).  enable != 0 resets and
+ * starts counting the activation values clamped by the operand passes of the following forwards; the counters are read
+ * (after a device synchronisation) whenever a pointer is given.  weight_count: weight values clamped at aid_finalize. */
+int aid_debug_saturation(aid_handle* h, int enable, uint64_t* act_count, uint64_t* weight_count) {
+    if (!h) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        Net& n = h->net;
+        if (!n.finalized) throw std::runtime_error("aid_debug_saturation before aid_finalize");
+        if (weight_count) *weight_count = n.weight_sat;
+        if (!n.d_sat) { if (act_count) *act_count = 0; n.count_sat = false; return; }   // conv_mode 0 / 1: nothing saturates
+        DeviceGuard guard(n.device);
+        if (act_count) {
+            unsigned long long v = 0;
+            AID_CUDA_CHECK(cudaDeviceSynchronize());
+            AID_CUDA_CHECK(cudaMemcpy(&v, n.d_sat, sizeof v, cudaMemcpyDeviceToHost));
+            *act_count = v;
+        }
+        if (enable && !n.count_sat) { AID_CUDA_CHECK(cudaDeviceSynchronize()); AID_CUDA_CHECK(cudaMemset(n.d_sat, 0, sizeof(unsigned long long))); }
+        n.count_sat = enable != 0;
     });
 }
 

@@ -283,6 +283,20 @@ class Unet_CQT_oct_with_attention(nn.Module):
                                                    _lib.ptr(ws), ws.numel(), st), self._handle)
         return out
 
+    def saturation_counts(self, enable=None):
+        """(activation, weight) operand values clamped to the finite fp16 range in conv_mode 2 (aid_debug_saturation).
+        enable=True resets the activation counter and counts during the following forwards, enable=False stops, None only reads."""
+        if self._handle is None or not self._weights_loaded:
+            raise _lib.AidError("saturation_counts needs an uploaded model (run a forward or _ensure_weights first)")
+        a, w = C.c_uint64(), C.c_uint64()
+        L = _lib.lib()
+        if enable is None:
+            _lib.check(L.aid_debug_saturation(self._handle, 1 if getattr(self, "_count_sat", False) else 0, C.byref(a), C.byref(w)), self._handle)
+        else:
+            self._count_sat = bool(enable)
+            _lib.check(L.aid_debug_saturation(self._handle, 1 if enable else 0, C.byref(a), C.byref(w)), self._handle)
+        return int(a.value), int(w.value)
+
     def forward_with_probes(self, inputs, sigma):
         """Debug/parity helper: forward plus the per-block intermediates {"enc<i>", "mid", "dec<i>"} (see aid_debug_probe)."""
         cfg, B, dev = self.cfg, inputs.shape[0], inputs.device

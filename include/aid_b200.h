@@ -7,8 +7,11 @@
  * Conventions: plain pointers and sizes only.  `*_dev` pointers are device pointers on the GPU the
  * handle was created for; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  * All entry points return 0 on success or a negative aid_status; aid_last_error() gives the message.
- * Calls are stream-ordered, never synchronise the device and never allocate device memory after
- * aid_finalize() (the caller owns the workspace).  One handle = one GPU = one host thread at a time.
+ * Calls that take a handle are stream-ordered, never synchronise the device and never allocate device memory after
+ * aid_finalize() (the caller owns the workspace); the one exception is the CQT entry points used BEFORE aid_finalize,
+ * which upload their tables on first use.  The handle-less single-operator and aid_debug_* entry points exist for unit
+ * parity tests and tuning: they allocate and free their own scratch and may synchronise.  The current CUDA device of the
+ * calling thread is left as it was found.  One handle = one GPU = one host thread at a time.
  */
 #ifndef AID_B200_H
 #define AID_B200_H
@@ -151,6 +154,12 @@ int aid_profile_read(aid_handle* h, int kind, uint64_t* launches, double* ms, do
  * (NULL removes the probe).  Names: "enc<i>" = encoder ResBlock output of level i (unet.py:780), "mid" = bottleneck
  * ResBlock output (unet.py:803), "dec<i>" = decoder ResBlock output (unet.py:815). */
 int aid_debug_probe(aid_handle* h, const char* name, float* dst_dev);
+
+/* Debug: conv_mode 2 converts its operands to fp16 with saturation (activations x 2^4, weights x 2^10, finite range 65504).
+ * enable != 0 resets the activation counter and counts, in the following forwards, every operand value the
+ * normalise/GELU/convert passes had to clamp; a non-NULL act_count reads it (synchronises the device).  weight_count:
+ * weight values clamped when aid_finalize packed them.  Both are 0 in conv_mode 0 / 1 (nothing is clamped there). */
+int aid_debug_saturation(aid_handle* h, int enable, uint64_t* act_count, uint64_t* weight_count);
 
 /* kernels launched by this library since load (the bench's gpu_launches counter) */
 uint64_t aid_launch_count(void);

@@ -1,0 +1,118 @@
+"""Parity at the BENCH shape: the paper network (186.3 M parameters) on 262144-sample clips, the configuration bench.py times.
+
+* against golden vectors the reference's OWN unet.py + edm.py produced at this size (tests/golden/make_golden_paper262144.py,
+  one clip, sigma = 1.0 and 0.05), in conv_mode 2 (the bench default, bar 1e-3 = the north star's tolerance) and in
+  conv_mode 1 (fp32-grade split fp16, bar 1e-4);
+* block by block against the CPU oracle run on this machine (one ~5-10 s forward), so an error in a deep block cannot hide
+  behind the end-to-end number;
+* at batch 32 (the bench batch): row k of the batch equals the clip evaluated alone;
+* no operand value is clamped by the saturating fp16 conversion of conv_mode 2 (aid_debug_saturation).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import rel_l2, seeded, make_oracle
+
+pytestmark = pytest.mark.gpu
+L = 262144
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_paper262144.npz")
+TOL = {1: 1e-4, 2: 1e-3}
+
+
+def _edm(aid):
+    return aid.EDM(aid.AttrDict.wrap({"diff_params": dict(sigma_min=1e-4, sigma_max=1.0, ro=13, sigma_data=0.063, Schurn=10,
+                                                          Stmin=0, Stmax=50, Snoise=1.0)}))
+
+
+@pytest.fixture(scope="module")
+def nets(aid, cuda):
+    out = {}
+    for mode in (1, 2):
+        cfg = aid.paper_22k(L, conv_mode=mode)
+        net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+        net.load_state_dict(aid.random_state_dict(cfg, seed=1234))
+        out[mode] = net
+    return out
+
+
+@pytest.mark.parametrize("mode", [2, 1])
+def test_paper_network_262144_matches_reference_golden(aid, cuda, nets, mode):
+    """EDM.denoiser (edm.py:133-148) of the reference's unet.py:730-845 at the bench shape vs the CUDA path."""
+    g = np.load(GOLD)
+    net, e = nets[mode], _edm(aid)
+    x = seeded((1, L), 0).to(cuda)
+    if mode == 2:
+        net._ensure_weights(cuda)
+        net.saturation_counts(enable=True)
+    errs = []
+    for i, sg in enumerate((1.0, 0.05)):
+        out = e.denoiser(x * sg, net, torch.tensor([sg], device=cuda))
+        errs.append(rel_l2(out, torch.from_numpy(g[f"paper262144_denoise_{i}"])))
+    print(f"conv_mode {mode}, paper network 1 x {L} vs reference golden: sigma=1 {errs[0]:.3e}, sigma=0.05 {errs[1]:.3e} (bar {TOL[mode]:g})")
+    assert max(errs) < TOL[mode], errs
+    if mode == 2:
+        act, wts = net.saturation_counts(enable=False)
+        assert (act, wts) == (0, 0), f"fp16 operand saturation: {act} activation values, {wts} weight values clamped"
+
+
+def test_paper_network_262144_blockwise_vs_oracle(aid, cuda, nets):
+    """Every encoder / bottleneck / decoder block of the paper network at 262144 samples against the CPU oracle, both modes."""
+    cfg = aid.paper_22k(L)
+    orc = make_oracle(cfg, aid.random_state_dict(cfg, seed=1234))
+    x = seeded((1, L), 21, 0.8)
+    cn = torch.tensor([[-0.9]])
+    probe = {}
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = orc(x, cn, probe=probe)
+    for mode in (2, 1):
+        out, got = nets[mode].forward_with_probes(x.to(cuda), cn.to(cuda))
+        errs = {k: rel_l2(got[k], probe[k]) for k in sorted(probe)}
+        errs["out"] = rel_l2(out, ref)
+        print(f"conv_mode {mode} rel-L2 per block at 1 x {L}:", {k: f"{v:.2e}" for k, v in errs.items()})
+        assert set(got) == set(probe)
+        for k, v in errs.items():
+            assert v < TOL[mode], (mode, k, v)
+        del got
+
+
+def test_bench_batch_32_rows_equal_solo_clips(aid, cuda, nets):
+    """The bench batch (32 x 262144, shared sigma, conv_mode 2): clips are independent -- row k of the batch equals
+    the clip evaluated alone, up to the run-to-run noise of the statistic atomics (measured 2e-5); no value saturates."""
+    net = nets[2]
+    x = torch.cat([seeded((1, L), 100 + k, 0.5) for k in range(32)]).to(cuda)
+    cn = torch.tensor([[-0.3]], device=cuda)
+    net._ensure_weights(cuda)
+    net.saturation_counts(enable=True)
+    full = net(x, cn)
+    act, wts = net.saturation_counts(enable=False)
+    assert (act, wts) == (0, 0)
+    assert torch.isfinite(full).all()
+    for k in (0, 13, 31):
+        solo = net(x[k:k + 1], cn)
+        e = rel_l2(full[k:k + 1], solo)
+        print(f"row {k} of the batch vs solo: {e:.2e}")
+        assert e < 1e-4, (k, e)
+    # and the golden clip placed inside a batch still matches the reference
+    g = np.load(GOLD)
+    xb = x[:4].clone()
+    xb[2] = seeded((1, L), 0)[0].to(cuda)
+    out = _edm(aid).denoiser(xb, net, torch.tensor([1.0], device=cuda))
+    assert rel_l2(out[2:3], torch.from_numpy(g["paper262144_denoise_0"])) < 1e-3
+
+
+def test_saturation_counter_counts(aid, cuda):
+    """The counter is live: activations scaled far beyond the fp16 range (|x| * 16 > 65504) are reported, ordinary ones are not."""
+    cfg = aid.NetConfig(audio_len=16384, Ns=[16, 16, 32, 32, 32, 48, 64], num_dils=[1, 2, 2, 3, 3, 3, 2], conv_mode=2)
+    net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+    net.load_state_dict(aid.random_state_dict(cfg, seed=77))
+    x = seeded((1, cfg.audio_len), 3).to(cuda)
+    cn = torch.tensor([[-0.5]], device=cuda)
+    net(x, cn)
+    net.saturation_counts(enable=True)
+    net(x, cn)
+    assert net.saturation_counts(enable=True)[0] == 0
+    net(x * 1e7, cn)          # un-normalised operands (proj_in / res_conv inputs) overflow 65504 / 16
+    assert net.saturation_counts(enable=False)[0] > 0
