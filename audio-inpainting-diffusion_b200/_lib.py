@@ -36,6 +36,10 @@ _SIGS = {
     "aid_finalize": (C.c_int, [_P]),
     "aid_workspace_bytes": (C.c_int, [_P, C.c_int, C.POINTER(C.c_size_t)]),
     "aid_unet_forward": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, C.c_float, C.c_float, C.c_float, _P, C.c_size_t, _P]),
+    "aid_unet_forward_ds": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_size_t, _P]),
+    "aid_edm_step_ds": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "aid_philox_normal": (C.c_int, [_P, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_int, _P, _P]),
+    "aid_sched_select": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "aid_cqt_layout": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "aid_cqt_fwd": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "aid_cqt_bwd": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),

@@ -130,6 +130,12 @@ def paper_22k(audio_len=262144, conv_mode=0):
     return NetConfig(audio_len=audio_len, conv_mode=conv_mode)
 
 
+def paper_44k(audio_len=184184, conv_mode=0):
+    """conf/network/paper_1912_unet_cqt_oct_attention_44k_2.yaml at fs=44100 (conf/exp/musicnet44k_4s.yaml): 8 octaves, 242 M parameters."""
+    return NetConfig(num_octs=8, sample_rate=44100.0, audio_len=audio_len, Ns=[64, 64, 96, 96, 128, 128, 256, 256],
+                     num_dils=[2, 3, 4, 5, 6, 7, 8, 8], attention_layers=[0, 0, 0, 0, 0, 1, 1, 1, 1], conv_mode=conv_mode)
+
+
 def small_test(audio_len=16384, conv_mode=0):
     """A narrow network with the same topology (7 octaves, attention on the deep levels) for fast tests."""
     return NetConfig(audio_len=audio_len, Ns=[16, 16, 24, 24, 32, 32, 32], num_dils=[1, 2, 2, 3, 3, 3, 2],

@@ -134,6 +134,9 @@ struct FftPlan {
     const float2* tw = nullptr;     // W_M^k = exp(-2*pi*i*k/M), k in [0, M)
     const float2* chirp = nullptr;  // Bluestein only: exp(-i*pi*n^2/L), n in [0, L)
     const float2* bfilt = nullptr;  // Bluestein only: FFT_M of the wrapped conj(chirp) filter
+    // optional device scalars [in, out, skip] (CUDA-graph replay of the sampler: the preconditioning of the current sigma lives in
+    // device memory): real input *= dscal[0], out_scale *= dscal[1], skip_scale = dscal[2] (a skip pointer must still be given)
+    const float* dscal = nullptr;
 };
 // batched length-L complex DFT (four-step split M = N1*N2 in shared memory; Bluestein around it when L is not a power of two).
 //  in_real != null : input is real [B][in_stride], scaled by in_scale;   in_cplx != null : input complex [B][L]
@@ -168,8 +171,15 @@ void launch_spec_mul_real(int B, int L, float2* spec, const float* h, cudaStream
 
 // EDM sampler element-wise steps (sampler.py:214, 141-147, 230-251)
 void launch_axpy_noise(float* x, const float* eps, float scale, long long n, cudaStream_t s);
+// sigma_h_dev != null: sigma = sigma_h_dev[0], h = sigma_h_dev[1] (device scalars, CUDA-graph replay)
 void launch_edm_step(const float* xin, const float* xhat, const float* y, const float* mask, long long mask_n, long long n,
                      float sigma, float h, int mode, const float* d_prev, const float* xbase, float* d_out, float* x_out,
-                     cudaStream_t s);
+                     cudaStream_t s, const float* sigma_h_dev = nullptr);
+// Philox4x32-10 standard normals keyed by (seed, stream, global clip index, draw): x[c][i] = (accumulate ? x : 0) + scale * N(0,1).
+// scale_draw_dev != null: [scale, draw, stream_id, clip0] (the last three as bit patterns) come from device memory instead
+void launch_philox_normal(float* x, int n_clips, long long L, unsigned long long seed, unsigned int stream_id, unsigned int clip0,
+                          unsigned int draw, float scale, bool accumulate, const float* scale_draw_dev, cudaStream_t s);
+// cur[0..row) = table[*counter][0..row); ++*counter   (one tiny launch at the head of a replayed sampler-step graph)
+void launch_sched_select(const float* table, int row, int* counter, float* cur, cudaStream_t s);
 
 }  // namespace aid

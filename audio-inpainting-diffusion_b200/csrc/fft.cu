@@ -50,8 +50,10 @@ __device__ __forceinline__ int brev(int i, int lg) { return lg == 0 ? 0 : (int)(
 // grid: (N2/CW, B)
 __global__ void __launch_bounds__(FNT)
 fft_cols_kernel(int lg1, int lg2, const float2* __restrict__ tw, bool inverse, const float* __restrict__ in_real,
-                long long in_stride, float in_scale, const float2* __restrict__ in_cplx, float2* __restrict__ tmp) {
+                long long in_stride, float in_scale, const float2* __restrict__ in_cplx, float2* __restrict__ tmp,
+                const float* __restrict__ dscal) {
     extern __shared__ float2 arr[];
+    if (dscal) in_scale *= dscal[0];
     const int N1 = 1 << lg1, N2 = 1 << lg2, lgL = lg1 + lg2;
     const long long L = (long long)N1 * N2;
     const int b = blockIdx.y, n20 = blockIdx.x * CW;
@@ -78,8 +80,9 @@ fft_cols_kernel(int lg1, int lg2, const float2* __restrict__ tw, bool inverse, c
 __global__ void __launch_bounds__(FNT)
 fft_rows_kernel(int lg1, int lg2, const float2* __restrict__ tw, bool inverse, const float2* __restrict__ tmp,
                 float2* __restrict__ out_cplx, float* __restrict__ out_real, long long out_stride, float out_scale,
-                const float* __restrict__ skip, long long skip_stride, float skip_scale) {
+                const float* __restrict__ skip, long long skip_stride, float skip_scale, const float* __restrict__ dscal) {
     extern __shared__ float2 arr[];
+    if (dscal) { out_scale *= dscal[1]; skip_scale = dscal[2]; }
     const int N1 = 1 << lg1, N2 = 1 << lg2, lgL = lg1 + lg2;
     const long long L = (long long)N1 * N2;
     const int b = blockIdx.y, k10 = blockIdx.x * CW;
@@ -109,13 +112,14 @@ static void fft_pow2(const FftPlan& plan, int B, bool inverse, const float* in_r
     while ((1 << lg1) < plan.N1) ++lg1;
     while ((1 << lg2) < plan.N2) ++lg2;
     const size_t sm1 = (size_t)plan.N1 * CW * sizeof(float2), sm2 = (size_t)plan.N2 * CW * sizeof(float2);
-    static size_t c1 = 0, c2 = 0;
-    if (sm1 > c1) { AID_CUDA_CHECK(cudaFuncSetAttribute(fft_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); c1 = sm1; }
-    if (sm2 > c2) { AID_CUDA_CHECK(cudaFuncSetAttribute(fft_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)); c2 = sm2; }
-    fft_cols_kernel<<<dim3(plan.N2 / CW, B), FNT, sm1, s>>>(lg1, lg2, plan.tw, inverse, in_real, in_stride, in_scale, in_cplx, tmp);
+    static SmemConfig c1, c2;
+    ensure_dyn_smem(fft_cols_kernel, sm1, c1);
+    ensure_dyn_smem(fft_rows_kernel, sm2, c2);
+    fft_cols_kernel<<<dim3(plan.N2 / CW, B), FNT, sm1, s>>>(lg1, lg2, plan.tw, inverse, in_real, in_stride, in_scale, in_cplx, tmp,
+                                                            in_real ? plan.dscal : nullptr);
     AID_COUNT_LAUNCH(1);
     fft_rows_kernel<<<dim3(plan.N1 / CW, B), FNT, sm2, s>>>(lg1, lg2, plan.tw, inverse, tmp, out_cplx, out_real, out_stride,
-                                                            out_scale, skip, skip_stride, skip_scale);
+                                                            out_scale, skip, skip_stride, skip_scale, out_real ? plan.dscal : nullptr);
     AID_COUNT_LAUNCH(1);
 }
 
@@ -123,8 +127,10 @@ static void fft_pow2(const FftPlan& plan, int B, bool inverse, const float* in_r
 //   X[k] = w[k] * sum_n (x[n] w[n]) conj(w)[k-n],  w[n] = exp(-i*pi*n^2/L): one circular convolution of power-of-two size M >= 2L-1.
 //   The inverse transform is conj(DFT(conj(x))).
 __global__ void bluestein_pre_kernel(int L, int M, bool inverse, const float* __restrict__ in_real, long long in_stride, float in_scale,
-                                     const float2* __restrict__ in_cplx, const float2* __restrict__ chirp, float2* __restrict__ A) {
+                                     const float2* __restrict__ in_cplx, const float2* __restrict__ chirp, float2* __restrict__ A,
+                                     const float* __restrict__ dscal) {
     const int b = blockIdx.y;
+    if (dscal) in_scale *= dscal[0];
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < M; n += gridDim.x * blockDim.x) {
         float2 v = make_float2(0.f, 0.f);
         if (n < L) {
@@ -142,9 +148,11 @@ __global__ void bluestein_mul_kernel(int M, const float2* __restrict__ bfilt, fl
 }
 __global__ void bluestein_post_kernel(int L, int M, bool inverse, const float2* __restrict__ A, const float2* __restrict__ chirp,
                                       float2* __restrict__ out_cplx, float* __restrict__ out_real, long long out_stride, float out_scale,
-                                      const float* __restrict__ skip, long long skip_stride, float skip_scale) {
+                                      const float* __restrict__ skip, long long skip_stride, float skip_scale,
+                                      const float* __restrict__ dscal) {
     const int b = blockIdx.y;
     const float inv = 1.f / (float)M;
+    if (dscal) { out_scale *= dscal[1]; skip_scale = dscal[2]; }
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
         float2 v = cmul(A[(long long)b * M + k], __ldg(chirp + k));
         v.x *= inv; v.y *= inv;
@@ -167,12 +175,14 @@ void launch_fft_big(const FftPlan& plan, int B, bool inverse, const float* in_re
         return;
     }
     const dim3 grid(device_sm_count() * 4, B);
-    bluestein_pre_kernel<<<grid, 256, 0, s>>>(plan.L, plan.M, inverse, in_real, in_stride, in_scale, in_cplx, plan.chirp, scratch);
-    fft_pow2(plan, B, false, nullptr, 0, 0.f, scratch, tmp, scratch, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
+    FftPlan inner = plan; inner.dscal = nullptr;     // the device scalars apply to the outer real input / output only
+    bluestein_pre_kernel<<<grid, 256, 0, s>>>(plan.L, plan.M, inverse, in_real, in_stride, in_scale, in_cplx, plan.chirp, scratch,
+                                              in_real ? plan.dscal : nullptr);
+    fft_pow2(inner, B, false, nullptr, 0, 0.f, scratch, tmp, scratch, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
     bluestein_mul_kernel<<<grid, 256, 0, s>>>(plan.M, plan.bfilt, scratch);
-    fft_pow2(plan, B, true, nullptr, 0, 0.f, scratch, tmp, scratch, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
+    fft_pow2(inner, B, true, nullptr, 0, 0.f, scratch, tmp, scratch, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
     bluestein_post_kernel<<<grid, 256, 0, s>>>(plan.L, plan.M, inverse, scratch, plan.chirp, out_cplx, out_real, out_stride, out_scale,
-                                               skip, skip_stride, skip_scale);
+                                               skip, skip_stride, skip_scale, out_real ? plan.dscal : nullptr);
     AID_COUNT_LAUNCH(3);
 }
 

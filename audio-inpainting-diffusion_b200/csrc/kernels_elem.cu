@@ -376,9 +376,10 @@ void launch_axpy_noise(float* x, const float* eps, float scale, long long n, cud
 __global__ void edm_step_kernel(const float* __restrict__ xin, const float* __restrict__ xhat, const float* __restrict__ y,
                                 const float* __restrict__ mask, long long mask_n, long long n, float sigma, float h,
                                 int mode, const float* __restrict__ d_prev, const float* __restrict__ xbase,
-                                float* __restrict__ d_out, float* __restrict__ x_out) {
+                                float* __restrict__ d_out, float* __restrict__ x_out, const float* __restrict__ sigma_h_dev) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    if (sigma_h_dev) { sigma = sigma_h_dev[0]; h = sigma_h_dev[1]; }
     const float inv = 1.f / sigma;
     for (; i < n; i += stride) {
         float xh = xhat[i];
@@ -398,9 +399,87 @@ __global__ void edm_step_kernel(const float* __restrict__ xin, const float* __re
 
 void launch_edm_step(const float* xin, const float* xhat, const float* y, const float* mask, long long mask_n, long long n,
                      float sigma, float h, int mode, const float* d_prev, const float* xbase, float* d_out, float* x_out,
-                     cudaStream_t s) {
+                     cudaStream_t s, const float* sigma_h_dev) {
     const int blocks = (int)min((long long)device_sm_count() * 8, (n + 255) / 256);
-    edm_step_kernel<<<blocks, 256, 0, s>>>(xin, xhat, y, mask, mask_n, n, sigma, h, mode, d_prev, xbase, d_out, x_out);
+    edm_step_kernel<<<blocks, 256, 0, s>>>(xin, xhat, y, mask, mask_n, n, sigma, h, mode, d_prev, xbase, d_out, x_out, sigma_h_dev);
+    AID_COUNT_LAUNCH(1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Device-resident noise (edm.py:94, sampler.py:212 draw it with the CPU generator and copy 4*B*L bytes per step).
+// Philox4x32-10 (Salmon et al., SC'11): counter = (i / 4, draw, global clip index, stream id), key = 64-bit seed; the four
+// 32-bit outputs of one call become elements 4q .. 4q+3 of the clip through two Box-Muller pairs.  A clip's noise depends only
+// on (seed, stream id, clip index, draw, element), never on the batch it is sampled in or on the number of ranks.
+// oracle/philox_oracle.py restates it in numpy (integer stream bit-exact, normals to float32 rounding).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// u in (0, 1): the top 24 bits, centred in their bin
+__device__ __forceinline__ float philox_uniform(unsigned int r) { return ((float)(r >> 8) + 0.5f) * 5.9604644775390625e-8f; }
+__device__ __forceinline__ void box_muller(unsigned int a, unsigned int b, float& n0, float& n1) {
+    const float rad = sqrtf(-2.f * logf(philox_uniform(a)));
+    float sn, cs;
+    sincospif(2.f * philox_uniform(b), &sn, &cs);
+    n0 = rad * cs; n1 = rad * sn;
+}
+
+// grid: (blocks over L/4 quads, n_clips)
+__global__ void __launch_bounds__(256)
+philox_normal_kernel(float* __restrict__ x, long long L, uint2 key, unsigned int stream_id, unsigned int clip0, unsigned int draw,
+                     float scale, int accumulate, const float* __restrict__ scale_draw_dev) {
+    if (scale_draw_dev) {
+        scale = scale_draw_dev[0]; draw = __float_as_uint(scale_draw_dev[1]);
+        stream_id = __float_as_uint(scale_draw_dev[2]); clip0 = __float_as_uint(scale_draw_dev[3]);
+    }
+    const unsigned int clip = clip0 + blockIdx.y;
+    float* row = x + (long long)blockIdx.y * L;
+    const long long nq = (L + 3) >> 2;
+    const bool vec = (L & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4((unsigned int)q, draw, clip, stream_id), key);
+        float n[4];
+        box_muller(r.x, r.y, n[0], n[1]);
+        box_muller(r.z, r.w, n[2], n[3]);
+        if (vec) {
+            float4* p4 = reinterpret_cast<float4*>(row) + q;
+            float4 v = accumulate ? *p4 : make_float4(0.f, 0.f, 0.f, 0.f);
+            v.x += scale * n[0]; v.y += scale * n[1]; v.z += scale * n[2]; v.w += scale * n[3];
+            *p4 = v;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long i = 4 * q + j;
+                if (i < L) row[i] = (accumulate ? row[i] : 0.f) + scale * n[j];
+            }
+        }
+    }
+}
+
+void launch_philox_normal(float* x, int n_clips, long long L, unsigned long long seed, unsigned int stream_id, unsigned int clip0,
+                          unsigned int draw, float scale, bool accumulate, const float* scale_draw_dev, cudaStream_t s) {
+    if (n_clips <= 0 || L <= 0) return;
+    const long long nq = (L + 3) / 4;
+    const int bx = (int)max(1ll, min((nq + 255) / 256, (long long)(device_sm_count() * 8 + n_clips - 1) / n_clips));
+    philox_normal_kernel<<<dim3(bx, n_clips), 256, 0, s>>>(x, L, make_uint2((unsigned int)(seed & 0xffffffffull), (unsigned int)(seed >> 32)),
+                                                           stream_id, clip0, draw, scale, accumulate ? 1 : 0, scale_draw_dev);
+    AID_COUNT_LAUNCH(1);
+}
+
+__global__ void sched_select_kernel(const float* __restrict__ table, int row, int* __restrict__ counter, float* __restrict__ cur) {
+    const int k = *counter;
+    if ((int)threadIdx.x < row) cur[threadIdx.x] = table[(long long)k * row + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) *counter = k + 1;
+}
+void launch_sched_select(const float* table, int row, int* counter, float* cur, cudaStream_t s) {
+    sched_select_kernel<<<1, 64, 0, s>>>(table, row, counter, cur);
     AID_COUNT_LAUNCH(1);
 }
 

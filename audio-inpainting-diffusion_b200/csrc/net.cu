@@ -604,8 +604,10 @@ static void probe(Ctx& c, const std::string& name, const TV& v) {
 }
 
 // unet.py:730-845
-static void forward(Ctx& c, const float* x, const float* c_noise, float* out, float in_scale, float out_scale, float skip_scale) {
+static void forward(Ctx& c, const float* x, const float* c_noise, float* out, float in_scale, float out_scale, float skip_scale,
+                    const float* dscal = nullptr) {
     Net& n = *c.n;
+    FftPlan fftd = n.fft; fftd.dscal = dscal;   // in / out / skip scales from device memory (aid_unet_forward_ds)
     const aid_config& cf = n.cfg;
     const int B = c.B, L = cf.audio_len, no = cf.num_octs, bins = cf.bins_per_oct;
     c.slot = 0;
@@ -619,7 +621,7 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
     float2* spec = (float2*)c.ar.alloc((size_t)B * L * sizeof(float2));
     float2* tmp = (float2*)c.ar.alloc((size_t)B * n.fft.M * sizeof(float2));
     float2* fscr = n.fft.M != L ? (float2*)c.ar.alloc((size_t)B * n.fft.M * sizeof(float2)) : nullptr;
-    RUN(launch_fft_big(n.fft, B, false, x, L, in_scale, nullptr, tmp, fscr, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, c.s));
+    RUN(launch_fft_big(fftd, B, false, x, L, in_scale, nullptr, tmp, fscr, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, c.s));
 
     auto Tof = [&](int lvl) { return n.tabs.M[no - 1 - lvl]; };
     std::vector<TV> cat(no);
@@ -699,8 +701,8 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
     }
     c.release(Xout.p);
     RUN(launch_cqt_synth_gather(n.tabs, B, Y, spec, c.s));
-    RUN(launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, fscr, nullptr, out, L, out_scale / (float)L,
-                       skip_scale != 0.f ? x : nullptr, L, skip_scale, c.s));
+    RUN(launch_fft_big(fftd, B, true, nullptr, 0, 0.f, spec, tmp, fscr, nullptr, out, L, out_scale / (float)L,
+                       (skip_scale != 0.f || dscal) ? x : nullptr, L, skip_scale, c.s));
     if (!c.dry()) AID_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -826,6 +828,19 @@ int aid_unet_forward(aid_handle* h, const float* x_dev, const float* c_noise_dev
     });
 }
 
+int aid_unet_forward_ds(aid_handle* h, const float* x_dev, const float* c_noise_dev, int n_sigma, float* out_dev, int B,
+                        const float* scales_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!h || !x_dev || !c_noise_dev || !out_dev || !workspace_dev || !scales_dev || B < 1) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        if (!h->net.finalized) throw std::runtime_error("aid_unet_forward_ds before aid_finalize");
+        if (n_sigma != 1 && n_sigma != B) throw std::invalid_argument("n_sigma must be 1 or B");
+        if (out_dev == x_dev) throw std::invalid_argument("out may not alias x (the skip term reads x)");
+        Ctx c; c.n = &h->net; c.B = B; c.nsig = n_sigma; c.s = (cudaStream_t)stream;
+        c.ar.reset((char*)workspace_dev, workspace_bytes, false);
+        forward(c, x_dev, c_noise_dev, out_dev, 1.f, 1.f, 0.f, scales_dev);
+    });
+}
+
 int aid_cqt_layout(const aid_handle* h, int B, int64_t* offsets, int32_t* frames) {
     if (!h || !offsets) return AID_ERR_INVALID;
     const Net& n = h->net;
@@ -930,6 +945,28 @@ int aid_edm_step(const float* xin, const float* xhat, const float* y, const floa
     if (!xin || !xhat || !x_out || n < 0 || (mask && (!y || mask_n <= 0)) || (mode == 1 && (!d_prev || !xbase)) || (mode != 0 && mode != 1))
         return AID_ERR_INVALID;
     launch_edm_step(xin, xhat, y, mask, mask_n, n, sigma, hstep, mode, d_prev, xbase, d_out, x_out, (cudaStream_t)stream);
+    return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+int aid_edm_step_ds(const float* xin, const float* xhat, const float* y, const float* mask, int64_t mask_n, int64_t n,
+                    const float* sigma_h_dev, int mode, const float* d_prev, const float* xbase, float* d_out, float* x_out, void* stream) {
+    if (!xin || !xhat || !x_out || !sigma_h_dev || n < 0 || (mask && (!y || mask_n <= 0)) || (mode == 1 && (!d_prev || !xbase)) ||
+        (mode != 0 && mode != 1))
+        return AID_ERR_INVALID;
+    launch_edm_step(xin, xhat, y, mask, mask_n, n, 1.f, 0.f, mode, d_prev, xbase, d_out, x_out, (cudaStream_t)stream, sigma_h_dev);
+    return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+int aid_philox_normal(float* x_dev, int n_clips, int64_t L, uint64_t seed, uint32_t stream_id, uint32_t clip0, uint32_t draw, float scale,
+                      int accumulate, const float* scale_draw_dev, void* stream) {
+    if (!x_dev || n_clips < 0 || L < 0 || L > (1ll << 33)) return AID_ERR_INVALID;
+    launch_philox_normal(x_dev, n_clips, L, seed, stream_id, clip0, draw, scale, accumulate != 0, scale_draw_dev, (cudaStream_t)stream);
+    return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+int aid_sched_select(const float* table_dev, int row_floats, int32_t* counter_dev, float* cur_dev, void* stream) {
+    if (!table_dev || !counter_dev || !cur_dev || row_floats < 1 || row_floats > 64) return AID_ERR_INVALID;
+    launch_sched_select(table_dev, row_floats, counter_dev, cur_dev, (cudaStream_t)stream);
     return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
 }
 

@@ -5,12 +5,17 @@ the xi = 0 sampler, so the batch is partitioned into contiguous slices, one proc
 communication inside the 35-step loop.  The only collective is the result gather at the end
 (`torch.distributed.all_gather_into_tensor`: NCCL over NVLink on GPUs, gloo in the CPU tests).
 
-Noise is drawn per clip from a generator seeded with (seed, clip index), so the gathered result does not depend
-on the number of ranks.  (The reference draws one `torch.randn(shape)` for the whole batch, sampler.py:212; that
-single-stream behaviour is what the un-sharded Sampler reproduces.)
+Noise is keyed by (seed, call number, global clip index, draw), so the gathered result does not depend on the number of
+ranks, and consecutive predict_* calls of one ShardedSampler draw fresh noise (the reference advances the global RNG
+between calls).  On CUDA with this package's denoiser the noise is generated on the device (Philox, aid_philox_normal) and the
+step loop is replayed from CUDA graphs; elsewhere (the gloo CPU tests) per-clip torch generators are used.  (The reference
+draws one `torch.randn(shape)` for the whole batch, sampler.py:212; that single-stream behaviour is what the un-sharded
+Sampler reproduces by default.)
 """
 import torch
 import torch.distributed as dist
+
+from .sampler import DeviceNoise
 
 
 def shard_bounds(B, rank, world):
@@ -21,10 +26,10 @@ def shard_bounds(B, rank, world):
 
 
 class ClipNoise:
-    """Iterator of N(0,1) tensors [hi-lo, L] whose row b depends only on (seed, global clip index b, draw number)."""
+    """Iterator of N(0,1) tensors [hi-lo, L] whose row b depends only on (seed, call number, global clip index b, draw number)."""
 
-    def __init__(self, seed, lo, hi, L):
-        self.gens = [torch.Generator().manual_seed((int(seed) * 1000003 + b) % (2 ** 63 - 1)) for b in range(lo, hi)]
+    def __init__(self, seed, lo, hi, L, call=0):
+        self.gens = [torch.Generator().manual_seed(((int(seed) * 1000003 + int(call)) * 1000003 + b) % (2 ** 63 - 1)) for b in range(lo, hi)]
         self.L = L
 
     def __iter__(self):
@@ -54,8 +59,22 @@ def gather_clips(x_local, B, group=None):
 class ShardedSampler:
     """Wraps a Sampler: each rank samples its slice of the batch, one gather at the end."""
 
-    def __init__(self, sampler, seed=0, group=None):
+    def __init__(self, sampler, seed=0, group=None, device_noise=True):
         self.sampler, self.seed, self.group = sampler, seed, group
+        self.device_noise = device_noise      # False: per-clip host generators even on CUDA
+        self.calls = 0                        # folded into the noise key: every predict_* call draws a fresh stream
+
+    def _set_noise(self, lo, hi, L, device):
+        """Install this call's noise stream on the wrapped sampler (same call number on every rank)."""
+        call, self.calls = self.calls, self.calls + 1
+        on_gpu = torch.device(device).type == "cuda" and hasattr(self.sampler.model, "denoise_fused")
+        if on_gpu and self.device_noise:
+            self.sampler.device_noise, self.sampler.noise_source = DeviceNoise(self.seed, stream_id=call, clip0=lo), None
+        else:
+            self.sampler.device_noise, self.sampler.noise_source = None, ClipNoise(self.seed, lo, hi, L, call)
+
+    def _clear_noise(self):
+        self.sampler.noise_source = self.sampler.device_noise = None
 
     def _rank_world(self):
         if dist.is_available() and dist.is_initialized():
@@ -67,7 +86,7 @@ class ShardedSampler:
         rank, world = self._rank_world()
         B, L = y_masked.shape
         lo, hi = shard_bounds(B, rank, world)
-        self.sampler.noise_source = ClipNoise(self.seed, lo, hi, L)
+        self._set_noise(lo, hi, L, y_masked.device)
         try:
             m = mask if mask.shape[0] == 1 else mask[lo:hi]
             if hi > lo:
@@ -75,7 +94,7 @@ class ShardedSampler:
             else:
                 x = y_masked[lo:hi]
         finally:
-            self.sampler.noise_source = None
+            self._clear_noise()
         return gather_clips(x, B, self.group)
 
     def predict_spectrogram_inpainting(self, y_masked, mask):
@@ -83,20 +102,20 @@ class ShardedSampler:
         rank, world = self._rank_world()
         B, L = y_masked.shape
         lo, hi = shard_bounds(B, rank, world)
-        self.sampler.noise_source = ClipNoise(self.seed, lo, hi, L)
+        self._set_noise(lo, hi, L, y_masked.device)
         try:
             x = self.sampler.predict_spectrogram_inpainting(y_masked[lo:hi], mask) if hi > lo else y_masked[lo:hi]
         finally:
-            self.sampler.noise_source = None
+            self._clear_noise()
         return gather_clips(x, B, self.group)
 
     def predict_unconditional(self, shape, device):
         rank, world = self._rank_world()
         B, L = shape
         lo, hi = shard_bounds(B, rank, world)
-        self.sampler.noise_source = ClipNoise(self.seed, lo, hi, L)
+        self._set_noise(lo, hi, L, device)
         try:
             x = self.sampler.predict_unconditional((hi - lo, L), device) if hi > lo else torch.empty(0, L, device=device)
         finally:
-            self.sampler.noise_source = None
+            self._clear_noise()
         return gather_clips(x, B, self.group)

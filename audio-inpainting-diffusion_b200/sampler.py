@@ -17,14 +17,30 @@ Differences that are deliberate and documented:
     itself fails for batch > 1 (autograd.grad of a vector norm, sampler.py:78): here the per-clip norms are summed and the
     step size is normalised per clip, which is the reference's arithmetic at batch 1.
   * `prepare_smooth_mask` is vectorised (the reference loops over L samples in Python, sampler.py:311-324).
+  * Noise.  By default it is drawn with torch's CPU generator and copied, exactly as the reference does (edm.py:94,
+    sampler.py:212), so seeded runs reproduce the reference's trajectories.  `sampler.device_noise = DeviceNoise(seed, ...)`
+    switches to device-resident Philox4x32-10 normals keyed by (seed, stream id, global clip index, draw) (aid_philox_normal,
+    restated in oracle/philox_oracle.py): no host work and no H2D copy per step, and a clip's noise does not depend on the batch or
+    the rank it is sampled in.  With device noise on a CUDA denoiser of this package the step loop is replayed from two captured
+    CUDA graphs (one Heun step, one final Euler step; `use_cuda_graph`, default on): every per-step scalar (noise scale, draw,
+    c_in / c_out / c_skip / c_noise, sigma, h) lives in a device table that the graph's head node indexes (aid_sched_select), so
+    one graph serves all 35 steps.
   * Spectrogram inpainting (sampler.py:271-290, 348-364): on CUDA tensors the STFT -> mask -> inverse STFT degradation and the
     projection `y + x - S(x)` are hand-written kernels (csrc/stft.cu, aid_spectral_mask); on CPU tensors (host-logic tests
     only) the reference's torch.stft / torch.istft calls are used.
 """
+import numpy as np
 import torch
 
 from . import _lib
 from .config import cfg_get
+
+
+class DeviceNoise:
+    """Device-resident noise stream: seed (64 bit), stream_id (e.g. a per-call counter), clip0 = global index of the batch's first clip."""
+
+    def __init__(self, seed, stream_id=0, clip0=0):
+        self.seed, self.stream_id, self.clip0 = int(seed) & (2 ** 64 - 1), int(stream_id) & 0xFFFFFFFF, int(clip0) & 0xFFFFFFFF
 
 
 class Sampler:
@@ -45,6 +61,9 @@ class Sampler:
         self.nb_steps = cfg_get(args, "tester.T")
         self.rid = rid
         self.noise_source = None  # optional iterator of pre-drawn N(0,1) tensors (prior first), for parity tests
+        self.device_noise = None  # DeviceNoise: Philox normals generated on the GPU instead of torch.randn on the host
+        self.use_cuda_graph = True  # with device noise on the fused CUDA path: replay the step loop from captured CUDA graphs
+        self._graphs = {}
         self.y = self.mask = self.degradation = None
         self._smooth_mask = None
         self._spectral = False      # True while the projection is the spectrogram one (predict_spectrogram_inpainting)
@@ -169,7 +188,12 @@ class Sampler:
             rec_grads = torch.autograd.grad(outputs=norm.sum(), inputs=x)[0]     # clips are independent: per-clip gradients
         audio_len = cfg_get(self.args, "exp.audio_len")
         gdim = tuple(range(1, rec_grads.dim()))
-        normguide = torch.linalg.norm(rec_grads.reshape(rec_grads.shape[0], -1), dim=1).reshape((-1,) + (1,) * len(gdim)) / audio_len ** 0.5
+        if kind == "smoothl1":
+            # the reference runs at any batch size here (a scalar loss) and normalises by ONE norm over the whole batch (sampler.py:83)
+            normguide = torch.linalg.norm(rec_grads) / audio_len ** 0.5
+        else:
+            # sampler.py:78 fails for batch > 1 (autograd.grad of a vector); per-clip norms are the batch-1 arithmetic, clip by clip
+            normguide = torch.linalg.norm(rec_grads.reshape(rec_grads.shape[0], -1), dim=1).reshape((-1,) + (1,) * len(gdim)) / audio_len ** 0.5
         s = t_i * self.xi / (normguide + 1e-6)
         x_hat = x_hat.detach()
         x_hat_old = x_hat.clone() if self.rid else None
@@ -240,22 +264,38 @@ class Sampler:
         dev = torch.device(device)
         t = dp.create_schedule(self.nb_steps)        # host, fp32
         gamma = dp.get_gamma(t)
-        x = self._randn(shape, dev) * t[0].to(dev)
         use_proj = conditional and self.data_consistency
         if conditional and not use_proj and not hasattr(self, "proj_convex_set"):
             raise AttributeError("'Sampler' object has no attribute 'proj_convex_set'")  # sampler.py:145 with consistency off
         hpf = (not conditional) and bool(cfg_get(self.args, "tester.filter_out_cqt_DC_Nyq"))
         fused = dev.type == "cuda" and hasattr(self.model, "denoise_fused") and (not conditional or self._smooth_mask is not None or self._spectral)
+        dn = self.device_noise if self.noise_source is None else None
+        if dn is not None and not fused:
+            raise NotImplementedError("device_noise needs CUDA tensors and this package's CUDA denoiser (with data consistency when conditional)")
+        if dn is not None and self.use_cuda_graph and len(shape) == 2 and self.order in (1, 2):
+            x = _GraphedLoop.get(self, shape, dev, conditional, hpf).run(t, gamma, dn)
+            if self.data_consistency_end:
+                x = self.proj_convex_set(x)
+            return x.detach()
         ops = _CudaOps(self, dev) if fused else _TorchOps(self)
+        draw = 0
+        if dn is not None:
+            x = ops.philox(torch.empty(shape, device=dev, dtype=torch.float32), dn, draw, float(t[0]), False)
+        else:
+            x = self._randn(shape, dev) * t[0].to(dev)
 
         for i in range(self.nb_steps):
             if gamma[i] == 0:
                 t_hat = t[i]
             else:
                 t_hat = t[i] + gamma[i] * t[i]
-                eps = self._randn(shape, dev)
-                x = ops.add_noise(x, eps, ((t_hat ** 2 - t[i] ** 2) ** (1 / 2)), dp.Snoise)
-                del eps
+                if dn is not None:
+                    draw += 1
+                    x = ops.philox(x, dn, draw, float((t_hat ** 2 - t[i] ** 2) ** (1 / 2)) * float(dp.Snoise), True)
+                else:
+                    eps = self._randn(shape, dev)
+                    x = ops.add_noise(x, eps, ((t_hat ** 2 - t[i] ** 2) ** (1 / 2)), dp.Snoise)
+                    del eps
             h = t[i + 1] - t_hat
             second = bool(t[i + 1] != 0) and self.order == 2
             xh = ops.denoise(x, t_hat, hpf)
@@ -358,6 +398,15 @@ class _CudaOps:
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
+    def philox(self, x, dn, draw, scale, accumulate):
+        """x[c] = (accumulate ? x[c] : 0) + scale * N(seed, stream, clip0 + c, draw)   (edm.py:94, sampler.py:212-214 on the device)"""
+        x = x.contiguous()
+        flat = x.reshape(x.shape[0], -1)
+        with torch.cuda.device(self.dev):
+            _lib.check(self.L.aid_philox_normal(_lib.ptr(flat), flat.shape[0], flat.shape[1], dn.seed, dn.stream_id, dn.clip0, draw,
+                                                float(scale), 1 if accumulate else 0, None, self._stream()))
+        return x
+
     def add_noise(self, x, eps, scale, snoise):
         x = x.contiguous()
         with torch.cuda.device(self.dev):
@@ -385,3 +434,151 @@ class _CudaOps:
                                            0 if mask is None else mask.numel(), xin.numel(), float(sigma), float(h), mode,
                                            _lib.ptr(d_prev), _lib.ptr(xbase), _lib.ptr(d_out), _lib.ptr(x_out), self._stream()))
         return d_out, x_out
+
+
+class _GraphedLoop:
+    """The 35-step loop of Sampler.predict (sampler.py:201-251) as replays of two captured CUDA graphs.
+
+    Graph A (Heun step): select row -> x += scale * Philox -> xh = D(x; t_hat) [-> HPF | projection] -> d, x1 = Euler ->
+    xh2 = D(x1; t_next) [...] -> x = x + h (d + d2) / 2, all on the static buffers below, x updated in place.
+    Graph B (last step, t_next = 0, or every step when order == 1): the first half, x = x + h d.
+    Nothing of the schedule is baked into the graphs: every scalar comes from row `counter` of a device table
+    (row = [noise scale, draw, stream id, clip0 | c_in, c_out, c_skip, c_noise, sigma, h of evaluation 1 | the same of evaluation 2])."""
+    ROW, E1, E2, MAX_STEPS = 16, 4, 10, 1024
+
+    @staticmethod
+    def get(s, shape, dev, conditional, hpf):
+        kind = "spectral" if (conditional and s._spectral) else ("inpaint" if conditional else "uncond")
+        key = (tuple(shape), str(dev), kind, bool(hpf), id(s.model))
+        g = s._graphs.get(key)
+        if g is None:
+            s._graphs.clear()          # one live set of static buffers per sampler
+            g = s._graphs[key] = _GraphedLoop(s, shape, dev, kind, hpf)
+        g.bind_inputs()
+        return g
+
+    def __init__(self, s, shape, dev, kind, hpf):
+        self.s, self.dev, self.kind, self.hpf, self.shape = s, dev, kind, hpf, tuple(shape)
+        self.L = _lib.lib()
+        B, n = self.shape
+        f = lambda: torch.empty(B, n, device=dev, dtype=torch.float32)
+        self.x, self.xh, self.d, self.x1, self.xh2 = f(), f(), f(), f(), f()
+        self.hp = f() if hpf else None
+        self.y = f() if kind != "uncond" else None
+        self.mask = torch.empty(n, device=dev, dtype=torch.float32) if kind == "inpaint" else None
+        self.cur = torch.zeros(self.ROW, device=dev, dtype=torch.float32)
+        self.counter = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.table = torch.zeros(self.MAX_STEPS, self.ROW, device=dev, dtype=torch.float32)
+        self.seed = None
+        self.graphs = {}               # heun (bool) -> torch.cuda.CUDAGraph
+        m = s.model
+        m._ensure_weights(dev)
+        self.ws = m._workspace(B, dev)
+        if hpf:
+            nb = _lib.C.c_size_t()
+            _lib.check(self.L.aid_cqt_workspace_bytes(m._handle, B, _lib.C.byref(nb)), m._handle)
+            self.hws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+
+    def bind_inputs(self):
+        """Copy the current call's y / mask into the static buffers the graphs read."""
+        s = self.s
+        if self.kind == "inpaint":
+            m = s._smooth_mask
+            m = m[0] if (m.dim() == 2 and (m.stride(0) == 0 or m.shape[0] == 1)) else m
+            if m.dim() != 1:
+                raise NotImplementedError("the graphed loop takes one mask shared by the batch (sampler.py:307 uses mask[0] only)")
+            self.mask.copy_(m.to(self.dev, torch.float32))
+            self.y.copy_(s._proj_y.to(self.dev, torch.float32))
+        elif self.kind == "spectral":
+            self.y.copy_(s.y.to(self.dev, torch.float32))
+
+    # ---- the launches of one step on the current stream --------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _denoise(self, xin, e, out):
+        s, m, cur, B = self.s, self.s.model, self.cur, self.shape[0]
+        _lib.check(self.L.aid_unet_forward_ds(m._handle, _lib.ptr(xin), _lib.ptr(cur[e + 3:]), 1, _lib.ptr(out), B, _lib.ptr(cur[e:]),
+                                              _lib.ptr(self.ws), self.ws.numel(), self._stream()), m._handle)
+        if self.hpf:
+            _lib.check(self.L.aid_hpf_dc(m._handle, _lib.ptr(out), _lib.ptr(self.hp), B, _lib.ptr(self.hws), self.hws.numel(), self._stream()), m._handle)
+            out.copy_(self.hp)
+        if self.kind == "spectral":          # xhat <- y + xhat - S(xhat)
+            out.copy_(s.apply_spectral_mask(out, self.y))
+
+    def _edm(self, xin, xh, e, mode, d_prev, xbase, d_out, x_out):
+        mk = self.mask if self.kind == "inpaint" else None
+        y = self.y if self.kind == "inpaint" else None
+        _lib.check(self.L.aid_edm_step_ds(_lib.ptr(xin), _lib.ptr(xh), _lib.ptr(y), _lib.ptr(mk), 0 if mk is None else mk.numel(), xin.numel(),
+                                          _lib.ptr(self.cur[e + 4:]), mode, _lib.ptr(d_prev), _lib.ptr(xbase), _lib.ptr(d_out), _lib.ptr(x_out),
+                                          self._stream()))
+
+    def _step(self, heun):
+        B, n = self.shape
+        _lib.check(self.L.aid_sched_select(_lib.ptr(self.table), self.ROW, _lib.ptr(self.counter), _lib.ptr(self.cur), self._stream()))
+        _lib.check(self.L.aid_philox_normal(_lib.ptr(self.x), B, n, self.seed, 0, 0, 0, 0.0, 1, _lib.ptr(self.cur), self._stream()))
+        self._denoise(self.x, self.E1, self.xh)
+        if heun:
+            self._edm(self.x, self.xh, self.E1, 0, None, None, self.d, self.x1)
+            self._denoise(self.x1, self.E2, self.xh2)
+            self._edm(self.x1, self.xh2, self.E2, 1, self.d, self.x, None, self.x)
+        else:
+            self._edm(self.x, self.xh, self.E1, 0, None, None, None, self.x)
+
+    def _graph(self, heun):
+        g = self.graphs.get(heun)
+        if g is None:
+            # one eager step first (module loading, shared-memory attributes), on a side stream as capture requires
+            side = torch.cuda.Stream(self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(side):
+                self.x.zero_(); self.counter.zero_()
+                self._step(heun)
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step(heun)
+            self.graphs[heun] = g
+        return g
+
+    def _rows(self, t, gamma, dn):
+        """Host-built schedule rows, the same fp32 scalar arithmetic as the eager loop (edm.py:97-128, sampler.py:204-236)."""
+        s, dp = self.s, self.s.diff_params
+        rows, ints, kinds, draw = [], [], [], 0
+        for i in range(s.nb_steps):
+            r = [0.0] * self.ROW
+            if gamma[i] == 0:
+                t_hat = t[i]
+            else:
+                t_hat = t[i] + gamma[i] * t[i]
+                draw += 1
+                r[0] = float((t_hat ** 2 - t[i] ** 2) ** (1 / 2)) * float(dp.Snoise)
+            h = t[i + 1] - t_hat
+            heun = bool(t[i + 1] != 0) and s.order == 2
+            for e, sg in ((self.E1, t_hat),) + (((self.E2, t[i + 1]),) if heun else ()):
+                sig = sg.reshape(1, 1)
+                r[e:e + 6] = [float(dp.cin(sig)), float(dp.cout(sig)), float(dp.cskip(sig)), float(dp.cnoise(sig)), float(sg), float(h)]
+            rows.append(r)
+            ints.append([draw, dn.stream_id, dn.clip0])
+            kinds.append(heun)
+        tab = torch.tensor(rows, dtype=torch.float32)
+        tab[:, 1:4] = torch.from_numpy(np.array(ints, dtype=np.uint32).view(np.float32))     # draw, stream id, clip0 as bit patterns
+        return tab, kinds
+
+    def run(self, t, gamma, dn):
+        s = self.s
+        if s.nb_steps > self.MAX_STEPS:
+            raise ValueError(f"the graphed loop holds at most {self.MAX_STEPS} steps")
+        tab, kinds = self._rows(t, gamma, dn)
+        with torch.cuda.device(self.dev):
+            if self.seed != dn.seed:     # the Philox key is a launch parameter of the captured noise node
+                self.seed, self.graphs = dn.seed, {}
+            graphs = {h: self._graph(h) for h in sorted(set(kinds))}
+            self.table[: tab.shape[0]].copy_(tab.to(self.dev))
+            self.counter.zero_()
+            _lib.check(self.L.aid_philox_normal(_lib.ptr(self.x), self.shape[0], self.shape[1], dn.seed, dn.stream_id, dn.clip0, 0, float(t[0]),
+                                                0, None, self._stream()))
+            for heun in kinds:
+                graphs[heun].replay()
+            return self.x.clone()

@@ -9,9 +9,12 @@ A step = one forward of the 186.3 M-parameter CQT-octave U-Net over one batch of
   value       clips/s with the batch resident in HBM, CUDA events, max over ranks, whole job
   e2e         the same through the public nn.Module call with pinned HOST buffers (H2D + forward + D2H per step)
   roofline    dominant kernel (the dilated 5x3 convolutions): algorithmic FLOPs / CUDA-event time vs measured peak
-  cpu_baseline the CPU oracle (port of the reference's PyTorch path) on a bounded sample, rank 0, N=1 only
-`--impl reference` times the reference's CPU path (the oracle port: the reference is Python + an un-vendored
-dependency and cannot travel to the GPU box) on the host cores, on the same workload definition.
+  cpu_baseline the reference's CPU path on a bounded sample (one clip of the full length), rank 0, N=1 only
+  fp32_grade  the same step in conv_mode 1 (split fp16 x3, <= 1e-4 from the fp32 reference), N=1 only
+`--impl reference` times the reference's CPU implementation of the path on the host cores, on the same workload definition:
+the reference's own unet.py when build() could copy it into the git-ignored oracle/_ref/ (kind "reference"; the un-vendored
+CQT dependency comes from oracle/cqt_oracle.py), else the oracle restatement (kind "port").  That arm never imports the
+product package and never loads libaid_b200.so.
 """
 import argparse
 import ctypes as C
@@ -88,45 +91,113 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_forward_time(L, n_clips, threads):
-    """Seconds per forward of the CPU oracle (the reference's PyTorch path restated) on n_clips x L, best of 2."""
+class _Args(dict):
+    """Attribute dict for the reference's `args.network.*` / `args.exp.*` reads (unet.py:595-655); no product import."""
+    __getattr__ = dict.__getitem__
+
+    @staticmethod
+    def wrap(o):
+        return _Args({k: _Args.wrap(v) for k, v in o.items()}) if isinstance(o, dict) else o
+
+
+def paper_args(L):
+    """conf/network/paper_1912_unet_cqt_oct_attention_adaLN_2.yaml + conf/exp/maestro22k_*.yaml as the reference reads them."""
+    return _Args.wrap({
+        "exp": {"sample_rate": 22050, "audio_len": L},
+        "network": {"use_fencoding": False, "use_norm": True, "emb_dim": 256, "Ns": [64, 96, 96, 128, 128, 256, 256], "Ss": [2] * 6,
+                    "num_dils": [2, 3, 4, 5, 6, 7, 7], "attention_layers": [0, 0, 0, 0, 1, 1, 1, 1], "bottleneck_type": "res_dil_convs",
+                    "num_bottleneck_layers": 1, "cqt": {"window": "kaiser", "beta": 1, "num_octs": 7, "bins_per_oct": 64},
+                    "attention_dict": {"num_heads": 8, "attn_dropout": 0.0, "bias_qkv": False, "N": 0, "rel_pos_num_buckets": 32,
+                                       "rel_pos_max_distance": 64, "use_rel_pos": False, "Nproj": 8}},
+    })
+
+
+def cpu_denoiser(L):
+    """The reference's CPU implementation of the path -> (forward(x[B,L], c_noise[1,1]), kind, description).
+
+    kind "reference": the reference's own unet.py (build() copies it, unmodified, into the git-ignored oracle/_ref/ when
+    /root/reference exists; its un-vendored CQT dependency is supplied by oracle/cqt_oracle.py), default-initialised by its own
+    constructor.  kind "port": oracle/unet_oracle.py (the restatement; its resampler is a depthwise conv1d instead of the
+    reference's dense [F,F,8] weight, so it is somewhat FASTER than the real reference) with random weights of the schema
+    stored in tests/golden/golden_meta.json.  Neither imports the product package or loads libaid_b200.so."""
     import torch
-    sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
-    import aid_b200
-    from util import make_oracle
-    torch.set_num_threads(threads)
-    cfg = aid_b200.paper_22k(L)
-    orc = make_oracle(cfg, aid_b200.random_state_dict(cfg, seed=1234))
-    x = torch.randn(n_clips, L, generator=torch.Generator().manual_seed(0)) * 0.5
-    cn = torch.tensor([[-0.3]])
-    return orc, x, cn
+    sys.path[:0] = [os.path.join(ROOT, "oracle")]
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.exists(os.path.join(ref_dir, "networks", "unet_cqt_oct_with_projattention_adaLN_2.py")):
+        import cqt_oracle
+        cqt_oracle.install_as_cqt_nsgt_pytorch()
+        sys.path.insert(0, ref_dir)
+        from networks.unet_cqt_oct_with_projattention_adaLN_2 import Unet_CQT_oct_with_attention as RefNet
+        torch.manual_seed(1234)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):     # the constructor prints its layer plan
+            net = RefNet(paper_args(L), "cpu")
+
+        def fwd(x, cn):
+            with torch.no_grad():
+                return net(x, cn)
+        return fwd, "reference", "the reference's own unet.py (oracle/_ref copy) + the CQT restatement, default init"
+    import unet_oracle
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_meta.json")))
+    g = torch.Generator().manual_seed(1234)
+    sd = {}
+    for name, shape in meta["schema_paper"]:
+        fan = 1
+        for d in shape[1:]:
+            fan *= d
+        sd[name] = (torch.rand(shape, generator=g) * 2 - 1) / max(fan, 1) ** 0.5
+    cfg = dict(num_octs=7, bins_per_oct=64, sample_rate=22050, audio_len=L, window="kaiser", beta=1, Ns=[64, 96, 96, 128, 128, 256, 256],
+               num_dils=[2, 3, 4, 5, 6, 7, 7], attention_layers=[0, 0, 0, 0, 1, 1, 1, 1])
+    orc = unet_oracle.UnetOracle(cfg, sd)
+    return (lambda x, cn: orc(x, cn)), "port", "oracle/unet_oracle.py (restatement of the reference's PyTorch path), random weights"
+
+
+def bench_config(B, L):
+    """The workload both arms report (the reference arm echoes it verbatim)."""
+    return {"workload": f"denoiser forward, paper_1912 CQT-octave U-Net (186.3M params, random init), batch {B} x {L} samples per GPU, shared sigma",
+            "batch_per_gpu": B, "audio_len": L,
+            "l2": "per-step working set is tens of GB of activations, far larger than the 126 MB L2 (no flush needed)"}
+
+
+METRIC = "denoiser-fwd clips/s at 22.05 kHz, 262144-len, batch 32"
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path (oracle port), all host threads."""
+    """Reference arm: the reference's own CPU implementation of the path on all host cores.  A step is a bounded sample of
+    the batch-B workload (n clips of the full length per forward); value = clips/s."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     L, B = args.len, args.batch
-    orc, x, cn = oracle_forward_time(L, 1, threads)
-    # a step = one clip of the batch-32 workload (bounded sample); no JIT or clocks to warm on the CPU, so one warm-up
-    t0 = time.perf_counter(); orc(x, cn); t_first = time.perf_counter() - t0
-    k_eff = max(1, min(args.steps, int(240.0 / max(t_first, 1e-3))))
+    fwd, kind, what = cpu_denoiser(L)
+    cn = torch.tensor([[-0.3]])
+    g = torch.Generator().manual_seed(0)
+    x1 = torch.randn(1, L, generator=g) * 0.5
+    t0 = time.perf_counter(); fwd(x1, cn); t_first = time.perf_counter() - t0          # also pages everything in
+    # clips per step: 2 when the whole run (W + K steps) stays within ~5 minutes, else 1; K is cut only if even that is too long
+    total = args.steps + args.warmup
+    n = 2 if 2 * t_first * total <= 300.0 else 1
+    n = min(n, B)
+    k_eff = args.steps if n * t_first * total <= 600.0 else max(1, int(600.0 / (n * t_first)) - args.warmup)
+    x = torch.randn(n, L, generator=g) * 0.5
+    for _ in range(args.warmup):
+        fwd(x, cn)
     ts = []
     for _ in range(k_eff):
-        t0 = time.perf_counter(); orc(x, cn); ts.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); fwd(x, cn); ts.append(time.perf_counter() - t0)
     ms = 1e3 * sum(ts) / len(ts)
-    val = 1.0 / (ms / 1e3)
-    sample = f"1 clip x {L} samples per step (of the batch-{B} workload), {k_eff} timed steps after 1 warm-up"
+    val = n / (ms / 1e3)
+    sample = (f"{what}; each step = one forward over {n} clip(s) x {L} samples (a bounded sample of the batch-{B} step: "
+              f"a full step would be {B / n:.0f}x longer), {k_eff} timed steps after {args.warmup} warm-up steps, {threads} threads")
     print(json.dumps({
-        "impl": "reference", "metric": "denoiser-fwd clips/s at 22.05 kHz, 262144-len, batch 32", "value": val, "unit": "clips/s",
-        "n_gpus": args.gpus, "steps": k_eff, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "clips/s",
+        "n_gpus": args.gpus, "steps": k_eff, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"denoiser forward, paper_1912 CQT-octave U-Net (186.3M params), batch {B} x {L} samples per GPU",
-                   "batch_per_gpu": B, "audio_len": L},
-        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": bench_config(B, L), "sample_clips_per_step": n,
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -142,6 +213,7 @@ def main():
     ap.add_argument("--len", type=int, default=262144)
     ap.add_argument("--conv-mode", type=int, default=int(os.environ.get("AID_CONV_MODE", "2")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32-grade", action="store_true", help="skip the secondary conv_mode 1 measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -220,6 +292,30 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1) / args.steps
 
+    fp32_grade = None
+    if world == 1 and args.conv_mode == 2 and not args.no_fp32_grade:
+        # the same step in conv_mode 1 (error-compensated split fp16, 3 MMAs per tap: <= 1e-4 from the fp32 reference)
+        net._release()
+        torch.cuda.empty_cache()
+        cfg1 = aid_b200.paper_22k(L, conv_mode=1)
+        net1 = aid_b200.Unet_CQT_oct_with_attention(cfg1, dev)
+        net1.load_state_dict(aid_b200.random_state_dict(cfg1, seed=1234))
+        for _ in range(3):
+            net1.denoise_fused(x, cn, out=out)
+        k1 = min(args.steps, 5)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record()
+        for _ in range(k1):
+            net1.denoise_fused(x, cn, out=out)
+        g1.record()
+        torch.cuda.synchronize()
+        ms1 = g0.elapsed_time(g1) / k1
+        fp32_grade = {"conv_mode": 1, "dtype": "f16x3-split (fp32 accumulate), <= 1e-4 rel-L2 from the fp32 reference", "value": B / (ms1 / 1e3),
+                      "unit": "clips/s", "ms_per_step": ms1, "steps": k1, "warmup": 3}
+        net1._release()
+        del net1
+
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -236,14 +332,12 @@ def main():
             except Exception:
                 traffic = None
         line = {
-            "metric": "denoiser-fwd clips/s at 22.05 kHz, 262144-len, batch 32", "value": world * B / (ms / 1e3), "unit": "clips/s",
+            "metric": METRIC, "value": world * B / (ms / 1e3), "unit": "clips/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": {0: "f32", 1: "f16x3-split (fp32 accumulate)", 2: "f16 (fp32 accumulate)"}[args.conv_mode],
             "data": "synthetic",
-            "config": {"workload": f"denoiser forward, paper_1912 CQT-octave U-Net (186.3M params, random init), batch {B} x {L} samples per GPU, shared sigma",
-                       "batch_per_gpu": B, "audio_len": L, "conv_mode": args.conv_mode,
-                       "parallelism": f"batch sharded over {world} rank(s), no collective inside the step",
-                       "l2": "per-step working set is tens of GB of activations, far larger than the 126 MB L2 (no flush needed)"},
+            "config": bench_config(B, L), "conv_mode": args.conv_mode,
+            "parallelism": f"batch sharded over {world} rank(s), {B} clips each, no collective inside the step",
             "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * L * 4},
             "gpu_launches": int(launches),
             "clocks": clk,
@@ -260,15 +354,21 @@ def main():
                                            "algorithmic_gbs": B * GB_PER_CLIP.get(L, 0) / (ms / 1e3),
                                            "frac_of_hbm_roof": B * GB_PER_CLIP.get(L, 0) / (ms / 1e3) / pk["hbm"]}},
         }
+        if fp32_grade is not None:
+            line["fp32_grade"] = fp32_grade
         if world == 1 and not args.no_cpu_baseline:
+            # bounded sample of the same workload on the host cores: one clip of the full length, 1 warm-up + 1 timed forward
+            del net
+            torch.cuda.empty_cache()
             threads = os.cpu_count() or 1
-            Ls = 65536  # bounded sample: one clip of a quarter of the length (work per sample is length-independent: 15.5 MFLOP)
-            orc, xs, cns = oracle_forward_time(Ls, 1, threads)
-            orc(xs, cns)
-            t0 = time.perf_counter(); orc(xs, cns); tt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": (Ls / L) / tt, "unit": "clips/s", "cores": threads, "kind": "port",
-                                    "sample": f"oracle (reference PyTorch path restated) on 1 clip x {Ls} samples, 1 warm-up + 1 timed forward, "
-                                              f"scaled by {Ls}/{L} to 262144-sample clips (work per sample is constant)"}
+            torch.set_num_threads(threads)
+            fwd, kind, what = cpu_denoiser(L)
+            xs = torch.randn(1, L, generator=torch.Generator().manual_seed(0)) * 0.5
+            cns = torch.tensor([[-0.3]])
+            fwd(xs, cns)
+            t0 = time.perf_counter(); fwd(xs, cns); tt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1.0 / tt, "unit": "clips/s", "cores": threads, "kind": kind,
+                                    "sample": f"{what}; 1 clip x {L} samples (one of the {B} clips of a step), 1 warm-up + 1 timed forward, {threads} threads"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

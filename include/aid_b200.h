@@ -80,6 +80,12 @@ int aid_unet_forward(aid_handle* h, const float* x_dev, const float* c_noise_dev
                      float in_scale, float out_scale, float skip_scale, void* workspace_dev, size_t workspace_bytes,
                      void* stream);
 
+/* The same forward with the preconditioning scalars in DEVICE memory: scales_dev = [in_scale, out_scale, skip_scale].  Nothing
+ * of the current noise level is baked into the launch parameters, so a captured CUDA graph of a sampler step can be replayed for
+ * every step of the schedule (sampler.py:201-251); out_dev may not alias x_dev. */
+int aid_unet_forward_ds(aid_handle* h, const float* x_dev, const float* c_noise_dev, int n_sigma, float* out_dev, int B,
+                        const float* scales_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* CQT_nsgt.fwd / bwd / apply_hpf_DC                         unet.py:743, unet.py:841, sampler.py:63,123
  * coefficient layout: per octave o (ascending frequency) a [B, 2, bins, T_o] fp32 tensor (re, im planes),
  * octave tensors concatenated in one buffer at offsets aid_cqt_layout() reports (in floats, for batch B). */
@@ -100,6 +106,24 @@ int aid_edm_add_noise(float* x_dev, const float* eps_dev, float scale, int64_t n
 int aid_edm_step(const float* xin_dev, const float* xhat_dev, const float* y_dev, const float* mask_dev, int64_t mask_n,
                  int64_t n, float sigma, float h, int mode, const float* d_prev_dev, const float* xbase_dev,
                  float* d_out_dev, float* x_out_dev, void* stream);
+
+/* aid_edm_step with sigma = sigma_h_dev[0], h = sigma_h_dev[1] read on the device (graph replay) */
+int aid_edm_step_ds(const float* xin_dev, const float* xhat_dev, const float* y_dev, const float* mask_dev, int64_t mask_n, int64_t n,
+                    const float* sigma_h_dev, int mode, const float* d_prev_dev, const float* xbase_dev, float* d_out_dev,
+                    float* x_out_dev, void* stream);
+
+/* Device-resident noise for sample_prior (edm.py:87-95) and the churn noise (sampler.py:210-214), which the reference draws on the
+ * CPU generator and copies (4*B*L bytes per step): x[c][i] = (accumulate ? x[c][i] : 0) + scale * n(seed, stream_id, clip0 + c, draw, i)
+ * for c < n_clips, i < L, where n() are standard normals from Philox4x32-10 (counter = (i/4, draw, clip, stream_id), key = seed) and
+ * Box-Muller.  A clip's noise does not depend on the batch or rank it is sampled in.  scale_draw_dev (may be NULL): device scalars
+ * [scale, draw, stream_id, clip0] (the last three as 32-bit patterns) overriding the by-value arguments (graph replay).  Restated in oracle/philox_oracle.py. */
+int aid_philox_normal(float* x_dev, int n_clips, int64_t L, uint64_t seed, uint32_t stream_id, uint32_t clip0, uint32_t draw,
+                      float scale, int accumulate, const float* scale_draw_dev, void* stream);
+
+/* cur_dev[0..row_floats) = table_dev[*counter_dev][0..row_floats); ++*counter_dev -- the head node of a replayed sampler-step graph:
+ * row k of the host-built schedule table (noise scale, draw, c_in / c_out / c_skip / c_noise / sigma / h of the step's evaluations)
+ * becomes the current device scalars.  row_floats <= 64. */
+int aid_sched_select(const float* table_dev, int row_floats, int32_t* counter_dev, float* cur_dev, void* stream);
 
 /* Spectrogram-inpainting degradation S(x) = crop(istft(mask * stft(zero-pad(x)))) with a periodic Hann window of n_fft samples,
  * centre = True / reflect padding, as Sampler.apply_spectral_mask does with torch.stft / torch.istft   sampler.py:271-290

@@ -61,10 +61,25 @@ def test_sharded_sampling_is_independent_of_world_size(aid):
     y = torch.randn(B, L, generator=torch.Generator().manual_seed(1)) * 0.063
     mask = torch.ones(1, L)
     mask[..., 900:1100] = 0
-    out1 = ShardedSampler(aid.Sampler(_FakeNet(), aid.EDM(args), args), seed=7).predict_inpainting(y * mask, mask)
-    assert out1.shape == (B, L) and torch.equal(out1, out2)
-    # spectrogram mode: shared [513, frames] mask, clips sharded the same way
-    assert torch.equal(ret["out_s"], ret["out_s1"])
     sh = ShardedSampler(aid.Sampler(_FakeNet(), aid.EDM(args), args), seed=7)
+    out1 = sh.predict_inpainting(y * mask, mask)
+    assert out1.shape == (B, L) and torch.equal(out1, out2)
+    # spectrogram mode: shared [513, frames] mask, clips sharded the same way (second call of the sampler, as in the workers)
+    assert torch.equal(ret["out_s"], ret["out_s1"])
     smask, ym = _spectral_inputs(sh.sampler, y)
     assert torch.equal(sh.predict_spectrogram_inpainting(ym, smask), ret["out_s"])
+
+
+def test_consecutive_calls_draw_fresh_noise(aid):
+    """The call number is part of the noise key: two calls of one ShardedSampler differ (the reference advances the global RNG
+    between calls), two samplers with the same seed agree call by call."""
+    from aid_b200.dist import ShardedSampler
+    from test_host import _FakeNet, _tester_args
+    args = _tester_args(aid, T=4)
+    mk = lambda: ShardedSampler(aid.Sampler(_FakeNet(), aid.EDM(args), args), seed=3)
+    a, b = mk(), mk()
+    a0, a1 = a.predict_unconditional((2, 1024), "cpu"), a.predict_unconditional((2, 1024), "cpu")
+    b0, b1 = b.predict_unconditional((2, 1024), "cpu"), b.predict_unconditional((2, 1024), "cpu")
+    assert not torch.equal(a0, a1)
+    assert torch.equal(a0, b0) and torch.equal(a1, b1)
+    assert a.sampler.noise_source is None and a.sampler.device_noise is None

@@ -200,3 +200,44 @@ def test_forward_reference_trained_length_184184(aid, cuda, mode):
     cn = torch.tensor([[-0.6]])
     ref = make_oracle(cfg, sd)(x, cn)
     assert rel_l2(net(x.to(cuda), cn.to(cuda)), ref) < (1e-3 if mode == 2 else 1e-4)
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_forward_eight_octave_44k_network(aid, cuda, mode):
+    """conf/network/paper_1912_unet_cqt_oct_attention_44k_2.yaml (8 octaves, fs = 44100, dilations up to 2^7, attention on T = 64 / 32 / 16
+    frames) at the reference's trained length 184184: a narrowed copy of the topology block by block against the oracle
+    (which tests/test_oracle_vs_reference.py pins to the reference module for this configuration)."""
+    cfg = aid.paper_44k(184184, conv_mode=mode)
+    cfg.Ns = [16, 16, 32, 32, 32, 48, 64, 64]
+    sd = aid.random_state_dict(cfg, seed=44)
+    net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+    net.load_state_dict(sd)
+    x = seeded((2, cfg.audio_len), 4, 0.7)
+    cn = torch.tensor([[-0.4]])
+    probe = {}
+    ref = make_oracle(cfg, sd)(x, cn, probe=probe)
+    out, got = net.forward_with_probes(x.to(cuda), cn.to(cuda))
+    tol = 1e-4 if mode == 0 else 1e-3
+    errs = {k: rel_l2(got[k], probe[k]) for k in sorted(probe)}
+    errs["out"] = rel_l2(out, ref)
+    print(f"8-octave 44.1 kHz network, conv_mode {mode}:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert len(probe) == 17
+    for k, v in errs.items():
+        assert v < tol, (k, v)
+
+
+def test_forward_eight_octave_44k_full_width(aid, cuda):
+    """The full 242 M-parameter 44.1 kHz network (795 tensors) at 184184 samples, conv_mode 2, against the oracle."""
+    cfg = aid.paper_44k(184184, conv_mode=2)
+    sd = aid.random_state_dict(cfg, seed=45)
+    assert len(sd) == 795
+    net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+    net.load_state_dict(sd)
+    x = seeded((1, cfg.audio_len), 4, 0.7)
+    cn = torch.tensor([[-0.4]])
+    import os
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = make_oracle(cfg, sd)(x, cn)
+    e = rel_l2(net(x.to(cuda), cn.to(cuda)), ref)
+    print(f"full 44.1 kHz network 1 x 184184, conv_mode 2 vs oracle: {e:.3e}")
+    assert e < 1e-3

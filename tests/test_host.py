@@ -306,8 +306,17 @@ def test_bench_reference_arm_contract():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["gpu_launches"] == 0 and line["config"]["audio_len"] == 16384
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "networks", "unet_cqt_oct_with_projattention_adaLN_2.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")      # oracle/_ref is placed by build() when it can be
+    assert line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["steps"] == 1 and line["warmup"] == 0 and line["config"]["batch_per_gpu"] == 32
+    # the arm is the checker's side only: it must not import the product package (and with it libaid_b200.so)
+    probe = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--len', '16384', '--steps', '1', '--warmup', '0'];"
+             f"runpy.run_path({os.path.join(ROOT, 'bench.py')!r}, run_name='__main__');"
+             "bad = [m for m in sys.modules if m.startswith('aid_b200') or m.startswith('audio-inpainting')]; assert not bad, bad")
+    rp = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, env=env, timeout=600)
+    assert rp.returncode == 0, rp.stderr[-2000:]
     r1 = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=600)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
 

@@ -180,3 +180,60 @@ def test_mask_builders_equal_the_reference_tester(aid, ref):
         assert torch.equal(aid.prepare_spectral_mask(a), Tester.prepare_spectral_mask(ns))
         a["tester"]["spectrogram_inpainting"]["time_start_idx"] = 1000
         assert torch.equal(aid.prepare_spectral_mask(a), Tester.prepare_spectral_mask(ns))
+
+
+def test_eight_octave_44k_network_schema_and_forward(aid, ref):
+    """conf/network/paper_1912_unet_cqt_oct_attention_44k_2.yaml (8 octaves, fs = 44100, attention from level 5, dilations up to 2^7):
+    the full-width schema (795 tensors, 242.25 M parameters) equals the reference module's, and the oracle equals the reference's
+    forward on a narrowed copy of the same topology at the reference's trained length 184184 (conf/exp/musicnet44k_4s.yaml)."""
+    RefNet, _, _ = ref
+    full = aid.paper_44k()
+    sch = aid.schema_from_lib(full)
+    assert len(sch) == 795 and abs(sum(torch.Size(s).numel() for _, s in sch) / 1e6 - 242.25) < 0.01
+    cfg = aid.paper_44k(184184)
+    cfg.Ns, cfg.num_dils = [8, 8, 16, 16, 16, 24, 24, 32], [2, 3, 4, 5, 6, 7, 8, 8]
+    net = RefNet(cfg.to_args(), "cpu")
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == dict(aid.schema_from_lib(cfg))
+    sd = aid.random_state_dict(cfg, seed=44)
+    net.load_state_dict(sd, strict=True)
+    x = seeded((1, cfg.audio_len), 4, 0.7)
+    cn = torch.tensor([[-0.4]])
+    with torch.no_grad():
+        want = net(x, cn)
+    assert rel_l2(make_oracle(cfg, sd)(x, cn), want) < 1e-6
+
+
+def test_predict_resample_mirror_equals_reference_sampler(aid, ref):
+    """predict_resample(y, shape, degradation) (sampler.py:164-173): the generic conditional entry point -- the caller supplies the
+    degradation and, for xi = 0, must have set proj_convex_set (get_score reads it, sampler.py:145); without one both raise."""
+    from test_host import _FakeNet
+    _, RefEDM, RefSampler = ref
+    cfg = aid.small_test(16384)
+    args = _args(aid, cfg, 6)
+    net = _FakeNet()
+    L = 4096
+    y = seeded((2, L), 3, 0.063)
+    mask = torch.ones(1, L)
+    mask[..., 700:1500] = 0
+    deg = lambda x: mask * x
+    rs, s = RefSampler(net, RefEDM(args), args), aid.Sampler(net, aid.EDM(args), args)
+    with pytest.raises(AttributeError):
+        rs.predict_resample(y * mask, (2, L), deg)
+    with pytest.raises(AttributeError):
+        s.predict_resample(y * mask, (2, L), deg)
+    for smp in (rs, s):
+        smp.proj_convex_set = lambda x: mask * (y * mask) + (1 - mask) * x
+    torch.manual_seed(9)
+    want = rs.predict_resample(y * mask, (2, L), deg)
+    torch.manual_seed(9)
+    got = s.predict_resample(y * mask, (2, L), deg)
+    assert torch.equal(got, want)
+    # xi > 0 at batch 1: guidance through the caller's degradation, no projection needed when data consistency is off
+    args["tester"]["posterior_sampling"]["xi"] = 0.25
+    args["tester"]["data_consistency"]["use"] = False
+    rs, s = RefSampler(net, RefEDM(args), args), aid.Sampler(net, aid.EDM(args), args)
+    torch.manual_seed(10)
+    want = rs.predict_resample(y[:1] * mask, (1, L), deg)
+    torch.manual_seed(10)
+    got = s.predict_resample(y[:1] * mask, (1, L), deg)
+    assert rel_l2(got, want) < 1e-6
