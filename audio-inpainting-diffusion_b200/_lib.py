@@ -59,6 +59,7 @@ _SIGS = {
                                         _P, _P, C.c_float, _P, _P, C.c_int, C.POINTER(C.c_float)]),
     "aid_debug_tc2_operands": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "aid_debug_tc2_profile": (C.c_int, [C.POINTER(C.c_uint64)]),
     "aid_debug_time_gn_tc2": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "aid_profile": (C.c_int, [_P, C.c_int]),
     "aid_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -28,7 +28,7 @@ attention_kernel(TV h, const float* __restrict__ qk, TV out, float scale) {
     float* S = qs + (size_t)F * TQ;                   // [TQ][Tp]
     float* PT = S + (((size_t)TQ * Tp + 3) & ~(size_t)3);   // [T][TQ]
     float* hT = PT + (size_t)T * TQ;                  // [T][FCH]
-    float* red = hT + (size_t)T * FCH;                // [8][FCH * TQ]
+    float* red = hT + (size_t)T * FCH;                // [8][FCH * TQ]; during the scores phase: partial scores of the d-splits 1..3
 
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const int head = blockIdx.y, b = blockIdx.z;
@@ -44,12 +44,9 @@ attention_kernel(TV h, const float* __restrict__ qk, TV out, float scale) {
     __syncthreads();
 
     // scores: thread <-> (key column, slice of the feature dimension).  With fewer keys than threads (T = 64, 128 on the
-    // deepest levels) the threads of one key split d between them and combine with shared-memory atomics.
-    const int nsplit = (T < ANT && ANT % T == 0) ? ANT / T : 1;
-    if (nsplit > 1) {
-        for (int e = tid; e < TQ * Tp; e += ANT) S[e] = 0.f;
-        __syncthreads();
-    }
+    // deepest levels) the threads of one key split d between them; the partial scores of splits 1.. go to `red` (free until the
+    // P.V phase) and are added in a fixed order, so the result is reproducible run to run (no floating-point atomics).
+    const int nsplit = (T < ANT && ANT % T == 0 && (ANT / T - 1) * TQ * Tp <= (ANT / 32) * FCH * TQ) ? ANT / T : 1;
     for (int tk = tid % (nsplit > 1 ? T : ANT); tk < T; tk += ANT) {
         const int part = nsplit > 1 ? tid / T : 0;
         float acc[TQ];
@@ -68,13 +65,15 @@ attention_kernel(TV h, const float* __restrict__ qk, TV out, float scale) {
                 acc[j4 * 4 + 3] = fmaf(q.w, kv, acc[j4 * 4 + 3]);
             }
         }
-        if (nsplit > 1) {
+        float* dst = part == 0 ? S : red + (size_t)(part - 1) * TQ * Tp;
 #pragma unroll
-            for (int j = 0; j < TQ; ++j) atomicAdd(&S[j * Tp + tk], acc[j] * scale);
-        } else {
-#pragma unroll
-            for (int j = 0; j < TQ; ++j) S[j * Tp + tk] = acc[j] * scale;
-        }
+        for (int j = 0; j < TQ; ++j) dst[j * Tp + tk] = acc[j];
+    }
+    __syncthreads();
+    for (int e = tid; e < TQ * Tp; e += ANT) {
+        float v = S[e];
+        for (int pp = 1; pp < nsplit; ++pp) v += red[(size_t)(pp - 1) * TQ * Tp + e];
+        S[e] = v * scale;
     }
     __syncthreads();
 

@@ -115,6 +115,7 @@ void launch_conv_tc(const __half* a_hi, const __half* a_lo, int PF, const __half
 // second-generation tcgen05 path (conv_tc2.cu, conv_mode 2): single fp16 operands, channels-last [B][ceil(C/64)][F+2PF][T+2][64]
 size_t tc2_weight_halves(int Cout, int Cin, int KF, int KT);
 size_t tc2_act_halves(int B, int C, int F, int T, int PF);
+void tc2_read_profile(unsigned long long* out16);
 void launch_pack_weight_tc2(const float* w, __half* wp, int Cout, int Cin, int KF, int KT, cudaStream_t s, unsigned long long* sat = nullptr);
 // stft.cu: out = y ? y + x - S(x) : S(x), S = crop(istft(mask * stft(zero-pad(x))))  (sampler.py:271-290, 361); frames: [B][n_frames][n_fft] scratch
 void launch_spectral_mask(const float* x, const float* y, const float* mask, int B, int L, int n_fft, int hop, int n_frames,

@@ -55,6 +55,13 @@ struct Tc2Args {
 
 struct Unit2 { int exists, b, f_lo, f_hi, win_start, o0; };
 
+// Pipeline profile (AID_TC_DEBUG bit 2048, tuning only): cycles each role spent waiting / working, summed over the CTAs.
+//   0 MMA wait tmem_empty, 1 MMA wait a_full, 2 MMA wait b_full, 3 MMA issue + commit, 4 MMA total,
+//   5 A producer wait a_empty, 6 B producer wait b_empty, 7 epilogue warp 0 wait tmem_full, 8 epilogue warp 0 total, 9 CTAs
+__device__ unsigned long long g_tc2_prof[16];
+#define T2_PROF_T0(var) long long var = 0; if (prof) var = clock64()
+#define T2_PROF_ADD(slot, var) do { if (prof) prof_acc[slot] += clock64() - var; } while (0)
+
 // n / d and n % d with a host-computed magic = floor(2^32 / d) (0xffffffff for d == 1): the estimate is low by at most one
 __device__ __forceinline__ uint2 fast_divmod(uint32_t n, uint32_t d, uint32_t magic) {
     uint32_t q = __umulhi(n, magic), r = n - q * d;
@@ -136,6 +143,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
     if (warp == T2_WARP_A) {
         // ===================== activation producer: one 16.6 KB bulk copy per (unit, kf, 64-channel group) =====================
         int slot = 0; uint32_t phase = 0;
+        const bool prof = (p.dbg & 2048) != 0;
+        long long prof_acc[1] = {0};
         const size_t gstride = (size_t)p.rows_total * p.Tp * 64;   // halves per (clip, group) plane
         for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
             const int pair = (int)tile_decode(p, tile).y;
@@ -147,7 +156,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                 if (!(v0 || v1)) continue;
                 const int s0 = u0.win_start + foff * p.Tp, s1 = u1.win_start + foff * p.Tp;
                 for (int g = 0; g < p.G; ++g) {
+                    T2_PROF_T0(t_w);
                     mbar_wait(a_empty + slot, phase ^ 1);
+                    T2_PROF_ADD(0, t_w);
                     if (lane == 0) {
                         uint8_t* sa = ringA + (size_t)slot * a_slot_bytes;
                         const bool l1 = v1 && !p.pair;     // the peer CTA loads its own unit
@@ -163,9 +174,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                 }
             }
         }
+        if (prof && lane == 0) atomicAdd(&g_tc2_prof[5], (unsigned long long)prof_acc[0]);
     } else if (warp == T2_WARP_B) {
         // ===================== weight producer: one bulk copy per (kf, group, kt chunk) =====================
         int slot = 0; uint32_t phase = 0;
+        const bool prof = (p.dbg & 2048) != 0;
+        long long prof_acc[1] = {0};
         const size_t kt_halves = (size_t)p.Ntile * 64;
         for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
             const uint2 tdm = tile_decode(p, tile);
@@ -180,7 +194,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                     const __half* wg = p.w + (((size_t)nt * p.KF + kf) * p.G + g) * p.KT * kt_halves;
                     for (int c = 0; c < nktb; ++c) {
                         const int nkt = min(p.ktb, p.KT - c * p.ktb);
+                        T2_PROF_T0(t_w);
                         mbar_wait(b_empty + slot, phase ^ 1);
+                        T2_PROF_ADD(0, t_w);
                         if (lane == 0) {
                             const uint32_t bytes = (uint32_t)(nkt * kt_halves * 2);
                             mbar_expect_tx(b_full + slot, (p.dbg & 8) ? 0u : bytes);
@@ -202,65 +218,150 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                 }
             }
         }
+        if (prof && lane == 0) atomicAdd(&g_tc2_prof[6], (unsigned long long)prof_acc[0]);
     } else if (warp == T2_WARP_MMA) {
-        // ===================== MMA issuer (whole warp loops, lane 0 issues) =====================
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Ntile >> 3) << 17) | ((128u >> 4) << 24);  // F16 x F16 -> F32, K-major A/B
-        const uint32_t kt_bytes = (uint32_t)p.Ntile * 128u;
-        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int ab = 0; uint32_t aphase = 0;
-        for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
-            const int pair = (int)tile_decode(p, tile).y;
-            const Unit2 u0 = unit2_info(p, 2 * pair + uown), u1 = unit2_info(p, 2 * pair + upeer);
-            mbar_wait(tmem_empty + ab, aphase ^ 1);
-            tc_fence_after();
-            uint32_t started0 = 0u, started1 = 0u;
-            const uint32_t d0 = tmem_base + (uint32_t)(ab * (p.pair ? 1 : 2) * p.ncol_stride), d1 = d0 + (uint32_t)p.ncol_stride;
-            for (int kf = 0; kf < p.KF; ++kf) {
-                const int foff = (kf - p.KF / 2) * p.dil;
-                const bool v0 = u0.exists && u0.f_hi + foff >= 0 && u0.f_lo + foff < p.F;
-                const bool v1 = u1.exists && u1.f_hi + foff >= 0 && u1.f_lo + foff < p.F;
-                if (!(v0 || v1)) continue;
-                const uint32_t r0 = (uint32_t)((u0.win_start + foff * p.Tp) & 7), r1 = (uint32_t)((u1.win_start + foff * p.Tp) & 7);
-                for (int g = 0; g < p.G; ++g) {
-                    const int nk = min(4, (p.Cin - g * 64) >> 4);     // 16-channel k-steps in this group
-                    mbar_wait(a_full + sa, pha);
-                    const uint32_t abase = smem_u32(ringA + (size_t)sa * a_slot_bytes);
-                    for (int c = 0; c < nktb; ++c) {
-                        const int nkt = min(p.ktb, p.KT - c * p.ktb);
-                        mbar_wait(b_full + sb, phb);
-                        tc_fence_after();
-                        if (p.dbg & 32) __nanosleep(5000);
-                        if (p.dbg & 128) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        if (elect_one_sync()) {
-                            const uint32_t bbase = smem_u32(ringB + (size_t)sb * p.b_slot_bytes);
+        // ===================== MMA issuer: ONE elected thread runs the whole loop =====================
+        // Measured with the pipeline profile (AID_TC_DEBUG bit 2048) on the narrow layers: the issuing warp never waited for
+        // operands or accumulators (waits < 7 % of its time); it spent 60 % inside the per-stage issue region and 34 % in the
+        // code around it (per-tile unit arithmetic, per-stage elect / reconvergence / fences): ~1300 cycles of overhead per
+        // 24-MMA stage against ~1100 cycles of MMA issue, with the tensor pipe idle meanwhile (ncu: 30 % active at 64 couts).
+        // The whole role is therefore a single-thread region (no per-stage elect / __syncwarp, everything in uniform registers),
+        // descriptors are built from 32-bit words inside the asm, and a stage's MMAs are issued by unrolled asm blocks.
+        if (elect_one_sync()) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Ntile >> 3) << 17) | ((128u >> 4) << 24);  // F16 x F16 -> F32, K-major A/B
+            const uint32_t kt_bytes = (uint32_t)p.Ntile * 128u;
+            const uint32_t ringA_u = smem_u32(ringA), ringB_u = smem_u32(ringB);
+            const uint32_t acc_stride = (uint32_t)((p.pair ? 1 : 2) * p.ncol_stride);
+            const uint32_t abar = smem_u32(a_full), bbar = smem_u32(b_full);
+            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0; int ab = 0; uint32_t aphase = 0;
+            const bool prof = (p.dbg & 2048) != 0;
+            long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+            // loop invariants of the lean path, in 16-byte descriptor units
+            const bool lean = p.KT == 3 && p.ktb == 3 && !p.pair && (p.Cin & 63) == 0 && !(p.dbg & (2 | 32 | 8192));
+            const uint32_t adesc = desc_lo_sw128(ringA_u), bdesc = desc_lo_sw128(ringB_u);
+            const uint32_t a_slot_d = (uint32_t)a_slot_bytes >> 4, b_slot_d = (uint32_t)p.b_slot_bytes >> 4, ktd = kt_bytes >> 4, unit_d = T2_ASLOT_UNIT >> 4;
+            const int KFc = p.KF, KFh = p.KF / 2, Gc = p.G, dilTp = p.dil * p.Tp, nAc = p.nA, nBc = p.nB;
+            T2_PROF_T0(t_all);
+            for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
+                T2_PROF_T0(t_su);
+                const int pair = (int)tile_decode(p, tile).y;
+                const Unit2 u0 = unit2_info(p, 2 * pair + uown), u1 = unit2_info(p, 2 * pair + upeer);
+                uint32_t vm0 = 0, vm1 = 0, vmp = 0;      // per-kf validity bits of our unit(s) and, in pair mode, of the peer's
+                for (int kf = 0; kf < p.KF; ++kf) {
+                    const int foff = (kf - p.KF / 2) * p.dil;
+                    const bool w0 = u0.exists && u0.f_hi + foff >= 0 && u0.f_lo + foff < p.F;
+                    const bool w1 = u1.exists && u1.f_hi + foff >= 0 && u1.f_lo + foff < p.F;
+                    vm0 |= (w0 ? 1u : 0u) << kf;
+                    if (p.pair) vmp |= (w1 ? 1u : 0u) << kf; else vm1 |= (w1 ? 1u : 0u) << kf;
+                }
+                const uint32_t vany = vm0 | vm1 | vmp;
+                T2_PROF_ADD(5, t_su);
+                T2_PROF_T0(t_te);
+                mbar_wait(tmem_empty + ab, aphase ^ 1);
+                T2_PROF_ADD(0, t_te);
+                tc_fence_after();
+                uint32_t acc0 = 0u, acc1 = 0u;      // accumulate flags: 0 for the first MMA of each accumulator
+                const uint32_t d0 = tmem_base + (uint32_t)ab * acc_stride, d1 = d0 + (uint32_t)p.ncol_stride;
+                if (lean) {
+                    // hot configuration (3 kt taps in one weight slot, whole 64-channel groups, no cluster pair): per stage two waits,
+                    // three descriptor bases, 24 MMAs from unrolled asm blocks, two commits -- every other quantity is loop invariant
+                    for (int kf = 0; kf < KFc; ++kf) {
+                        if (!((vany >> kf) & 1u)) continue;
+                        const bool v0 = (vm0 >> kf) & 1u, v1 = (vm1 >> kf) & 1u;
+                        const int ft = (kf - KFh) * dilTp;
+                        const uint32_t r0d = (uint32_t)((u0.win_start + ft) & 7) * 8u, r1d = (uint32_t)((u1.win_start + ft) & 7) * 8u + unit_d;
+                        for (int g = 0; g < Gc; ++g) {
+                            T2_PROF_T0(t_af);
+                            mbar_wait(a_full + sa, pha);
+                            T2_PROF_ADD(1, t_af);
+                            T2_PROF_T0(t_bf);
+                            mbar_wait(b_full + sb, phb);
+                            T2_PROF_ADD(2, t_bf);
+                            tc_fence_after();
+                            T2_PROF_T0(t_is);
+                            const uint32_t ad = adesc + (uint32_t)sa * a_slot_d, b = bdesc + (uint32_t)sb * b_slot_d;
+                            const uint32_t a0 = ad + r0d, a1 = ad + r1d;
+                            if (v0 && v1) {
+                                tc_mma4x2_f16(d0, d1, a0, a1, b, idesc, acc0, acc1);
+                                tc_mma4x2_f16(d0, d1, a0 + 8u, a1 + 8u, b + ktd, idesc, 1u, 1u);
+                                tc_mma4x2_f16(d0, d1, a0 + 16u, a1 + 16u, b + 2u * ktd, idesc, 1u, 1u);
+                                acc0 = 1u; acc1 = 1u;
+                            } else if (v0) {
+                                tc_mma4_f16(d0, a0, b, idesc, acc0);
+                                tc_mma4_f16(d0, a0 + 8u, b + ktd, idesc, 1u);
+                                tc_mma4_f16(d0, a0 + 16u, b + 2u * ktd, idesc, 1u);
+                                acc0 = 1u;
+                            } else {
+                                tc_mma4_f16(d1, a1, b, idesc, acc1);
+                                tc_mma4_f16(d1, a1 + 8u, b + ktd, idesc, 1u);
+                                tc_mma4_f16(d1, a1 + 16u, b + 2u * ktd, idesc, 1u);
+                                acc1 = 1u;
+                            }
+                            tc_commit(b_empty + sb);
+                            tc_commit(a_empty + sa);
+                            T2_PROF_ADD(3, t_is);
+                            if (++sb == nBc) { sb = 0; phb ^= 1; }
+                            if (++sa == nAc) { sa = 0; pha ^= 1; }
+                        }
+                    }
+                } else
+                for (int kf = 0; kf < p.KF; ++kf) {
+                    if (!((vany >> kf) & 1u)) continue;
+                    const int foff = (kf - p.KF / 2) * p.dil;
+                    const bool v0 = (vm0 >> kf) & 1u, v1 = (vm1 >> kf) & 1u;
+                    const uint32_t r0 = (uint32_t)((u0.win_start + foff * p.Tp) & 7), r1 = (uint32_t)((u1.win_start + foff * p.Tp) & 7);
+                    for (int g = 0; g < p.G; ++g) {
+                        const int nk = min(4, (p.Cin - g * 64) >> 4);     // 16-channel k-steps in this group
+                        T2_PROF_T0(t_af);
+                        mbar_wait(a_full + sa, pha);
+                        T2_PROF_ADD(1, t_af);
+                        const uint32_t abase = ringA_u + (uint32_t)sa * (uint32_t)a_slot_bytes;
+                        const uint32_t a0row = desc_lo_sw128(abase + r0 * 128u), a1row = desc_lo_sw128(abase + T2_ASLOT_UNIT + r1 * 128u);
+                        for (int c = 0; c < nktb; ++c) {
+                            const int nkt = min(p.ktb, p.KT - c * p.ktb);
+                            T2_PROF_T0(t_bf);
+                            mbar_wait(b_full + sb, phb);
+                            T2_PROF_ADD(2, t_bf);
+                            tc_fence_after();
+                            T2_PROF_T0(t_is);
+                            const uint32_t bbase = desc_lo_sw128(ringB_u + (uint32_t)sb * (uint32_t)p.b_slot_bytes);
                             if (!(p.dbg & 2)) {
                                 for (int k = 0; k < nkt; ++k) {
-                                    const uint32_t kt = (uint32_t)(c * p.ktb + k + p.kt_shift);
-                                    const uint32_t blo = desc_lo_sw128(bbase + (uint32_t)k * kt_bytes);
-                                    const uint32_t alo0 = desc_lo_sw128(abase + (r0 + kt) * 128u);
-                                    const uint32_t alo1 = desc_lo_sw128(abase + T2_ASLOT_UNIT + (r1 + kt) * 128u);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        if (j < nk) {
-                                            const uint64_t bd = ((uint64_t)DESC_HI_SW128 << 32) | (blo + 2u * j);
-                                            if (v0) { tc_mma_f16(d0, ((uint64_t)DESC_HI_SW128 << 32) | (alo0 + 2u * j), bd, idesc, started0); started0 = 1u; }
-                                            if (v1 && !p.pair) { tc_mma_f16(d1, ((uint64_t)DESC_HI_SW128 << 32) | (alo1 + 2u * j), bd, idesc, started1); started1 = 1u; }
+                                    // one 128-byte pixel row per kt tap (descriptor units of 16 bytes: +8), kt_bytes per weight sub-tile
+                                    const uint32_t kt8 = (uint32_t)(c * p.ktb + k + p.kt_shift) * 8u;
+                                    const uint32_t blo = bbase + (uint32_t)k * (kt_bytes >> 4);
+                                    if (nk == 4) {
+                                        if (v0 && v1) { tc_mma4x2_f16(d0, d1, a0row + kt8, a1row + kt8, blo, idesc, acc0, acc1); acc0 = 1u; acc1 = 1u; }
+                                        else if (v0) { tc_mma4_f16(d0, a0row + kt8, blo, idesc, acc0); acc0 = 1u; }
+                                        else if (v1) { tc_mma4_f16(d1, a1row + kt8, blo, idesc, acc1); acc1 = 1u; }
+                                    } else {
+                                        for (int j = 0; j < nk; ++j) {
+                                            if (v0) { tc_mma_f16_lo(d0, a0row + kt8 + 2u * j, blo + 2u * j, idesc, acc0); acc0 = 1u; }
+                                            if (v1) { tc_mma_f16_lo(d1, a1row + kt8 + 2u * j, blo + 2u * j, idesc, acc1); acc1 = 1u; }
                                         }
                                     }
                                 }
                             }
                             if (p.pair) tc_commit_mc2(b_empty + sb); else tc_commit(b_empty + sb);
                             if (c == nktb - 1) tc_commit(a_empty + sa);
+                            T2_PROF_ADD(3, t_is);
+                            if (++sb == p.nB) { sb = 0; phb ^= 1; }
                         }
-                        __syncwarp();
-                        if (++sb == p.nB) { sb = 0; phb ^= 1; }
+                        if (++sa == p.nA) { sa = 0; pha ^= 1; }
                     }
-                    if (++sa == p.nA) { sa = 0; pha ^= 1; }
                 }
+                tc_commit(tmem_full + ab);
+                if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
             }
-            if (elect_one_sync()) tc_commit(tmem_full + ab);
-            __syncwarp();
-            if (++ab == p.acc_bufs) { ab = 0; aphase ^= 1; }
+            T2_PROF_ADD(4, t_all);
+            if (prof) {
+                for (int k = 0; k < 5; ++k) atomicAdd(&g_tc2_prof[k], (unsigned long long)prof_acc[k]);
+                atomicAdd(&g_tc2_prof[10], (unsigned long long)prof_acc[5]);
+                atomicAdd(&g_tc2_prof[9], 1ull);
+            }
+            (void)abar; (void)bbar;
         }
+        __syncwarp();
     } else if (warp < T2_EPI_WARP0 + T2_EPI_WARPS) {
         // ===================== epilogue: TMEM -> registers -> out = alpha*(acc*gate + R), statistics =====================
         // 8 warps: warp e reads TMEM lane quadrant (e & 3) (one pixel per thread) and column half (e >> 2).  The work is a flat
@@ -285,9 +386,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
 
         // batch descriptors as plain scalars (a struct passed through lambdas ends up in local memory)
         float* c_po = nullptr; uint32_t c_oo = 0; uint32_t c_tcol = 0; int c_ui = 0, c_c0 = 0, c_b = 0, c_ab = 0, c_nt = 0;
-        uint32_t c_aphase = 0; bool c_ok = false, c_last = false;
+        uint32_t c_aphase = 0; bool c_ok = false, c_last = false, c_ulast = false;
         const float* n_pr = nullptr; float* n_po = nullptr; uint32_t n_ro = 0, n_oo = 0; uint32_t n_tcol = 0; int n_ui = 0, n_c0 = 0, n_b = 0, n_ab = 0, n_nt = 0;
-        uint32_t n_aphase = 0; bool n_ok = false, n_valid = false, n_last = false;
+        uint32_t n_aphase = 0; bool n_ok = false, n_valid = false, n_last = false, n_ulast = false;
         // iterator state of the next batch to set up; per-unit values are recomputed only at the first batch of a unit
         int it_tile = tile0, it_ui = 0, it_c0 = 0, it_ab = 0; uint32_t it_aphase = 0;
         const float* u_pr = nullptr; float* u_po = nullptr; uint32_t u_ro = 0, u_oo = 0; int u_b = 0, u_nt = 0; bool u_ok = false, u_has1 = false;
@@ -318,10 +419,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
             n_ro = u_ro + (p.r_cl ? (uint32_t)it_c0 : (uint32_t)it_c0 * (uint32_t)rsc);
             n_tcol = tq + (uint32_t)(it_ab * (p.pair ? 1 : 2) * p.ncol_stride + it_ui * p.ncol_stride + it_c0);
             n_ui = it_ui; n_c0 = it_c0; n_b = u_b; n_nt = u_nt; n_ab = it_ab; n_aphase = it_aphase; n_ok = u_ok;
-            n_last = false;
+            n_last = false; n_ulast = false;
             it_c0 += 32;
             if (it_c0 >= ncols) {
-                it_c0 = 0;
+                it_c0 = 0; n_ulast = true;
                 if (it_ui == 1 || !u_has1) {
                     n_last = true;
                     it_ui = 0; it_tile += tstep;
@@ -329,6 +430,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                 } else it_ui = 1;
             }
         };
+        // (Tried and dropped, measured: pulling the NEXT tile's residual lines into L2 with prefetch.global.L2 at the start of each
+        // tile changed nothing at 64 couts and cost 1-3 % on the wider layers -- the epilogue is not bound by the latency of
+        // its residual loads.)
         float rr[32], rn[32];
         auto load_next = [&]() {
             if (n_valid && has_r && !(p.dbg & 1)) {
@@ -352,14 +456,33 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                 for (int j = 0; j < 32; ++j) rn[j] = 0.f;
             }
         };
-        // per-thread statistics of the current clip: (sum, sumsq) of the 4 groups this warp's columns cover
+        // Statistics: (sum, sumsq) of the 4 groups this warp's columns cover.  A thread sums ONE unit's values of its pixel in
+        // fp32 registers (a fixed set of values in a fixed order, whatever the batch size or the tile -> CTA assignment), adds that
+        // partial to its private double accumulators in shared memory at the end of the unit, and the doubles are reduced and
+        // added to the global accumulators when the clip changes.  Everything order-dependent happens in double on fp32 terms,
+        // so the statistics -- and with them the fp16 roundings of the next layer's operands -- are reproducible run to run and
+        // identical for a clip evaluated alone or inside a batch (to ~1e-16 relative).
         float S0 = 0.f, S1 = 0.f, S2 = 0.f, S3 = 0.f, Q0 = 0.f, Q1 = 0.f, Q2 = 0.f, Q3 = 0.f;
         int b_cur = -1, nt_cur = 0, gk = 0, gpos = 0;
+        double* sacc = reinterpret_cast<double*>(bar_base + 256 + T2_EPI_WARPS * 128 * sizeof(float)) + (e * 32 + lane);   // [k][256 threads]
+        if (do_stats) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sacc[k * 256] = 0.0;
+        }
+        auto unit_end = [&]() {
+            if (do_stats) {
+                const float v[8] = {S0, Q0, S1, Q1, S2, Q2, S3, Q3};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sacc[k * 256] += (double)v[k];
+            }
+            S0 = S1 = S2 = S3 = Q0 = Q1 = Q2 = Q3 = 0.f;
+        };
         auto flush_stats = [&]() {
             if (do_stats && b_cur >= 0) {
-                float v[8] = {S0, Q0, S1, Q1, S2, Q2, S3, Q3};
+                double v[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
+                    v[k] = sacc[k * 256]; sacc[k * 256] = 0.0;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
                 }
@@ -367,10 +490,9 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                     const int g0 = (nt_cur * p.Ntile + cbeg) / gcn;
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        if (g0 + (k >> 1) < 8) atomicAdd(p.stats + (long long)b_cur * 16 + (g0 + (k >> 1)) * 2 + (k & 1), (double)v[k]);
+                        if (g0 + (k >> 1) < 8) atomicAdd(p.stats + (long long)b_cur * 16 + (g0 + (k >> 1)) * 2 + (k & 1), v[k]);
                 }
             }
-            S0 = S1 = S2 = S3 = Q0 = Q1 = Q2 = Q3 = 0.f;
         };
         auto add_group = [&](float s, float qq) {
             if (gk == 0) { S0 += s; Q0 += qq; } else if (gk == 1) { S1 += s; Q1 += qq; } else if (gk == 2) { S2 += s; Q2 += qq; } else { S3 += s; Q3 += qq; }
@@ -422,17 +544,20 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
             }
         };
 
+        const bool prof = (p.dbg & 2048) != 0 && e == 0;
+        long long prof_acc[2] = {0, 0};
+        T2_PROF_T0(t_all);
         setup_next();
         load_next();
         while (n_valid) {
             // the prefetched batch becomes the current one
             c_po = n_po; c_oo = n_oo; c_tcol = n_tcol; c_ui = n_ui; c_c0 = n_c0; c_b = n_b; c_ab = n_ab; c_nt = n_nt; c_aphase = n_aphase;
-            c_ok = n_ok; c_last = n_last;
+            c_ok = n_ok; c_last = n_last; c_ulast = n_ulast;
 #pragma unroll
             for (int j = 0; j < 32; ++j) rr[j] = rn[j];
             setup_next();
             load_next();
-            if (c_ui == 0 && c_c0 == 0) { mbar_wait(tmem_full + c_ab, c_aphase); tc_fence_after(); }
+            if (c_ui == 0 && c_c0 == 0) { T2_PROF_T0(t_w); mbar_wait(tmem_full + c_ab, c_aphase); T2_PROF_ADD(0, t_w); tc_fence_after(); }
             if (c_c0 == 0) {
                 gk = 0; gpos = 0;
                 if (c_b != b_cur || c_nt != nt_cur) { flush_stats(); b_cur = c_b; nt_cur = c_nt; }
@@ -465,6 +590,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
                         if (j8 * 8 < nb) chunk(acc + j8 * 8, rr + j8 * 8, gq + j8 * 32, c_oo + (p.out_cl ? (uint32_t)(j8 * 8) : (uint32_t)(j8 * 8) * (uint32_t)osc));
                 }
             }
+            if (c_ulast) unit_end();
             if (c_last) {      // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory pipe
                 tc_fence_before();
                 __syncwarp();
@@ -472,6 +598,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(Tc2Args p) {
             }
         }
         flush_stats();
+        T2_PROF_ADD(1, t_all);
+        if (prof && lane == 0) { atomicAdd(&g_tc2_prof[7], (unsigned long long)prof_acc[0]); atomicAdd(&g_tc2_prof[8], (unsigned long long)prof_acc[1]); }
     }
 
     tc_fence_before();
@@ -769,6 +897,14 @@ gn_act_tc2_cl_kernel(const float* __restrict__ x, int B, int C, int F, int T, co
     }
 }
 
+// tuning: read and clear the pipeline profile counters (AID_TC_DEBUG bit 2048)
+void tc2_read_profile(unsigned long long* out16) {
+    AID_CUDA_CHECK(cudaDeviceSynchronize());
+    AID_CUDA_CHECK(cudaMemcpyFromSymbol(out16, g_tc2_prof, 16 * sizeof(unsigned long long)));
+    unsigned long long z[16] = {0};
+    AID_CUDA_CHECK(cudaMemcpyToSymbol(g_tc2_prof, z, sizeof z));
+}
+
 size_t tc2_act_halves(int B, int C, int F, int T, int PF) { return (size_t)B * ((C + 63) / 64) * 64 * (F + 2 * PF) * (T + 2); }
 
 void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
@@ -845,7 +981,8 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     const int env_pair = getenv("AID_TC2_PAIR") ? atoi(getenv("AID_TC2_PAIR")) : 0;
     p.pair = (env_pair && p.Ntile == 256 && p.ktb == 1 && num_sms % 2 == 0) ? 1 : 0;
     p.a_slot_bytes = (p.pair ? 1 : 2) * T2_ASLOT_UNIT;
-    const int budget = 224 * 1024 - 1024 - 256 - T2_EPI_WARPS * 128 * (int)sizeof(float);
+    const int stat_smem = T2_EPI_WARPS * 32 * 8 * (int)sizeof(double);   // per-thread double statistics accumulators of the epilogue warps
+    const int budget = 224 * 1024 - 1024 - 256 - T2_EPI_WARPS * 128 * (int)sizeof(float) - stat_smem;
     while (p.nA > 2 && budget - p.nA * p.a_slot_bytes < 2 * p.b_slot_bytes) --p.nA;
     p.nB = min(8, (budget - p.nA * p.a_slot_bytes) / p.b_slot_bytes);
     if (p.nB < 2) throw CudaError(cudaErrorInvalidValue, "conv_tc2: shared memory budget", __FILE__, __LINE__);
@@ -854,7 +991,7 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     // an epilogue warp owns Ntile / 2 columns: they must be whole statistics groups, at most four of them
     if (ep.stats && p.n_ntiles != 1 && ((p.Ntile / 2) % (p.Ntot / 8) != 0 || p.Ntile / 2 > 4 * (p.Ntot / 8)))
         throw CudaError(cudaErrorInvalidValue, "conv_tc2: statistics groups do not align with the n-tiles", __FILE__, __LINE__);
-    const size_t smem = 1024 + (size_t)p.nA * p.a_slot_bytes + (size_t)p.nB * p.b_slot_bytes + 256 + T2_EPI_WARPS * 128 * sizeof(float);
+    const size_t smem = 1024 + (size_t)p.nA * p.a_slot_bytes + (size_t)p.nB * p.b_slot_bytes + 256 + T2_EPI_WARPS * 128 * sizeof(float) + stat_smem;
     static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
     p.dbg = dbg;
     static SmemConfig configured;

@@ -1102,6 +1102,12 @@ int aid_debug_time_gn_tc2(const float* x_dev, int B, int C, int F, int T, int PF
     } catch (const CudaError& e) { fprintf(stderr, "aid_debug_time_gn_tc2: CUDA error %s\n", cudaGetErrorString(e.code)); return AID_ERR_CUDA; }
 }
 
+/* debug / tuning: conv_tc2 pipeline profile (cycles per role, summed over CTAs; enabled by AID_TC_DEBUG bit 2048), read and cleared */
+int aid_debug_tc2_profile(uint64_t* out16) {
+    if (!out16) return AID_ERR_INVALID;
+    try { tc2_read_profile(reinterpret_cast<unsigned long long*>(out16)); return AID_OK; } catch (const CudaError&) { return AID_ERR_CUDA; }
+}
+
 int aid_op_groupnorm_act(const float* x_dev, const float* gamma_dev, const float* affine_dev, int B, int C, int F, int T, int gelu,
                          float* out_dev, double* stats_scratch_dev, void* stream) {
     if (!x_dev || !gamma_dev || !out_dev || !stats_scratch_dev || C % 8 != 0) return AID_ERR_INVALID;

@@ -91,6 +91,55 @@ __device__ __forceinline__ bool elect_one_sync() {
 __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 static constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 
+// tcgen05.mma with the descriptors given as their low words (the high word of a K-major SWIZZLE_128B descriptor with SBO = 1024 is
+// a constant): the 64-bit descriptors are assembled inside the asm, so a uniform low word stays in a uniform register
+__device__ __forceinline__ void tc_mma_f16_lo(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128)
+        : "memory");
+}
+// the four 16-channel k-steps of a 64-channel group (descriptor start advanced by 32 bytes = 2 units each), one accumulator
+__device__ __forceinline__ void tc_mma4_f16(uint32_t d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 q, 0, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "add.u32 a, %1, 2;\n\t add.u32 b, %2, 2;\n\t mov.b64 da, {a, %5};\n\t mov.b64 db, {b, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
+        "add.u32 a, %1, 4;\n\t add.u32 b, %2, 4;\n\t mov.b64 da, {a, %5};\n\t mov.b64 db, {b, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
+        "add.u32 a, %1, 6;\n\t add.u32 b, %2, 6;\n\t mov.b64 da, {a, %5};\n\t mov.b64 db, {b, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t}" ::"r"(d), "r"(alo), "r"(blo), "r"(idesc), "r"(acc), "r"(DESC_HI_SW128)
+        : "memory");
+}
+// the same for two accumulators that share the B operand (the two pixel units of a tile), interleaved unit 0 / unit 1
+__device__ __forceinline__ void tc_mma4x2_f16(uint32_t d0, uint32_t d1, uint32_t alo0, uint32_t alo1, uint32_t blo, uint32_t idesc, uint32_t acc0,
+                                              uint32_t acc1) {
+    asm volatile(
+        "{\n\t.reg .pred p0, p1, q;\n\t.reg .b64 da0, da1, db;\n\t.reg .b32 a0, a1, b;\n\t"
+        "setp.ne.b32 p0, %6, 0;\n\t setp.ne.b32 p1, %7, 0;\n\t setp.eq.b32 q, 0, 0;\n\t"
+        "mov.b64 da0, {%2, %8};\n\t mov.b64 da1, {%3, %8};\n\t mov.b64 db, {%4, %8};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, %5, p0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db, %5, p1;\n\t"
+        "add.u32 a0, %2, 2;\n\t add.u32 a1, %3, 2;\n\t add.u32 b, %4, 2;\n\t mov.b64 da0, {a0, %8};\n\t mov.b64 da1, {a1, %8};\n\t mov.b64 db, {b, %8};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, %5, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db, %5, q;\n\t"
+        "add.u32 a0, %2, 4;\n\t add.u32 a1, %3, 4;\n\t add.u32 b, %4, 4;\n\t mov.b64 da0, {a0, %8};\n\t mov.b64 da1, {a1, %8};\n\t mov.b64 db, {b, %8};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, %5, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db, %5, q;\n\t"
+        "add.u32 a0, %2, 6;\n\t add.u32 a1, %3, 6;\n\t add.u32 b, %4, 6;\n\t mov.b64 da0, {a0, %8};\n\t mov.b64 da1, {a1, %8};\n\t mov.b64 db, {b, %8};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, %5, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db, %5, q;\n\t}" ::"r"(d0), "r"(d1), "r"(alo0), "r"(alo1), "r"(blo), "r"(idesc), "r"(acc0), "r"(acc1),
+        "r"(DESC_HI_SW128)
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"

@@ -99,15 +99,17 @@ class Sampler:
         n_fft, hop, win = (int(cfg_get(self.args, st + k)) for k in ("n_fft", "hop_length", "win_length"))
         return n_fft, hop, win
 
-    def apply_spectral_mask(self, x, y=None):
-        """sampler.py:271-290: S(x) = crop(istft(mask * stft(zero-pad(x)))) with self.mask [n_fft/2+1, frames].
+    def apply_spectral_mask(self, x, y=None, mask=None):
+        """sampler.py:271-290: S(x) = crop(istft(mask * stft(zero-pad(x)))) with self.mask [n_fft/2+1, frames] (or the given one).
         With `y` the projection of the spectrogram mode, y + x - S(x) (sampler.py:361), comes out of the same kernel."""
         n_fft, hop, win = self._stft_params()
+        if mask is None:
+            mask = self.mask
         L = x.shape[-1]
         if not x.is_cuda:
             window = torch.hann_window(win).to(x.device)
             xp = torch.nn.functional.pad(x, (0, n_fft - L % n_fft), mode="constant", value=0)
-            X = torch.stft(xp, n_fft, hop, win, window, return_complex=True) * self.mask.unsqueeze(0)
+            X = torch.stft(xp, n_fft, hop, win, window, return_complex=True) * mask.unsqueeze(0)
             s = torch.istft(X, n_fft, hop, win, window, return_complex=False)[..., 0:L]
             return s if y is None else y + x - s
         if win != n_fft:
@@ -116,7 +118,7 @@ class Sampler:
         x2 = x.reshape(-1, L).contiguous().float()
         B = x2.shape[0]
         n_frames = 1 + (L + n_fft - L % n_fft) // hop
-        mask = self.mask.to(x.device, torch.float32).contiguous()
+        mask = mask.to(x.device, torch.float32).contiguous()
         if tuple(mask.shape) != (n_fft // 2 + 1, n_frames):
             raise ValueError(f"spectral mask has shape {tuple(mask.shape)}, the STFT of this input has {(n_fft // 2 + 1, n_frames)}")
         need = B * n_frames * n_fft
@@ -466,6 +468,7 @@ class _GraphedLoop:
         self.hp = f() if hpf else None
         self.y = f() if kind != "uncond" else None
         self.mask = torch.empty(n, device=dev, dtype=torch.float32) if kind == "inpaint" else None
+        self.smask = None              # spectral mode: static copy of the [n_fft/2+1, frames] mask
         self.cur = torch.zeros(self.ROW, device=dev, dtype=torch.float32)
         self.counter = torch.zeros(1, device=dev, dtype=torch.int32)
         self.table = torch.zeros(self.MAX_STEPS, self.ROW, device=dev, dtype=torch.float32)
@@ -491,6 +494,10 @@ class _GraphedLoop:
             self.y.copy_(s._proj_y.to(self.dev, torch.float32))
         elif self.kind == "spectral":
             self.y.copy_(s.y.to(self.dev, torch.float32))
+            m = s.mask.to(self.dev, torch.float32)
+            if self.smask is None or self.smask.shape != m.shape:
+                self.smask, self.graphs = torch.empty_like(m), {}
+            self.smask.copy_(m)
 
     # ---- the launches of one step on the current stream --------------------------------------------------
     def _stream(self):
@@ -504,7 +511,7 @@ class _GraphedLoop:
             _lib.check(self.L.aid_hpf_dc(m._handle, _lib.ptr(out), _lib.ptr(self.hp), B, _lib.ptr(self.hws), self.hws.numel(), self._stream()), m._handle)
             out.copy_(self.hp)
         if self.kind == "spectral":          # xhat <- y + xhat - S(xhat)
-            out.copy_(s.apply_spectral_mask(out, self.y))
+            out.copy_(s.apply_spectral_mask(out, self.y, self.smask))
 
     def _edm(self, xin, xh, e, mode, d_prev, xbase, d_out, x_out):
         mk = self.mask if self.kind == "inpaint" else None

@@ -164,6 +164,11 @@ int aid_debug_time_conv2d(const float* a_dev, const float* w_dev, int B, int Cin
 int aid_debug_tc2_operands(const float* x_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int PF,
                            void* a_out_dev, void* w_out_dev, uint64_t* a_halves, uint64_t* w_halves);
 
+/* Debug / tuning: with AID_TC_DEBUG bit 2048 set, conv_tc2_kernel sums the cycles its warp roles spend waiting and working:
+ * [0] MMA wait tmem_empty, [1] MMA wait a_full, [2] MMA wait b_full, [3] MMA issue + commit, [4] MMA total, [5] A producer wait
+ * a_empty, [6] B producer wait b_empty, [7] epilogue warp 0 wait tmem_full, [8] epilogue warp 0 total, [9] CTAs.  Read and cleared. */
+int aid_debug_tc2_profile(uint64_t* out16);
+
 /* Debug / tuning: ms per launch of the conv_mode 2 normalise + GELU + operand-layout pass on x[B,C,F,T]. */
 int aid_debug_time_gn_tc2(const float* x_dev, int B, int C, int F, int T, int PF, int iters, float* ms_out);
 

@@ -25,6 +25,8 @@ ap.add_argument("--len", type=int, default=262144)
 ap.add_argument("--gap-ms", type=float, default=300.0)
 ap.add_argument("--steps", type=int, default=35)
 ap.add_argument("--conv-mode", type=int, default=2)
+ap.add_argument("--noise", default="device", choices=["device", "host"], help="device: Philox on the GPU + CUDA-graph replay; host: per-clip torch generators + H2D")
+ap.add_argument("--no-graph", action="store_true", help="device noise, eager launches")
 a = ap.parse_args()
 
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -43,10 +45,8 @@ args = aid_b200.AttrDict.wrap({
                                "Schurn": 10, "Snoise": 1.0, "Stmin": 0, "Stmax": 50}},
     "diff_params": {"sigma_data": 0.063, "sigma_min": 1e-5, "sigma_max": 10, "ro": 13, "Schurn": 5, "Snoise": 1, "Stmin": 0, "Stmax": 50},
 })
-calls = [0]
-orig = net.denoise_fused
-net.denoise_fused = lambda *x, **k: (calls.__setitem__(0, calls[0] + 1), orig(*x, **k))[1]
-smp = ShardedSampler(aid_b200.Sampler(net, aid_b200.EDM(args), args), seed=42)
+smp = ShardedSampler(aid_b200.Sampler(net, aid_b200.EDM(args), args), seed=42, device_noise=(a.noise == "device"))
+smp.sampler.use_cuda_graph = not a.no_graph
 B, L = a.batch, a.len
 # MAESTRO-shaped synthetic clips: zero mean, RMS = sigma_data
 y = (torch.randn(B, L, generator=torch.Generator().manual_seed(7)) * 0.063).to(dev)
@@ -60,15 +60,26 @@ def run():
     return smp.predict_unconditional((B, L), dev)
 
 net._ensure_weights(dev)
+smp.sampler.nb_steps = 2          # warm-up: module loading, workspace, graph capture (the graphs do not depend on the step count)
+run()
+smp.sampler.nb_steps = a.steps
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0 = time.perf_counter()
-out = run()
+e0.record()
+out = run()                       # includes the result gather (the only collective)
+e1.record()
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
-dt = time.perf_counter() - t0
+dt_wall = time.perf_counter() - t0
+tt = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+dt = float(tt)                    # device time, max over ranks
+evals = 2 * a.steps - 1
 ok = bool(torch.isfinite(out).all()) and tuple(out.shape) == (B, L)
 if a.config == "inpaint":
     keep = mask[0].bool().clone()
@@ -77,7 +88,9 @@ if a.config == "inpaint":
 if rank == 0:
     lo, hi = shard_bounds(B, 0, world)
     print(json.dumps({"config": a.config, "batch": B, "len": L, "gap_ms": a.gap_ms if a.config == "inpaint" else None, "n_gpus": world,
-                      "sampler_steps": a.steps, "denoiser_evals": calls[0], "seconds": dt, "clips_per_s": B / dt,
-                      "seconds_per_eval": dt / max(calls[0], 1), "clips_per_rank": hi - lo, "output_ok": ok, "conv_mode": a.conv_mode}))
+                      "sampler_steps": a.steps, "denoiser_evals": evals, "seconds": dt, "seconds_wall": dt_wall, "clips_per_s": B / dt,
+                      "seconds_per_eval": dt / evals, "clips_per_rank": hi - lo, "output_ok": ok, "conv_mode": a.conv_mode,
+                      "noise": a.noise, "cuda_graph": a.noise == "device" and not a.no_graph,
+                      "timing": "CUDA events around the whole predict call incl. the result gather, max over ranks; 1 warm-up call of 2 steps before"}))
 if world > 1:
     dist.destroy_process_group()

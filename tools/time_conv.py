@@ -18,6 +18,12 @@ def run(B, Ci, Co, Fd, T, K, dil, useR=True):
     _lib.check(L.aid_debug_time_conv2d(_lib.ptr(a), _lib.ptr(w), B, Ci, Co, Fd, T, KF, KT, dil, _lib.ptr(g), _lib.ptr(R), 0.7071, _lib.ptr(out), _lib.ptr(st), mode, C.byref(ms)))
     fl = 2.0 * Ci * Co * KF * KT * B * Fd * T
     gb = 4.0 * B * Fd * T * (Ci + Co * (2 if useR else 1)) / 1e9
+    if int(os.environ.get("AID_TC_DEBUG", "0")) & 2048:
+        buf = (C.c_uint64 * 16)()
+        _lib.check(L.aid_debug_tc2_profile(buf))
+        n = max(1, buf[9]) * 2      # two launches (warm-up + timed) were summed
+        names = ["mma:wait_tmem_empty", "mma:wait_a_full", "mma:wait_b_full", "mma:issue", "mma:total", "A:wait_empty", "B:wait_empty", "epi:wait_full", "epi:total"]
+        print("   profile (k cycles per CTA): " + ", ".join(f"{nm} {buf[i] / buf[9] / 1e3:.1f}" for i, nm in enumerate(names)) + f", mma:tile_setup {buf[10] / buf[9] / 1e3:.1f}")
     print(f"mode {mode} dbg {os.environ.get('AID_TC_DEBUG','0')} nt {os.environ.get('AID_TC_NTILE','0')} nostats {int(os.environ.get('NOSTATS') is not None)} {K}x B{B} Ci{Ci} Co{Co} F{Fd} T{T} d{dil} R{int(useR)}: {ms.value:8.3f} ms  {fl/ms.value/1e9:8.1f} TFLOP/s  {gb/ms.value*1e3:7.0f} GB/s (algorithmic)", flush=True)
 
 which = sys.argv[2] if len(sys.argv) > 2 else "all"
