@@ -40,6 +40,9 @@ _SIGS = {
     "aid_edm_step_ds": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int, _P, _P, _P, _P, _P]),
     "aid_philox_normal": (C.c_int, [_P, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_int, _P, _P]),
     "aid_sched_select": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "aid_vjp_workspace_bytes": (C.c_int, [_P, C.c_int, C.POINTER(C.c_size_t)]),
+    "aid_unet_forward_tape": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, C.c_float, C.c_float, C.c_float, _P, C.c_size_t, _P]),
+    "aid_unet_backward": (C.c_int, [_P, _P, _P, _P]),
     "aid_cqt_layout": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "aid_cqt_fwd": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "aid_cqt_bwd": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
@@ -54,6 +57,12 @@ _SIGS = {
     "aid_op_groupnorm_act": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "aid_op_resample": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "aid_op_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "aid_op_resample_adj": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "aid_op_groupnorm_act_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "aid_op_attention_bwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "aid_op_conv2d_bwd_input": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "aid_cqt_fwd_vjp": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
+    "aid_cqt_bwd_vjp": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "aid_op_embedding": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "aid_debug_time_conv2d": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         _P, _P, C.c_float, _P, _P, C.c_int, C.POINTER(C.c_float)]),

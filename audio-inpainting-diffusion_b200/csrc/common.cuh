@@ -169,6 +169,29 @@ void launch_cqt_synth_oct(const CqtTables& t, const FftPlan& fp, int oct, const 
 // gather Y into the Hermitian full spectrum fr [B][L]
 void launch_cqt_synth_gather(const CqtTables& t, int B, const float2* Y, float2* fr, cudaStream_t s);
 void launch_spec_mul_real(int B, int L, float2* spec, const float* h, cudaStream_t s);
+// adjoint pieces (backward.cu): full-circle gather without Hermitian completion (t.dual = analysis windows / M); spectrum factors of
+// the synthesis adjoint
+void launch_cqt_gather_adj(const CqtTables& t, int B, int oct_lo, int oct_hi, const float2* Y, float2* X, bool accumulate, cudaStream_t s);
+void launch_spec_synth_adj(int B, int L, float2* G, float scale, cudaStream_t s);
+
+// ---- backward (input gradient) kernels, backward.cu ---------------------------------------------------
+void launch_scale_channels(const TV& in, const float* vec, long long vstride, float alpha, const TV& out, cudaStream_t s);
+// out = cres * gres + d/dx [act(GroupNorm(x) * (affine + 1))]^T g ; D_scratch: [B][8] doubles; gres.p may be null; out may alias gres / g
+void launch_gn_bwd(const TV& g, const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
+                   long long abstride, bool gelu, double* D_scratch, const TV& gres, float cres, const TV& out, cudaStream_t s);
+// gx = beta * gx + adjoint of the resampler applied to gy (gx: the resampler's input shape, gy: its output shape)
+void launch_resample_down_adj(const TV& gy, const TV& gx, float beta, cudaStream_t s);
+void launch_resample_up_adj(const TV& gy, const TV& gx, float beta, cudaStream_t s);
+struct BGemm {   // C[z](m,n) = alpha * sum_k A[z](m,k) B[z](k,n) + beta * C[z](m,n); element strides
+    const float* A; const float* B; float* C;
+    int M, N, K, batch;
+    long long sAm, sAk, sAz, sBk, sBn, sBz, sCm, sCn, sCz;
+    float alpha, beta;
+};
+void launch_bgemm(const BGemm& p, cudaStream_t s);
+void launch_softmax_rows(float* S, long long rows, int T, cudaStream_t s);
+void launch_softmax_bwd(const float* P, float* gP, long long rows, int T, float scale, cudaStream_t s);
+void launch_pack_conv_weight_T(const float* wp, float* wpT, int Cout, int Cin, int KF, int KT, cudaStream_t s);
 
 // EDM sampler element-wise steps (sampler.py:214, 141-147, 230-251)
 void launch_axpy_noise(float* x, const float* eps, float scale, long long n, cudaStream_t s);

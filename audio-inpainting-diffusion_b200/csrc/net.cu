@@ -46,7 +46,10 @@ struct Weight {
     size_t numel() const { size_t n = 1; for (auto d : shape) n *= (size_t)d; return n; }
 };
 
-struct ConvW { int widx = -1; float* wp = nullptr; __half* wtc = nullptr; int Cin = 0, Cout = 0, KF = 1, KT = 1; };
+struct ConvW {
+    int widx = -1; float* wp = nullptr; __half* wtc = nullptr; int Cin = 0, Cout = 0, KF = 1, KT = 1;
+    float* wpT = nullptr;   // K-major weights of the transposed (data-gradient) convolution, built on the first VJP call
+};
 struct LinRef { int w = -1, b = -1; int off = -1, N = 0; };
 struct NormRef { int widx = -1; float* gamma = nullptr; };
 
@@ -62,6 +65,24 @@ struct ResBlk {
 };
 
 struct Level { ResBlk init, main; ConvW pyr; };
+
+// What a ResnetBlock's backward needs from its forward (views into the caller's workspace, kept alive by the taped forward)
+struct BlkTape {
+    TV in, x0;            // block input; after proj_in (== in when the block has none); x0.stats valid
+    TV h, qk, x1;         // attention sub-block: projected heads [B,8,F,T], q|k [B,16F,1,T], its output (== x0 without attention)
+    std::vector<TV> xs;   // xs[i] = input of dilated layer i (stats valid)
+};
+struct Tape {
+    bool valid = false;
+    int B = 0, nsig = 1;
+    float in_scale = 1.f, out_scale = 1.f, skip_scale = 0.f;
+    float* mod = nullptr;
+    std::vector<BlkTape> init, main, ups_main, ups_out;
+    BlkTape mid_main, mid_out;
+    float2 *spec = nullptr, *tmp = nullptr, *fscr = nullptr, *Y = nullptr;
+    char* ws = nullptr; size_t ws_bytes = 0;
+    unsigned long long generation = 0;
+};
 
 // ---- workspace arena: first-fit over a caller-owned slab; "dry" mode only measures the peak -----------
 struct Arena {
@@ -124,6 +145,13 @@ struct Net {
     unsigned long long* d_sat = nullptr;
     bool count_sat = false;
     unsigned long long weight_sat = 0;
+    // input-gradient path (aid_unet_forward_tape / aid_unet_backward)
+    Tape tape;
+    Arena tape_arena;              // arena state behind the taped forward: the backward keeps allocating in the same workspace
+    float* dweights_T = nullptr;   // transposed convolution weights (lazy)
+    float* d_adj_tables = nullptr; // CQT adjoint window tables (lazy)
+    CqtTables tabs_adjA, tabs_adjS;   // analysis adjoint: dual := win / M; synthesis adjoint: win := dual * M
+    bool vjp_ready = false;
 };
 
 static int add_weight(Net& n, const std::string& name, std::vector<int64_t> shape, bool ignored = false) {
@@ -412,6 +440,7 @@ static void fill_host_tables(Net& n) {
 struct Ctx {
     Net* n = nullptr; Arena ar; cudaStream_t s = nullptr; int B = 0, nsig = 1;
     float* mod = nullptr; double* stats_base = nullptr; int slot = 0;
+    Tape* tape = nullptr;   // non-null: taped forward (nothing the backward needs is released or overwritten)
     bool dry() const { return ar.dry; }
     float* allocf(long long nfl) { return (float*)ar.alloc((size_t)nfl * sizeof(float)); }
     void release(void* p) { ar.release(p); }
@@ -461,8 +490,10 @@ static void conv_tc(Ctx& c, const __half* a_hi, const __half* a_lo, int PF, cons
 }
 
 // unet.py:452-493.  `accum` (decoder out blocks, unet.py:817): out = (accum + block(x)) / sqrt(2), may alias out.
-static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = nullptr) {
+// `bt` (taped forward, input-gradient path): every intermediate the backward needs gets its own buffer and is recorded.
+static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = nullptr, BlkTape* bt = nullptr) {
     const int B = in.B, F = in.F, T = in.T, N = k.N;
+    const bool tp = bt != nullptr;
     if (in.C != k.dim || out.C != k.dim_out) throw std::runtime_error("resblock: channel mismatch");
     const long long plane = (long long)B * N * F * T;
     const long long n_grp = (long long)(N / 8) * F * T;
@@ -485,6 +516,8 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
     float* abuf = c.allocf(std::max(plane, operand_floats(N, pf_max, F)));
     __half* a_hi = reinterpret_cast<__half*>(abuf);
     TV x = make_tv(xbuf, B, N, F, T), a = make_tv(abuf, B, N, F, T);
+    auto fresh = [&]() { return tp ? make_tv(c.allocf(plane), B, N, F, T) : x; };   // taped: layer outputs never overwrite each other
+    if (tp) { bt->in = in; bt->xs.clear(); }
     // tcgen05 path: the block input is converted once to the fp16 operand layout and shared by proj_in and res_conv
     __half* pin_hi = nullptr; __half* pin_lo = nullptr; float* pin_buf = nullptr;
     const int pf1 = tc_pad_rows(T, 1, 1);
@@ -496,14 +529,16 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
     }
     TV cur;
     if (k.dim != N) {
-        ConvEpilogue ep; ep.stats = x.stats = c.new_slot();
-        if (k.proj_in.wtc) conv_tc(c, pin_hi, pin_lo, pf1, k.proj_in, 1, x, ep);
-        else conv(c, in, k.proj_in, 1, x, ep);
-        cur = x;
+        TV xo = fresh();
+        ConvEpilogue ep; ep.stats = xo.stats = c.new_slot();
+        if (k.proj_in.wtc) conv_tc(c, pin_hi, pin_lo, pf1, k.proj_in, 1, xo, ep);
+        else conv(c, in, k.proj_in, 1, xo, ep);
+        cur = xo;
     } else {
         cur = in;
         if (!cur.stats) { cur.stats = c.new_slot(); RUN(launch_group_stats(cur, cur.stats, c.s)); }
     }
+    if (tp) bt->x0 = cur;
     if (k.attn) {
         const int heads = k.a_in.Cout;
         RUN(launch_gn_act(cur, cur.stats, n_grp, k.norm2.gamma, c.mod + k.affine2.off, c.modstride(), false, a, c.s));
@@ -527,16 +562,19 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         ConvEpilogue ep;
         ep.gate = c.mod + k.gate2.off; ep.gate_bstride = c.modstride();
         ep.R = cur; ep.alpha = kInvSqrt2; ep.stats = c.new_slot();
-        x.stats = ep.stats;
-        conv(c, o, k.a_out, 1, x, ep);
-        c.release(h.p); c.release(qk.p); c.release(o.p);
-        cur = x;
+        TV xo = fresh();
+        xo.stats = ep.stats;
+        conv(c, o, k.a_out, 1, xo, ep);
+        if (tp) { bt->h = h; bt->qk = qk; } else { c.release(h.p); c.release(qk.p); }
+        c.release(o.p);
+        cur = xo;
     }
+    if (tp) bt->x1 = cur;
     // conv_mode 2, dilated blocks: between the layers the residual stream lives channels-last ([B][F][T][N] fp32), so that a
     // unit's 128 x N output tile and residual tile are contiguous in HBM (the NCHW planes give 512-byte fragments 1 MB apart,
     // which the DRAM serves at a fraction of its streaming rate).  Layer 0 reads NCHW, the last layer writes NCHW.
     static const bool env_cl = getenv("AID_TC2_CL") && atoi(getenv("AID_TC2_CL")) != 0;   // measured slower than NCHW so far: off by default
-    bool use_cl = env_cl && cmode == 2 && !k.k1x1 && k.nd >= 2;
+    bool use_cl = env_cl && cmode == 2 && !k.k1x1 && k.nd >= 2 && !tp;
     for (auto& h : k.H) use_cl = use_cl && h.wtc != nullptr;
     float* xcl = use_cl ? c.allocf(plane) : nullptr;
     TV xc = make_tv_cl(xcl, B, N, F, T);
@@ -547,6 +585,7 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         ep.R = cur; ep.alpha = kInvSqrt2;
         ep.stats = (i + 1 < k.nd) ? c.new_slot() : nullptr;
         const double* cur_stats = cur.stats;
+        if (tp) { bt->xs.push_back(cur); x = fresh(); }
         if (k.H[i].wtc) {
             const int dil = k.k1x1 ? 1 : (1 << i);
             const int pf = tc_pad_rows(T, k.H[i].KF, dil);
@@ -611,6 +650,12 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
     const aid_config& cf = n.cfg;
     const int B = c.B, L = cf.audio_len, no = cf.num_octs, bins = cf.bins_per_oct;
     c.slot = 0;
+    Tape* tp = c.tape;
+    auto keep = [&](void* p) { if (!tp) c.release(p); };   // released in the plain forward, kept for the backward in the taped one
+    if (tp) {
+        tp->init.assign(no, BlkTape()); tp->main.assign(no, BlkTape()); tp->ups_main.assign(no, BlkTape()); tp->ups_out.assign(no, BlkTape());
+        tp->mid_main = BlkTape(); tp->mid_out = BlkTape();
+    }
     c.mod = c.allocf((long long)B * n.total_mod);   // sized for per-clip sigma so the plan does not depend on n_sigma
     float* emb = c.allocf((long long)B * 256);
     RUN(launch_embedding(c_noise, c.nsig, n.d_emb[0], n.d_emb[1], n.d_emb[2], n.d_emb[3], n.d_emb[4], n.d_emb[5], n.d_emb[6], emb, c.s));
@@ -636,7 +681,7 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
         RUN(launch_cqt_analysis_oct(n.tabs, n.fft, no - 1 - i, spec, C, c.s));
         if (i == 0) { Xcat = make_tv(c.allocf((long long)B * din * Fi * Ti), B, din, Fi, Ti); Xcat.stats = c.new_slot(); }
         TV c2 = slice_f(Xcat, 0, bins); c2.stats = Xcat.stats;
-        resblock(c, n.downs[i].init, C, c2);
+        resblock(c, n.downs[i].init, C, c2, nullptr, tp ? &tp->init[i] : nullptr);
         TV pyr_new;
         if (i < no - 1) {
             pyr_new = make_tv(c.allocf((long long)B * 2 * Fi * (Ti / 2)), B, 2, Fi, Ti / 2);
@@ -647,13 +692,13 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
             RUN(launch_combine(C, TV(), 1.f, 0.f, slice_f(pyr_new, 0, bins), nullptr, c.s));
             if (i > 0) RUN(launch_combine(pyr, TV(), 1.f, 0.f, slice_f(pyr_new, bins, Fi - bins), nullptr, c.s));
         }
-        c.release(C.p);
+        keep(C.p);
         if (i > 0) c.release(pyr.p);
         pyr = pyr_new;
         TV skip = slice_c(cat[i], cf.Ns[i], cf.Ns[i]);
-        resblock(c, n.downs[i].main, Xcat, skip);
+        resblock(c, n.downs[i].main, Xcat, skip, nullptr, tp ? &tp->main[i] : nullptr);
         probe(c, "enc" + std::to_string(i), skip);
-        c.release(Xcat.p);
+        keep(Xcat.p);
         ConvEpilogue ep; ep.alpha = kInvSqrt2;
         if (i < no - 1) {
             TV Xd = make_tv(c.allocf((long long)B * cf.Ns[i] * Fi * (Ti / 2)), B, cf.Ns[i], Fi, Ti / 2);
@@ -674,20 +719,20 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
 
     const int Fl = bins * no, Tl = Tof(no - 1);
     TV Xm = slice_c(cat[no - 1], 0, cf.Ns[no - 1]); Xm.stats = c.new_slot();
-    resblock(c, n.mid_main, Xmid, Xm);
+    resblock(c, n.mid_main, Xmid, Xm, nullptr, tp ? &tp->mid_main : nullptr);
     probe(c, "mid", Xm);
-    c.release(Xmid.p);
+    keep(Xmid.p);
     TV Xout = make_tv(c.allocf((long long)B * 2 * Fl * Tl), B, 2, Fl, Tl);
-    resblock(c, n.mid_out, Xm, Xout);
+    resblock(c, n.mid_out, Xm, Xout, nullptr, tp ? &tp->mid_out : nullptr);
     float2* Y = (float2*)c.ar.alloc((size_t)B * n.tabs.ytotal * sizeof(float2));
     for (int i = 0; i < no; ++i) {
         const int j = no - 1 - i, Fj = bins * (j + 1), Tj = Tof(j);
         const int dout = j == 0 ? cf.Ns[0] : cf.Ns[j - 1];
         TV Xdec = make_tv(c.allocf((long long)B * dout * Fj * Tj), B, dout, Fj, Tj); Xdec.stats = c.new_slot();
-        resblock(c, n.ups_main[i], cat[j], Xdec);
+        resblock(c, n.ups_main[i], cat[j], Xdec, nullptr, tp ? &tp->ups_main[i] : nullptr);
         probe(c, "dec" + std::to_string(i), Xdec);
-        c.release(cat[j].p);
-        resblock(c, n.ups_out[i], Xdec, Xout, &Xout);
+        keep(cat[j].p);
+        resblock(c, n.ups_out[i], Xdec, Xout, &Xout, tp ? &tp->ups_out[i] : nullptr);
         RUN(launch_cqt_synth_oct(n.tabs, n.fft, i, slice_f(Xout, 0, bins), Y, c.s));
         if (j > 0) {
             TV Xn = slice_c(cat[j - 1], 0, cf.Ns[j - 1]);
@@ -697,12 +742,13 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
             c.release(Xout.p);
             Xout = Xo2;
         }
-        c.release(Xdec.p);
+        keep(Xdec.p);
     }
     c.release(Xout.p);
     RUN(launch_cqt_synth_gather(n.tabs, B, Y, spec, c.s));
     RUN(launch_fft_big(fftd, B, true, nullptr, 0, 0.f, spec, tmp, fscr, nullptr, out, L, out_scale / (float)L,
                        (skip_scale != 0.f || dscal) ? x : nullptr, L, skip_scale, c.s));
+    if (tp) { tp->mod = c.mod; tp->spec = spec; tp->tmp = tmp; tp->fscr = fscr; tp->Y = Y; }
     if (!c.dry()) AID_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -710,6 +756,244 @@ static size_t plan_forward(Net& n, int B, int* slots) {
     Ctx c; c.n = &n; c.B = B; c.nsig = 1; c.ar.reset(nullptr, 0, true);
     forward(c, nullptr, nullptr, nullptr, 1.f, 1.f, 0.f);
     if (slots) *slots = c.slot;
+    return c.ar.peak + 4096;
+}
+
+// ======================================================================================================
+// Input gradient (VJP) of the denoiser: reconstruction guidance, sampler.py:57-113 (torch.autograd.grad(norm, x) through
+// edm.py:133-148 and unet.py:730-845).  The taped forward keeps every block input / layer input alive in the workspace; the
+// backward below walks the network in reverse.  All backward arithmetic is fp32 on CUDA cores (the data-gradient convolutions
+// are the forward convolution kernels run with transposed, tap-mirrored weights).
+// Convention: every backward routine ACCUMULATES into its destination (zero-initialised by the caller), through the
+// convolution epilogue's R2 input or the beta argument of the adjoint kernels.
+
+// transposed weights + CQT adjoint tables, built once per handle on the first VJP call (allocates; documented in the header)
+static void ensure_vjp(Net& n) {
+    if (n.vjp_ready) return;
+    DeviceGuard guard(n.device);
+    std::vector<ConvW*> convs;
+    auto visit = [&](ResBlk& k) {
+        for (ConvW* c : {&k.proj_in, &k.res_conv, &k.proj_out, &k.a_in, &k.a_out, &k.qk}) if (c->widx >= 0) convs.push_back(c);
+        for (auto& c : k.H) convs.push_back(&c);
+    };
+    for (auto& l : n.downs) { visit(l.init); visit(l.main); convs.push_back(&l.pyr); }
+    visit(n.mid_main); visit(n.mid_out);
+    for (auto& k : n.ups_main) visit(k);
+    for (auto& k : n.ups_out) visit(k);
+    auto al = [](size_t v) { return (v + 63) & ~(size_t)63; };
+    size_t total = 0;
+    for (auto* c : convs) total += al((size_t)c->Cout * c->Cin * c->KF * c->KT);
+    AID_CUDA_CHECK(cudaMalloc(&n.dweights_T, total * sizeof(float)));
+    size_t off = 0;
+    for (auto* c : convs) {
+        c->wpT = n.dweights_T + off;
+        launch_pack_conv_weight_T(c->wp, c->wpT, c->Cout, c->Cin, c->KF, c->KT, nullptr);
+        off += al((size_t)c->Cout * c->Cin * c->KF * c->KT);
+    }
+    AID_CUDA_CHECK(cudaGetLastError());
+    const CqtPlanHost& p = n.plan;
+    std::vector<float> winM(p.win.size()), dualM(p.dual.size());
+    for (int k = 0; k < p.K; ++k) {
+        const float M = (float)p.size_per_oct[k / p.bins];
+        for (int i = 0; i < p.Lg[k]; ++i) { winM[p.woff[k] + i] = p.win[p.woff[k] + i] / M; dualM[p.woff[k] + i] = p.dual[p.woff[k] + i] * M; }
+    }
+    AID_CUDA_CHECK(cudaMalloc(&n.d_adj_tables, (winM.size() + dualM.size()) * sizeof(float)));
+    AID_CUDA_CHECK(cudaMemcpy(n.d_adj_tables, winM.data(), winM.size() * sizeof(float), cudaMemcpyHostToDevice));
+    AID_CUDA_CHECK(cudaMemcpy(n.d_adj_tables + winM.size(), dualM.data(), dualM.size() * sizeof(float), cudaMemcpyHostToDevice));
+    n.tabs_adjA = n.tabs; n.tabs_adjA.dual = n.d_adj_tables;                    // gather with the analysis windows / M
+    n.tabs_adjS = n.tabs; n.tabs_adjS.win = n.d_adj_tables + winM.size();       // window-and-fold with the dual windows * M
+    AID_CUDA_CHECK(cudaDeviceSynchronize());
+    n.vjp_ready = true;
+}
+
+static TV alloc_tv(Ctx& c, int C, int F, int T, bool zero) {
+    TV v = make_tv(c.allocf((long long)c.B * C * F * T), c.B, C, F, T);
+    if (zero) RUN(AID_CUDA_CHECK(cudaMemsetAsync(v.p, 0, (size_t)c.B * C * F * T * sizeof(float), c.s)));
+    return v;
+}
+
+// dst += alpha * conv_transposed(g)      (dst: [B, w.Cin, F, T], g: [B, w.Cout, F, T])
+static void conv_T(Ctx& c, const TV& g, const ConvW& w, int dil, const TV& dst, float alpha) {
+    ConvW wt; wt.Cin = w.Cout; wt.Cout = w.Cin; wt.KF = w.KF; wt.KT = w.KT; wt.wp = w.wpT; wt.widx = w.widx;
+    ConvEpilogue ep; ep.alpha = alpha; ep.beta = 1.f; ep.R2 = dst;
+    conv(c, g, wt, dil, dst, ep);
+}
+
+// unet.py:353-374 backward.  h [B,heads,F,T], qk [B,2*heads*F,1,T], g_o [B,heads,F,T] -> g_h (overwritten) [B,heads,F,T]
+static void attention_core_bwd(Ctx& c, const TV& h, const TV& qk, const TV& g_o, const TV& g_h, const TV& gqk) {
+    const int B = c.B, heads = h.C, F = h.F, T = h.T, Z = B * heads;
+    const long long FT = (long long)F * T, TT = (long long)T * T;
+    const float scale = 1.0f / sqrtf((float)F);
+    float* P = c.allocf((long long)Z * TT);
+    float* gP = c.allocf((long long)Z * TT);
+    const float* Qt = qk.p;            // [z][d][t] at z * 2FT
+    const float* Kt = qk.p + FT;
+    BGemm g{};
+    g.batch = Z; g.beta = 0.f;
+    // S[t,tk] = scale * sum_d q[t,d] k[tk,d]
+    g.A = Qt; g.sAm = 1; g.sAk = T; g.sAz = 2 * FT; g.B = Kt; g.sBk = T; g.sBn = 1; g.sBz = 2 * FT;
+    g.C = P; g.sCm = T; g.sCn = 1; g.sCz = TT; g.M = T; g.N = T; g.K = F; g.alpha = scale;
+    RUN(launch_bgemm(g, c.s));
+    RUN(launch_softmax_rows(P, (long long)Z * T, T, c.s));
+    // gP[t,tk] = sum_f g_o[f,t] h[f,tk]
+    g.A = g_o.p; g.sAm = 1; g.sAk = T; g.sAz = FT; g.B = h.p; g.sBk = T; g.sBn = 1; g.sBz = FT;
+    g.C = gP; g.sCm = T; g.sCn = 1; g.sCz = TT; g.M = T; g.N = T; g.K = F; g.alpha = 1.f;
+    RUN(launch_bgemm(g, c.s));
+    RUN(launch_softmax_bwd(P, gP, (long long)Z * T, T, scale, c.s));     // gP <- gS (includes the logit scale)
+    // g_q^T[d,t] = sum_tk k^T[d,tk] gS[t,tk]
+    g.A = Kt; g.sAm = T; g.sAk = 1; g.sAz = 2 * FT; g.B = gP; g.sBk = 1; g.sBn = T; g.sBz = TT;
+    g.C = gqk.p; g.sCm = T; g.sCn = 1; g.sCz = 2 * FT; g.M = F; g.N = T; g.K = T; g.alpha = 1.f;
+    RUN(launch_bgemm(g, c.s));
+    // g_k^T[d,tk] = sum_t q^T[d,t] gS[t,tk]
+    g.A = Qt; g.sAm = T; g.sAk = 1; g.sAz = 2 * FT; g.B = gP; g.sBk = T; g.sBn = 1; g.sBz = TT;
+    g.C = gqk.p + FT; g.M = F; g.N = T; g.K = T;
+    RUN(launch_bgemm(g, c.s));
+    // value path: g_h[f,tk] = sum_t g_o[f,t] P[t,tk]
+    g.A = g_o.p; g.sAm = T; g.sAk = 1; g.sAz = FT; g.B = P; g.sBk = T; g.sBn = 1; g.sBz = TT;
+    g.C = g_h.p; g.sCm = T; g.sCn = 1; g.sCz = FT; g.M = F; g.N = T; g.K = T;
+    RUN(launch_bgemm(g, c.s));
+    c.release(P); c.release(gP);
+}
+static void attention_bwd(Ctx& c, const ResBlk& k, const TV& h, const TV& qk, const TV& g_o, const TV& g_h) {
+    const int heads = h.C, F = h.F, T = h.T;
+    TV gqk = alloc_tv(c, 2 * heads * F, 1, T, false);
+    attention_core_bwd(c, h, qk, g_o, g_h, gqk);
+    // q|k path: g_h (as [B, heads*F, 1, T]) += Wqk^T g_qk
+    conv_T(c, gqk, k.qk, 1, make_tv(g_h.p, c.B, heads * F, 1, T), 1.f);
+    c.release(gqk.p);
+}
+
+// Backward of resblock(): g_in += d out / d in ^T (a_tail-scaled g_out).  a_tail: the coefficient of the block's own path in its
+// output (1/sqrt 2, or 0.5 for the decoder out blocks whose output is (accum + block) / sqrt 2 after the block's own / sqrt 2).
+static void resblock_bwd(Ctx& c, const ResBlk& k, const BlkTape& bt, const TV& g_out, float a_tail, const TV& g_in) {
+    const int F = g_out.F, T = g_out.T, N = k.N;
+    const long long n_grp = (long long)(N / 8) * F * T;
+    double* D = (double*)c.ar.alloc((size_t)c.B * 8 * sizeof(double));
+    TV g_cur = alloc_tv(c, N, F, T, false);
+    if (k.after && N != k.dim_out) {
+        conv_T(c, g_out, k.res_conv, 1, g_in, a_tail);
+        RUN(AID_CUDA_CHECK(cudaMemsetAsync(g_cur.p, 0, (size_t)c.B * N * F * T * sizeof(float), c.s)));
+        conv_T(c, g_out, k.proj_out, 1, g_cur, a_tail);
+    } else if (k.dim != k.dim_out) {
+        conv_T(c, g_out, k.res_conv, 1, g_in, a_tail);
+        RUN(launch_scale_channels(g_out, nullptr, 0, a_tail, g_cur, c.s));
+    } else {
+        RUN(launch_combine(g_out, g_in, a_tail, 1.f, g_in, nullptr, c.s));
+        RUN(launch_scale_channels(g_out, nullptr, 0, a_tail, g_cur, c.s));
+    }
+    TV tmp = alloc_tv(c, N, F, T, false), ga = alloc_tv(c, N, F, T, false);
+    for (int i = k.nd - 1; i >= 0; --i) {
+        // x_{i+1} = (x_i + H_i(gelu(GN_i(x_i) (1 + affine_i))) gate_i) / sqrt 2
+        const TV& xi = bt.xs[i];
+        RUN(launch_scale_channels(g_cur, c.mod + k.gate[i].off, c.modstride(), kInvSqrt2, tmp, c.s));
+        RUN(AID_CUDA_CHECK(cudaMemsetAsync(ga.p, 0, (size_t)c.B * N * F * T * sizeof(float), c.s)));
+        conv_T(c, tmp, k.H[i], k.k1x1 ? 1 : (1 << i), ga, 1.f);
+        RUN(launch_gn_bwd(ga, xi, xi.stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, D, g_cur, kInvSqrt2, g_cur, c.s));
+    }
+    if (k.attn) {
+        // x1 = (x0 + a_out(attention(a_in(GN2(x0) (1 + affine2)))) gate2) / sqrt 2
+        const int heads = k.a_in.Cout;
+        RUN(launch_scale_channels(g_cur, c.mod + k.gate2.off, c.modstride(), kInvSqrt2, tmp, c.s));
+        TV g_o = alloc_tv(c, heads, F, T, true), g_h = alloc_tv(c, heads, F, T, false);
+        conv_T(c, tmp, k.a_out, 1, g_o, 1.f);
+        attention_bwd(c, k, bt.h, bt.qk, g_o, g_h);
+        RUN(AID_CUDA_CHECK(cudaMemsetAsync(ga.p, 0, (size_t)c.B * N * F * T * sizeof(float), c.s)));
+        conv_T(c, g_h, k.a_in, 1, ga, 1.f);
+        RUN(launch_gn_bwd(ga, bt.x0, bt.x0.stats, n_grp, k.norm2.gamma, c.mod + k.affine2.off, c.modstride(), false, D, g_cur, kInvSqrt2, g_cur, c.s));
+        c.release(g_o.p); c.release(g_h.p);
+    }
+    if (k.dim != N) conv_T(c, g_cur, k.proj_in, 1, g_in, 1.f);
+    else RUN(launch_combine(g_cur, g_in, 1.f, 1.f, g_in, nullptr, c.s));
+    c.release(tmp.p); c.release(ga.p); c.release(g_cur.p); c.release(D);
+}
+
+// g_x = in_scale * out_scale * J_net^T g_out + skip_scale * g_out, for the forward recorded in the tape
+static void backward(Ctx& c, Tape& tp, const float* g_out, float* g_x) {
+    Net& n = *c.n;
+    const aid_config& cf = n.cfg;
+    const int B = c.B, L = cf.audio_len, no = cf.num_octs, bins = cf.bins_per_oct;
+    auto Tof = [&](int lvl) { return n.tabs.M[no - 1 - lvl]; };
+    // ---- synthesis adjoint: gradient of every octave's output coefficients (unet.py:841, 826-836) ----
+    RUN(launch_fft_big(n.fft, B, false, g_out, L, 1.f, nullptr, tp.tmp, tp.fscr, tp.spec, nullptr, 0, 0.f, nullptr, 0, 0.f, c.s));
+    RUN(launch_spec_synth_adj(B, L, tp.spec, tp.out_scale / (float)L, c.s));
+    std::vector<TV> gTop(no);
+    for (int i = 0; i < no; ++i) {
+        gTop[i] = alloc_tv(c, 2, bins, n.tabs.M[i], false);
+        RUN(launch_cqt_analysis_oct(n.tabs_adjS, n.fft, i, tp.spec, gTop[i], c.s));
+    }
+    std::vector<TV> gcat(no);
+    for (int j = 0; j < no; ++j) gcat[j] = alloc_tv(c, 2 * cf.Ns[j], bins * (j + 1), Tof(j), true);
+    // ---- decoder, last step first (unet.py:807-839) ----
+    TV gXoutPrev;      // gradient with respect to the out-block accumulator input of the step processed before (i + 1)
+    for (int i = no - 1; i >= 0; --i) {
+        const int j = no - 1 - i, Fj = bins * (j + 1), Tj = Tof(j);
+        const int dout = j == 0 ? cf.Ns[0] : cf.Ns[j - 1];
+        TV gXout = alloc_tv(c, 2, Fj, Tj, false);
+        RUN(launch_combine(gTop[i], TV(), 1.f, 0.f, slice_f(gXout, 0, bins), nullptr, c.s));
+        if (j > 0) { RUN(launch_resample_up_adj(gXoutPrev, slice_f(gXout, bins, Fj - bins), 0.f, c.s)); c.release(gXoutPrev.p); }
+        c.release(gTop[i].p);
+        TV gXdec = alloc_tv(c, dout, Fj, Tj, true);
+        resblock_bwd(c, n.ups_out[i], tp.ups_out[i], gXout, 0.5f, gXdec);
+        RUN(launch_scale_channels(gXout, nullptr, 0, kInvSqrt2, gXout, c.s));     // -> gradient of the accumulator input
+        gXoutPrev = gXout;
+        if (j > 0) RUN(launch_resample_up_adj(slice_c(gcat[j - 1], 0, cf.Ns[j - 1]), slice_f(gXdec, bins, Fj - bins), 1.f, c.s));
+        resblock_bwd(c, n.ups_main[i], tp.ups_main[i], gXdec, kInvSqrt2, gcat[j]);
+        c.release(gXdec.p);
+    }
+    // ---- bottleneck (unet.py:800-804) ----
+    const int Fl = bins * no, Tl = Tof(no - 1);
+    TV gXm = slice_c(gcat[no - 1], 0, cf.Ns[no - 1]);
+    resblock_bwd(c, n.mid_out, tp.mid_out, gXoutPrev, kInvSqrt2, gXm);
+    c.release(gXoutPrev.p);
+    TV gXmid = alloc_tv(c, cf.Ns[no - 1], Fl, Tl, true);
+    resblock_bwd(c, n.mid_main, tp.mid_main, gXm, kInvSqrt2, gXmid);
+    // ---- encoder, deepest level first (unet.py:747-795) ----
+    TV gXcatNext, gpyrNext;
+    for (int i = no - 1; i >= 0; --i) {
+        const int Ti = Tof(i), Fi = bins * (i + 1);
+        const int din = i == 0 ? cf.Ns[0] : cf.Ns[i - 1];
+        TV gskip = slice_c(gcat[i], cf.Ns[i], cf.Ns[i]);
+        const int Tpy = i < no - 1 ? Ti / 2 : Ti;
+        TV gpyr = alloc_tv(c, 2, Fi, Tpy, true);
+        if (i == no - 1) {    // Xmid = (pyr_down_proj(pyr) + skip) / sqrt 2
+            RUN(launch_combine(gXmid, gskip, kInvSqrt2, 1.f, gskip, nullptr, c.s));
+            conv_T(c, gXmid, n.downs[i].pyr, 1, gpyr, kInvSqrt2);
+            c.release(gXmid.p);
+        } else {              // Xcat_{i+1}[:, :, bins:] = (pyr_down_proj(pyr) + down(skip)) / sqrt 2
+            TV gsl = slice_f(gXcatNext, bins, Fi);
+            RUN(launch_scale_channels(gsl, nullptr, 0, kInvSqrt2, gsl, c.s));
+            RUN(launch_resample_down_adj(gsl, gskip, 1.f, c.s));
+            conv_T(c, gsl, n.downs[i].pyr, 1, gpyr, 1.f);
+            // the pyramid of level i is also the lower rows of the next level's pyramid (down-sampled, or copied at the last level)
+            TV src = slice_f(gpyrNext, bins, Fi);
+            if (i + 1 < no - 1) RUN(launch_resample_down_adj(src, gpyr, 1.f, c.s));
+            else RUN(launch_combine(src, gpyr, 1.f, 1.f, gpyr, nullptr, c.s));
+            c.release(gXcatNext.p); c.release(gpyrNext.p);
+        }
+        TV gXcat = alloc_tv(c, din, Fi, Ti, true);
+        resblock_bwd(c, n.downs[i].main, tp.main[i], gskip, kInvSqrt2, gXcat);
+        c.release(gcat[i].p);
+        TV gC = alloc_tv(c, 2, bins, Ti, true);
+        resblock_bwd(c, n.downs[i].init, tp.init[i], slice_f(gXcat, 0, bins), kInvSqrt2, gC);
+        if (i < no - 1) RUN(launch_resample_down_adj(slice_f(gpyr, 0, bins), gC, 1.f, c.s));
+        else RUN(launch_combine(slice_f(gpyr, 0, bins), gC, 1.f, 1.f, gC, nullptr, c.s));
+        RUN(launch_cqt_synth_oct(n.tabs_adjA, n.fft, no - 1 - i, gC, tp.Y, c.s));   // FFT_M of the coefficient gradients
+        c.release(gC.p);
+        gXcatNext = gXcat; gpyrNext = gpyr;
+    }
+    c.release(gXcatNext.p); c.release(gpyrNext.p);
+    // ---- analysis adjoint (unet.py:743): spectrum gradient on the whole circle, then the adjoint of the real-input FFT ----
+    RUN(launch_cqt_gather_adj(n.tabs_adjA, B, 0, no - 1, tp.Y, tp.spec, false, c.s));
+    RUN(launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, tp.spec, tp.tmp, tp.fscr, nullptr, g_x, L, tp.in_scale,
+                       tp.skip_scale != 0.f ? g_out : nullptr, L, tp.skip_scale, c.s));
+    if (!c.dry()) AID_CUDA_CHECK(cudaGetLastError());
+}
+
+static size_t plan_vjp(Net& n, int B) {
+    Ctx c; c.n = &n; c.B = B; c.nsig = 1; c.ar.reset(nullptr, 0, true);
+    Tape t; c.tape = &t;
+    forward(c, nullptr, nullptr, nullptr, 1.f, 1.f, 0.f);
+    backward(c, t, nullptr, nullptr);
     return c.ar.peak + 4096;
 }
 
@@ -771,6 +1055,8 @@ void aid_destroy(aid_handle* h) {
     if (h->net.dweights_tc) cudaFree(h->net.dweights_tc);
     if (h->net.d_tables) cudaFree(h->net.d_tables);
     if (h->net.d_sat) cudaFree(h->net.d_sat);
+    if (h->net.dweights_T) cudaFree(h->net.dweights_T);
+    if (h->net.d_adj_tables) cudaFree(h->net.d_adj_tables);
     for (auto& r : h->net.prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto& e : h->net.prof_pool) cudaEventDestroy(e);
     if (prev >= 0) cudaSetDevice(prev);
@@ -838,6 +1124,46 @@ int aid_unet_forward_ds(aid_handle* h, const float* x_dev, const float* c_noise_
         Ctx c; c.n = &h->net; c.B = B; c.nsig = n_sigma; c.s = (cudaStream_t)stream;
         c.ar.reset((char*)workspace_dev, workspace_bytes, false);
         forward(c, x_dev, c_noise_dev, out_dev, 1.f, 1.f, 0.f, scales_dev);
+    });
+}
+
+int aid_vjp_workspace_bytes(aid_handle* h, int B, size_t* bytes) {
+    if (!h || !bytes || B < 1) return AID_ERR_INVALID;
+    return guarded(h, [&] { *bytes = plan_vjp(h->net, B); });
+}
+
+int aid_unet_forward_tape(aid_handle* h, const float* x_dev, const float* c_noise_dev, int n_sigma, float* out_dev, int B,
+                          float in_scale, float out_scale, float skip_scale, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!h || !x_dev || !c_noise_dev || !out_dev || !workspace_dev || B < 1) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        Net& n = h->net;
+        if (!n.finalized) throw std::runtime_error("aid_unet_forward_tape before aid_finalize");
+        if (n_sigma != 1 && n_sigma != B) throw std::invalid_argument("n_sigma must be 1 or B");
+        if (out_dev == x_dev) throw std::invalid_argument("out may not alias x on the taped path");
+        ensure_vjp(n);
+        n.tape.valid = false;
+        Ctx c; c.n = &n; c.B = B; c.nsig = n_sigma; c.s = (cudaStream_t)stream;
+        c.ar.reset((char*)workspace_dev, workspace_bytes, false);
+        c.tape = &n.tape;
+        forward(c, x_dev, c_noise_dev, out_dev, in_scale, out_scale, skip_scale);
+        n.tape.B = B; n.tape.nsig = n_sigma; n.tape.in_scale = in_scale; n.tape.out_scale = out_scale; n.tape.skip_scale = skip_scale;
+        n.tape.ws = (char*)workspace_dev; n.tape.ws_bytes = workspace_bytes;
+        n.tape_arena = c.ar;
+        ++n.tape.generation;
+        n.tape.valid = true;
+    });
+}
+
+int aid_unet_backward(aid_handle* h, const float* grad_out_dev, float* grad_x_dev, void* stream) {
+    if (!h || !grad_out_dev || !grad_x_dev) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        Net& n = h->net;
+        if (!n.tape.valid) throw std::runtime_error("aid_unet_backward without a live tape (call aid_unet_forward_tape first; its workspace must stay untouched)");
+        if (grad_out_dev == grad_x_dev) throw std::invalid_argument("grad_x may not alias grad_out");
+        Ctx c; c.n = &n; c.B = n.tape.B; c.nsig = n.tape.nsig; c.s = (cudaStream_t)stream;
+        c.ar = n.tape_arena;       // a copy: the tape's own allocations stay, everything the backward takes is returned
+        c.mod = n.tape.mod;
+        backward(c, n.tape, grad_out_dev, grad_x_dev);
     });
 }
 
@@ -1134,6 +1460,103 @@ int aid_op_attention(const float* h_dev, const float* qk_dev, int B, int heads, 
         launch_attention(h, qk_dev, out, (cudaStream_t)stream);
         return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
     } catch (...) { return AID_ERR_INVALID; }
+}
+
+/* ---- backward single-operator entry points (unit parity of the VJP pieces) ---------------------------------------------- */
+int aid_op_resample_adj(const float* gy_dev, int B, int C, int F, int T, int up, float* gx_dev, void* stream) {
+    if (!gy_dev || !gx_dev || T < 4 || (T & 1)) return AID_ERR_INVALID;
+    TV gx = make_tv(gx_dev, B, C, F, T), gy = make_tv(const_cast<float*>(gy_dev), B, C, F, up ? 2 * T : T / 2);
+    if (up) launch_resample_up_adj(gy, gx, 0.f, (cudaStream_t)stream); else launch_resample_down_adj(gy, gx, 0.f, (cudaStream_t)stream);
+    return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+}
+
+int aid_op_groupnorm_act_bwd(const float* g_dev, const float* x_dev, const float* gamma_dev, const float* affine_dev, int B, int C, int F, int T,
+                             int gelu, float* gx_dev, double* scratch_dev /*[B][8][3]*/, void* stream) {
+    if (!g_dev || !x_dev || !gamma_dev || !gx_dev || !scratch_dev || C % 8 != 0) return AID_ERR_INVALID;
+    try {
+        cudaStream_t s = (cudaStream_t)stream;
+        TV x = make_tv(const_cast<float*>(x_dev), B, C, F, T), g = make_tv(const_cast<float*>(g_dev), B, C, F, T), gx = make_tv(gx_dev, B, C, F, T);
+        AID_CUDA_CHECK(cudaMemsetAsync(scratch_dev, 0, (size_t)B * 24 * sizeof(double), s));
+        launch_group_stats(x, scratch_dev, s);
+        launch_gn_bwd(g, x, scratch_dev, (long long)(C / 8) * F * T, gamma_dev, affine_dev, 0, gelu != 0, scratch_dev + (size_t)B * 16, TV(), 0.f, gx, s);
+        return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+    } catch (const CudaError&) { return AID_ERR_CUDA; }
+}
+
+int aid_op_attention_bwd(const float* h_dev, const float* qk_dev, const float* go_dev, int B, int heads, int F, int T, float* gh_dev,
+                         float* gqk_dev, void* scratch_dev, size_t scratch_bytes, void* stream) {
+    if (!h_dev || !qk_dev || !go_dev || !gh_dev || !gqk_dev || !scratch_dev) return AID_ERR_INVALID;
+    try {
+        Ctx c; c.B = B; c.s = (cudaStream_t)stream;
+        c.ar.reset((char*)scratch_dev, scratch_bytes, false);
+        TV h = make_tv(const_cast<float*>(h_dev), B, heads, F, T), qk = make_tv(const_cast<float*>(qk_dev), B, 2 * heads * F, 1, T);
+        TV go = make_tv(const_cast<float*>(go_dev), B, heads, F, T), gh = make_tv(gh_dev, B, heads, F, T), gqk = make_tv(gqk_dev, B, 2 * heads * F, 1, T);
+        attention_core_bwd(c, h, qk, go, gh, gqk);
+        return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
+    } catch (const std::exception&) { return AID_ERR_WORKSPACE; } catch (const CudaError&) { return AID_ERR_CUDA; }
+}
+
+/* transposed (data-gradient) convolution: gx[B,Cin,F,T] = conv^T(gy[B,Cout,F,T]; w[Cout,Cin,KF,KT]), the forward kernels with
+ * tap-mirrored, channel-swapped weights */
+int aid_op_conv2d_bwd_input(const float* gy_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
+                            float* gx_dev, void* stream) {
+    if (!gy_dev || !w_dev || !gx_dev) return AID_ERR_INVALID;
+    try {
+        cudaStream_t s = (cudaStream_t)stream;
+        const size_t e = (size_t)Cout * Cin * KF * KT;
+        float *wp = nullptr, *wpT = nullptr;
+        AID_CUDA_CHECK(cudaMalloc(&wp, e * sizeof(float))); AID_CUDA_CHECK(cudaMalloc(&wpT, e * sizeof(float)));
+        pack_conv_weight_kernel<<<(int)std::min<size_t>(4096, (e + 255) / 256), 256, 0, s>>>(w_dev, wp, Cout, Cin, KF * KT);
+        launch_pack_conv_weight_T(wp, wpT, Cout, Cin, KF, KT, s);
+        TV gy = make_tv(const_cast<float*>(gy_dev), B, Cout, F, T), gx = make_tv(gx_dev, B, Cin, F, T);
+        ConvEpilogue ep;
+        if (!launch_conv_thin(gy, wpT, KF, KT, dil, gx, ep, s)) launch_conv_simt(gy, wpT, KF, KT, dil, gx, ep, s);
+        AID_CUDA_CHECK(cudaGetLastError());
+        AID_CUDA_CHECK(cudaStreamSynchronize(s));
+        cudaFree(wp); cudaFree(wpT);
+        return AID_OK;
+    } catch (const CudaError&) { return AID_ERR_CUDA; }
+}
+
+/* adjoints of aid_cqt_fwd / aid_cqt_bwd (same coefficient layout and workspace) */
+int aid_cqt_fwd_vjp(aid_handle* h, const float* gcoef_dev, float* gx_dev, int B, void* ws, size_t ws_bytes, void* stream) {
+    if (!h || !gcoef_dev || !gx_dev || !ws) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        Net& n = h->net; cudaStream_t s = (cudaStream_t)stream;
+        if (!n.finalized) throw std::runtime_error("aid_cqt_fwd_vjp before aid_finalize");
+        ensure_vjp(n);
+        float2 *spec, *tmp, *fscr, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &fscr, &Y);
+        const int L = n.cfg.audio_len, bins = n.cfg.bins_per_oct;
+        int64_t off = 0;
+        for (int o = 0; o < n.cfg.num_octs; ++o) {
+            TV C = make_tv(const_cast<float*>(gcoef_dev) + off, B, 2, bins, n.tabs.M[o]);
+            launch_cqt_synth_oct(n.tabs_adjA, n.fft, o, C, Y, s);
+            off += (int64_t)B * 2 * bins * n.tabs.M[o];
+        }
+        launch_cqt_gather_adj(n.tabs_adjA, B, 0, n.cfg.num_octs - 1, Y, spec, false, s);
+        launch_fft_big(n.fft, B, true, nullptr, 0, 0.f, spec, tmp, fscr, nullptr, gx_dev, L, 1.f, nullptr, 0, 0.f, s);
+        AID_CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int aid_cqt_bwd_vjp(aid_handle* h, const float* gx_dev, float* gcoef_dev, int B, void* ws, size_t ws_bytes, void* stream) {
+    if (!h || !gcoef_dev || !gx_dev || !ws) return AID_ERR_INVALID;
+    return guarded(h, [&] {
+        Net& n = h->net; cudaStream_t s = (cudaStream_t)stream;
+        if (!n.finalized) throw std::runtime_error("aid_cqt_bwd_vjp before aid_finalize");
+        ensure_vjp(n);
+        float2 *spec, *tmp, *fscr, *Y; cqt_ws_split(n, B, ws, ws_bytes, &spec, &tmp, &fscr, &Y);
+        const int L = n.cfg.audio_len, bins = n.cfg.bins_per_oct;
+        launch_fft_big(n.fft, B, false, gx_dev, L, 1.f, nullptr, tmp, fscr, spec, nullptr, 0, 0.f, nullptr, 0, 0.f, s);
+        launch_spec_synth_adj(B, L, spec, 1.f / (float)L, s);
+        int64_t off = 0;
+        for (int o = 0; o < n.cfg.num_octs; ++o) {
+            TV C = make_tv(gcoef_dev + off, B, 2, bins, n.tabs.M[o]);
+            launch_cqt_analysis_oct(n.tabs_adjS, n.fft, o, spec, C, s);
+            off += (int64_t)B * 2 * bins * n.tabs.M[o];
+        }
+        AID_CUDA_CHECK(cudaGetLastError());
+    });
 }
 
 int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float* emb_dev, void* stream) {

@@ -58,7 +58,6 @@ class EDM:
             sigma = sigma.unsqueeze(-1)
         cskip, cout, cin, cnoise = self.cskip(sigma), self.cout(sigma), self.cin(sigma), self.cnoise(sigma)
         if hasattr(net, "denoise_fused") and sigma.numel() == 1:
-            if torch.is_grad_enabled() and xn.requires_grad:
-                return cskip * xn + cout * net(cin * xn, cnoise)  # raises the forward-only error
+            # the preconditioning is fused into the CUDA call, on the differentiable path too (the VJP carries the same scales)
             return net.denoise_fused(xn, cnoise, float(cin), float(cout), float(cskip))
         return cskip * xn + cout * net(cin * xn, cnoise)

@@ -11,11 +11,11 @@ Differences that are deliberate and documented:
   * On CUDA tensors each step's element-wise work is one fused kernel (aid_edm_step) and the denoiser call is the
     fused EDM-preconditioned forward; on CPU tensors (only reachable with a non-product denoiser, e.g. the
     host-logic tests) the same updates are written with torch ops in the reference's order.
-  * Reconstruction guidance (xi > 0, sampler.py:55-113) needs the denoiser's vector-Jacobian product.  The branch is
-    mirrored for any denoiser torch can differentiate (host logic, torch ops); the CUDA denoiser of this package is
-    forward-only, so with it xi > 0 raises NotImplementedError -- use xi = 0 (replacement method) there.  The reference
-    itself fails for batch > 1 (autograd.grad of a vector norm, sampler.py:78): here the per-clip norms are summed and the
-    step size is normalised per clip, which is the reference's arithmetic at batch 1.
+  * Reconstruction guidance (xi > 0, sampler.py:55-113) needs the denoiser's vector-Jacobian product.  The branch is written
+    with torch ops around the denoiser call; this package's CUDA denoiser is differentiable with respect to its input (the
+    library's own VJP behind a torch.autograd.Function, unet.py), so `torch.autograd.grad(norm, x)` works exactly as in the
+    reference.  The reference itself fails for batch > 1 (autograd.grad of a vector norm, sampler.py:78): here the per-clip
+    norms are summed and the step size is normalised per clip, which is the reference's arithmetic at batch 1.
   * `prepare_smooth_mask` is vectorised (the reference loops over L samples in Python, sampler.py:311-324).
   * Noise.  By default it is drawn with torch's CPU generator and copied, exactly as the reference does (edm.py:94,
     sampler.py:212), so seeded runs reproduce the reference's trajectories.  `sampler.device_noise = DeviceNoise(seed, ...)`
@@ -106,10 +106,12 @@ class Sampler:
         if mask is None:
             mask = self.mask
         L = x.shape[-1]
-        if not x.is_cuda:
+        if not x.is_cuda or (torch.is_grad_enabled() and x.requires_grad):
+            # CPU tensors (host-logic tests), or the guidance branch differentiating through the degradation (sampler.py:68-78):
+            # the reference's own torch.stft / torch.istft calls, which autograd understands
             window = torch.hann_window(win).to(x.device)
             xp = torch.nn.functional.pad(x, (0, n_fft - L % n_fft), mode="constant", value=0)
-            X = torch.stft(xp, n_fft, hop, win, window, return_complex=True) * mask.unsqueeze(0)
+            X = torch.stft(xp, n_fft, hop, win, window, return_complex=True) * mask.to(x.device).unsqueeze(0)
             s = torch.istft(X, n_fft, hop, win, window, return_complex=False)[..., 0:L]
             return s if y is None else y + x - s
         if win != n_fft:
@@ -165,9 +167,9 @@ class Sampler:
             return (x_hat.detach() - x) / t_i ** 2
 
     def _refuse_guidance_on_forward_only_model(self):
-        if hasattr(self.model, "denoise_fused"):
+        if hasattr(self.model, "denoise_fused") and not hasattr(self.model, "_forward_tape"):
             raise NotImplementedError(
-                "reconstruction guidance (xi > 0) needs the denoiser's VJP, which this forward-only CUDA denoiser does not "
+                "reconstruction guidance (xi > 0) needs the denoiser's VJP, which this forward-only denoiser does not "
                 "provide; set tester.posterior_sampling.xi = 0 (replacement method)")
 
     def get_score_rec_guidance(self, x, y, t_i, degradation):

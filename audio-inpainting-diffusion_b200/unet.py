@@ -6,8 +6,10 @@ schema, and a `CQTransform` attribute exposing `fwd / bwd / a
 (unet.py:620, sampler.py:63,123).  Select it with
     network.callable: "audio-inpainting-diffusion_b200.unet.Unet_CQT_oct_with_attention"
 All arithmetic runs in libaid_b200.so (hand-written sm_100a kernels); torch only owns device memory and streams.
-Forward-only: a call with grad enabled on an input that requires grad raises (the reference's guidance
-branch, sampler.py:57-113, needs a VJP that this path does not provide).
+The module is differentiable with respect to its INPUT: when grad is enabled and the input requires grad (the reference's
+reconstruction-guidance branch, sampler.py:57-113), forward runs the taped CUDA forward and registers a torch.autograd.Function
+whose backward is the library's own vector-Jacobian product (aid_unet_forward_tape / aid_unet_backward).  Parameters and sigma
+get no gradient (training is out of scope).
 """
 import ctypes as C
 import math
@@ -88,6 +90,37 @@ class _Node(nn.Module):
     pass
 
 
+class _DenoiseFn(torch.autograd.Function):
+    """out = out_scale * net(in_scale * x, c_noise) + skip_scale * x with the library's VJP as backward (input gradient only)."""
+
+    @staticmethod
+    def forward(ctx, x, net, c_noise, in_scale, out_scale, skip_scale):
+        out = net._forward_tape(x.detach(), c_noise, in_scale, out_scale, skip_scale)
+        ctx.net, ctx.gen = net, net._tape_gen
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        net = ctx.net
+        if net._tape_gen != ctx.gen:
+            raise RuntimeError("the denoiser's tape was overwritten by a later differentiable forward: one backward per forward "
+                               "(the reference's guidance step, sampler.py:59-78, has this shape)")
+        return net._backward(g), None, None, None, None, None
+
+
+class _HpfFn(torch.autograd.Function):
+    """CQT_nsgt.apply_hpf_DC: a real, symmetric circular filter (H[k] real), hence self-adjoint."""
+
+    @staticmethod
+    def forward(ctx, x, cqt):
+        ctx.cqt = cqt
+        return cqt._hpf(x.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.cqt._hpf(g.contiguous()), None
+
+
 class CQTDevice:
     """`model.CQTransform` (unet.py:620): fwd / bwd / apply_hpf_DC on the GPU through the C ABI."""
 
@@ -148,7 +181,12 @@ class CQTDevice:
         return x.unsqueeze(1)
 
     def apply_hpf_DC(self, x):
-        """[B,L'] (L' <= L, zero padded) -> [B,L']   (sampler.py:63,123)"""
+        """[B,L'] (L' <= L, zero padded) -> [B,L']   (sampler.py:63,123); differentiable (guidance branch, sampler.py:62-63)"""
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _HpfFn.apply(x, self)
+        return self._hpf(x)
+
+    def _hpf(self, x):
         o = self._o
         o._ensure_handle(x.device)
         Lin, L = x.shape[-1], o.cfg.audio_len
@@ -184,6 +222,8 @@ class Unet_CQT_oct_with_attention(nn.Module):
         self._handle_dev = None
         self._weights_loaded = False
         self._ws = {}
+        self._tape_ws = None
+        self._tape_gen = 0
         gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 31))
         for name, shape in schema_from_lib(self.cfg):
             node = self
@@ -239,6 +279,7 @@ class Unet_CQT_oct_with_attention(nn.Module):
             _lib.lib().aid_destroy(self._handle)
         self._handle, self._handle_dev, self._weights_loaded = None, None, False
         self._ws = {}
+        self._tape_ws = None
 
     def __del__(self):
         try:
@@ -260,8 +301,49 @@ class Unet_CQT_oct_with_attention(nn.Module):
         return self._ws[key]
 
     # ---- forward ----------------------------------------------------------------------------------
+    def _prep(self, x, c_noise):
+        if x.dim() != 2 or x.shape[1] != self.cfg.audio_len:
+            raise AssertionError("bad shapes")  # unet.py:844
+        x = x.float().contiguous()
+        self._ensure_weights(x.device)
+        cn = c_noise.detach().reshape(-1).to(device=x.device, dtype=torch.float32).contiguous()
+        if cn.numel() not in (1, x.shape[0]):
+            raise ValueError("sigma must have 1 or B entries")
+        return x, cn
+
+    def _forward_tape(self, x, c_noise, in_scale, out_scale, skip_scale):
+        """Taped forward (aid_unet_forward_tape): the workspace keeps what `_backward` needs until the next taped forward."""
+        x, cn = self._prep(x, c_noise)
+        B, dev = x.shape[0], x.device
+        L = _lib.lib()
+        need = C.c_size_t()
+        _lib.check(L.aid_vjp_workspace_bytes(self._handle, B, C.byref(need)), self._handle)
+        if self._tape_ws is None or self._tape_ws.numel() < need.value or self._tape_ws.device != dev:
+            self._tape_ws = None
+            self._tape_ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+        out = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.aid_unet_forward_tape(self._handle, _lib.ptr(x), _lib.ptr(cn), cn.numel(), _lib.ptr(out), B, float(in_scale),
+                                               float(out_scale), float(skip_scale), _lib.ptr(self._tape_ws), self._tape_ws.numel(), st),
+                       self._handle)
+        self._tape_gen += 1
+        self._tape_x = x          # keeps the input alive (the backward does not read it, the caller's graph might)
+        return out
+
+    def _backward(self, g):
+        """grad_x for the last taped forward (aid_unet_backward)."""
+        g = g.float().contiguous()
+        gx = torch.empty_like(g)
+        with torch.cuda.device(g.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.lib().aid_unet_backward(self._handle, _lib.ptr(g), _lib.ptr(gx), st), self._handle)
+        return gx
+
     def denoise_fused(self, x, c_noise, in_scale=1.0, out_scale=1.0, skip_scale=0.0, out=None):
         """out = out_scale * net(in_scale * x, c_noise) + skip_scale * x  (EDM.denoiser fused, edm.py:133-148)."""
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _DenoiseFn.apply(x, self, c_noise, float(in_scale), float(out_scale), float(skip_scale))
         if x.dim() != 2 or x.shape[1] != self.cfg.audio_len:
             raise AssertionError("bad shapes")  # unet.py:844
         if x.dtype != torch.float32:
@@ -323,7 +405,4 @@ class Unet_CQT_oct_with_attention(nn.Module):
 
     def forward(self, inputs, sigma):
         """inputs [B,T] time-domain signal, sigma [B,1] or [1,1] noise-level embedding input (c_noise)."""
-        if torch.is_grad_enabled() and inputs.requires_grad:
-            raise RuntimeError("this denoiser is forward-only: it cannot back-propagate to its input "
-                               "(reconstruction guidance, xi > 0, is not supported; use xi = 0)")
-        return self.denoise_fused(inputs, sigma)
+        return self.denoise_fused(inputs, sigma)      # differentiable with respect to `inputs` (see _DenoiseFn)

@@ -86,6 +86,20 @@ int aid_unet_forward(aid_handle* h, const float* x_dev, const float* c_noise_dev
 int aid_unet_forward_ds(aid_handle* h, const float* x_dev, const float* c_noise_dev, int n_sigma, float* out_dev, int B,
                         const float* scales_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Input gradient of the denoiser (reconstruction guidance, sampler.py:57-113: torch.autograd.grad(norm, x) through
+ * EDM.denoiser, edm.py:133-148, and Unet_CQT_oct_with_attention.forward, unet.py:730-845).  Weights get no gradient.
+ *   aid_unet_forward_tape : the forward of aid_unet_forward, keeping in the workspace everything the backward needs (every block
+ *                           and layer input, group statistics, attention q|k); workspace size from aid_vjp_workspace_bytes.
+ *   aid_unet_backward     : grad_x = in_scale * out_scale * J_net(in_scale * x)^T grad_out + skip_scale * grad_out for the taped
+ *                           forward.  The workspace must be untouched since aid_unet_forward_tape; may be called repeatedly.
+ * The first call on a handle builds the transposed convolution weights and the CQT adjoint tables (one device allocation each).
+ * Backward arithmetic is fp32 on CUDA cores in every conv_mode; the taped forward runs in the handle's conv_mode. */
+int aid_vjp_workspace_bytes(aid_handle* h, int B, size_t* bytes);
+int aid_unet_forward_tape(aid_handle* h, const float* x_dev, const float* c_noise_dev, int n_sigma, float* out_dev, int B,
+                          float in_scale, float out_scale, float skip_scale, void* workspace_dev, size_t workspace_bytes,
+                          void* stream);
+int aid_unet_backward(aid_handle* h, const float* grad_out_dev, float* grad_x_dev, void* stream);
+
 /* CQT_nsgt.fwd / bwd / apply_hpf_DC                         unet.py:743, unet.py:841, sampler.py:63,123
  * coefficient layout: per octave o (ascending frequency) a [B, 2, bins, T_o] fp32 tensor (re, im planes),
  * octave tensors concatenated in one buffer at offsets aid_cqt_layout() reports (in floats, for batch B). */
@@ -152,6 +166,23 @@ int aid_op_resample(const float* x_dev, int B, int C, int F, int T, int up, floa
 int aid_op_attention(const float* h_dev, const float* qk_dev, int B, int heads, int F, int T, float* out_dev, void* stream);
 /* RFF_MLP_Block + every adaLN Linear: returns the emb [n_sigma,256]                          unet.py:184-211 */
 int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float* emb_dev, void* stream);
+
+/* Backward (input-gradient) single operators, the pieces of aid_unet_backward:
+ *   aid_op_resample_adj       adjoint of aid_op_resample: gy [.., up ? 2T : T/2] -> gx [.., T]                    unet.py:549-580
+ *   aid_op_groupnorm_act_bwd  gx = d/dx [act(GroupNorm(x) * (affine + 1))]^T g; scratch_dev: [B][8][3] doubles     unet.py:147-163
+ *   aid_op_attention_bwd      g_o [B,heads,F,T] -> gh (value path only) [B,heads,F,T] and gqk [B,2*heads*F,T];
+ *                             scratch: 2 * B * heads * T * T floats (+ alignment)                               unet.py:353-374
+ *   aid_op_conv2d_bwd_input   gx = conv^T(gy): the forward kernels with tap-mirrored, channel-swapped weights      unet.py:79-88
+ *   aid_cqt_fwd_vjp / aid_cqt_bwd_vjp  adjoints of aid_cqt_fwd / aid_cqt_bwd (same layout and workspace; after aid_finalize) */
+int aid_op_resample_adj(const float* gy_dev, int B, int C, int F, int T, int up, float* gx_dev, void* stream);
+int aid_op_groupnorm_act_bwd(const float* g_dev, const float* x_dev, const float* gamma_dev, const float* affine_dev, int B, int C, int F,
+                             int T, int gelu, float* gx_dev, double* scratch_dev, void* stream);
+int aid_op_attention_bwd(const float* h_dev, const float* qk_dev, const float* go_dev, int B, int heads, int F, int T, float* gh_dev,
+                         float* gqk_dev, void* scratch_dev, size_t scratch_bytes, void* stream);
+int aid_op_conv2d_bwd_input(const float* gy_dev, const float* w_dev, int B, int Cin, int Cout, int F, int T, int KF, int KT, int dil,
+                            float* gx_dev, void* stream);
+int aid_cqt_fwd_vjp(aid_handle* h, const float* gcoef_dev, float* gx_dev, int B, void* workspace_dev, size_t workspace_bytes, void* stream);
+int aid_cqt_bwd_vjp(aid_handle* h, const float* gx_dev, float* gcoef_dev, int B, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* Debug/tuning (not part of the drop-in surface): aid_op_conv2d run twice, returning the device time in ms of the
  * second convolution launch alone. */

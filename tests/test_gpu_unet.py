@@ -103,13 +103,17 @@ def test_forward_fused_preconditioning(small, cuda):
     assert rel_l2(out, ref) < 1e-4
 
 
-def test_forward_requires_grad_raises(small, cuda):
+def test_forward_with_grad_builds_a_graph_only_when_needed(small, cuda):
+    """The module is differentiable with respect to its input (tests/test_gpu_vjp.py); under no_grad, or for inputs that do not
+    require grad, it stays on the plain forward path."""
     cfg, sd, net, orc = small
-    x = seeded((1, cfg.audio_len), 1).to(cuda).requires_grad_()
-    with pytest.raises(RuntimeError, match="forward-only"):
-        net(x, torch.tensor([[0.0]], device=cuda))
+    x = seeded((1, cfg.audio_len), 1).to(cuda)
+    cn = torch.tensor([[0.0]], device=cuda)
+    assert net(x, cn).grad_fn is None
+    xg = x.clone().requires_grad_()
+    assert net(xg, cn).grad_fn is not None
     with torch.no_grad():
-        net(x, torch.tensor([[0.0]], device=cuda))
+        assert net(xg, cn).grad_fn is None
 
 
 def test_forward_paper_network_config1(aid, cuda):
