@@ -121,6 +121,14 @@ class UnetOracle:
 
     @torch.no_grad()
     def __call__(self, inputs, sigma, probe=None):
+        return self._forward(inputs, sigma, probe)
+
+    def differentiable(self, inputs, sigma):
+        """The same forward with autograd recording (reference for the input gradient, sampler.py:59-78)."""
+        with torch.enable_grad():
+            return self._forward(inputs, sigma, None)
+
+    def _forward(self, inputs, sigma, probe=None):
         cfg, sd = self.cfg, self.sd
         Ns, nd, att, bins, no = cfg["Ns"], cfg["num_dils"], cfg["attention_layers"], cfg["bins_per_oct"], cfg["num_octs"]
         emb = embedding(sd, sigma)

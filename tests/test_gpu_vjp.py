@@ -31,8 +31,8 @@ def test_resample_adjoint(cuda, up, T):
     y = unet_oracle.up_t(x) if up else unet_oracle.down_t(x)
     g = seeded(tuple(y.shape), 2)
     want = torch.autograd.grad(y, x, g)[0]
-    gx = torch.empty(B, Cc, F, T, device=cuda)
-    _l.check(L.aid_op_resample_adj(_l.ptr(g.to(cuda)), B, Cc, F, T, up, _l.ptr(gx), None))
+    gx, gd = torch.empty(B, Cc, F, T, device=cuda), g.to(cuda)      # named device tensors: a temporary would be freed before the call
+    _l.check(L.aid_op_resample_adj(_l.ptr(gd), B, Cc, F, T, up, _l.ptr(gx), None))
     assert rel_l2(gx, want) < 1e-6
 
 
@@ -50,8 +50,8 @@ def test_groupnorm_act_backward(cuda, gelu):
     want = torch.autograd.grad(y, x, g)[0]
     gx = torch.empty(B, Cc, F, T, device=cuda)
     scr = torch.empty(B * 24, dtype=torch.float64, device=cuda)
-    _l.check(L.aid_op_groupnorm_act_bwd(_l.ptr(g.to(cuda)), _l.ptr(x.detach().to(cuda)), _l.ptr(gamma.to(cuda)), _l.ptr(aff.to(cuda)), B, Cc, F, T,
-                                        gelu, _l.ptr(gx), _l.ptr(scr), None))
+    gd, xd, gam, af = g.to(cuda), x.detach().to(cuda), gamma.to(cuda), aff.to(cuda)
+    _l.check(L.aid_op_groupnorm_act_bwd(_l.ptr(gd), _l.ptr(xd), _l.ptr(gam), _l.ptr(af), B, Cc, F, T, gelu, _l.ptr(gx), _l.ptr(scr), None))
     assert rel_l2(gx, want) < 2e-5
 
 
@@ -66,8 +66,8 @@ def test_conv_backward_input(cuda, case):
     y = Fn.conv2d(x, w.double(), padding="same", dilation=(dil, 1))
     g = seeded(tuple(y.shape), 3)
     want = torch.autograd.grad(y, x, g.double())[0]
-    gx = torch.empty(B, Cin, F, T, device=cuda)
-    _l.check(L.aid_op_conv2d_bwd_input(_l.ptr(g.to(cuda)), _l.ptr(w.to(cuda)), B, Cin, Cout, F, T, KF, KT, dil, _l.ptr(gx), None))
+    gx, gd, wd = torch.empty(B, Cin, F, T, device=cuda), g.to(cuda), w.to(cuda)
+    _l.check(L.aid_op_conv2d_bwd_input(_l.ptr(gd), _l.ptr(wd), B, Cin, Cout, F, T, KF, KT, dil, _l.ptr(gx), None))
     assert rel_l2(gx, want) < 2e-6
 
 
@@ -86,8 +86,8 @@ def test_attention_core_backward(cuda, shape):
     wh, wqk = torch.autograd.grad(o, (h, qk), g)
     gh, gqk = torch.empty(B, H, F, T, device=cuda), torch.empty(B, 2 * H * F, T, device=cuda)
     scr = torch.empty(2 * B * H * T * T * 4 + 4096, dtype=torch.uint8, device=cuda)
-    _l.check(L.aid_op_attention_bwd(_l.ptr(h.detach().to(cuda)), _l.ptr(qk.detach().to(cuda)), _l.ptr(g.to(cuda)), B, H, F, T, _l.ptr(gh), _l.ptr(gqk),
-                                    _l.ptr(scr), scr.numel(), None))
+    hd, qkd, gd = h.detach().to(cuda), qk.detach().to(cuda), g.to(cuda)
+    _l.check(L.aid_op_attention_bwd(_l.ptr(hd), _l.ptr(qkd), _l.ptr(gd), B, H, F, T, _l.ptr(gh), _l.ptr(gqk), _l.ptr(scr), scr.numel(), None))
     assert rel_l2(gh, wh) < 1e-5 and rel_l2(gqk, wqk) < 1e-5
 
 
@@ -123,7 +123,8 @@ def test_cqt_adjoints(aid, cuda, L):
     gy = seeded(tuple(y.shape), 5)
     wants = torch.autograd.grad(y, coefs, gy)
     gcoef2 = torch.empty(offs[-1], device=cuda)
-    _l.check(Lb.aid_cqt_bwd_vjp(net._handle, _l.ptr(gy[:, 0, :L].contiguous().to(cuda)), _l.ptr(gcoef2), B, _l.ptr(ws), ws.numel(), None), net._handle)
+    gyd = gy[:, 0, :L].contiguous().to(cuda)
+    _l.check(Lb.aid_cqt_bwd_vjp(net._handle, _l.ptr(gyd), _l.ptr(gcoef2), B, _l.ptr(ws), ws.numel(), None), net._handle)
     for i, w in enumerate(wants):
         got = gcoef2[offs[i]:offs[i + 1]].view(B, 2, cfg.bins_per_oct, frames[i])
         # torch's gradient of a real loss with respect to a complex leaf is dL/dRe + i dL/dIm
@@ -146,7 +147,7 @@ def test_denoiser_vjp_vs_oracle_autograd(aid, cuda, mode):
     g = seeded((2, cfg.audio_len), 9)
     sigma = torch.tensor([0.37])
     xo = x.clone().requires_grad_()
-    want_out = edm_o.denoiser(xo, orc, sigma)
+    want_out = edm_o.denoiser(xo, orc.differentiable, sigma)
     want = torch.autograd.grad(want_out, xo, g)[0]
     xc = x.to(cuda).requires_grad_()
     with torch.enable_grad():
@@ -159,7 +160,7 @@ def test_denoiser_vjp_vs_oracle_autograd(aid, cuda, mode):
     # bare module call (no preconditioning), per-clip sigma, and the no-grad path still works afterwards
     cn = torch.tensor([[-0.5], [0.1]])
     xo2 = x.clone().requires_grad_()
-    w2 = torch.autograd.grad(orc(xo2, cn), xo2, g)[0]
+    w2 = torch.autograd.grad(orc.differentiable(xo2, cn), xo2, g)[0]
     xc2 = x.to(cuda).requires_grad_()
     g2 = torch.autograd.grad(net(xc2, cn.to(cuda)), xc2, g.to(cuda))[0]
     assert rel_l2(g2, w2) < (1e-4 if mode == 0 else 2e-3)
