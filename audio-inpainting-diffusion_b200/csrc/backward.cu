@@ -86,8 +86,9 @@ gn_bwd_reduce_kernel(TV g, TV x, const double* __restrict__ stats, double npg, c
 // apply: out = cres * gres + dx   (gres may be null; out may alias gres or g)
 __global__ void __launch_bounds__(BT)
 gn_bwd_apply_kernel(TV g, TV x, const double* __restrict__ stats, double npg, const float* __restrict__ gamma, const float* __restrict__ affine,
-                    long long abstride, int gelu, const double* __restrict__ D, TV gres, float cres, TV out) {
+                    long long abstride, int gelu, const double* __restrict__ D, TV gres, float cres, TV out, unsigned int* __restrict__ amax) {
     const int c = blockIdx.y, b = blockIdx.z;
+    float vmax = 0.f;
     const int grp = c / (x.C / 8);
     float mean, stdv;
     group_moments(stats + ((long long)b * 8 + grp) * 2, npg, mean, stdv);
@@ -108,15 +109,22 @@ gn_bwd_apply_kernel(TV g, TV x, const double* __restrict__ stats, double npg, co
         float v = sw * gz - k2 * (xv - mean);
         if (pr) v = fmaf(cres, pr[e], v);
         po[e] = v;
+        vmax = fmaxf(vmax, fabsf(v));
+    }
+    if (amax) {      // max |out| for the per-tensor fp16 scaling of the next data-gradient convolution
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if ((threadIdx.x & 31) == 0 && vmax > 0.f) atomicMax(amax, __float_as_uint(vmax));
     }
 }
 void launch_gn_bwd(const TV& g, const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
-                   long long abstride, bool gelu, double* D_scratch, const TV& gres, float cres, const TV& out, cudaStream_t s) {
+                   long long abstride, bool gelu, double* D_scratch, const TV& gres, float cres, const TV& out, cudaStream_t s,
+                   unsigned int* amax_out) {
     const long long P = (long long)x.F * x.T;
     const dim3 grid((unsigned)((P + kChunk - 1) / kChunk), x.C, x.B);
     AID_CUDA_CHECK(cudaMemsetAsync(D_scratch, 0, (size_t)x.B * 8 * sizeof(double), s));
     gn_bwd_reduce_kernel<<<grid, BT, 0, s>>>(g, x, stats, (double)n_per_group, gamma, affine, abstride, gelu ? 1 : 0, D_scratch);
-    gn_bwd_apply_kernel<<<grid, BT, 0, s>>>(g, x, stats, (double)n_per_group, gamma, affine, abstride, gelu ? 1 : 0, D_scratch, gres, cres, out);
+    gn_bwd_apply_kernel<<<grid, BT, 0, s>>>(g, x, stats, (double)n_per_group, gamma, affine, abstride, gelu ? 1 : 0, D_scratch, gres, cres, out, amax_out);
     AID_COUNT_LAUNCH(2);
 }
 
@@ -318,6 +326,56 @@ __global__ void spec_synth_adj_kernel(int L, float2* __restrict__ G, float scale
 }
 void launch_spec_synth_adj(int B, int L, float2* G, float scale, cudaStream_t s) {
     spec_synth_adj_kernel<<<dim3(device_sm_count() * 4, B), 256, 0, s>>>(L, G, scale);
+    AID_COUNT_LAUNCH(1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-tensor scaling of a gradient before its fp16 tensor-core convolution.  amax: max |x| as the bit pattern of a non-negative
+// float (atomicMax on unsigned); tc_scale: kappa = 2^floor(log2(192 / amax)) (1 when amax == 0), scal[0] = kappa * pre,
+// inv_vec[0..n) = post / kappa.
+__global__ void __launch_bounds__(BT) absmax_kernel(TV x, unsigned int* __restrict__ amax) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const long long P = (long long)x.F * x.T;
+    const float* src = x.p + (long long)b * x.sb + (long long)c * x.sc;
+    const long long start = (long long)blockIdx.x * kChunk, end = min(P, start + kChunk);
+    float m = 0.f;
+    for (long long e = start + threadIdx.x; e < end; e += BT) m = fmaxf(m, fabsf(src[e]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax, __float_as_uint(m));
+}
+__global__ void tc_scale_kernel(unsigned int* __restrict__ amax, float pre, float post, float* __restrict__ scal, float* __restrict__ inv_vec, int n) {
+    const float m = __uint_as_float(*amax);
+    float kappa = 1.f;
+    if (m > 0.f && isfinite(m)) kappa = exp2f(floorf(log2f(192.f / m)));
+    if (threadIdx.x == 0) scal[0] = kappa * pre;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) inv_vec[i] = post / kappa;
+    __syncthreads();
+    if (threadIdx.x == 0) *amax = 0u;     // ready for the next tensor
+}
+void launch_absmax(const TV& x, unsigned int* amax, cudaStream_t s) {
+    const long long P = (long long)x.F * x.T;
+    absmax_kernel<<<dim3((unsigned)((P + kChunk - 1) / kChunk), x.C, x.B), BT, 0, s>>>(x, amax);
+    AID_COUNT_LAUNCH(1);
+}
+void launch_tc_scale(unsigned int* amax, float pre, float post, float* scal, float* inv_vec, int n, cudaStream_t s) {
+    tc_scale_kernel<<<1, 256, 0, s>>>(amax, pre, post, scal, inv_vec, n);
+    AID_COUNT_LAUNCH(1);
+}
+// w_std[co' = ci][ci' = co][tap'] = wp[(ci*taps + taps-1-tap')*Cout + co]: the transposed, tap-mirrored weight in the standard
+// [Cout'][Cin'][KF][KT] layout the tensor-core packers take
+__global__ void transpose_weight_std_kernel(const float* __restrict__ wp, float* __restrict__ wstd, int Cout, int Cin, int taps) {
+    const long long n = (long long)Cout * Cin * taps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int tp = (int)(i % taps);
+        long long r = i / taps;
+        const int co = (int)(r % Cout), ci = (int)(r / Cout);
+        wstd[i] = wp[((long long)ci * taps + (taps - 1 - tp)) * Cout + co];
+    }
+}
+void launch_transpose_weight_std(const float* wp, float* wstd, int Cout, int Cin, int taps, cudaStream_t s) {
+    const long long n = (long long)Cout * Cin * taps;
+    transpose_weight_std_kernel<<<(int)min((long long)4096, (n + 255) / 256), 256, 0, s>>>(wp, wstd, Cout, Cin, taps);
     AID_COUNT_LAUNCH(1);
 }
 

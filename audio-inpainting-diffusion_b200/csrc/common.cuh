@@ -178,7 +178,13 @@ void launch_spec_synth_adj(int B, int L, float2* G, float scale, cudaStream_t s)
 void launch_scale_channels(const TV& in, const float* vec, long long vstride, float alpha, const TV& out, cudaStream_t s);
 // out = cres * gres + d/dx [act(GroupNorm(x) * (affine + 1))]^T g ; D_scratch: [B][8] doubles; gres.p may be null; out may alias gres / g
 void launch_gn_bwd(const TV& g, const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine,
-                   long long abstride, bool gelu, double* D_scratch, const TV& gres, float cres, const TV& out, cudaStream_t s);
+                   long long abstride, bool gelu, double* D_scratch, const TV& gres, float cres, const TV& out, cudaStream_t s,
+                   unsigned int* amax_out = nullptr);
+// per-tensor fp16 scaling of a gradient operand: amax accumulates max |x| (float bits); tc_scale turns it into the operand
+// multiplier scal[0] = kappa * pre and the epilogue vector inv_vec[0..n) = post / kappa, kappa a power of two, and clears amax
+void launch_absmax(const TV& x, unsigned int* amax, cudaStream_t s);
+void launch_tc_scale(unsigned int* amax, float pre, float post, float* scal, float* inv_vec, int n, cudaStream_t s);
+void launch_transpose_weight_std(const float* wp, float* wstd, int Cout, int Cin, int taps, cudaStream_t s);
 // gx = beta * gx + adjoint of the resampler applied to gy (gx: the resampler's input shape, gy: its output shape)
 void launch_resample_down_adj(const TV& gy, const TV& gx, float beta, cudaStream_t s);
 void launch_resample_up_adj(const TV& gy, const TV& gx, float beta, cudaStream_t s);

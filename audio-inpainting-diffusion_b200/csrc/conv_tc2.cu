@@ -739,6 +739,11 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
             if (stats) {
                 const float mod = affine ? (1.f + affine[b * affine_bstride + c]) : 1.f;
                 sc = gamma[c] * mod * s_inv[c / (x.C / 8)];
+            } else {
+                // plain conversion (no normalisation): optional per-channel vector gamma[b * affine_bstride + c] and per-tensor
+                // device scalar affine[0] (the data-gradient path scales its operand into the fp16 range this way)
+                if (gamma) sc = gamma[b * affine_bstride + c];
+                if (affine) sc *= affine[0];
             }
         }
         s_scale[threadIdx.x] = sc;

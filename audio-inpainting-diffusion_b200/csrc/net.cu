@@ -49,6 +49,7 @@ struct Weight {
 struct ConvW {
     int widx = -1; float* wp = nullptr; __half* wtc = nullptr; int Cin = 0, Cout = 0, KF = 1, KT = 1;
     float* wpT = nullptr;   // K-major weights of the transposed (data-gradient) convolution, built on the first VJP call
+    __half* wtcT = nullptr; // conv_mode 2: the same for the tcgen05 path (dilated 5x3 layers only)
 };
 struct LinRef { int w = -1, b = -1; int off = -1, N = 0; };
 struct NormRef { int widx = -1; float* gamma = nullptr; };
@@ -149,6 +150,7 @@ struct Net {
     Tape tape;
     Arena tape_arena;              // arena state behind the taped forward: the backward keeps allocating in the same workspace
     float* dweights_T = nullptr;   // transposed convolution weights (lazy)
+    __half* dweights_tcT = nullptr; // conv_mode 2: fp16 operand-layout weights of the transposed dilated convolutions (lazy)
     float* d_adj_tables = nullptr; // CQT adjoint window tables (lazy)
     CqtTables tabs_adjA, tabs_adjS;   // analysis adjoint: dual := win / M; synthesis adjoint: win := dual * M
     bool vjp_ready = false;
@@ -791,6 +793,29 @@ static void ensure_vjp(Net& n) {
         off += al((size_t)c->Cout * c->Cin * c->KF * c->KT);
     }
     AID_CUDA_CHECK(cudaGetLastError());
+    if (n.cfg.conv_mode == 2) {
+        // the data gradient of the dilated 5x3 layers (95 % of the backward FLOPs) runs on tcgen05 too
+        size_t tct = 0, stage_n = 0;
+        for (auto* c : convs)
+            if (c->KF == 5 && c->wtc && conv_tc_supported(c->Cout, c->Cin, c->KF, c->KT)) {
+                tct += al(tc2_weight_halves(c->Cin, c->Cout, c->KF, c->KT)); stage_n = std::max(stage_n, (size_t)c->Cout * c->Cin * 15);
+            }
+        if (tct) {
+            float* stage = nullptr;
+            AID_CUDA_CHECK(cudaMalloc(&n.dweights_tcT, tct * sizeof(__half)));
+            AID_CUDA_CHECK(cudaMalloc(&stage, stage_n * sizeof(float)));
+            size_t toff = 0;
+            for (auto* c : convs) {
+                if (!(c->KF == 5 && c->wtc && conv_tc_supported(c->Cout, c->Cin, c->KF, c->KT))) continue;
+                launch_transpose_weight_std(c->wp, stage, c->Cout, c->Cin, c->KF * c->KT, nullptr);
+                c->wtcT = n.dweights_tcT + toff;
+                launch_pack_weight_tc2(stage, c->wtcT, /*Cout'=*/c->Cin, /*Cin'=*/c->Cout, c->KF, c->KT, nullptr, nullptr);
+                AID_CUDA_CHECK(cudaDeviceSynchronize());
+                toff += al(tc2_weight_halves(c->Cin, c->Cout, c->KF, c->KT));
+            }
+            AID_CUDA_CHECK(cudaFree(stage));
+        }
+    }
     const CqtPlanHost& p = n.plan;
     std::vector<float> winM(p.win.size()), dualM(p.dual.size());
     for (int k = 0; k < p.K; ++k) {
@@ -882,14 +907,40 @@ static void resblock_bwd(Ctx& c, const ResBlk& k, const BlkTape& bt, const TV& g
         RUN(launch_scale_channels(g_out, nullptr, 0, a_tail, g_cur, c.s));
     }
     TV tmp = alloc_tv(c, N, F, T, false), ga = alloc_tv(c, N, F, T, false);
+    // conv_mode 2: the data gradient of the dilated layers on tcgen05.  The gradient is scaled per tensor by a power of two
+    // (max |g| -> [96, 192), found on the device) so that its fp16 image keeps full relative precision, multiplied by the layer's
+    // gate per channel in the same pass, and the convolution's epilogue undoes the scale.
+    bool tc = c.n->cfg.conv_mode == 2 && !k.k1x1 && k.nd > 0;
+    for (auto& hw : k.H) tc = tc && hw.wtc != nullptr && conv_tc_supported(hw.Cout, hw.Cin, hw.KF, hw.KT);   // == ensure_vjp's condition for wtcT
+    __half* a16 = nullptr; unsigned int* amax = nullptr; float* scal = nullptr; float* inv_vec = nullptr; float* abuf16 = nullptr;
+    if (tc) {
+        const int pf_max = tc_pad_rows(T, 5, 1 << std::max(0, k.nd - 1));
+        abuf16 = c.allocf((long long)((tc2_act_halves(c.B, N, F, T, pf_max) + 1) / 2));
+        a16 = reinterpret_cast<__half*>(abuf16);
+        float* sc = c.allocf(2 + N);
+        amax = reinterpret_cast<unsigned int*>(sc); scal = sc + 1; inv_vec = sc + 2;
+        RUN(AID_CUDA_CHECK(cudaMemsetAsync(amax, 0, sizeof(unsigned int), c.s)));
+        RUN(launch_absmax(g_cur, amax, c.s));
+    }
     for (int i = k.nd - 1; i >= 0; --i) {
         // x_{i+1} = (x_i + H_i(gelu(GN_i(x_i) (1 + affine_i))) gate_i) / sqrt 2
         const TV& xi = bt.xs[i];
-        RUN(launch_scale_channels(g_cur, c.mod + k.gate[i].off, c.modstride(), kInvSqrt2, tmp, c.s));
-        RUN(AID_CUDA_CHECK(cudaMemsetAsync(ga.p, 0, (size_t)c.B * N * F * T * sizeof(float), c.s)));
-        conv_T(c, tmp, k.H[i], k.k1x1 ? 1 : (1 << i), ga, 1.f);
-        RUN(launch_gn_bwd(ga, xi, xi.stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, D, g_cur, kInvSqrt2, g_cur, c.s));
+        const int dil = k.k1x1 ? 1 : (1 << i);
+        if (tc) {
+            const int pf = tc_pad_rows(T, 5, dil);
+            RUN(launch_tc_scale(amax, kInvSqrt2, 1.f, scal, inv_vec, N, c.s));
+            RUN(launch_gn_act_tc2(g_cur, nullptr, 1, c.mod + k.gate[i].off, scal, c.modstride(), false, pf, a16, c.s, nullptr));
+            ConvEpilogue ep; ep.gate = inv_vec; ep.gate_bstride = 0; ep.alpha = 1.f;
+            if (!c.dry()) launch_conv_tc2(a16, pf, k.H[i].wtcT, c.B, N, F, T, 5, 3, dil, ga, ep, c.n->num_sms, c.s);
+        } else {
+            RUN(launch_scale_channels(g_cur, c.mod + k.gate[i].off, c.modstride(), kInvSqrt2, tmp, c.s));
+            RUN(AID_CUDA_CHECK(cudaMemsetAsync(ga.p, 0, (size_t)c.B * N * F * T * sizeof(float), c.s)));
+            conv_T(c, tmp, k.H[i], dil, ga, 1.f);
+        }
+        RUN(launch_gn_bwd(ga, xi, xi.stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, D, g_cur, kInvSqrt2, g_cur, c.s,
+                          tc && i > 0 ? amax : nullptr));
     }
+    if (tc) { c.release(abuf16); c.release(reinterpret_cast<float*>(amax)); }
     if (k.attn) {
         // x1 = (x0 + a_out(attention(a_in(GN2(x0) (1 + affine2)))) gate2) / sqrt 2
         const int heads = k.a_in.Cout;
@@ -1056,6 +1107,7 @@ void aid_destroy(aid_handle* h) {
     if (h->net.d_tables) cudaFree(h->net.d_tables);
     if (h->net.d_sat) cudaFree(h->net.d_sat);
     if (h->net.dweights_T) cudaFree(h->net.dweights_T);
+    if (h->net.dweights_tcT) cudaFree(h->net.dweights_tcT);
     if (h->net.d_adj_tables) cudaFree(h->net.d_adj_tables);
     for (auto& r : h->net.prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto& e : h->net.prof_pool) cudaEventDestroy(e);
@@ -1129,7 +1181,10 @@ int aid_unet_forward_ds(aid_handle* h, const float* x_dev, const float* c_noise_
 
 int aid_vjp_workspace_bytes(aid_handle* h, int B, size_t* bytes) {
     if (!h || !bytes || B < 1) return AID_ERR_INVALID;
-    return guarded(h, [&] { *bytes = plan_vjp(h->net, B); });
+    return guarded(h, [&] {
+        if (!h->net.finalized) throw std::runtime_error("aid_vjp_workspace_bytes before aid_finalize");
+        *bytes = plan_vjp(h->net, B);
+    });
 }
 
 int aid_unet_forward_tape(aid_handle* h, const float* x_dev, const float* c_noise_dev, int n_sigma, float* out_dev, int B,

@@ -223,3 +223,24 @@ def test_guided_sampler_batch_gt_1_is_per_clip(aid, cuda):
         s.noise_source = iter([n[k:k + 1] for n in noise])
         solo = s.predict_inpainting((y * mask)[k:k + 1], mask)
         assert rel_l2(both[k:k + 1], solo) < 1e-4
+
+
+def test_paper_network_vjp_vs_oracle_autograd(aid, cuda):
+    """The 186 M-parameter network (BASELINE config 1 shape, 1 x 65536) in conv_mode 2, where the data gradient of the dilated 5x3
+    layers runs on tcgen05 with per-tensor power-of-two scaling: input gradient against autograd through the oracle on the host."""
+    cfg = aid.paper_22k(65536, conv_mode=2)
+    sd = aid.random_state_dict(cfg, seed=1234)
+    net = aid.Unet_CQT_oct_with_attention(cfg, cuda)
+    net.load_state_dict(sd)
+    orc = make_oracle(cfg, sd)
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, g, cn = seeded((1, 65536), 0, 0.4), seeded((1, 65536), 9), torch.tensor([[-0.5]])
+    xo = x.clone().requires_grad_()
+    yo = orc.differentiable(xo, cn)
+    want = torch.autograd.grad(yo, xo, g)[0]
+    xc = x.to(cuda).requires_grad_()
+    yc = net(xc, cn.to(cuda))
+    got = torch.autograd.grad(yc, xc, g.to(cuda))[0]
+    e_f, e_g = rel_l2(yc, yo), rel_l2(got, want)
+    print(f"paper network 1 x 65536, conv_mode 2: forward {e_f:.3e}, input gradient {e_g:.3e} vs oracle autograd")
+    assert e_f < 1e-3 and e_g < 1e-3
