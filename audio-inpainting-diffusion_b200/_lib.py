@@ -63,6 +63,7 @@ _SIGS = {
     "aid_op_conv2d_bwd_input": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "aid_cqt_fwd_vjp": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "aid_cqt_bwd_vjp": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t, _P]),
+    "aid_op_attention_mode": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
     "aid_op_embedding": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "aid_debug_time_conv2d": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         _P, _P, C.c_float, _P, _P, C.c_int, C.POINTER(C.c_float)]),

@@ -3,7 +3,10 @@
 //   out[b, head, f, t] = sum_tk softmax_tk(F^-0.5 * q[t,:].k[tk,:]) * v[tk, f]
 // One CTA handles TQ queries of one (clip, head): scores live in shared memory (T <= ~1000 frames).
 // fp32 CUDA-core version (exact-parity path; < 0.1 % of the forward's FLOPs).
+#include <algorithm>
+
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace aid {
 
@@ -141,6 +144,203 @@ attention_kernel(TV h, const float* __restrict__ qk, TV out, float scale) {
             if (fc + r < F && t0 + j < T) obase[(long long)(fc + r) * T + t0 + j] = sacc;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// tcgen05 version (conv_mode 2): one CTA per (clip, head, tile of 128 queries).
+//   S[128, T]  = Q K^T     tcgen05.mma kind::f16, operands split hi + lo in fp16 (q_hi k_hi + q_lo k_hi + q_hi k_lo: fp32-grade
+//                          logits), accumulated in TMEM over the feature dimension in chunks of 64
+//   P          = exp(scale (S - rowmax))   read from TMEM by the row's thread (tcgen05.ld), written to shared memory as the fp16
+//                          A operand of the second product; the row sums stay in registers
+//   O[128, F]  = P V       tcgen05.mma, V = h^T staged 64 value rows at a time; O reuses the TMEM columns of S
+//   out        = O / rowsum, stored from TMEM lanes (one query per thread, coalesced along t for every value row)
+// Operand layout in shared memory: K-major SWIZZLE_NONE canonical form, [8-element k chunk][row][8] fp16 (rows 16 bytes apart,
+// SBO = 128, LBO = rows * 16), filled by the CTA's threads (the sources are fp32 [d][t] / [f][t] planes, so a bulk copy could not
+// convert or transpose): a thread loads 8 features of one query / key (each load coalesced across the warp) and stores one
+// 16-byte row.  T <= 256 keys (N of the first product), F <= 512.
+static constexpr int ATC_THREADS = 256;
+static constexpr int ATC_DC = 64;      // features per stage of Q K^T
+static constexpr int ATC_NF = 64;      // value rows per stage of P V
+
+__device__ __forceinline__ void split_store8(const float* v, uint4* hi, uint4* lo) {
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half a = __float2half_rn(v[2 * i]), b = __float2half_rn(v[2 * i + 1]);
+        h[i] = __halves2half2(a, b);
+        if (lo) l[i] = __halves2half2(__float2half_rn(v[2 * i] - __half2float(a)), __float2half_rn(v[2 * i + 1] - __half2float(b)));
+    }
+    *hi = *reinterpret_cast<uint4*>(h);
+    if (lo) *lo = *reinterpret_cast<uint4*>(l);
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_kernel(TV h, const float* __restrict__ qk, TV out, float scale, int Tk16) {
+    extern __shared__ uint8_t sm_raw[];
+    uint8_t* smem = sm_raw + ((128u - (smem_u32(sm_raw) & 127u)) & 127u);
+    const int F = h.F, T = h.T;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int head = blockIdx.y, b = blockIdx.z, t0 = blockIdx.x * 128;
+    const float* qbase = qk + ((long long)b * h.C * 2 * F + (long long)head * 2 * F) * T;
+    const float* kbase = qbase + (long long)F * T;
+    const float* hbase = h.p + (long long)b * h.sb + (long long)head * h.sc;
+    float* obase = out.p + (long long)b * out.sb + (long long)head * out.sc;
+    // shared memory map (bytes): phase 1: Qhi | Qlo (8 planes x 128 rows x 16) | Khi | Klo (8 planes x Tk16 rows x 16);
+    //                            phase 2: P (Tk16/8 planes x 128 rows x 16) | V (Tk16/8 planes x 64 rows x 16)
+    const uint32_t planeQ = 128u * 16u, planeK = (uint32_t)Tk16 * 16u, planeV = (uint32_t)ATC_NF * 16u;
+    uint8_t* Qhi = smem; uint8_t* Qlo = Qhi + 8 * planeQ; uint8_t* Khi = Qlo + 8 * planeQ; uint8_t* Klo = Khi + 8 * planeK;
+    uint8_t* Ps = smem; uint8_t* Vs = Ps + (size_t)(Tk16 / 8) * planeQ;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    if (warp == 0) {
+        if (lane == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    uint32_t phase = 0;
+
+    // ---------------- S = Q K^T ----------------
+    const uint32_t idesc_s = (1u << 4) | ((uint32_t)(Tk16 >> 3) << 17) | ((128u >> 4) << 24);
+    for (int d0 = 0; d0 < F; d0 += ATC_DC) {
+        const int np = min(ATC_DC, F - d0) / 8;            // feature planes in this stage (F is a multiple of 8... checked by the launcher)
+        // queries: 128 rows x np planes; keys: Tk16 rows x np planes.  item = (plane, row), rows fastest across lanes
+        for (int it = tid; it < np * 128; it += ATC_THREADS) {
+            const int pl = it >> 7, r = it & 127, t = t0 + r;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = t < T ? __ldg(qbase + (long long)(d0 + pl * 8 + j) * T + t) : 0.f;
+            split_store8(v, reinterpret_cast<uint4*>(Qhi + pl * planeQ + r * 16), reinterpret_cast<uint4*>(Qlo + pl * planeQ + r * 16));
+        }
+        for (int it = tid; it < np * Tk16; it += ATC_THREADS) {
+            const int pl = it / Tk16, r = it - pl * Tk16;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = r < T ? __ldg(kbase + (long long)(d0 + pl * 8 + j) * T + r) : 0.f;
+            split_store8(v, reinterpret_cast<uint4*>(Khi + pl * planeK + r * 16), reinterpret_cast<uint4*>(Klo + pl * planeK + r * 16));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < np / 2; ++ks) {          // 16 features per MMA = 2 planes
+                const uint64_t ah = make_desc(smem_u32(Qhi + 2 * ks * planeQ), planeQ, 128), al = make_desc(smem_u32(Qlo + 2 * ks * planeQ), planeQ, 128);
+                const uint64_t bh = make_desc(smem_u32(Khi + 2 * ks * planeK), planeK, 128), bl = make_desc(smem_u32(Klo + 2 * ks * planeK), planeK, 128);
+                tc_mma_f16(tmem, ah, bh, idesc_s, (d0 > 0 || ks > 0) ? 1u : 0u);
+                tc_mma_f16(tmem, al, bh, idesc_s, 1u);
+                tc_mma_f16(tmem, ah, bl, idesc_s, 1u);
+            }
+            tc_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1;                 // the stage's operands are free again, S is up to date
+    }
+    tc_fence_after();
+
+    // ---------------- P = exp(scale (S - max)), row sums ----------------
+    float rsum = 1.f;
+    if (warp < 4) {
+        const int r = warp * 32 + lane;                    // TMEM lane = query row
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < Tk16; c0 += 32) {
+            uint32_t a[32];
+            tmem_ld32_nowait(trow + (uint32_t)c0, a);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(a[j]));
+        }
+        float sum = 0.f;
+        for (int c0 = 0; c0 < Tk16; c0 += 32) {
+            uint32_t a[32];
+            tmem_ld32_nowait(trow + (uint32_t)c0, a);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+                if (c0 + j8 * 8 >= Tk16) break;
+                float e[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + j8 * 8 + j;
+                    e[j] = c < T ? expf(scale * (__uint_as_float(a[j8 * 8 + j]) - mx)) : 0.f;
+                    e[j] = __half2float(__float2half_rn(e[j]));      // the value the second product will see: keep the sum consistent
+                    sum += e[j];
+                }
+                split_store8(e, reinterpret_cast<uint4*>(Ps + (size_t)((c0 >> 3) + j8) * planeQ + r * 16), nullptr);
+            }
+        }
+        rsum = sum;
+    }
+    tc_fence_before();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    // ---------------- O = P V, value rows in stages of 64; out = O / rowsum ----------------
+    const uint32_t idesc_o = (1u << 4) | ((uint32_t)(ATC_NF >> 3) << 17) | ((128u >> 4) << 24);
+    const int npk = Tk16 / 8;                               // key planes
+    for (int f0 = 0; f0 < F; f0 += ATC_NF) {
+        // V stage: rows = value rows f0 .. f0+63 (zero beyond F), K = keys.  item = (plane, row), rows fastest across lanes
+        for (int it = tid; it < npk * ATC_NF; it += ATC_THREADS) {
+            const int pl = it / ATC_NF, r = it - pl * ATC_NF, f = f0 + r;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const int tk = pl * 8 + j; v[j] = (f < F && tk < T) ? __ldg(hbase + (long long)f * T + tk) : 0.f; }
+            split_store8(v, reinterpret_cast<uint4*>(Vs + pl * planeV + r * 16), nullptr);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < npk / 2; ++ks) {
+                const uint64_t a = make_desc(smem_u32(Ps + (size_t)2 * ks * planeQ), planeQ, 128);
+                const uint64_t bd = make_desc(smem_u32(Vs + (size_t)2 * ks * planeV), planeV, 128);
+                tc_mma_f16(tmem + (uint32_t)f0, a, bd, idesc_o, ks > 0 ? 1u : 0u);
+            }
+            tc_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        if (warp < 4) {
+            const int t = t0 + warp * 32 + lane;
+            const float inv = 1.f / rsum;
+            const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)f0;
+#pragma unroll
+            for (int c0 = 0; c0 < ATC_NF; c0 += 32) {
+                uint32_t a[32];
+                tmem_ld32_nowait(trow + (uint32_t)c0, a);
+                tmem_wait_ld();
+                if (t < T) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (f0 + c0 + j < F) obase[(long long)(f0 + c0 + j) * T + t] = __uint_as_float(a[j]) * inv;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+bool attention_tc_supported(int F, int T) { return F % 16 == 0 && F <= 512 && T >= 1 && T <= 256; }
+
+void launch_attention_tc(const TV& h, const float* qk, const TV& out, cudaStream_t s) {
+    const int F = h.F, T = h.T;
+    const int Tk16 = (T + 15) & ~15;
+    const size_t p1 = (size_t)16 * 128 * 16 + (size_t)16 * Tk16 * 16;                       // Q hi|lo + K hi|lo, 8 planes each
+    const size_t p2 = (size_t)(Tk16 / 8) * 128 * 16 + (size_t)(Tk16 / 8) * ATC_NF * 16;      // P + one V stage
+    const size_t smem = std::max(p1, p2) + 128;
+    static SmemConfig configured;
+    ensure_dyn_smem(attention_tc_kernel, smem, configured);
+    dim3 grid((T + 127) / 128, h.C, h.B);
+    attention_tc_kernel<<<grid, ATC_THREADS, smem, s>>>(h, qk, out, 1.0f / sqrtf((float)F), Tk16);
+    AID_COUNT_LAUNCH(1);
 }
 
 void launch_attention(const TV& h, const float* qk, const TV& out, cudaStream_t s) {

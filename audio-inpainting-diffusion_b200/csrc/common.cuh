@@ -96,6 +96,9 @@ void launch_conv_simt(const TV& a, const float* wp, int KF, int KT, int dil, con
 // thin convolutions (conv_thin.cu); returns false when the shape is not covered
 bool launch_conv_thin(const TV& a, const float* wp, int KF, int KT, int dil, const TV& out, const ConvEpilogue& ep, cudaStream_t s);
 void launch_attention(const TV& h, const float* qk, const TV& out, cudaStream_t s);
+// tcgen05 version (attention.cu): Q K^T with split-fp16 operands, softmax from TMEM, P V with fp16 operands
+bool attention_tc_supported(int F, int T);
+void launch_attention_tc(const TV& h, const float* qk, const TV& out, cudaStream_t s);
 void launch_embedding(const float* c_noise, int n_sigma, const float* rff, const float* w0, const float* b0,
                       const float* w1, const float* b1, const float* w2, const float* b2, float* emb, cudaStream_t s);
 void launch_mod_vectors(const float* emb, int n_sigma, const float* W, const float* bias, int total, float* out,

@@ -560,7 +560,9 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
             conv(c, hflat, k.qk, 1, qk, ConvEpilogue());
         }
         TV o = make_tv(c.allocf((long long)B * heads * F * T), B, heads, F, T);
-        RUN(launch_attention(h, qk.p, o, c.s));
+        static const bool env_att_simt = getenv("AID_ATT_SIMT") && atoi(getenv("AID_ATT_SIMT")) != 0;
+        if (cmode == 2 && !env_att_simt && attention_tc_supported(F, T)) RUN(launch_attention_tc(h, qk.p, o, c.s));
+        else RUN(launch_attention(h, qk.p, o, c.s));
         ConvEpilogue ep;
         ep.gate = c.mod + k.gate2.off; ep.gate_bstride = c.modstride();
         ep.R = cur; ep.alpha = kInvSqrt2; ep.stats = c.new_slot();
@@ -1509,10 +1511,17 @@ int aid_op_resample(const float* x_dev, int B, int C, int F, int T, int up, floa
 }
 
 int aid_op_attention(const float* h_dev, const float* qk_dev, int B, int heads, int F, int T, float* out_dev, void* stream) {
+    return aid_op_attention_mode(h_dev, qk_dev, B, heads, F, T, out_dev, 0, stream);
+}
+
+int aid_op_attention_mode(const float* h_dev, const float* qk_dev, int B, int heads, int F, int T, float* out_dev, int tensor_core, void* stream) {
     if (!h_dev || !qk_dev || !out_dev) return AID_ERR_INVALID;
     try {
         TV h = make_tv(const_cast<float*>(h_dev), B, heads, F, T), out = make_tv(out_dev, B, heads, F, T);
-        launch_attention(h, qk_dev, out, (cudaStream_t)stream);
+        if (tensor_core) {
+            if (!attention_tc_supported(F, T)) return AID_ERR_INVALID;
+            launch_attention_tc(h, qk_dev, out, (cudaStream_t)stream);
+        } else launch_attention(h, qk_dev, out, (cudaStream_t)stream);
         return cudaGetLastError() == cudaSuccess ? AID_OK : AID_ERR_CUDA;
     } catch (...) { return AID_ERR_INVALID; }
 }

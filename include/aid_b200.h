@@ -164,6 +164,10 @@ int aid_op_groupnorm_act(const float* x_dev, const float* gamma_dev, const float
 int aid_op_resample(const float* x_dev, int B, int C, int F, int T, int up, float* out_dev, void* stream);
 /* attention core of TimeAttentionBlock: h[B,heads,F,T], qk[B,2*heads*F,T] -> out[B,heads,F,T]   unet.py:353-374 */
 int aid_op_attention(const float* h_dev, const float* qk_dev, int B, int heads, int F, int T, float* out_dev, void* stream);
+/* the same with the kernel chosen: tensor_core = 0 fp32 CUDA cores (conv_mode 0 / 1), 1 = tcgen05 (conv_mode 2: Q K^T with split-fp16
+ * operands accumulated in TMEM, softmax read from TMEM, P V with fp16 operands; T <= 256, F % 16 == 0, F <= 512) */
+int aid_op_attention_mode(const float* h_dev, const float* qk_dev, int B, int heads, int F, int T, float* out_dev, int tensor_core,
+                          void* stream);
 /* RFF_MLP_Block + every adaLN Linear: returns the emb [n_sigma,256]                          unet.py:184-211 */
 int aid_op_embedding(aid_handle* h, const float* c_noise_dev, int n_sigma, float* emb_dev, void* stream);
 

@@ -155,3 +155,30 @@ def test_attention(cuda, B, heads, Fd, T):
     L.check(L.lib().aid_op_attention(L.ptr(hd), L.ptr(qd), B, heads, Fd, T, L.ptr(out), None))
     torch.cuda.synchronize()
     assert rel_l2(out, ref) < 3e-6
+
+
+@pytest.mark.parametrize("B,heads,Fd,T", [(2, 8, 64, 16), (1, 8, 320, 256), (2, 8, 384, 128), (1, 8, 448, 64), (1, 8, 448, 256), (1, 4, 48, 50),
+                                          (1, 8, 512, 32), (3, 2, 80, 200)])
+def test_attention_tcgen05(cuda, B, heads, Fd, T):
+    """The tcgen05 attention core of conv_mode 2 (Q K^T split fp16 -> TMEM, softmax from TMEM, P V fp16) against the fp64
+    definition (unet.py:353-374): the published bar is 1e-3; the logits are fp32-grade, P and V carry fp16 rounding."""
+    L = _lib()
+    h = seeded((B, heads, Fd, T), 1)
+    qk = seeded((B, 2 * heads * Fd, T), 2, 1.5 / math.sqrt(math.sqrt(Fd)))
+    q4 = qk.double().reshape(B, heads, 2 * Fd, T).permute(0, 1, 3, 2)
+    q, k = q4[..., :Fd], q4[..., Fd:]
+    sim = torch.matmul(q, k.transpose(-1, -2)) * Fd ** -0.5
+    ref = torch.matmul(sim.softmax(-1), h.double().permute(0, 1, 3, 2)).permute(0, 1, 3, 2)
+    hd, qd = h.to(cuda), qk.to(cuda)
+    out = torch.full_like(hd, float("nan"))
+    L.check(L.lib().aid_op_attention_mode(L.ptr(hd), L.ptr(qd), B, heads, Fd, T, L.ptr(out), 1, None))
+    torch.cuda.synchronize()
+    e = rel_l2(out, ref)
+    print(f"tcgen05 attention B{B} heads{heads} F{Fd} T{T}: rel-L2 {e:.2e}")
+    assert torch.isfinite(out).all() and e < 5e-4
+    # sharper logits (larger q, k): the softmax is close to one-hot, the split operands keep the logits accurate
+    qk2 = (qk * 4).to(cuda)
+    sim2 = sim * 16
+    ref2 = torch.matmul(sim2.softmax(-1), h.double().permute(0, 1, 3, 2)).permute(0, 1, 3, 2)
+    L.check(L.lib().aid_op_attention_mode(L.ptr(hd), L.ptr(qk2), B, heads, Fd, T, L.ptr(out), 1, None))
+    assert rel_l2(out, ref2) < 5e-4
