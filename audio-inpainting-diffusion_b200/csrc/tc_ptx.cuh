@@ -29,14 +29,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// multicast variants for a cluster of 2 CTAs: the copy lands at the same offset of both CTAs' shared memory and signals the
-// mbarrier at the same offset in both; the commit arrives on the barrier of both CTAs
-__device__ __forceinline__ void bulk_g2s_mc2(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+// ---- CTA pair (cta_group::2) helpers: the two CTAs of a cluster issue one M = 256 MMA; the leader's commit arrives on the
+// barrier at the same offset of both CTAs, the peer's warps arrive on the leader's barriers through the cluster window
+__device__ __forceinline__ void tc_commit_cg2(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void tc_commit_mc2(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics (release at CTA scope),
+// as CUTLASS' ClusterBarrier::arrive: a .release.cluster arrive makes the thread wait for its outstanding global stores to be
+// performed cluster-wide, which cost the epilogue warps ~5 K cycles per tile (measured: epilogue 40-60 % slower).
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -102,42 +111,62 @@ __device__ __forceinline__ void tc_mma_f16_lo(uint32_t d_tmem, uint32_t alo, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem), "r"(alo), "r"(blo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128)
         : "memory");
 }
-// the four 16-channel k-steps of a 64-channel group (descriptor start advanced by 32 bytes = 2 units each), one accumulator
-__device__ __forceinline__ void tc_mma4_f16(uint32_t d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "setp.eq.b32 q, 0, 0;\n\t"
-        "mov.b64 da, {%1, %5};\n\t mov.b64 db, {%2, %5};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
-        "add.u32 a, %1, 2;\n\t add.u32 b, %2, 2;\n\t mov.b64 da, {a, %5};\n\t mov.b64 db, {b, %5};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
-        "add.u32 a, %1, 4;\n\t add.u32 b, %2, 4;\n\t mov.b64 da, {a, %5};\n\t mov.b64 db, {b, %5};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t"
-        "add.u32 a, %1, 6;\n\t add.u32 b, %2, 6;\n\t mov.b64 da, {a, %5};\n\t mov.b64 db, {b, %5};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t}" ::"r"(d), "r"(alo), "r"(blo), "r"(idesc), "r"(acc), "r"(DESC_HI_SW128)
-        : "memory");
+// NK (4 or 2) consecutive 16-channel k-steps of a 64-channel group (descriptor start advanced by 32 bytes = 2 units each) as
+// one asm block, for one accumulator or for two accumulators that share the B operand (the two pixel units of a tile,
+// interleaved unit 0 / unit 1).  CG = 1: cta_group::1 (M = 128); CG = 2: cta_group::2 (M = 256 over a CTA pair, issued by
+// the leader, the descriptors address the same shared-memory offsets in both CTAs).
+#define AID_MMA1(CG, P) "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %3, " P ";\n\t"
+#define AID_MMA1_STEP(CG, OFF) "add.u32 a, %1, " OFF ";\n\t add.u32 b, %2, " OFF ";\n\t mov.b64 da, {a, %5};\n\t mov.b64 db, {b, %5};\n\t" AID_MMA1(CG, "q")
+#define AID_MMA1_HEAD(CG)                                                                                            \
+    "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"                                              \
+    "setp.ne.b32 p, %4, 0;\n\t setp.eq.b32 q, 0, 0;\n\t mov.b64 da, {%1, %5};\n\t mov.b64 db, {%2, %5};\n\t" AID_MMA1(CG, "p")
+template <int CG, int NK>
+__device__ __forceinline__ void tc_mma_k(uint32_t d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t acc) {
+    static_assert((CG == 1 || CG == 2) && (NK == 2 || NK == 4), "tc_mma_k");
+#define AID_OPS1 ::"r"(d), "r"(alo), "r"(blo), "r"(idesc), "r"(acc), "r"(DESC_HI_SW128) : "memory"
+    if constexpr (CG == 1 && NK == 4) asm volatile(AID_MMA1_HEAD("1") AID_MMA1_STEP("1", "2") AID_MMA1_STEP("1", "4") AID_MMA1_STEP("1", "6") "}" AID_OPS1);
+    if constexpr (CG == 1 && NK == 2) asm volatile(AID_MMA1_HEAD("1") AID_MMA1_STEP("1", "2") "}" AID_OPS1);
+    if constexpr (CG == 2 && NK == 4) asm volatile(AID_MMA1_HEAD("2") AID_MMA1_STEP("2", "2") AID_MMA1_STEP("2", "4") AID_MMA1_STEP("2", "6") "}" AID_OPS1);
+    if constexpr (CG == 2 && NK == 2) asm volatile(AID_MMA1_HEAD("2") AID_MMA1_STEP("2", "2") "}" AID_OPS1);
+#undef AID_OPS1
 }
-// the same for two accumulators that share the B operand (the two pixel units of a tile), interleaved unit 0 / unit 1
-__device__ __forceinline__ void tc_mma4x2_f16(uint32_t d0, uint32_t d1, uint32_t alo0, uint32_t alo1, uint32_t blo, uint32_t idesc, uint32_t acc0,
-                                              uint32_t acc1) {
-    asm volatile(
-        "{\n\t.reg .pred p0, p1, q;\n\t.reg .b64 da0, da1, db;\n\t.reg .b32 a0, a1, b;\n\t"
-        "setp.ne.b32 p0, %6, 0;\n\t setp.ne.b32 p1, %7, 0;\n\t setp.eq.b32 q, 0, 0;\n\t"
-        "mov.b64 da0, {%2, %8};\n\t mov.b64 da1, {%3, %8};\n\t mov.b64 db, {%4, %8};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, %5, p0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db, %5, p1;\n\t"
-        "add.u32 a0, %2, 2;\n\t add.u32 a1, %3, 2;\n\t add.u32 b, %4, 2;\n\t mov.b64 da0, {a0, %8};\n\t mov.b64 da1, {a1, %8};\n\t mov.b64 db, {b, %8};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, %5, q;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db, %5, q;\n\t"
-        "add.u32 a0, %2, 4;\n\t add.u32 a1, %3, 4;\n\t add.u32 b, %4, 4;\n\t mov.b64 da0, {a0, %8};\n\t mov.b64 da1, {a1, %8};\n\t mov.b64 db, {b, %8};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, %5, q;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db, %5, q;\n\t"
-        "add.u32 a0, %2, 6;\n\t add.u32 a1, %3, 6;\n\t add.u32 b, %4, 6;\n\t mov.b64 da0, {a0, %8};\n\t mov.b64 da1, {a1, %8};\n\t mov.b64 db, {b, %8};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da0, db, %5, q;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%1], da1, db, %5, q;\n\t}" ::"r"(d0), "r"(d1), "r"(alo0), "r"(alo1), "r"(blo), "r"(idesc), "r"(acc0), "r"(acc1),
-        "r"(DESC_HI_SW128)
-        : "memory");
+#define AID_MMA2(CG, P0, P1) "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da0, db, %5, " P0 ";\n\t" "tcgen05.mma.cta_group::" CG ".kind::f16 [%1], da1, db, %5, " P1 ";\n\t"
+#define AID_MMA2_STEP(CG, OFF)                                                                                       \
+    "add.u32 a0, %2, " OFF ";\n\t add.u32 a1, %3, " OFF ";\n\t add.u32 b, %4, " OFF ";\n\t"                          \
+    "mov.b64 da0, {a0, %8};\n\t mov.b64 da1, {a1, %8};\n\t mov.b64 db, {b, %8};\n\t" AID_MMA2(CG, "q", "q")
+#define AID_MMA2_HEAD(CG)                                                                                            \
+    "{\n\t.reg .pred p0, p1, q;\n\t.reg .b64 da0, da1, db;\n\t.reg .b32 a0, a1, b;\n\t"                              \
+    "setp.ne.b32 p0, %6, 0;\n\t setp.ne.b32 p1, %7, 0;\n\t setp.eq.b32 q, 0, 0;\n\t"                                 \
+    "mov.b64 da0, {%2, %8};\n\t mov.b64 da1, {%3, %8};\n\t mov.b64 db, {%4, %8};\n\t" AID_MMA2(CG, "p0", "p1")
+template <int CG, int NK>
+__device__ __forceinline__ void tc_mma_kx2(uint32_t d0, uint32_t d1, uint32_t alo0, uint32_t alo1, uint32_t blo, uint32_t idesc, uint32_t acc0,
+                                           uint32_t acc1) {
+    static_assert((CG == 1 || CG == 2) && (NK == 2 || NK == 4), "tc_mma_kx2");
+#define AID_OPS2 ::"r"(d0), "r"(d1), "r"(alo0), "r"(alo1), "r"(blo), "r"(idesc), "r"(acc0), "r"(acc1), "r"(DESC_HI_SW128) : "memory"
+    if constexpr (CG == 1 && NK == 4) asm volatile(AID_MMA2_HEAD("1") AID_MMA2_STEP("1", "2") AID_MMA2_STEP("1", "4") AID_MMA2_STEP("1", "6") "}" AID_OPS2);
+    if constexpr (CG == 1 && NK == 2) asm volatile(AID_MMA2_HEAD("1") AID_MMA2_STEP("1", "2") "}" AID_OPS2);
+    if constexpr (CG == 2 && NK == 4) asm volatile(AID_MMA2_HEAD("2") AID_MMA2_STEP("2", "2") AID_MMA2_STEP("2", "4") AID_MMA2_STEP("2", "6") "}" AID_OPS2);
+    if constexpr (CG == 2 && NK == 2) asm volatile(AID_MMA2_HEAD("2") AID_MMA2_STEP("2", "2") "}" AID_OPS2);
+#undef AID_OPS2
+}
+// one (kf, group) stage of the 5x3 layers: the three kt taps (activation descriptor advanced by one 128-byte pixel row = 8
+// units, weight descriptor by ktd) for the accumulators whose unit is in range (v0 / v1)
+template <int CG, int NK>
+__device__ __forceinline__ void tc_stage3(uint32_t d0, uint32_t d1, uint32_t a0, uint32_t a1, uint32_t b, uint32_t ktd, uint32_t idesc, bool v0,
+                                          bool v1, uint32_t acc0, uint32_t acc1) {
+    if (v0 && v1) {
+        tc_mma_kx2<CG, NK>(d0, d1, a0, a1, b, idesc, acc0, acc1);
+        tc_mma_kx2<CG, NK>(d0, d1, a0 + 8u, a1 + 8u, b + ktd, idesc, 1u, 1u);
+        tc_mma_kx2<CG, NK>(d0, d1, a0 + 16u, a1 + 16u, b + 2u * ktd, idesc, 1u, 1u);
+    } else if (v0) {
+        tc_mma_k<CG, NK>(d0, a0, b, idesc, acc0);
+        tc_mma_k<CG, NK>(d0, a0 + 8u, b + ktd, idesc, 1u);
+        tc_mma_k<CG, NK>(d0, a0 + 16u, b + 2u * ktd, idesc, 1u);
+    } else if (v1) {
+        tc_mma_k<CG, NK>(d1, a1, b, idesc, acc1);
+        tc_mma_k<CG, NK>(d1, a1 + 8u, b + ktd, idesc, 1u);
+        tc_mma_k<CG, NK>(d1, a1 + 16u, b + 2u * ktd, idesc, 1u);
+    }
 }
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {

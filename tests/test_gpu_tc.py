@@ -237,12 +237,54 @@ def test_forward_single_fp16_paper_network_matches_reference_golden(aid, cuda):
     assert e0 < 1e-3 and e1 < 1e-3
 
 
-def test_conv_tc2_cluster_pair_mode(cuda, monkeypatch):
-    """AID_TC2_PAIR=1: the two units of an N = 256 tile in the two CTAs of a cluster, weight ring shared by multicast."""
-    monkeypatch.setenv("AID_TC2_PAIR", "1")
-    for case in [(1, 256, 256, 24, 64, 64, True), (2, 256, 256, 9, 128, 2, True), (1, 64, 256, 7, 256, 1, True)]:
-        test_conv_tc_single_fp16(cuda, case)
-    test_conv_tc_single_fp16(cuda, (1, 512, 768, 1, 256, 0, False))     # 3 n-tiles, 1x1
+CG2_CASES = [
+    # B, Cin, Cout, F, T, dil, stats      shapes the launcher runs as cta_group::2 (a CTA pair per quad of four units)
+    (2, 64, 64, 16, 512, 2, True),      # quad = four t-tiles of one row (tiles_t % 4 == 0)
+    (1, 96, 96, 24, 512, 4, True),      # 96 channels: the second 64-channel group holds two k-steps
+    (2, 128, 128, 16, 256, 1, True),    # tiles_t == 2: rows f and f + 4 share an MMA; their tap validity differs at the edges (zero windows)
+    (1, 64, 64, 24, 256, 4, True),
+    (2, 128, 128, 16, 128, 2, True),    # tiles_t == 1: rows {2h + j, 2h + j + 4}
+    (1, 256, 256, 16, 128, 8, True),    # two 128-wide n-tiles per quad
+    (1, 96, 96, 8, 128, 1, True),
+    (3, 64, 64, 9, 64, 1, True),        # stream units (T < 128), 15 units: the last quad is partial
+    (2, 256, 256, 21, 64, 16, True),    # level-6-like: stream, two n-tiles, most tap rows out of range
+    (1, 48, 32, 12, 1024, 2, True),     # Cin = 48 (one group of three k-steps): not eligible, stays cta_group::1
+]
+
+
+def _conv53(cuda, case):
+    B, Cin, Cout, Fd, T, dil, use_stats = case
+    L = _lib()
+    a = seeded((B, Cin, Fd, T), 1)
+    w = seeded((Cout, Cin, 5, 3), 2, 1.0 / math.sqrt(Cin * 15))
+    gate, R = seeded((Cout,), 3), seeded((B, Cout, Fd, T), 4)
+    out = torch.full((B, Cout, Fd, T), float("nan"), device=cuda)
+    stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=cuda)
+    L.check(L.lib().aid_op_conv2d(L.ptr(a.to(cuda)), L.ptr(w.to(cuda)), B, Cin, Cout, Fd, T, 5, 3, dil, L.ptr(gate.to(cuda)), L.ptr(R.to(cuda)), None,
+                                  0.70710678, 0.0, L.ptr(out), L.ptr(stats), 3, None))
+    torch.cuda.synchronize()
+    return out, stats
+
+
+@pytest.mark.parametrize("case", CG2_CASES)
+def test_conv_tc2_cta_pair(cuda, case, monkeypatch):
+    """cta_group::2 (M = 256 MMAs over a CTA pair, half of every weight slot per CTA, zero windows for taps that are out of
+    range for one unit of a pair only): parity with the fp64 reference, and bit-identical to the cta_group::1 schedule (every
+    accumulator sees the same MMAs in the same order; the statistics are order-independent by construction)."""
+    monkeypatch.setenv("AID_TC2_CG2", "1")
+    test_conv_tc_single_fp16(cuda, case)
+    out2, st2 = _conv53(cuda, case)
+    monkeypatch.setenv("AID_TC2_CG2", "0")
+    out1, st1 = _conv53(cuda, case)
+    assert torch.equal(out1, out2)
+    assert torch.allclose(st1, st2, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc2_single_cta(cuda, case, monkeypatch):
+    """AID_TC2_CG2=0: the cta_group::1 schedule stays covered for the shapes the pair mode would take."""
+    monkeypatch.setenv("AID_TC2_CG2", "0")
+    test_conv_tc_single_fp16(cuda, case)
 
 
 def test_forward_single_fp16_per_clip_sigma_and_full_size_properties(aid, cuda):
