@@ -29,11 +29,16 @@
 
 namespace aid {
 
-// warps 0-7: epilogue, 8: activation producer, 9: weight producer, 10: cta_group::2 relay (else idle), 11: MMA issuer.  The SM's warp arbiter favours
-// the highest warp id of a sub-partition, and the MMA issuer is the one serial, latency-critical instruction stream.
-static constexpr int T2_THREADS = 384;
-static constexpr int T2_EPI_WARP0 = 0, T2_EPI_WARPS = 8, T2_WARP_A = 8, T2_WARP_B = 9, T2_WARP_RELAY = 10, T2_WARP_MMA = 11;
+// warps 0 .. EW-1: epilogue, EW: activation producer, EW+1: weight producer, EW+2: cta_group::2 relay (else idle), EW+3: MMA issuer.
+// The SM's warp arbiter favours the highest warp id of a sub-partition, and the MMA issuer is the one serial, latency-critical
+// instruction stream.  EW = 16 (four column groups x four TMEM lane quadrants, 16-column batches, <= 96 registers per thread)
+// when the n-tile splits into four column groups of whole 8-column chunks, else EW = 8 (two column groups, 32-column batches).
+// The epilogue is a dependent instruction stream per thread (address, load, FMA, store, statistics): what it needs is more
+// warps to interleave, not more bytes in flight per warp.
+static constexpr int T2_EPI_WARP0 = 0;
 static constexpr int T2_BAR_BYTES = 512;        // mbarriers + TMEM slot at the end of the rings
+static constexpr int T2_STAT_GATE_BYTES = 4096;  // the epilogue warps' private gate tables (EW x 256 / NCW floats)
+static constexpr int T2_STAT_SMEM = 16384;       // their double statistics accumulators
 static constexpr int T2_ASLOT_UNIT = 18 * 1024; // one unit's window: (130 + 7) rows x 128 B, rounded to 1 KB
 static constexpr float T2_A_SCALE = 16.f, T2_W_SCALE = 1024.f, T2_OUT_SCALE = 1.f / (16.f * 1024.f);
 
@@ -52,6 +57,7 @@ struct Tc2Args {
                         //    leader; each CTA holds half of the couts of a weight slot
     int qmode;          // cg2: how the four units of a quad are chosen (unit_index)
     int a_slot_bytes;   // activation ring slot: 2 unit windows
+    int epi_class;      // 0: generic epilogue, 1-5: epilogue_fast<BW, NB, GCN> instantiation (launch_conv_tc2)
     int nt_minor;       // 1: tile = 2 * pair + n-tile (two n-tiles), else tile = n-tile * n_pairs + pair
     int out_cl, r_cl;   // 1: that tensor is channels-last [B][F][T][C] (C = its TV's channel count), else NCHW
     int dbg;  // AID_TC_DEBUG bits (tuning only): 1 skip epilogue body, 2 skip MMAs, 4 skip A loads, 8 skip B loads
@@ -152,10 +158,177 @@ __device__ __forceinline__ TileUnits tile_units(const Tc2Args& p, int tp, int r)
     return t;
 }
 
+// ---- fast epilogue ------------------------------------------------------------------------------------------------------------
+// The generic epilogue below handles every layout and group width with run-time bookkeeping; its inner loop compiled to ~20
+// instructions per output element with indirect branches in the statistics (ncu: 148 M warp instructions for 134 M outputs of a
+// 64-channel layer, issue slots 38 % busy with two epilogue warps per scheduler) and bounded the layers with <= 128 couts.
+// This version covers the shapes of the paper networks (NCHW out / R, 8 epilogue warps, a warp's columns = NB batches of BW
+// columns whose boundaries coincide with the statistics groups of GCN columns) with everything static: the batch loop is
+// unrolled, residuals ping-pong between two register arrays (no copies), group sums are fixed trees, stores and loads use
+// running pointers.  Same arithmetic contract as the generic one: per-unit fp32 partial sums -> private double accumulators in
+// shared memory -> one double atomic per (clip, group, warp).
+template <bool CG2, int BW, int NB, int GCN>
+__device__ __forceinline__ void epilogue_fast(const Tc2Args& p, const int e, const int lane, const uint32_t crank, const int tile0, const int tstep,
+                                              const uint32_t tmem_base, uint8_t* bar_base, uint64_t* tmem_full, uint64_t* tmem_empty) {
+    constexpr int NCOLS = BW * NB;                  // columns of this warp (half of the n-tile)
+    constexpr int NG = NCOLS / GCN;                 // statistics groups they span
+    constexpr int GPB = BW / GCN;                   // groups per batch
+    static_assert(NB % 2 == 0 && BW % 8 == 0 && BW <= 32 && BW % GCN == 0 && NG >= 1 && NG <= 4, "epilogue_fast shape");
+    const int q = e & 3, cw = e >> 2, cbeg = cw * NCOLS;
+    const float al = p.alpha, gs = T2_OUT_SCALE * p.alpha;
+    const long long osc = p.out.sc, rsc = p.R.sc;
+    const bool has_r = p.R.p != nullptr, has_gate = p.gate != nullptr, do_stats = p.stats != nullptr;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
+    float* gsm = reinterpret_cast<float*>(bar_base + T2_BAR_BYTES) + e * 128;
+    const uint32_t gsm_addr = smem_u32(gsm);
+    const int pofs = q * 32 + lane;
+    double* sacc = reinterpret_cast<double*>(bar_base + T2_BAR_BYTES + T2_STAT_GATE_BYTES) + (e * 32 + lane);   // [k][256 threads]
+    float S[NG], Q[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) { S[k] = 0.f; Q[k] = 0.f; }
+    if (do_stats) {
+#pragma unroll
+        for (int k = 0; k < 2 * NG; ++k) sacc[k * 256] = 0.0;
+    }
+    int b_cur = -1, nt_cur = 0, gate_key = -2;
+    auto flush_stats = [&]() {
+        if (do_stats && b_cur >= 0) {
+            double v[2 * NG];
+#pragma unroll
+            for (int k = 0; k < 2 * NG; ++k) {
+                v[k] = sacc[k * 256]; sacc[k * 256] = 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            }
+            if (lane == 0) {
+                const int g0 = (nt_cur * p.Ntile + cbeg) / GCN;
+#pragma unroll
+                for (int k = 0; k < 2 * NG; ++k) atomicAdd(p.stats + (long long)b_cur * 16 + (g0 + (k >> 1)) * 2 + (k & 1), v[k]);
+            }
+        }
+    };
+    // unit iterator and the descriptor of the next unit (its first batch of residuals is prefetched during our last batch)
+    int it_tile = tile0, it_ui = 0, it_ab = 0; uint32_t it_aph = 0;
+    float* n_po = nullptr; const float* n_pr = nullptr; uint32_t n_tcol = 0, n_aph = 0; int n_b = 0, n_nt = 0, n_ab = 0;
+    bool n_valid = false, n_ok = false, n_first = false, n_last = false;
+    auto advance = [&]() {
+        n_valid = it_tile < p.n_tiles;
+        if (!n_valid) return;
+        uint32_t pair = (uint32_t)it_tile; n_nt = 0;
+        if (p.n_ntiles > 1) { const uint2 dm = tile_decode(p, it_tile); n_nt = (int)dm.x; pair = dm.y; }
+        const bool has1 = unit_index(p, (int)pair, (int)crank, 1) < p.n_units;
+        Unit2 u = unit2_info(p, unit_index(p, (int)pair, (int)crank, it_ui));
+        if (!u.exists) u.b = 0;                   // cta_group::2, last quad: this CTA only keeps the handshakes going
+        const int o = u.o0 + pofs;                // output position in the padded stream of the real rows
+        const int row = (int)fast_divmod((uint32_t)o, (uint32_t)p.Tp, p.mg_Tp).x, tp = o - row * p.Tp;
+        n_ok = u.exists && tp >= 1 && tp <= p.T && row <= u.f_hi;
+        // lanes that own no real pixel read (never write) pixel 0 of their clip: the loads need no predicate
+        const long long pix = n_ok ? (long long)row * p.T + (tp - 1) : 0;
+        const long long co0 = n_nt * p.Ntile + cbeg;
+        n_po = p.out.p + (long long)u.b * p.out.sb + co0 * osc + pix;
+        n_pr = p.R.p + (long long)u.b * p.R.sb + co0 * rsc + pix;
+        n_b = u.b; n_ab = it_ab; n_aph = it_aph;
+        n_tcol = tq + (uint32_t)(it_ab * 2 * p.ncol_stride + it_ui * p.ncol_stride);
+        n_first = it_ui == 0;
+        n_last = it_ui == 1 || !has1;
+        if (n_last) {
+            it_ui = 0; it_tile += tstep;
+            if (++it_ab == p.acc_bufs) { it_ab = 0; it_aph ^= 1; }
+        } else it_ui = 1;
+    };
+    float ra[BW], rb[BW];
+    auto load_batch = [&](float (&dst)[BW], const float* src) {
+        if (has_r) {
+#pragma unroll
+            for (int j = 0; j < BW; ++j) { dst[j] = *src; src += rsc; }     // may alias out: plain loads
+        } else {
+#pragma unroll
+            for (int j = 0; j < BW; ++j) dst[j] = 0.f;
+        }
+    };
+    advance();
+    if (n_valid) load_batch(ra, n_pr);
+    while (n_valid) {
+        float* c_po = n_po; const float* c_pr = n_pr;
+        const uint32_t c_tcol = n_tcol, c_aph = n_aph; const int c_b = n_b, c_nt = n_nt, c_ab = n_ab;
+        const bool c_ok = n_ok, c_first = n_first, c_last = n_last;
+        advance();
+        if (c_first) { mbar_wait(tmem_full + c_ab, c_aph); tc_fence_after(); }
+        if (c_b != b_cur || c_nt != nt_cur) { flush_stats(); b_cur = c_b; nt_cur = c_nt; }
+        const int gkey = p.gate_bstride ? c_b * p.n_ntiles + c_nt : c_nt;
+        if (gkey != gate_key) {
+            gate_key = gkey;
+            __syncwarp();
+            for (int k = lane; k < NCOLS; k += 32)
+                gsm[k] = has_gate ? __ldg(p.gate + (long long)c_b * p.gate_bstride + c_nt * p.Ntile + cbeg + k) * gs : gs;
+            __syncwarp();
+        }
+        const float m = c_ok ? 1.f : 0.f;
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi) {
+            float (&cur)[BW] = (bi & 1) ? rb : ra;
+            float (&nxt)[BW] = (bi & 1) ? ra : rb;
+            if (bi + 1 < NB) load_batch(nxt, c_pr + (long long)(bi + 1) * BW * rsc);
+            else if (n_valid) load_batch(nxt, n_pr);
+            uint32_t acc[BW];
+            if constexpr (BW == 32) tmem_ld32_nowait(c_tcol + bi * BW, acc);
+            else if constexpr (BW == 24) { tmem_ld16_nowait(c_tcol + bi * BW, acc); tmem_ld8p_nowait(c_tcol + bi * BW + 16, acc + 16); }
+            else if constexpr (BW == 16) tmem_ld16_nowait(c_tcol + bi * BW, acc);
+            else tmem_ld8p_nowait(c_tcol + bi * BW, acc);
+            float g[BW];
+#pragma unroll
+            for (int j = 0; j < BW; j += 4)
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g[j]), "=f"(g[j + 1]), "=f"(g[j + 2]), "=f"(g[j + 3]) : "r"(gsm_addr + (uint32_t)(bi * BW + j) * 4u));
+            tmem_wait_ld();
+            float v[BW];
+#pragma unroll
+            for (int j = 0; j < BW; ++j) v[j] = fmaf(__uint_as_float(acc[j]), g[j], cur[j] * al);
+            if (c_ok) {
+                float* po = c_po + (long long)(bi * BW) * osc;
+#pragma unroll
+                for (int j = 0; j < BW; ++j) { *po = v[j]; po += osc; }
+            }
+            if (do_stats) {
+#pragma unroll
+                for (int gg = 0; gg < GPB; ++gg) {
+                    // fixed trees over the GCN columns of the group (GCN is a multiple of 4)
+                    float s4[GCN / 4], q4[GCN / 4];
+#pragma unroll
+                    for (int k = 0; k < GCN / 4; ++k) {
+                        const float* w = v + gg * GCN + 4 * k;
+                        s4[k] = (w[0] + w[1]) + (w[2] + w[3]);
+                        q4[k] = fmaf(w[0], w[0], w[1] * w[1]) + fmaf(w[2], w[2], w[3] * w[3]);
+                    }
+                    float s = s4[0], qq = q4[0];
+#pragma unroll
+                    for (int k = 1; k < GCN / 4; ++k) { s += s4[k]; qq += q4[k]; }
+                    S[bi * GPB + gg] = fmaf(s, m, S[bi * GPB + gg]);
+                    Q[bi * GPB + gg] = fmaf(qq, m, Q[bi * GPB + gg]);
+                }
+            }
+        }
+        if (do_stats) {
+#pragma unroll
+            for (int k = 0; k < NG; ++k) { sacc[(2 * k) * 256] += (double)S[k]; sacc[(2 * k + 1) * 256] += (double)Q[k]; S[k] = 0.f; Q[k] = 0.f; }
+        }
+        if (c_last) {      // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory pipe
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(tmem_empty + c_ab, 0u); else mbar_arrive(tmem_empty + c_ab); }
+        }
+    }
+    flush_stats();
+}
+
 // CG2 = false: cta_group::1, plain launch.  CG2 = true: cta_group::2, launched in clusters of two CTAs (a kernel that contains
 // cta_group::2 instructions cannot be launched without a cluster, hence two instantiations).
-template <bool CG2>
+template <bool CG2, int EW>
 __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
+    constexpr int T2_EPI_WARPS = EW, T2_WARP_A = EW, T2_WARP_B = EW + 1, T2_WARP_RELAY = EW + 2, T2_WARP_MMA = EW + 3;
+    constexpr int NCW = EW / 4;                 // column groups of an n-tile (one per 4 epilogue warps)
+    constexpr int BW = EW == 8 ? 32 : 16;       // columns per epilogue batch
+    constexpr int GP = 8 / NCW;                 // statistics groups a warp's columns can span
+    constexpr int GSM_W = 256 / NCW;            // floats of a warp's private gate table
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1 KB aligned, still a shared-space pointer for the compiler
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,7 +354,7 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
         if (lane == 0) {
             for (int s = 0; s < p.nA; ++s) { mbar_init(a_full + s, 1); mbar_init(a_empty + s, 1); }
             for (int s = 0; s < p.nB; ++s) { mbar_init(b_full + s, 1); mbar_init(b_empty + s, 1); mbar_init(ready + s, 2); }
-            for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, cg2 ? 2 * T2_EPI_WARPS : T2_EPI_WARPS); }
+            for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, cg2 ? 2 * EW : EW); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -435,13 +608,26 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
         __syncwarp();
     } else if (warp < T2_EPI_WARP0 + T2_EPI_WARPS) {
         // ===================== epilogue: TMEM -> registers -> out = alpha*(acc*gate + R), statistics =====================
-        // 8 warps: warp e reads TMEM lane quadrant (e & 3) (one pixel per thread) and column half (e >> 2).  The work is a flat
-        // sequence of 32-column batches (tile -> unit -> batch); the residual loads of batch k+1 are issued before batch k is
+        // EW warps: warp e reads TMEM lane quadrant (e & 3) (one pixel per thread) and column group (e >> 2).  The work is a flat
+        // sequence of BW-column batches (tile -> unit -> batch); the residual loads of batch k+1 are issued before batch k is
         // processed, so one batch of loads is always in flight, also across the wait for the next tile's accumulator.
         const int e = warp - T2_EPI_WARP0;
+        bool fast = false;
+        if constexpr (EW == 8) {
+            fast = true;
+            switch (p.epi_class) {      // host: launch_conv_tc2
+                case 1: epilogue_fast<CG2, 16, 2, 8>(p, e, lane, crank, tile0, tstep, tmem_base, bar_base, tmem_full, tmem_empty); break;
+                case 2: epilogue_fast<CG2, 24, 2, 12>(p, e, lane, crank, tile0, tstep, tmem_base, bar_base, tmem_full, tmem_empty); break;
+                case 3: epilogue_fast<CG2, 32, 2, 16>(p, e, lane, crank, tile0, tstep, tmem_base, bar_base, tmem_full, tmem_empty); break;
+                case 4: epilogue_fast<CG2, 32, 2, 32>(p, e, lane, crank, tile0, tstep, tmem_base, bar_base, tmem_full, tmem_empty); break;
+                case 5: epilogue_fast<CG2, 32, 4, 32>(p, e, lane, crank, tile0, tstep, tmem_base, bar_base, tmem_full, tmem_empty); break;
+                default: fast = false;
+            }
+        }
+        if (!fast) {
         const int q = warp & 3;
         const int cw = e >> 2;
-        const int ncols = p.Ntile / 2;          // multiple of 8; equals 4 statistics groups when Ntile == Ntot
+        const int ncols = p.Ntile / NCW;        // multiple of 8; equals GP statistics groups when Ntile == Ntot
         const int cbeg = cw * ncols;
         const int gcn = p.Ntot / 8;
         const float al = p.alpha, gs = T2_OUT_SCALE * p.alpha;
@@ -450,7 +636,7 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
         const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
 
         // gate[c] * 2^-14 * alpha of this warp's columns, private copy in shared memory (refreshed when the clip changes)
-        float* gsm = reinterpret_cast<float*>(bar_base + T2_BAR_BYTES) + e * 128;
+        float* gsm = reinterpret_cast<float*>(bar_base + T2_BAR_BYTES) + e * GSM_W;
         int gate_key = -2;
         const uint32_t gsm_addr = smem_u32(gsm);
         const int pofs = q * 32 + lane;           // this thread's pixel inside a unit
@@ -491,7 +677,7 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
             n_tcol = tq + (uint32_t)(it_ab * 2 * p.ncol_stride + it_ui * p.ncol_stride + it_c0);
             n_ui = it_ui; n_c0 = it_c0; n_b = u_b; n_nt = u_nt; n_ab = it_ab; n_aphase = it_aphase; n_ok = u_ok;
             n_last = false; n_ulast = false;
-            it_c0 += 32;
+            it_c0 += BW;
             if (it_c0 >= ncols) {
                 it_c0 = 0; n_ulast = true;
                 if (it_ui == 1 || !u_has1) {
@@ -504,27 +690,27 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
         // (Tried and dropped, measured: pulling the NEXT tile's residual lines into L2 with prefetch.global.L2 at the start of each
         // tile changed nothing at 64 couts and cost 1-3 % on the wider layers -- the epilogue is not bound by the latency of
         // its residual loads.)
-        float rr[32], rn[32];
+        float rr[BW], rn[BW];
         auto load_next = [&]() {
             if (n_valid && has_r && !(p.dbg & 1)) {
                 const int nb = ncols - n_c0;      // >= 8, multiple of 8; columns past it are not loaded
                 if (p.r_cl) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
+                    for (int j4 = 0; j4 < BW / 4; ++j4) {
                         float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (j4 * 4 < nb) t4 = __ldg(reinterpret_cast<const float4*>(n_pr + n_ro) + j4);
                         rn[j4 * 4 + 0] = t4.x; rn[j4 * 4 + 1] = t4.y; rn[j4 * 4 + 2] = t4.z; rn[j4 * 4 + 3] = t4.w;
                     }
-                } else if (nb >= 32) {
+                } else if (nb >= BW) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) rn[j] = n_pr[n_ro + (uint32_t)j * (uint32_t)rsc];   // may alias out: plain loads
+                    for (int j = 0; j < BW; ++j) rn[j] = n_pr[n_ro + (uint32_t)j * (uint32_t)rsc];   // may alias out: plain loads
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) rn[j] = (j < nb) ? n_pr[n_ro + (uint32_t)j * (uint32_t)rsc] : 0.f;
+                    for (int j = 0; j < BW; ++j) rn[j] = (j < nb) ? n_pr[n_ro + (uint32_t)j * (uint32_t)rsc] : 0.f;
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) rn[j] = 0.f;
+                for (int j = 0; j < BW; ++j) rn[j] = 0.f;
             }
         };
         // Statistics: (sum, sumsq) of the 4 groups this warp's columns cover.  A thread sums ONE unit's values of its pixel in
@@ -533,40 +719,45 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
         // added to the global accumulators when the clip changes.  Everything order-dependent happens in double on fp32 terms,
         // so the statistics -- and with them the fp16 roundings of the next layer's operands -- are reproducible run to run and
         // identical for a clip evaluated alone or inside a batch (to ~1e-16 relative).
-        float S0 = 0.f, S1 = 0.f, S2 = 0.f, S3 = 0.f, Q0 = 0.f, Q1 = 0.f, Q2 = 0.f, Q3 = 0.f;
+        float SQ[2 * GP];                    // (sum, sumsq) of group k at [2k], [2k + 1]
+#pragma unroll
+        for (int k = 0; k < 2 * GP; ++k) SQ[k] = 0.f;
         int b_cur = -1, nt_cur = 0, gk = 0, gpos = 0;
-        double* sacc = reinterpret_cast<double*>(bar_base + T2_BAR_BYTES + T2_EPI_WARPS * 128 * sizeof(float)) + (e * 32 + lane);   // [k][256 threads]
+        constexpr int SACC_STRIDE = EW * 32;   // [k < 2 GP][epilogue threads]: 16 KB for either EW
+        double* sacc = reinterpret_cast<double*>(bar_base + T2_BAR_BYTES + T2_STAT_GATE_BYTES) + (e * 32 + lane);
         if (do_stats) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sacc[k * 256] = 0.0;
+            for (int k = 0; k < 2 * GP; ++k) sacc[k * SACC_STRIDE] = 0.0;
         }
         auto unit_end = [&]() {
             if (do_stats) {
-                const float v[8] = {S0, Q0, S1, Q1, S2, Q2, S3, Q3};
 #pragma unroll
-                for (int k = 0; k < 8; ++k) sacc[k * 256] += (double)v[k];
+                for (int k = 0; k < 2 * GP; ++k) sacc[k * SACC_STRIDE] += (double)SQ[k];
             }
-            S0 = S1 = S2 = S3 = Q0 = Q1 = Q2 = Q3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 2 * GP; ++k) SQ[k] = 0.f;
         };
         auto flush_stats = [&]() {
             if (do_stats && b_cur >= 0) {
-                double v[8];
+                double v[2 * GP];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    v[k] = sacc[k * 256]; sacc[k * 256] = 0.0;
+                for (int k = 0; k < 2 * GP; ++k) {
+                    v[k] = sacc[k * SACC_STRIDE]; sacc[k * SACC_STRIDE] = 0.0;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
                 }
                 if (lane == 0) {
                     const int g0 = (nt_cur * p.Ntile + cbeg) / gcn;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
+                    for (int k = 0; k < 2 * GP; ++k)
                         if (g0 + (k >> 1) < 8) atomicAdd(p.stats + (long long)b_cur * 16 + (g0 + (k >> 1)) * 2 + (k & 1), v[k]);
                 }
             }
         };
         auto add_group = [&](float s, float qq) {
-            if (gk == 0) { S0 += s; Q0 += qq; } else if (gk == 1) { S1 += s; Q1 += qq; } else if (gk == 2) { S2 += s; Q2 += qq; } else { S3 += s; Q3 += qq; }
+#pragma unroll
+            for (int k = 0; k < GP; ++k)
+                if (gk == k) { SQ[2 * k] += s; SQ[2 * k + 1] += qq; }
         };
         // one 8-column chunk: out = acc*gate' + R*alpha, store, statistics
         auto chunk = [&](const uint32_t* acc8, const float* r8, uint32_t g8, uint32_t oo8) {
@@ -625,7 +816,7 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
             c_po = n_po; c_oo = n_oo; c_tcol = n_tcol; c_ui = n_ui; c_c0 = n_c0; c_b = n_b; c_ab = n_ab; c_nt = n_nt; c_aphase = n_aphase;
             c_ok = n_ok; c_last = n_last; c_ulast = n_ulast;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) rr[j] = rn[j];
+            for (int j = 0; j < BW; ++j) rr[j] = rn[j];
             setup_next();
             load_next();
             if (c_ui == 0 && c_c0 == 0) { T2_PROF_T0(t_w); mbar_wait(tmem_full + c_ab, c_aphase); T2_PROF_ADD(0, t_w); tc_fence_after(); }
@@ -642,22 +833,22 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
                 }
             }
             if (!(p.dbg & 1)) {
-                uint32_t acc[32];
+                uint32_t acc[BW];
                 if (!(p.dbg & 512)) {
-                    tmem_ld32_nowait(c_tcol, acc);     // columns past this warp's range are read but never used
+                    if constexpr (BW == 32) tmem_ld32_nowait(c_tcol, acc); else tmem_ld16_nowait(c_tcol, acc);   // columns past this warp's range are read but never used
                     tmem_wait_ld();
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] = 0x3f800000u;
+                    for (int j = 0; j < BW; ++j) acc[j] = 0x3f800000u;
                 }
                 const int nb = ncols - c_c0;
                 const uint32_t gq = gsm_addr + (uint32_t)c_c0 * 4u;
-                if (nb >= 32) {
+                if (nb >= BW) {
 #pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) chunk(acc + j8 * 8, rr + j8 * 8, gq + j8 * 32, c_oo + (p.out_cl ? (uint32_t)(j8 * 8) : (uint32_t)(j8 * 8) * (uint32_t)osc));
+                    for (int j8 = 0; j8 < BW / 8; ++j8) chunk(acc + j8 * 8, rr + j8 * 8, gq + j8 * 32, c_oo + (p.out_cl ? (uint32_t)(j8 * 8) : (uint32_t)(j8 * 8) * (uint32_t)osc));
                 } else {
 #pragma unroll
-                    for (int j8 = 0; j8 < 3; ++j8)
+                    for (int j8 = 0; j8 < BW / 8 - 1; ++j8)
                         if (j8 * 8 < nb) chunk(acc + j8 * 8, rr + j8 * 8, gq + j8 * 32, c_oo + (p.out_cl ? (uint32_t)(j8 * 8) : (uint32_t)(j8 * 8) * (uint32_t)osc));
                 }
             }
@@ -671,6 +862,7 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
         flush_stats();
         T2_PROF_ADD(1, t_all);
         if (prof && lane == 0) { atomicAdd(&g_tc2_prof[7], (unsigned long long)prof_acc[0]); atomicAdd(&g_tc2_prof[8], (unsigned long long)prof_acc[1]); }
+        }   // generic epilogue
     }
 
     tc_fence_before();
@@ -683,8 +875,8 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
     }
 }
 
-__global__ void __launch_bounds__(T2_THREADS, 1) conv_tc2_kernel(const __grid_constant__ Tc2Args p) { conv_tc2_body<false>(p); }
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1) conv_tc2_cg2_kernel(const __grid_constant__ Tc2Args p) { conv_tc2_body<true>(p); }
+template <int EW> __global__ void __launch_bounds__((EW + 4) * 32, 1) conv_tc2_kernel(const __grid_constant__ Tc2Args p) { conv_tc2_body<false, EW>(p); }
+template <int EW> __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EW + 4) * 32, 1) conv_tc2_cg2_kernel(const __grid_constant__ Tc2Args p) { conv_tc2_body<true, EW>(p); }
 
 // ---- operand preparation ---------------------------------------------------------------------------------
 // Couts per tile.  256-wide tiles fill TMEM with one accumulator (2 units x 256 columns), so their epilogue cannot overlap the
@@ -1069,36 +1261,45 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     p.b_slot_bytes = p.ktb * kt_bytes / (p.cg2 ? 2 : 1);
     p.nA = max(2, min(4, env_nA));
     p.a_slot_bytes = 2 * T2_ASLOT_UNIT;
-    const int stat_smem = T2_EPI_WARPS * 32 * 8 * (int)sizeof(double);   // per-thread double statistics accumulators of the epilogue warps
-    const int budget = 224 * 1024 - 1024 - T2_BAR_BYTES - T2_EPI_WARPS * 128 * (int)sizeof(float) - stat_smem;
+    const int budget = 224 * 1024 - 1024 - T2_BAR_BYTES - T2_STAT_GATE_BYTES - T2_STAT_SMEM;
     while (p.nA > 2 && budget - p.nA * p.a_slot_bytes < 2 * p.b_slot_bytes) --p.nA;
     p.nB = min(8, (budget - p.nA * p.a_slot_bytes) / p.b_slot_bytes);
     if (p.nB < 2) throw CudaError(cudaErrorInvalidValue, "conv_tc2: shared memory budget", __FILE__, __LINE__);
     p.ncol_stride = p.Ntile <= 64 ? 64 : (p.Ntile <= 128 ? 128 : 256);
     p.acc_bufs = p.ncol_stride <= 128 ? 2 : 1;
-    // an epilogue warp owns Ntile / 2 columns: they must be whole statistics groups, at most four of them
-    if (ep.stats && p.n_ntiles != 1 && ((p.Ntile / 2) % (p.Ntot / 8) != 0 || p.Ntile / 2 > 4 * (p.Ntot / 8)))
+    // epilogue warps: 16 (four column groups) when the n-tile splits into four groups of whole 8-column chunks (AID_TC2_EW=8 forces 8)
+    // (16 epilogue warps with 16-column batches and 96 registers measured no faster than 8 -- AID_TC2_EW=16 keeps it reachable)
+    const int env_ew = getenv("AID_TC2_EW") ? atoi(getenv("AID_TC2_EW")) : 8;
+    const int ew = (env_ew == 16 && p.Ntile % 32 == 0) ? 16 : 8;
+    // static epilogue for the shapes of the paper networks (AID_TC2_FASTEPI=0: generic one everywhere)
+    const int env_fe = getenv("AID_TC2_FASTEPI") ? atoi(getenv("AID_TC2_FASTEPI")) : 1;
+    p.epi_class = 0;
+    if (env_fe && ew == 8 && !p.out_cl && !p.r_cl && !(dbg & (1 | 256 | 512 | 2048))) {
+        const int hc = p.Ntile / 2, g8 = p.Ntot / 8;
+        const bool st = ep.stats != nullptr;
+        if (hc == 32 && (!st || g8 == 8)) p.epi_class = 1;
+        else if (hc == 48 && (!st || g8 == 12)) p.epi_class = 2;
+        else if (hc == 64 && (!st || g8 == 16)) p.epi_class = 3;
+        else if (hc == 64 && g8 == 32) p.epi_class = 4;
+        else if (hc == 128 && (!st || g8 == 32)) p.epi_class = 5;
+    }
+    // an epilogue warp owns Ntile / NCW columns: they must be whole statistics groups, at most 8 / NCW of them
+    const int ncw = ew / 4, wcols = p.Ntile / ncw, gcn = p.Ntot / 8;
+    if (ep.stats && p.n_ntiles != 1 && (wcols % gcn != 0 || wcols > (8 / ncw) * gcn))
         throw CudaError(cudaErrorInvalidValue, "conv_tc2: statistics groups do not align with the n-tiles", __FILE__, __LINE__);
-    const size_t smem = 1024 + (size_t)p.nA * p.a_slot_bytes + (size_t)p.nB * p.b_slot_bytes + T2_BAR_BYTES + T2_EPI_WARPS * 128 * sizeof(float) + stat_smem;
+    const size_t smem = 1024 + (size_t)p.nA * p.a_slot_bytes + (size_t)p.nB * p.b_slot_bytes + T2_BAR_BYTES + T2_STAT_GATE_BYTES + T2_STAT_SMEM;
     p.dbg = dbg;
+    const int threads = (ew + 4) * 32;
+    static SmemConfig cfg_8, cfg_16, cfg2_8, cfg2_16;
     if (p.cg2) {
-        static SmemConfig configured2;
-        ensure_dyn_smem(conv_tc2_cg2_kernel, smem, configured2);
-        if (dbg & 4096) {     // tuning: how many CTA pairs the device can hold at once (a persistent grid assumes all of them)
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(num_sms); cfg.blockDim = dim3(T2_THREADS); cfg.dynamicSmemBytes = smem;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            int ncl = -1;
-            cudaOccupancyMaxActiveClusters(&ncl, conv_tc2_cg2_kernel, &cfg);
-            fprintf(stderr, "conv_tc2 cta_group::2: %d active clusters possible, grid %d CTAs, smem %zu, nA %d nB %d qmode %d\n", ncl, 2 * min(p.n_tiles, num_sms / 2), smem, p.nA, p.nB, p.qmode);
-        }
-        conv_tc2_cg2_kernel<<<2 * min(p.n_tiles, num_sms / 2), T2_THREADS, smem, s>>>(p);   // __cluster_dims__(2, 1, 1)
+        const int grid = 2 * min(p.n_tiles, num_sms / 2);     // __cluster_dims__(2, 1, 1)
+        if (dbg & 4096) fprintf(stderr, "conv_tc2 cta_group::2: grid %d CTAs x %d threads, smem %zu, nA %d nB %d qmode %d\n", grid, threads, smem, p.nA, p.nB, p.qmode);
+        if (ew == 16) { ensure_dyn_smem(conv_tc2_cg2_kernel<16>, smem, cfg2_16); conv_tc2_cg2_kernel<16><<<grid, threads, smem, s>>>(p); }
+        else { ensure_dyn_smem(conv_tc2_cg2_kernel<8>, smem, cfg2_8); conv_tc2_cg2_kernel<8><<<grid, threads, smem, s>>>(p); }
     } else {
-        static SmemConfig configured;
-        ensure_dyn_smem(conv_tc2_kernel, smem, configured);
-        conv_tc2_kernel<<<min(p.n_tiles, num_sms), T2_THREADS, smem, s>>>(p);
+        const int grid = min(p.n_tiles, num_sms);
+        if (ew == 16) { ensure_dyn_smem(conv_tc2_kernel<16>, smem, cfg_16); conv_tc2_kernel<16><<<grid, threads, smem, s>>>(p); }
+        else { ensure_dyn_smem(conv_tc2_kernel<8>, smem, cfg_8); conv_tc2_kernel<8><<<grid, threads, smem, s>>>(p); }
     }
     AID_COUNT_LAUNCH(1);
 }
