@@ -280,30 +280,32 @@ __device__ __forceinline__ void epilogue_fast(const Tc2Args& p, const int e, con
             for (int j = 0; j < BW; j += 4)
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g[j]), "=f"(g[j + 1]), "=f"(g[j + 2]), "=f"(g[j + 3]) : "r"(gsm_addr + (uint32_t)(bi * BW + j) * 4u));
             tmem_wait_ld();
-            float v[BW];
+            // packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 of sm_100): half the math instructions, the same IEEE results per lane
+            float2 v2[BW / 2];
 #pragma unroll
-            for (int j = 0; j < BW; ++j) v[j] = fmaf(__uint_as_float(acc[j]), g[j], cur[j] * al);
+            for (int j = 0; j < BW / 2; ++j)
+                v2[j] = __ffma2_rn(make_float2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])), make_float2(g[2 * j], g[2 * j + 1]),
+                                   __fmul2_rn(make_float2(cur[2 * j], cur[2 * j + 1]), make_float2(al, al)));
             if (c_ok) {
                 float* po = c_po + (long long)(bi * BW) * osc;
 #pragma unroll
-                for (int j = 0; j < BW; ++j) { *po = v[j]; po += osc; }
+                for (int j = 0; j < BW / 2; ++j) { *po = v2[j].x; po += osc; *po = v2[j].y; po += osc; }
             }
             if (do_stats) {
 #pragma unroll
                 for (int gg = 0; gg < GPB; ++gg) {
-                    // fixed trees over the GCN columns of the group (GCN is a multiple of 4)
-                    float s4[GCN / 4], q4[GCN / 4];
+                    // fixed order over the GCN columns of the group: two interleaved packed chains, then the four lanes
+                    constexpr int H = GCN / 2;       // float2 values of the group (even)
+                    const float2* w = v2 + gg * H;
+                    float2 sa = w[0], sb = w[1], qa = __fmul2_rn(w[0], w[0]), qb = __fmul2_rn(w[1], w[1]);
 #pragma unroll
-                    for (int k = 0; k < GCN / 4; ++k) {
-                        const float* w = v + gg * GCN + 4 * k;
-                        s4[k] = (w[0] + w[1]) + (w[2] + w[3]);
-                        q4[k] = fmaf(w[0], w[0], w[1] * w[1]) + fmaf(w[2], w[2], w[3] * w[3]);
+                    for (int k = 2; k < H; k += 2) {
+                        sa = __fadd2_rn(sa, w[k]); sb = __fadd2_rn(sb, w[k + 1]);
+                        qa = __ffma2_rn(w[k], w[k], qa); qb = __ffma2_rn(w[k + 1], w[k + 1], qb);
                     }
-                    float s = s4[0], qq = q4[0];
-#pragma unroll
-                    for (int k = 1; k < GCN / 4; ++k) { s += s4[k]; qq += q4[k]; }
-                    S[bi * GPB + gg] = fmaf(s, m, S[bi * GPB + gg]);
-                    Q[bi * GPB + gg] = fmaf(qq, m, Q[bi * GPB + gg]);
+                    const float2 s2 = __fadd2_rn(sa, sb), q2 = __fadd2_rn(qa, qb);
+                    S[bi * GPB + gg] = fmaf(s2.x + s2.y, m, S[bi * GPB + gg]);
+                    Q[bi * GPB + gg] = fmaf(q2.x + q2.y, m, Q[bi * GPB + gg]);
                 }
             }
         }
@@ -1244,10 +1246,15 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
     // layers are bound by shared-memory bandwidth, not by the tensor pipe.  With the MMA spanning a CTA pair (M = 256) each CTA
     // reads its own A tile but only half of B (and fetches only half of every weight slot): 5 KB / 6 KB per MMA.  Taken for the
     // multi-tap layers with n-tiles <= 128 wide whose units can be grouped into quads of equal window phase (unit_index).
-    const int env_cg2 = getenv("AID_TC2_CG2") ? atoi(getenv("AID_TC2_CG2")) : 0;     // read per launch (tests switch it); off by default, see above
+    // AID_TC2_CG2: 0 = never, 1 = wherever the shape allows, unset = where it measured faster with the whole kernel (B200, B = 8):
+    // the 256-cout layers as two 128-wide n-tiles (0.499 -> 0.466 ms, 0.374 -> 0.351 ms) and the 96-channel layers (0.640 -> 0.619);
+    // at 64 / 128 couts the main loop gains 3-11 % but the epilogue, which bounds those layers, runs slower next to the
+    // pair's operand exchange (0.388 -> 0.402, 0.427 -> 0.437, 0.263 -> 0.280 ms).
+    const int env_cg2 = getenv("AID_TC2_CG2") ? atoi(getenv("AID_TC2_CG2")) : -1;     // read per launch (tests switch it)
     static const int dbg = getenv("AID_TC_DEBUG") ? atoi(getenv("AID_TC_DEBUG")) : 0;
     p.cg2 = 0; p.qmode = 0;
-    if (env_cg2 && !(dbg & (2 | 32 | 8192)) && KT == 3 && p.ktb == 3 && p.Ntile <= 128 && p.Ntile % 16 == 0 && Cin % 16 == 0 && (Cin % 64 == 0 || Cin % 64 == 32) && num_sms % 2 == 0 &&
+    const bool cg2_wanted = env_cg2 > 0 || (env_cg2 < 0 && (p.n_ntiles == 2 || p.Ntile == 96));
+    if (cg2_wanted && !(dbg & (2 | 32 | 8192)) && KT == 3 && p.ktb == 3 && p.Ntile <= 128 && p.Ntile % 16 == 0 && Cin % 16 == 0 && (Cin % 64 == 0 || Cin % 64 == 32) && num_sms % 2 == 0 &&
         num_sms >= 2 && !p.out_cl && !p.r_cl) {
         if (p.stream || p.tiles_t % 4 == 0) { p.cg2 = 1; p.qmode = 0; }
         else if (p.tiles_t == 2 && F % 8 == 0) { p.cg2 = 1; p.qmode = 1; }
