@@ -131,6 +131,12 @@ void launch_gn_act_tc2_cl(const float* x_cl, int B, int C, int F, int T, const d
 void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, int F, int T, int KF, int KT, int dil,
                      const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s);
 
+// fused dilated residual layer (conv_comb.cu): normalise + modulate + GELU + operand conversion inside the convolution kernel;
+// ep.R must be x itself, out must not overlap x
+bool conv_comb_supported(int C, int F, int T, int dil);
+void launch_conv_comb(const TV& x, const double* stats_in, long long n_per_group, const float* gamma, const float* affine, long long affine_bstride,
+                      const __half* wp, int dil, const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s);
+
 // FFT / CQT
 struct FftPlan {
     int L = 0;                      // transform length (even)

@@ -1,0 +1,330 @@
+// Fused dilated residual layer of conv_mode 2 for 64-channel blocks (unet.py:470-482): group-norm apply, adaLN modulation, GELU and the
+// conversion to the fp16 tensor-core operand happen INSIDE the convolution kernel, so a layer reads its input once and writes
+// its output once (8 B per element instead of 6 B for the operand pass + 10 B for conv_tc2_kernel).
+//
+// Generating the operand in the consumer is only affordable if every input row is transformed once although five output rows
+// (the kf taps, dil rows apart) use it.  A work item is therefore a COMB: one clip, one 128-pixel t-tile and the rows
+// f = r, r + dil, r + 2 dil, ... of one residue r mod dil.  Walking the comb, output row k needs the transformed rows k-2 .. k+2 of
+// the same comb: they live in a ring of five shared-memory slots (130 pixels x 64 channels, fp16, K-major SWIZZLE_128B -- the
+// layout conv_tc2 loads with a bulk copy is written here by the transform warps), each new output row costs ONE new input row.
+// All 15 weight taps (64 x 64 fp16 each, 120 KB) stay resident in shared memory for the whole launch.
+//   warps 0-7   epilogue (tc_epilogue.cuh: TMEM -> out = alpha * (acc * gate + x), statistics of the output for the next layer)
+//   warps 8-15  transform: warp w owns channels 8w .. 8w+7 (one 16-byte operand chunk), lane l the pixels l, l+32, l+64, l+96 of
+//               the tile; raw values are held one row ahead in registers, the row after that is pulled into L2
+//   warp 16     loads the weights once, then transforms the two halo pixels (t0 - 1, t0 + 128) of every row
+//   warp 17     one elected thread issues the MMAs: per output row 5 kf x 3 kt x 4 k-steps of M = 128, N = 64, K = 16
+// Ring protocol (global row sequence number n per CTA, slot = n % 5): row_ready[slot] <- the 8 transform warps + the halo warp;
+// slot_free[slot] <- tcgen05.commit after the last MMAs that read the row (its kf = 0 use two output rows later, or the end of
+// the comb).  With the kf taps issued in ascending order a row is needed last, at the very end of an output row, so the
+// transform of row n+5 overlaps 1.6 output rows of MMAs.
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_epilogue.cuh"
+
+namespace aid {
+
+static constexpr int CB_C = 64;                  // channels (in = out)
+static constexpr int CB_EPI_WARPS = 8, CB_TR_WARPS = 8, CB_WARP_W = 16, CB_WARP_MMA = 17, CB_THREADS = 18 * 32;
+static constexpr int CB_SLOT = 17408;            // one transformed row window: 136 rows x 128 B (130 used), 1 KB aligned
+static constexpr int CB_RING = 5, CB_NACC = 4;
+static constexpr int CB_W_BYTES = 15 * CB_C * 128;   // 15 taps x [64 couts][64 cins] fp16
+static constexpr int CB_BAR_BYTES = 256, CB_GATE_BYTES = 4096, CB_STAT_BYTES = 16384;
+static constexpr size_t CB_SMEM = 1024 + (size_t)CB_RING * CB_SLOT + CB_W_BYTES + CB_BAR_BYTES + CB_GATE_BYTES + CB_STAT_BYTES;
+
+struct CombArgs {
+    TV x, out;                       // layer input (operand source and residual) and output; must not overlap
+    const double* stats_in; double n_per_group;   // (sum, sumsq) of x per (clip, group of 8 channels)
+    const float* gamma; const float* affine; long long affine_bstride;
+    const float* gate; long long gate_bstride;
+    float alpha; double* stats_out;
+    const __half* w;                 // launch_pack_weight_tc2 layout: [kf][kt][64 couts][64 cins], chunks swizzled by (cout & 7)
+    int B, F, T, dil, tiles_t, n_items;
+    int dbg;                         // AID_COMB_DEBUG=1 (tuning): block 0 prints the cycles its roles spent waiting
+};
+
+struct CombItem { int b, r, t0, K; };     // clip, comb residue, first pixel of the t-tile, rows of the comb
+__device__ __forceinline__ CombItem comb_item(const CombArgs& p, int item) {
+    CombItem it;
+    const int tt = item % p.tiles_t, br = item / p.tiles_t;
+    it.r = br % p.dil; it.b = br / p.dil; it.t0 = tt * 128;
+    it.K = (p.F - it.r + p.dil - 1) / p.dil;
+    return it;
+}
+
+// unit sequence of an epilogue thread: item -> its output rows, one accumulator each
+struct CombUnitIter {
+    const CombArgs& p; int pofs, step;
+    int item, k = 0, ab = 0; uint32_t aph = 0;
+    CombItem ci;
+    __device__ CombUnitIter(const CombArgs& p_, int item0, int step_, int pofs_) : p(p_), pofs(pofs_), step(step_), item(item0 - step_) { advance_item(); }
+    __device__ __forceinline__ void advance_item() {      // next item with at least one row (dil > F leaves empty combs)
+        do { item += step; if (item < p.n_items) ci = comb_item(p, item); } while (item < p.n_items && ci.K <= 0);
+    }
+    __device__ __forceinline__ bool next(EpiUnit& d) {
+        if (item >= p.n_items) return false;
+        const int f = ci.r + k * p.dil;
+        d.b = ci.b; d.nt = 0; d.ok = true;
+        d.pix = (long long)f * p.T + ci.t0 + pofs;
+        d.tcol = (uint32_t)(ab * CB_C); d.ab = ab; d.aph = aph; d.first = true; d.last = true;
+        if (++ab == CB_NACC) { ab = 0; aph ^= 1; }
+        if (++k == ci.K) { k = 0; advance_item(); }
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(CB_THREADS, 1) conv_comb_kernel(const __grid_constant__ CombArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* ring = smem;
+    uint8_t* wsm = smem + (size_t)CB_RING * CB_SLOT;
+    uint8_t* bar_base = wsm + CB_W_BYTES;
+    uint64_t* row_ready = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* slot_free = row_ready + CB_RING;
+    uint64_t* tmem_full = slot_free + CB_RING;
+    uint64_t* tmem_empty = tmem_full + CB_NACC;
+    uint64_t* w_full = tmem_empty + CB_NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+    float* gsm_base = reinterpret_cast<float*>(bar_base + CB_BAR_BYTES);
+    double* sacc_base = reinterpret_cast<double*>(bar_base + CB_BAR_BYTES + CB_GATE_BYTES);
+    const int item0 = blockIdx.x, istep = gridDim.x;
+
+    if (warp == CB_WARP_MMA) {
+        if (lane == 0) {
+            for (int s = 0; s < CB_RING; ++s) { mbar_init(row_ready + s, CB_TR_WARPS + 1); mbar_init(slot_free + s, 1); }
+            for (int s = 0; s < CB_NACC; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, CB_EPI_WARPS); }
+            mbar_init(w_full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // per-channel operand scale of clip b, the arithmetic of gn_act_tc2_kernel: gamma * (1 + affine) / (unbiased std + eps)
+    auto channel_scale = [&](int b, int c) {
+        const double s1 = p.stats_in[((long long)b * 8 + (c >> 3)) * 2 + 0], s2 = p.stats_in[((long long)b * 8 + (c >> 3)) * 2 + 1];
+        double var = (s2 - s1 * s1 / p.n_per_group) / (p.n_per_group - 1.0);
+        var = var > 0.0 ? var : 0.0;
+        const float inv = 1.f / ((float)sqrt(var) + 1e-7f);
+        const float mod = p.affine ? (1.f + p.affine[b * p.affine_bstride + c]) : 1.f;
+        return p.gamma[c] * mod * inv;
+    };
+    if (warp == CB_WARP_W) {
+        // ===================== weights (resident for the whole launch), then the two halo pixels of every row =====================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, (uint32_t)CB_W_BYTES);
+            for (int k = 0; k < 15; ++k) bulk_g2s(wsm + k * (CB_C * 128), p.w + (size_t)k * CB_C * 64, CB_C * 128, w_full);
+        }
+        __syncwarp();
+        // lanes 0-7: window position 0 (pixel t0 - 1), lanes 8-15: position 129 (t0 + 128); lane & 7 = the 8-channel operand chunk.
+        // One row of loads ahead of the arithmetic; zero outside the row.
+        const int side = (lane >> 3) & 1, chunk = lane & 7;
+        const bool act = lane < 16;
+        const long long sc = p.x.sc;
+        const uint32_t ring_u = smem_u32(ring);
+        int n = 0, b_cur = -1;
+        float cu[8], chh[8];
+        for (int item = item0; item < p.n_items; item += istep) {
+            const CombItem ci = comb_item(p, item);
+            if (ci.b != b_cur) {
+                b_cur = ci.b;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float sj = channel_scale(ci.b, 8 * chunk + j);
+                    cu[j] = fabsf(sj) * 0.84932180028801904272f; chh[j] = 8.f * sj;
+                }
+            }
+            const int th = side ? ci.t0 + 128 : ci.t0 - 1;
+            const bool ld = act && th >= 0 && th < p.T;
+            const float* xh = p.x.p + (long long)ci.b * p.x.sb + (long long)(8 * chunk) * sc + (ld ? th : 0);
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (ld && ci.K > 0) ? __ldg(xh + (long long)ci.r * p.T + (long long)j * sc) : 0.f;
+            for (int k = 0; k < ci.K; ++k, ++n) {
+                float cv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cv[j] = v[j];
+                if (k + 1 < ci.K) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = ld ? __ldg(xh + (long long)(ci.r + (k + 1) * p.dil) * p.T + (long long)j * sc) : 0.f;
+                }
+                uint32_t hh[4];
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {
+                    const float2 rh = gelu16_tc2_folded2(make_float2(cv[2 * pr], cv[2 * pr + 1]), make_float2(cu[2 * pr], cu[2 * pr + 1]), make_float2(chh[2 * pr], chh[2 * pr + 1]));
+                    hh[pr] = pack_half2_sat(rh.x, rh.y);
+                }
+                const int slot = n % CB_RING;
+                if (n >= CB_RING) mbar_wait(slot_free + slot, (uint32_t)((n / CB_RING) - 1) & 1u);
+                if (act) {
+                    const uint32_t row = side ? 129u : 0u;
+                    const uint32_t addr = ring_u + (uint32_t)slot * CB_SLOT + row * 128u + (((uint32_t)chunk ^ (row & 7u)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hh[0]), "r"(hh[1]), "r"(hh[2]), "r"(hh[3]) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(row_ready + slot);
+            }
+        }
+    } else if (warp >= CB_EPI_WARPS && warp < CB_EPI_WARPS + CB_TR_WARPS) {
+        // ===================== transform: x row -> 16 * GELU(x * scale) fp16, K-major SWIZZLE_128B window =====================
+        const int w = warp - CB_EPI_WARPS;             // channels 8w .. 8w+7 = operand chunk w
+        int n = 0;                                     // global row sequence number of this CTA
+        long long t_wait = 0, t_all = clock64();
+        int b_cur = -1;
+        // this warp's scale constants live in shared memory (the unused half of epilogue warp w's gate table), one LDS.128 per
+        // channel pair: [pair][cu0, cu1, ch0, ch1] -- 16 registers the 96-register budget of an 18-warp CTA does not have
+        float* sct = gsm_base + w * 128 + 64;
+        const long long sc = p.x.sc;
+        const uint32_t ring_u = smem_u32(ring);
+        for (int item = item0; item < p.n_items; item += istep) {
+            const CombItem ci = comb_item(p, item);
+            if (ci.b != b_cur) {
+                b_cur = ci.b;
+                __syncwarp();
+                if (lane < 8) {
+                    const float sj = channel_scale(ci.b, 8 * w + lane);
+                    sct[(lane >> 1) * 4 + (lane & 1)] = fabsf(sj) * 0.84932180028801904272f;
+                    sct[(lane >> 1) * 4 + 2 + (lane & 1)] = 8.f * sj;
+                }
+                __syncwarp();
+            }
+            const float* xb = p.x.p + (long long)ci.b * p.x.sb + (long long)(8 * w) * sc + ci.t0 + lane;
+            // The raw values of a row stay in registers one whole row ahead of the arithmetic: as soon as a channel pair of row k
+            // has been consumed its registers receive the same pair of row k + 1 (L2 latency is ~800 cycles, a row of GELUs ~1500),
+            // and the row after that is pulled into L2 meanwhile.
+            float v[8][4];
+            if (ci.K > 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[j][i] = __ldg(xb + (long long)ci.r * p.T + (long long)j * sc + i * 32);
+            }
+            for (int k = 0; k < ci.K; ++k, ++n) {
+                const float* xr = xb + (long long)(ci.r + k * p.dil) * p.T;
+                if (k + 2 < ci.K) {     // lane -> (channel lane / 4, 128-byte line lane % 4) of the row after the next
+                    const float* nx = xr - lane + 2ll * p.dil * p.T + (long long)(lane >> 2) * sc + (lane & 3) * 32;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                }
+                const float* xn = xr + (long long)p.dil * p.T;
+                const bool more = k + 1 < ci.K;
+                uint32_t hp[4][4];
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(sct + pr * 4);
+                    const float2 cu2 = make_float2(s4.x, s4.y), ch2 = make_float2(s4.z, s4.w);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 r2 = gelu16_tc2_folded2(make_float2(v[2 * pr][i], v[2 * pr + 1][i]), cu2, ch2);
+                        hp[i][pr] = pack_half2_sat(r2.x, r2.y);
+                    }
+                    if (more) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) v[2 * pr + c][i] = __ldg(xn + (long long)(2 * pr + c) * sc + i * 32);
+                    }
+                }
+                const int slot = n % CB_RING;
+                if (n >= CB_RING) { const long long t0 = clock64(); mbar_wait(slot_free + slot, (uint32_t)((n / CB_RING) - 1) & 1u); t_wait += clock64() - t0; }
+                const uint32_t sbase = ring_u + (uint32_t)slot * CB_SLOT;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t row = 1u + (uint32_t)(i * 32 + lane);      // window position of pixel i * 32 + lane
+                    const uint32_t addr = sbase + row * 128u + (((uint32_t)w ^ (row & 7u)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hp[i][0]), "r"(hp[i][1]), "r"(hp[i][2]), "r"(hp[i][3]) : "memory");
+                }
+                // generic-proxy writes -> visible to the tensor core (async proxy), then one arrival per warp
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(row_ready + slot);
+            }
+        }
+        if (p.dbg && blockIdx.x == 0 && w == 0 && lane == 0) printf("comb transform: %d rows, total %lld cycles, waiting for a slot %lld\n", n, clock64() - t_all, t_wait);
+    } else if (warp == CB_WARP_MMA) {
+        // ===================== MMA issuer =====================
+        if (elect_one_sync()) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(CB_C >> 3) << 17) | ((128u >> 4) << 24);   // F16 x F16 -> F32, K-major A/B, M = 128, N = 64
+            const uint32_t adesc = desc_lo_sw128(smem_u32(ring)), bdesc = desc_lo_sw128(smem_u32(wsm));
+            const uint32_t slot_d = CB_SLOT >> 4, tap_d = (CB_C * 128) >> 4;
+            mbar_wait(w_full, 0);
+            int n0 = 0;                  // sequence number of row 0 of the current item
+            int ready = 0;               // rows [0, ready) of this CTA are known to be transformed
+            int ab = 0; uint32_t aph = 0;
+            long long t_te = 0, t_rr = 0, t_all = clock64();
+            for (int item = item0; item < p.n_items; item += istep) {
+                const CombItem ci = comb_item(p, item);
+                for (int k = 0; k < ci.K; ++k) {
+                    { const long long t0 = clock64(); mbar_wait(tmem_empty + ab, aph ^ 1); t_te += clock64() - t0; }
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(ab * CB_C);
+                    uint32_t acc = 0u;
+                    for (int kf = 0; kf < 5; ++kf) {
+                        const int j = k + kf - 2;                 // comb row of this tap
+                        if (j < 0 || j >= ci.K) continue;         // outside the plane: zero padding
+                        const int n = n0 + j, slot = n % CB_RING;
+                        if (n >= ready) { const long long t0 = clock64(); mbar_wait(row_ready + slot, (uint32_t)(n / CB_RING) & 1u); t_rr += clock64() - t0; ready = n + 1; tc_fence_after(); }
+                        const uint32_t a = adesc + (uint32_t)slot * slot_d, b = bdesc + (uint32_t)(kf * 3) * tap_d;
+                        tc_mma_k<1, 4>(d, a, b, idesc, acc);
+                        tc_mma_k<1, 4>(d, a + 8u, b + tap_d, idesc, 1u);
+                        tc_mma_k<1, 4>(d, a + 16u, b + 2u * tap_d, idesc, 1u);
+                        acc = 1u;
+                        // last reader of row j: its kf = 0 use (output row j + 2), or this output row if it is the last of the comb
+                        if (kf == 0 || k == ci.K - 1) tc_commit(slot_free + slot);
+                    }
+                    tc_commit(tmem_full + ab);
+                    if (++ab == CB_NACC) { ab = 0; aph ^= 1; }
+                }
+                // rows K-2, K-1 are read last by output row K-1 (released there); a comb shorter than 3 rows releases everything there too
+                n0 += ci.K;
+            }
+            if (p.dbg && blockIdx.x == 0) printf("comb mma: %d rows, total %lld cycles, waiting for an accumulator %lld, for a row %lld\n", n0, clock64() - t_all, t_te, t_rr);
+        }
+        __syncwarp();
+    } else if (warp < CB_EPI_WARPS) {
+        EpiArgs ea{p.out, p.x, p.gate, p.gate_bstride, p.alpha, p.stats_out, CB_C, 1};
+        CombUnitIter it(p, item0, istep, (warp & 3) * 32 + lane);
+        epilogue_fast<false, 16, 2, 8>(ea, it, warp, lane, tmem_base, gsm_base, sacc_base, tmem_full, tmem_empty);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == CB_WARP_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+bool conv_comb_supported(int C, int F, int T, int dil) { return C == CB_C && T % 128 == 0 && dil >= 1 && F >= 1; }
+
+// out = alpha * (x + gate * conv5x3_dil(GELU(GroupNorm(x) * (1 + affine)))), statistics of out -> stats_out (may be null)
+void launch_conv_comb(const TV& x, const double* stats_in, long long n_per_group, const float* gamma, const float* affine, long long affine_bstride,
+                      const __half* wp, int dil, const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s) {
+    if (!conv_comb_supported(x.C, x.F, x.T, dil) || out.C != x.C) throw CudaError(cudaErrorInvalidValue, "conv_comb: unsupported shape", __FILE__, __LINE__);
+    if (ep.R.p != x.p || ep.R2.p) throw CudaError(cudaErrorInvalidValue, "conv_comb: the residual must be the layer input", __FILE__, __LINE__);
+    if (out.p == x.p) throw CudaError(cudaErrorInvalidValue, "conv_comb: in-place update is not possible (t-tile halos)", __FILE__, __LINE__);
+    CombArgs p{};
+    p.x = x; p.out = out; p.stats_in = stats_in; p.n_per_group = (double)n_per_group; p.gamma = gamma; p.affine = affine; p.affine_bstride = affine_bstride;
+    p.gate = ep.gate; p.gate_bstride = ep.gate_bstride; p.alpha = ep.alpha; p.stats_out = ep.stats; p.w = wp;
+    p.B = x.B; p.F = x.F; p.T = x.T; p.dil = dil; p.tiles_t = x.T / 128;
+    p.n_items = x.B * dil * p.tiles_t;
+    static const int dbg = getenv("AID_COMB_DEBUG") ? atoi(getenv("AID_COMB_DEBUG")) : 0;
+    p.dbg = dbg;
+    static SmemConfig configured;
+    ensure_dyn_smem(conv_comb_kernel, CB_SMEM, configured);
+    conv_comb_kernel<<<std::min(p.n_items, num_sms), CB_THREADS, CB_SMEM, s>>>(p);
+    AID_COUNT_LAUNCH(1);
+}
+
+}  // namespace aid

@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "tc_epilogue.cuh"
 
 namespace aid {
 
@@ -40,7 +41,6 @@ static constexpr int T2_BAR_BYTES = 512;        // mbarriers + TMEM slot at the 
 static constexpr int T2_STAT_GATE_BYTES = 4096;  // the epilogue warps' private gate tables (EW x 256 / NCW floats)
 static constexpr int T2_STAT_SMEM = 16384;       // their double statistics accumulators
 static constexpr int T2_ASLOT_UNIT = 18 * 1024; // one unit's window: (130 + 7) rows x 128 B, rounded to 1 KB
-static constexpr float T2_A_SCALE = 16.f, T2_W_SCALE = 1024.f, T2_OUT_SCALE = 1.f / (16.f * 1024.f);
 
 struct Tc2Args {
     const __half* a; const __half* w;
@@ -158,169 +158,34 @@ __device__ __forceinline__ TileUnits tile_units(const Tc2Args& p, int tp, int r)
     return t;
 }
 
-// ---- fast epilogue ------------------------------------------------------------------------------------------------------------
-// The generic epilogue below handles every layout and group width with run-time bookkeeping; its inner loop compiled to ~20
-// instructions per output element with indirect branches in the statistics (ncu: 148 M warp instructions for 134 M outputs of a
-// 64-channel layer, issue slots 38 % busy with two epilogue warps per scheduler) and bounded the layers with <= 128 couts.
-// This version covers the shapes of the paper networks (NCHW out / R, 8 epilogue warps, a warp's columns = NB batches of BW
-// columns whose boundaries coincide with the statistics groups of GCN columns) with everything static: the batch loop is
-// unrolled, residuals ping-pong between two register arrays (no copies), group sums are fixed trees, stores and loads use
-// running pointers.  Same arithmetic contract as the generic one: per-unit fp32 partial sums -> private double accumulators in
-// shared memory -> one double atomic per (clip, group, warp).
-template <bool CG2, int BW, int NB, int GCN>
-__device__ __forceinline__ void epilogue_fast(const Tc2Args& p, const int e, const int lane, const uint32_t crank, const int tile0, const int tstep,
-                                              const uint32_t tmem_base, uint8_t* bar_base, uint64_t* tmem_full, uint64_t* tmem_empty) {
-    constexpr int NCOLS = BW * NB;                  // columns of this warp (half of the n-tile)
-    constexpr int NG = NCOLS / GCN;                 // statistics groups they span
-    constexpr int GPB = BW / GCN;                   // groups per batch
-    static_assert(NB % 2 == 0 && BW % 8 == 0 && BW <= 32 && BW % GCN == 0 && NG >= 1 && NG <= 4, "epilogue_fast shape");
-    const int q = e & 3, cw = e >> 2, cbeg = cw * NCOLS;
-    const float al = p.alpha, gs = T2_OUT_SCALE * p.alpha;
-    const long long osc = p.out.sc, rsc = p.R.sc;
-    const bool has_r = p.R.p != nullptr, has_gate = p.gate != nullptr, do_stats = p.stats != nullptr;
-    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
-    float* gsm = reinterpret_cast<float*>(bar_base + T2_BAR_BYTES) + e * 128;
-    const uint32_t gsm_addr = smem_u32(gsm);
-    const int pofs = q * 32 + lane;
-    double* sacc = reinterpret_cast<double*>(bar_base + T2_BAR_BYTES + T2_STAT_GATE_BYTES) + (e * 32 + lane);   // [k][256 threads]
-    float S[NG], Q[NG];
-#pragma unroll
-    for (int k = 0; k < NG; ++k) { S[k] = 0.f; Q[k] = 0.f; }
-    if (do_stats) {
-#pragma unroll
-        for (int k = 0; k < 2 * NG; ++k) sacc[k * 256] = 0.0;
-    }
-    int b_cur = -1, nt_cur = 0, gate_key = -2;
-    auto flush_stats = [&]() {
-        if (do_stats && b_cur >= 0) {
-            double v[2 * NG];
-#pragma unroll
-            for (int k = 0; k < 2 * NG; ++k) {
-                v[k] = sacc[k * 256]; sacc[k * 256] = 0.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-            }
-            if (lane == 0) {
-                const int g0 = (nt_cur * p.Ntile + cbeg) / GCN;
-#pragma unroll
-                for (int k = 0; k < 2 * NG; ++k) atomicAdd(p.stats + (long long)b_cur * 16 + (g0 + (k >> 1)) * 2 + (k & 1), v[k]);
-            }
-        }
-    };
-    // unit iterator and the descriptor of the next unit (its first batch of residuals is prefetched during our last batch)
-    int it_tile = tile0, it_ui = 0, it_ab = 0; uint32_t it_aph = 0;
-    float* n_po = nullptr; const float* n_pr = nullptr; uint32_t n_tcol = 0, n_aph = 0; int n_b = 0, n_nt = 0, n_ab = 0;
-    bool n_valid = false, n_ok = false, n_first = false, n_last = false;
-    auto advance = [&]() {
-        n_valid = it_tile < p.n_tiles;
-        if (!n_valid) return;
-        uint32_t pair = (uint32_t)it_tile; n_nt = 0;
-        if (p.n_ntiles > 1) { const uint2 dm = tile_decode(p, it_tile); n_nt = (int)dm.x; pair = dm.y; }
-        const bool has1 = unit_index(p, (int)pair, (int)crank, 1) < p.n_units;
-        Unit2 u = unit2_info(p, unit_index(p, (int)pair, (int)crank, it_ui));
+// unit sequence of one epilogue thread of conv_tc2 (tile -> its one or two units), for epilogue_fast
+struct Tc2UnitIter {
+    const Tc2Args& p; int crank, tstep, pofs;
+    int it_tile, it_ui = 0, it_ab = 0; uint32_t it_aph = 0;
+    __device__ Tc2UnitIter(const Tc2Args& p_, int crank_, int tile0, int tstep_, int pofs_) : p(p_), crank(crank_), tstep(tstep_), pofs(pofs_), it_tile(tile0) {}
+    __device__ __forceinline__ bool next(EpiUnit& d) {
+        if (it_tile >= p.n_tiles) return false;
+        uint32_t pair = (uint32_t)it_tile; d.nt = 0;
+        if (p.n_ntiles > 1) { const uint2 dm = tile_decode(p, it_tile); d.nt = (int)dm.x; pair = dm.y; }
+        const bool has1 = unit_index(p, (int)pair, crank, 1) < p.n_units;
+        Unit2 u = unit2_info(p, unit_index(p, (int)pair, crank, it_ui));
         if (!u.exists) u.b = 0;                   // cta_group::2, last quad: this CTA only keeps the handshakes going
         const int o = u.o0 + pofs;                // output position in the padded stream of the real rows
         const int row = (int)fast_divmod((uint32_t)o, (uint32_t)p.Tp, p.mg_Tp).x, tp = o - row * p.Tp;
-        n_ok = u.exists && tp >= 1 && tp <= p.T && row <= u.f_hi;
+        d.ok = u.exists && tp >= 1 && tp <= p.T && row <= u.f_hi;
         // lanes that own no real pixel read (never write) pixel 0 of their clip: the loads need no predicate
-        const long long pix = n_ok ? (long long)row * p.T + (tp - 1) : 0;
-        const long long co0 = n_nt * p.Ntile + cbeg;
-        n_po = p.out.p + (long long)u.b * p.out.sb + co0 * osc + pix;
-        n_pr = p.R.p + (long long)u.b * p.R.sb + co0 * rsc + pix;
-        n_b = u.b; n_ab = it_ab; n_aph = it_aph;
-        n_tcol = tq + (uint32_t)(it_ab * 2 * p.ncol_stride + it_ui * p.ncol_stride);
-        n_first = it_ui == 0;
-        n_last = it_ui == 1 || !has1;
-        if (n_last) {
+        d.pix = d.ok ? (long long)row * p.T + (tp - 1) : 0;
+        d.b = u.b; d.ab = it_ab; d.aph = it_aph;
+        d.tcol = (uint32_t)(it_ab * 2 * p.ncol_stride + it_ui * p.ncol_stride);
+        d.first = it_ui == 0;
+        d.last = it_ui == 1 || !has1;
+        if (d.last) {
             it_ui = 0; it_tile += tstep;
             if (++it_ab == p.acc_bufs) { it_ab = 0; it_aph ^= 1; }
         } else it_ui = 1;
-    };
-    float ra[BW], rb[BW];
-    auto load_batch = [&](float (&dst)[BW], const float* src) {
-        if (has_r) {
-#pragma unroll
-            for (int j = 0; j < BW; ++j) { dst[j] = *src; src += rsc; }     // may alias out: plain loads
-        } else {
-#pragma unroll
-            for (int j = 0; j < BW; ++j) dst[j] = 0.f;
-        }
-    };
-    advance();
-    if (n_valid) load_batch(ra, n_pr);
-    while (n_valid) {
-        float* c_po = n_po; const float* c_pr = n_pr;
-        const uint32_t c_tcol = n_tcol, c_aph = n_aph; const int c_b = n_b, c_nt = n_nt, c_ab = n_ab;
-        const bool c_ok = n_ok, c_first = n_first, c_last = n_last;
-        advance();
-        if (c_first) { mbar_wait(tmem_full + c_ab, c_aph); tc_fence_after(); }
-        if (c_b != b_cur || c_nt != nt_cur) { flush_stats(); b_cur = c_b; nt_cur = c_nt; }
-        const int gkey = p.gate_bstride ? c_b * p.n_ntiles + c_nt : c_nt;
-        if (gkey != gate_key) {
-            gate_key = gkey;
-            __syncwarp();
-            for (int k = lane; k < NCOLS; k += 32)
-                gsm[k] = has_gate ? __ldg(p.gate + (long long)c_b * p.gate_bstride + c_nt * p.Ntile + cbeg + k) * gs : gs;
-            __syncwarp();
-        }
-        const float m = c_ok ? 1.f : 0.f;
-#pragma unroll
-        for (int bi = 0; bi < NB; ++bi) {
-            float (&cur)[BW] = (bi & 1) ? rb : ra;
-            float (&nxt)[BW] = (bi & 1) ? ra : rb;
-            if (bi + 1 < NB) load_batch(nxt, c_pr + (long long)(bi + 1) * BW * rsc);
-            else if (n_valid) load_batch(nxt, n_pr);
-            uint32_t acc[BW];
-            if constexpr (BW == 32) tmem_ld32_nowait(c_tcol + bi * BW, acc);
-            else if constexpr (BW == 24) { tmem_ld16_nowait(c_tcol + bi * BW, acc); tmem_ld8p_nowait(c_tcol + bi * BW + 16, acc + 16); }
-            else if constexpr (BW == 16) tmem_ld16_nowait(c_tcol + bi * BW, acc);
-            else tmem_ld8p_nowait(c_tcol + bi * BW, acc);
-            float g[BW];
-#pragma unroll
-            for (int j = 0; j < BW; j += 4)
-                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g[j]), "=f"(g[j + 1]), "=f"(g[j + 2]), "=f"(g[j + 3]) : "r"(gsm_addr + (uint32_t)(bi * BW + j) * 4u));
-            tmem_wait_ld();
-            // packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 of sm_100): half the math instructions, the same IEEE results per lane
-            float2 v2[BW / 2];
-#pragma unroll
-            for (int j = 0; j < BW / 2; ++j)
-                v2[j] = __ffma2_rn(make_float2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])), make_float2(g[2 * j], g[2 * j + 1]),
-                                   __fmul2_rn(make_float2(cur[2 * j], cur[2 * j + 1]), make_float2(al, al)));
-            if (c_ok) {
-                float* po = c_po + (long long)(bi * BW) * osc;
-#pragma unroll
-                for (int j = 0; j < BW / 2; ++j) { *po = v2[j].x; po += osc; *po = v2[j].y; po += osc; }
-            }
-            if (do_stats) {
-#pragma unroll
-                for (int gg = 0; gg < GPB; ++gg) {
-                    // fixed order over the GCN columns of the group: two interleaved packed chains, then the four lanes
-                    constexpr int H = GCN / 2;       // float2 values of the group (even)
-                    const float2* w = v2 + gg * H;
-                    float2 sa = w[0], sb = w[1], qa = __fmul2_rn(w[0], w[0]), qb = __fmul2_rn(w[1], w[1]);
-#pragma unroll
-                    for (int k = 2; k < H; k += 2) {
-                        sa = __fadd2_rn(sa, w[k]); sb = __fadd2_rn(sb, w[k + 1]);
-                        qa = __ffma2_rn(w[k], w[k], qa); qb = __ffma2_rn(w[k + 1], w[k + 1], qb);
-                    }
-                    const float2 s2 = __fadd2_rn(sa, sb), q2 = __fadd2_rn(qa, qb);
-                    S[bi * GPB + gg] = fmaf(s2.x + s2.y, m, S[bi * GPB + gg]);
-                    Q[bi * GPB + gg] = fmaf(q2.x + q2.y, m, Q[bi * GPB + gg]);
-                }
-            }
-        }
-        if (do_stats) {
-#pragma unroll
-            for (int k = 0; k < NG; ++k) { sacc[(2 * k) * 256] += (double)S[k]; sacc[(2 * k + 1) * 256] += (double)Q[k]; S[k] = 0.f; Q[k] = 0.f; }
-        }
-        if (c_last) {      // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory pipe
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if constexpr (CG2) mbar_arrive_cluster(tmem_empty + c_ab, 0u); else mbar_arrive(tmem_empty + c_ab); }
-        }
+        return true;
     }
-    flush_stats();
-}
+};
 
 // CG2 = false: cta_group::1, plain launch.  CG2 = true: cta_group::2, launched in clusters of two CTAs (a kernel that contains
 // cta_group::2 instructions cannot be launched without a cluster, hence two instantiations).
@@ -616,14 +481,19 @@ __device__ __forceinline__ void conv_tc2_body(const Tc2Args& p) {
         const int e = warp - T2_EPI_WARP0;
         bool fast = false;
         if constexpr (EW == 8) {
-            fast = true;
-            switch (p.epi_class) {      // host: launch_conv_tc2
-                case 1: epilogue_fast<CG2, 16, 2, 8>(p, e, lane, crank, tile0, tstep, tmem_base, bar_base, tmem_full, tmem_empty); break;
-                case 2: epilogue_fast<CG2, 24, 2, 12>(p, e, lane, crank, tile0, tstep, tmem_base, bar_base, tmem_full, tmem_empty); break;
-                case 3: epilogue_fast<CG2, 32, 2, 16>(p, e, lane, crank, tile0, tstep, tmem_base, bar_base, tmem_full, tmem_empty); break;
-                case 4: epilogue_fast<CG2, 32, 2, 32>(p, e, lane, crank, tile0, tstep, tmem_base, bar_base, tmem_full, tmem_empty); break;
-                case 5: epilogue_fast<CG2, 32, 4, 32>(p, e, lane, crank, tile0, tstep, tmem_base, bar_base, tmem_full, tmem_empty); break;
-                default: fast = false;
+            if (p.epi_class) {      // host: launch_conv_tc2
+                fast = true;
+                EpiArgs ea{p.out, p.R, p.gate, p.gate_bstride, p.alpha, p.stats, p.Ntile, p.n_ntiles};
+                Tc2UnitIter it(p, (int)crank, tile0, tstep, (warp & 3) * 32 + lane);
+                float* gsm_base = reinterpret_cast<float*>(bar_base + T2_BAR_BYTES);
+                double* sacc_base = reinterpret_cast<double*>(bar_base + T2_BAR_BYTES + T2_STAT_GATE_BYTES);
+                switch (p.epi_class) {
+                    case 1: epilogue_fast<CG2, 16, 2, 8>(ea, it, e, lane, tmem_base, gsm_base, sacc_base, tmem_full, tmem_empty); break;
+                    case 2: epilogue_fast<CG2, 24, 2, 12>(ea, it, e, lane, tmem_base, gsm_base, sacc_base, tmem_full, tmem_empty); break;
+                    case 3: epilogue_fast<CG2, 32, 2, 16>(ea, it, e, lane, tmem_base, gsm_base, sacc_base, tmem_full, tmem_empty); break;
+                    case 4: epilogue_fast<CG2, 32, 2, 32>(ea, it, e, lane, tmem_base, gsm_base, sacc_base, tmem_full, tmem_empty); break;
+                    default: epilogue_fast<CG2, 32, 4, 32>(ea, it, e, lane, tmem_base, gsm_base, sacc_base, tmem_full, tmem_empty); break;
+                }
             }
         }
         if (!fast) {
@@ -959,13 +829,6 @@ __device__ __forceinline__ float gelu16_tc2_folded(float x, float cu, float ch) 
     return fmaf(fabsf(h), erf_abs, h);
 }
 __device__ __forceinline__ bool ld_ok(int i, int n) { return i < n; }
-// two operand values (already x16) -> packed fp16x2, saturating to the finite range
-__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-
 // Normalise / modulate / GELU (unet.py:159-163, 479, 482) writing the channels-last fp16 operand:
 //   a[b][g][r][tp][chunk ^ ((r*Tp + tp) & 7)][8] = fp16(16 * act(x[b, 64g + 8 chunk + j, r - PF, tp - 1] * scale_c)),
 //   pad pixels (tp = 0, T+1), pad rows and channels past C = 0.  stats == nullptr: plain layout/precision conversion.
@@ -1059,8 +922,16 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
             uint4 hv = zero4;
             if (chok) {
                 float r[8];
+                if (gelu) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) r[j] = gelu ? gelu16_tc2_folded(v[j][i], cu[j], chh[j]) : v[j][i] * chh[j];
+                    for (int j = 0; j < 8; j += 2) {
+                        const float2 r2 = gelu16_tc2_folded2(make_float2(v[j][i], v[j + 1][i]), make_float2(cu[j], cu[j + 1]), make_float2(chh[j], chh[j + 1]));
+                        r[j] = r2.x; r[j + 1] = r2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = v[j][i] * chh[j];
+                }
                 if (COUNT) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) nsat += (!(fabsf(r[j]) <= 65504.f) && (ld_ok(st + i, n_src))) ? 1u : 0u;

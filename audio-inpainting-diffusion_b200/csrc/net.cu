@@ -491,6 +491,24 @@ static void conv_tc(Ctx& c, const __half* a_hi, const __half* a_lo, int PF, cons
     if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
+// conv_mode 2, 64-channel blocks: one fused kernel per dilated layer (conv_comb.cu); recorded like the other dilated convolutions
+static void conv_comb_layer(Ctx& c, const TV& x, const double* stats_in, long long n_grp, const float* gamma, const float* affine, long long abstride,
+                            const ConvW& w, int dil, const TV& out, const ConvEpilogue& ep) {
+    if (c.dry()) return;
+    Net& n = *c.n;
+    Net::ProfRec rec{};
+    if (n.prof) {
+        auto get = [&]() { cudaEvent_t e; if (n.prof_pool.empty()) { AID_CUDA_CHECK(cudaEventCreate(&e)); } else { e = n.prof_pool.back(); n.prof_pool.pop_back(); } return e; };
+        rec.e0 = get(); rec.e1 = get(); rec.kind = 0;
+        const double px = (double)out.B * out.F * out.T;
+        rec.flops = 2.0 * w.Cin * w.Cout * w.KF * w.KT * px;
+        rec.bytes = 4.0 * (px * (w.Cin + w.Cout + w.Cout) + (double)w.Cin * w.Cout * w.KF * w.KT);
+        AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
+    }
+    launch_conv_comb(x, stats_in, n_grp, gamma, affine, abstride, w.wtc, dil, out, ep, n.num_sms, c.s);
+    if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
+}
+
 // unet.py:452-493.  `accum` (decoder out blocks, unet.py:817): out = (accum + block(x)) / sqrt(2), may alias out.
 // `bt` (taped forward, input-gradient path): every intermediate the backward needs gets its own buffer and is recorded.
 static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = nullptr, BlkTape* bt = nullptr) {
@@ -594,6 +612,16 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
             const int dil = k.k1x1 ? 1 : (1 << i);
             const int pf = tc_pad_rows(T, k.H[i].KF, dil);
             __half* a_lo = parts == 2 ? a_hi + planar_halves(N, pf) : nullptr;
+            static const bool env_comb = !(getenv("AID_COMB") && atoi(getenv("AID_COMB")) == 0);
+            if (cmode == 2 && env_comb && !tp && !use_cl && !k.k1x1 && !sat && conv_comb_supported(N, F, T, dil)) {
+                // fused layer (conv_comb.cu): normalisation, modulation, GELU and the operand conversion happen inside the convolution;
+                // the t-tile halos forbid an in-place update, so the layers alternate between the block's two buffers
+                TV o = (cur.p == x.p) ? a : x;
+                o.stats = ep.stats;
+                conv_comb_layer(c, cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), k.H[i], dil, o, ep);
+                cur = o;
+                continue;
+            }
             if (cmode == 2) {
                 if (cur_is_cl) RUN(launch_gn_act_tc2_cl(xcl, B, N, F, T, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s));
                 else RUN(launch_gn_act_tc2(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s, sat));
@@ -1483,6 +1511,47 @@ int aid_debug_time_gn_tc2(const float* x_dev, int B, int C, int F, int T, int PF
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(st); cudaFree(gamma); cudaFree(aff); cudaFree(a);
         return AID_OK;
     } catch (const CudaError& e) { fprintf(stderr, "aid_debug_time_gn_tc2: CUDA error %s\n", cudaGetErrorString(e.code)); return AID_ERR_CUDA; }
+}
+
+/* debug / parity / tuning: one dilated residual layer of conv_mode 2, two-kernel path (fused = 0) or conv_comb_kernel (fused = 1) */
+int aid_debug_dilated_layer(const float* x_dev, const float* w_dev, int B, int C, int F, int T, int dil, const float* gamma_dev,
+                            const float* affine_dev, const float* gate_dev, float alpha, int fused, float* out_dev, double* stats_out_dev,
+                            float* ms_out) {
+    if (!x_dev || !w_dev || !gamma_dev || !out_dev || C % 8 != 0) return AID_ERR_INVALID;
+    try {
+        if (!conv_tc_supported(C, C, 5, 3) || (fused && !conv_comb_supported(C, F, T, dil))) throw std::invalid_argument("shape not supported");
+        TV x = make_tv(const_cast<float*>(x_dev), B, C, F, T), out = make_tv(out_dev, B, C, F, T);
+        int sms = 148, dev = 0;
+        AID_CUDA_CHECK(cudaGetDevice(&dev));
+        AID_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int pf = tc_pad_rows(T, 5, dil);
+        double* st = nullptr; __half *wtc = nullptr, *a = nullptr;
+        AID_CUDA_CHECK(cudaMalloc(&st, (size_t)B * 16 * sizeof(double)));
+        AID_CUDA_CHECK(cudaMemset(st, 0, (size_t)B * 16 * sizeof(double)));
+        AID_CUDA_CHECK(cudaMalloc(&wtc, tc2_weight_halves(C, C, 5, 3) * sizeof(__half)));
+        AID_CUDA_CHECK(cudaMalloc(&a, tc2_act_halves(B, C, F, T, pf) * sizeof(__half)));
+        launch_pack_weight_tc2(w_dev, wtc, C, C, 5, 3, nullptr);
+        launch_group_stats(x, st, nullptr);
+        const long long n_grp = (long long)(C / 8) * F * T;
+        ConvEpilogue ep; ep.gate = gate_dev; ep.gate_bstride = 0; ep.alpha = alpha; ep.R = x; ep.stats = stats_out_dev;
+        cudaEvent_t e0, e1; AID_CUDA_CHECK(cudaEventCreate(&e0)); AID_CUDA_CHECK(cudaEventCreate(&e1));
+        for (int rep = 0; rep < (ms_out ? 2 : 1); ++rep) {
+            if (stats_out_dev) AID_CUDA_CHECK(cudaMemsetAsync(stats_out_dev, 0, (size_t)B * 16 * sizeof(double), nullptr));
+            AID_CUDA_CHECK(cudaEventRecord(e0, nullptr));
+            if (fused) launch_conv_comb(x, st, n_grp, gamma_dev, affine_dev, 0, wtc, dil, out, ep, sms, nullptr);
+            else {
+                launch_gn_act_tc2(x, st, n_grp, gamma_dev, affine_dev, 0, true, pf, a, nullptr);
+                launch_conv_tc2(a, pf, wtc, B, C, F, T, 5, 3, dil, out, ep, sms, nullptr);
+            }
+            AID_CUDA_CHECK(cudaEventRecord(e1, nullptr));
+            AID_CUDA_CHECK(cudaGetLastError());
+            AID_CUDA_CHECK(cudaEventSynchronize(e1));
+        }
+        if (ms_out) AID_CUDA_CHECK(cudaEventElapsedTime(ms_out, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(st); cudaFree(wtc); cudaFree(a);
+        return AID_OK;
+    } catch (const CudaError& e) { fprintf(stderr, "aid_debug_dilated_layer: CUDA error %s at %s:%d\n", cudaGetErrorString(e.code), e.file, e.line); return AID_ERR_CUDA; }
+    catch (const std::exception& e) { fprintf(stderr, "aid_debug_dilated_layer: %s\n", e.what()); return AID_ERR_INVALID; }
 }
 
 /* debug / tuning: conv_tc2 pipeline profile (cycles per role, summed over CTAs; enabled by AID_TC_DEBUG bit 2048), read and cleared */

@@ -260,7 +260,8 @@ def _conv53(cuda, case):
     gate, R = seeded((Cout,), 3), seeded((B, Cout, Fd, T), 4)
     out = torch.full((B, Cout, Fd, T), float("nan"), device=cuda)
     stats = torch.zeros(B, 8, 2, dtype=torch.float64, device=cuda)
-    L.check(L.lib().aid_op_conv2d(L.ptr(a.to(cuda)), L.ptr(w.to(cuda)), B, Cin, Cout, Fd, T, 5, 3, dil, L.ptr(gate.to(cuda)), L.ptr(R.to(cuda)), None,
+    ad, wd, gd, Rd = a.to(cuda), w.to(cuda), gate.to(cuda), R.to(cuda)      # keep the device copies alive
+    L.check(L.lib().aid_op_conv2d(L.ptr(ad), L.ptr(wd), B, Cin, Cout, Fd, T, 5, 3, dil, L.ptr(gd), L.ptr(Rd), None,
                                   0.70710678, 0.0, L.ptr(out), L.ptr(stats), 3, None))
     torch.cuda.synchronize()
     return out, stats
