@@ -134,6 +134,9 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
 // fused dilated residual layer (conv_comb.cu): normalise + modulate + GELU + operand conversion inside the convolution kernel;
 // ep.R must be x itself, out must not overlap x
 bool conv_comb_supported(int C, int F, int T, int dil);
+// 96 channels: the fused kernel has its own weight packing (64-channel group + 32-channel group per tap); 64 channels: launch_pack_weight_tc2's
+size_t comb_weight_halves(int C);
+void launch_pack_weight_comb(const float* w, __half* wp, int C, cudaStream_t s);
 void launch_conv_comb(const TV& x, const double* stats_in, long long n_per_group, const float* gamma, const float* affine, long long affine_bstride,
                       const __half* wp, int dil, const TV& out, const ConvEpilogue& ep, int num_sms, cudaStream_t s);
 

@@ -59,10 +59,11 @@ __device__ __forceinline__ CombItem comb_item(const CombArgs& p, int item) {
 
 // unit sequence of an epilogue thread: item -> its output rows, one accumulator each
 struct CombUnitIter {
-    const CombArgs& p; int pofs, step;
+    const CombArgs& p; int pofs, step, acc_stride;
     int item, k = 0, ab = 0; uint32_t aph = 0;
     CombItem ci;
-    __device__ CombUnitIter(const CombArgs& p_, int item0, int step_, int pofs_) : p(p_), pofs(pofs_), step(step_), item(item0 - step_) { advance_item(); }
+    __device__ CombUnitIter(const CombArgs& p_, int item0, int step_, int pofs_, int acc_stride_)
+        : p(p_), pofs(pofs_), step(step_), acc_stride(acc_stride_), item(item0 - step_) { advance_item(); }
     __device__ __forceinline__ void advance_item() {      // next item with at least one row (dil > F leaves empty combs)
         do { item += step; if (item < p.n_items) ci = comb_item(p, item); } while (item < p.n_items && ci.K <= 0);
     }
@@ -71,7 +72,7 @@ struct CombUnitIter {
         const int f = ci.r + k * p.dil;
         d.b = ci.b; d.nt = 0; d.ok = true;
         d.pix = (long long)f * p.T + ci.t0 + pofs;
-        d.tcol = (uint32_t)(ab * CB_C); d.ab = ab; d.aph = aph; d.first = true; d.last = true;
+        d.tcol = (uint32_t)(ab * acc_stride); d.ab = ab; d.aph = aph; d.first = true; d.last = true;
         if (++ab == CB_NACC) { ab = 0; aph ^= 1; }
         if (++k == ci.K) { k = 0; advance_item(); }
         return true;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_comb_kernel(const __grid_c
         __syncwarp();
     } else if (warp < CB_EPI_WARPS) {
         EpiArgs ea{p.out, p.x, p.gate, p.gate_bstride, p.alpha, p.stats_out, CB_C, 1};
-        CombUnitIter it(p, item0, istep, (warp & 3) * 32 + lane);
+        CombUnitIter it(p, item0, istep, (warp & 3) * 32 + lane, CB_C);
         epilogue_fast<false, 16, 2, 8>(ea, it, warp, lane, tmem_base, gsm_base, sacc_base, tmem_full, tmem_empty);
     }
 
@@ -306,7 +307,292 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_comb_kernel(const __grid_c
     }
 }
 
-bool conv_comb_supported(int C, int F, int T, int dil) { return C == CB_C && T % 128 == 0 && dil >= 1 && F >= 1; }
+
+// ---- 96 channels -------------------------------------------------------------------------------------------------------------------
+// The same scheme with K = 96 as a 64-channel group (128-byte rows, SWIZZLE_128B) plus a 32-channel group (64-byte rows,
+// SWIZZLE_64B: the padded 128-channel layout of conv_tc2 would not leave room for the ring), and the weights (270 KB) streamed
+// through a four-slot ring, one slot per (kf, kt): [96 couts][64 cins] then [96 couts][32 cins].  MMA order per output row:
+// kf, kt, group (conv_tc2: kf, group, kt), so the result agrees with the two-kernel path to fp32 accumulation order, not bitwise.
+//   warps 0-7   epilogue (TMEM lane quadrant x column half, 4 batches of 12 columns = one statistics group each; 4 epilogue warps
+//               measured twice as slow: the epilogue is a latency-bound stream per warp)
+//   warps 8-13  transform, warp w = operand chunks w and w + 6 (two 8-channel chunks: 17 warps keep 96 registers per thread);
+//               the raw values of the 8 channel pairs rotate through four register sets, loads four pairs ahead of the arithmetic
+//   warp 14 halo pixels, 15 weight producer, 16 MMA issuer
+static constexpr int C9 = 96, C9_EPI = 8, C9_TR = 6, C9_WARP_HALO = 14, C9_WARP_W = 15, C9_WARP_MMA = 16, C9_THREADS = 17 * 32;
+static constexpr int C9_SLOT0 = 17408, C9_SLOT1 = 9216;      // group 0: 136 rows x 128 B; group 1: 144 rows x 64 B (130 used), 1 KB aligned
+static constexpr int C9_WTAP0 = C9 * 128, C9_WTAP1 = C9 * 64, C9_WSLOT = C9_WTAP0 + C9_WTAP1;   // 12288 + 6144 = 18432 bytes per (kf, kt)
+static constexpr int C9_NW = 4, C9_NACC = 4, C9_ACC_STRIDE = 128;
+static constexpr size_t C9_SMEM = 1024 + (size_t)CB_RING * (C9_SLOT0 + C9_SLOT1) + (size_t)C9_NW * C9_WSLOT + CB_BAR_BYTES + CB_GATE_BYTES + CB_STAT_BYTES;
+
+size_t comb_weight_halves(int C) { return C == C9 ? (size_t)15 * C9_WSLOT / 2 : (size_t)15 * CB_C * 64; }
+
+// w[co][ci][5][3] fp32 -> per (kf, kt): [96][64] halves (x 2^10), 16-byte chunks swizzled by (co & 7), then [96][32] halves, chunks by ((co >> 1) & 3)
+__global__ void pack_weight_comb96_kernel(const float* __restrict__ w, __half* __restrict__ wp) {
+    const int total = 15 * C9 * C9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % C9, co = (i / C9) % C9, tap = i / (C9 * C9);     // tap = kf * 3 + kt
+        float v = w[((long long)co * C9 + ci) * 15 + tap] * T2_W_SCALE;
+        v = fminf(fmaxf(v, -60000.f), 60000.f);
+        size_t o;
+        if (ci < 64) o = (size_t)tap * (C9_WSLOT / 2) + (size_t)co * 64 + ((((ci >> 3) ^ (co & 7)) << 3) | (ci & 7));
+        else { const int c = ci - 64; o = (size_t)tap * (C9_WSLOT / 2) + C9_WTAP0 / 2 + (size_t)co * 32 + ((((c >> 3) ^ ((co >> 1) & 3)) << 3) | (c & 7)); }
+        wp[o] = __float2half_rn(v);
+    }
+}
+void launch_pack_weight_comb(const float* w, __half* wp, int C, cudaStream_t s) {
+    if (C != C9) throw CudaError(cudaErrorInvalidValue, "pack_weight_comb: 96 channels only (64 uses the conv_tc2 packing)", __FILE__, __LINE__);
+    pack_weight_comb96_kernel<<<270, 512, 0, s>>>(w, wp);
+    AID_COUNT_LAUNCH(1);
+}
+
+__global__ void __launch_bounds__(C9_THREADS, 1) conv_comb96_kernel(const __grid_constant__ CombArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* ring0 = smem;                                        // [5] group-0 windows
+    uint8_t* ring1 = ring0 + (size_t)CB_RING * C9_SLOT0;          // [5] group-1 windows
+    uint8_t* wring = ring1 + (size_t)CB_RING * C9_SLOT1;          // [4] weight slots
+    uint8_t* bar_base = wring + (size_t)C9_NW * C9_WSLOT;
+    uint64_t* row_ready = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* slot_free = row_ready + CB_RING;
+    uint64_t* tmem_full = slot_free + CB_RING;
+    uint64_t* tmem_empty = tmem_full + C9_NACC;
+    uint64_t* w_full = tmem_empty + C9_NACC;
+    uint64_t* w_empty = w_full + C9_NW;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + C9_NW);
+    float* gsm_base = reinterpret_cast<float*>(bar_base + CB_BAR_BYTES);
+    double* sacc_base = reinterpret_cast<double*>(bar_base + CB_BAR_BYTES + CB_GATE_BYTES);
+    const int item0 = blockIdx.x, istep = gridDim.x;
+
+    if (warp == C9_WARP_MMA) {
+        if (lane == 0) {
+            for (int s = 0; s < CB_RING; ++s) { mbar_init(row_ready + s, C9_TR + 1); mbar_init(slot_free + s, 1); }
+            for (int s = 0; s < C9_NACC; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, C9_EPI); }
+            for (int s = 0; s < C9_NW; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // per-channel operand scale of clip b (gn_act_tc2_kernel's arithmetic); 12 channels per statistics group
+    auto channel_scale = [&](int b, int c) {
+        const int g = c / (C9 / 8);
+        const double s1 = p.stats_in[((long long)b * 8 + g) * 2 + 0], s2 = p.stats_in[((long long)b * 8 + g) * 2 + 1];
+        double var = (s2 - s1 * s1 / p.n_per_group) / (p.n_per_group - 1.0);
+        var = var > 0.0 ? var : 0.0;
+        const float inv = 1.f / ((float)sqrt(var) + 1e-7f);
+        const float mod = p.affine ? (1.f + p.affine[b * p.affine_bstride + c]) : 1.f;
+        return p.gamma[c] * mod * inv;
+    };
+    // shared-memory address of the 16-byte chunk `chunk` (8 channels) of window row `row` in ring slot `slot`
+    auto chunk_addr = [&](int slot, uint32_t row, int chunk) -> uint32_t {
+        if (chunk < 8) return smem_u32(ring0) + (uint32_t)slot * C9_SLOT0 + row * 128u + (((uint32_t)chunk ^ (row & 7u)) << 4);
+        return smem_u32(ring1) + (uint32_t)slot * C9_SLOT1 + row * 64u + ((((uint32_t)chunk - 8u) ^ ((row >> 1) & 3u)) << 4);
+    };
+
+    if (warp == C9_WARP_W) {
+        // ===================== weight producer: one 18 KB slot per (kf, kt) of every output row =====================
+        if (lane == 0) {
+            int ws = 0; uint32_t wph = 0;
+            for (int item = item0; item < p.n_items; item += istep) {
+                const CombItem ci = comb_item(p, item);
+                for (int k = 0; k < ci.K; ++k)
+                    for (int kf = 0; kf < 5; ++kf) {
+                        const int j = k + kf - 2;
+                        if (j < 0 || j >= ci.K) continue;
+                        for (int kt = 0; kt < 3; ++kt) {
+                            mbar_wait(w_empty + ws, wph ^ 1);
+                            mbar_expect_tx(w_full + ws, (uint32_t)C9_WSLOT);
+                            bulk_g2s(wring + (size_t)ws * C9_WSLOT, reinterpret_cast<const uint8_t*>(p.w) + (size_t)(kf * 3 + kt) * C9_WSLOT, C9_WSLOT, w_full + ws);
+                            if (++ws == C9_NW) { ws = 0; wph ^= 1; }
+                        }
+                    }
+            }
+        }
+        __syncwarp();
+    } else if (warp == C9_WARP_HALO) {
+        // ===================== the two halo pixels of every row: lane -> (side = lane / 12, chunk = lane % 12) =====================
+        const int side = lane / 12, chunk = lane % 12;
+        const bool act = lane < 24;
+        const long long sc = p.x.sc;
+        int n = 0, b_cur = -1;
+        float cu[8], chh[8];
+        for (int item = item0; item < p.n_items; item += istep) {
+            const CombItem ci = comb_item(p, item);
+            if (ci.b != b_cur) {
+                b_cur = ci.b;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float sj = act ? channel_scale(ci.b, 8 * chunk + j) : 0.f;
+                    cu[j] = fabsf(sj) * 0.84932180028801904272f; chh[j] = 8.f * sj;
+                }
+            }
+            const int th = side ? ci.t0 + 128 : ci.t0 - 1;
+            const bool ld = act && th >= 0 && th < p.T;
+            const float* xh = p.x.p + (long long)ci.b * p.x.sb + (long long)(act ? 8 * chunk : 0) * sc + (ld ? th : 0);
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (ld && ci.K > 0) ? __ldg(xh + (long long)ci.r * p.T + (long long)j * sc) : 0.f;
+            for (int k = 0; k < ci.K; ++k, ++n) {
+                float cv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cv[j] = v[j];
+                if (k + 1 < ci.K) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = ld ? __ldg(xh + (long long)(ci.r + (k + 1) * p.dil) * p.T + (long long)j * sc) : 0.f;
+                }
+                uint32_t hh[4];
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {
+                    const float2 rh = gelu16_tc2_folded2(make_float2(cv[2 * pr], cv[2 * pr + 1]), make_float2(cu[2 * pr], cu[2 * pr + 1]), make_float2(chh[2 * pr], chh[2 * pr + 1]));
+                    hh[pr] = pack_half2_sat(rh.x, rh.y);
+                }
+                const int slot = n % CB_RING;
+                if (n >= CB_RING) mbar_wait(slot_free + slot, (uint32_t)((n / CB_RING) - 1) & 1u);
+                if (act) {
+                    const uint32_t addr = chunk_addr(slot, side ? 129u : 0u, chunk);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hh[0]), "r"(hh[1]), "r"(hh[2]), "r"(hh[3]) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(row_ready + slot);
+            }
+        }
+    } else if (warp >= C9_EPI && warp < C9_EPI + C9_TR) {
+        // ===================== transform: warp w = chunks w, w + 6; lane l = pixels l, l+32, l+64, l+96 =====================
+        const int w = warp - C9_EPI;
+        int n = 0, b_cur = -1;
+        float* sct = gsm_base + w * 128 + 64;          // [8 pairs][cu0, cu1, ch0, ch1] in the unused half of epilogue warp w's gate table
+        const long long sc = p.x.sc;
+        for (int item = item0; item < p.n_items; item += istep) {
+            const CombItem ci = comb_item(p, item);
+            if (ci.b != b_cur) {
+                b_cur = ci.b;
+                __syncwarp();
+                if (lane < 16) {
+                    const int c = 8 * (w + 6 * (lane >> 3)) + (lane & 7);
+                    const float sj = channel_scale(ci.b, c);
+                    sct[(lane >> 1) * 4 + (lane & 1)] = fabsf(sj) * 0.84932180028801904272f;
+                    sct[(lane >> 1) * 4 + 2 + (lane & 1)] = 8.f * sj;
+                }
+                __syncwarp();
+            }
+            // channel 8 (w + 6 h) + 2 q + c of pair position s = 4 h + q lives at xb + pair_off(s) + c * sc
+            const float* xb = p.x.p + (long long)ci.b * p.x.sb + ci.t0 + lane;
+            auto pair_ptr = [&](int srow, int s) { return xb + (long long)srow * p.T + (long long)(8 * (w + 6 * (s >> 2)) + 2 * (s & 3)) * sc; };
+            float v[4][2][4];       // register set s & 3 holds pair position s; refilled with position s + 4 as soon as it is consumed
+            if (ci.K > 0) {
+#pragma unroll
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const float* q = pair_ptr(ci.r, s4);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[s4][c][i] = __ldg(q + (long long)c * sc + i * 32);
+                }
+            }
+            for (int k = 0; k < ci.K; ++k, ++n) {
+                const int frow = ci.r + k * p.dil;
+                if (k + 2 < ci.K && lane < 16) {     // L2 prefetch of the row after the next: lane -> (chunk half lane / 8 ... 16 channels x 4 lines = 64 lines, 4 per lane)
+                    const float* nx = p.x.p + (long long)ci.b * p.x.sb + (long long)(frow + 2 * p.dil) * p.T + ci.t0 + (long long)(8 * (w + 6 * (lane >> 3)) + (lane & 7)) * sc;
+#pragma unroll
+                    for (int l4 = 0; l4 < 4; ++l4) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + l4 * 32));
+                }
+                const bool more = k + 1 < ci.K;
+                const int slot = n % CB_RING;
+                uint32_t hp[4][4];
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(sct + s8 * 4);
+                    const float2 cu2 = make_float2(s4.x, s4.y), ch2 = make_float2(s4.z, s4.w);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 r2 = gelu16_tc2_folded2(make_float2(v[s8 & 3][0][i], v[s8 & 3][1][i]), cu2, ch2);
+                        hp[i][s8 & 3] = pack_half2_sat(r2.x, r2.y);
+                    }
+                    if (s8 < 4 || more) {       // position s8 + 4: the other chunk of this row, or the first chunk of the next row
+                        const float* q = s8 < 4 ? pair_ptr(frow, s8 + 4) : pair_ptr(frow + p.dil, s8 - 4);
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) v[s8 & 3][c][i] = __ldg(q + (long long)c * sc + i * 32);
+                    }
+                    if ((s8 & 3) == 3) {        // a chunk is complete: four 16-byte stores per thread
+                        if (s8 == 3 && n >= CB_RING) mbar_wait(slot_free + slot, (uint32_t)((n / CB_RING) - 1) & 1u);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t addr = chunk_addr(slot, 1u + (uint32_t)(i * 32 + lane), w + 6 * (s8 >> 2));
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(hp[i][0]), "r"(hp[i][1]), "r"(hp[i][2]), "r"(hp[i][3]) : "memory");
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(row_ready + slot);
+            }
+        }
+    } else if (warp == C9_WARP_MMA) {
+        // ===================== MMA issuer: per output row 5 kf x 3 kt x (4 + 2) k-steps of M = 128, N = 96, K = 16 =====================
+        if (elect_one_sync()) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(C9 >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a0desc = desc_lo_sw128(smem_u32(ring0)), a1desc = desc_lo_sw128(smem_u32(ring1)), wdesc = desc_lo_sw128(smem_u32(wring));
+            int n0 = 0, ready = 0, ab = 0, ws = 0; uint32_t aph = 0, wph = 0;
+            long long t_te = 0, t_rr = 0, t_w = 0, t_all = clock64();
+            for (int item = item0; item < p.n_items; item += istep) {
+                const CombItem ci = comb_item(p, item);
+                for (int k = 0; k < ci.K; ++k) {
+                    { const long long t0 = clock64(); mbar_wait(tmem_empty + ab, aph ^ 1); t_te += clock64() - t0; }
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(ab * C9_ACC_STRIDE);
+                    uint32_t acc = 0u;
+                    for (int kf = 0; kf < 5; ++kf) {
+                        const int j = k + kf - 2;
+                        if (j < 0 || j >= ci.K) continue;
+                        const int n = n0 + j, slot = n % CB_RING;
+                        if (n >= ready) { const long long t0 = clock64(); mbar_wait(row_ready + slot, (uint32_t)(n / CB_RING) & 1u); t_rr += clock64() - t0; ready = n + 1; tc_fence_after(); }
+                        const uint32_t a0 = a0desc + (uint32_t)slot * (C9_SLOT0 >> 4), a1 = a1desc + (uint32_t)slot * (C9_SLOT1 >> 4);
+                        for (int kt = 0; kt < 3; ++kt) {
+                            { const long long t0 = clock64(); mbar_wait(w_full + ws, wph); t_w += clock64() - t0; }
+                            tc_fence_after();
+                            const uint32_t b0 = wdesc + (uint32_t)ws * (C9_WSLOT >> 4), b1 = b0 + (C9_WTAP0 >> 4);
+                            tc_mma_k<1, 4>(d, a0 + (uint32_t)kt * 8u, b0, idesc, acc);        // tap kt: one 128-byte pixel row further
+                            tc_mma_k2_sw64(d, a1 + (uint32_t)kt * 4u, b1, idesc, 1u);          // ... one 64-byte row further
+                            acc = 1u;
+                            tc_commit(w_empty + ws);
+                            if (++ws == C9_NW) { ws = 0; wph ^= 1; }
+                        }
+                        if (kf == 0 || k == ci.K - 1) tc_commit(slot_free + slot);
+                    }
+                    tc_commit(tmem_full + ab);
+                    if (++ab == C9_NACC) { ab = 0; aph ^= 1; }
+                }
+                n0 += ci.K;
+            }
+            if (p.dbg && blockIdx.x == 0)
+                printf("comb96 mma: %d rows, total %lld cycles, waiting for an accumulator %lld, for a row %lld, for weights %lld\n", n0, clock64() - t_all, t_te, t_rr, t_w);
+        }
+        __syncwarp();
+    } else if (warp < C9_EPI) {
+        EpiArgs ea{p.out, p.x, p.gate, p.gate_bstride, p.alpha, p.stats_out, C9, 1};
+        CombUnitIter it(p, item0, istep, (warp & 3) * 32 + lane, C9_ACC_STRIDE);
+        epilogue_fast<false, 12, 4, 12, CombUnitIter, C9_EPI>(ea, it, warp, lane, tmem_base, gsm_base, sacc_base, tmem_full, tmem_empty);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == C9_WARP_MMA) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+bool conv_comb_supported(int C, int F, int T, int dil) { return (C == CB_C || C == C9) && T % 128 == 0 && dil >= 1 && F >= 1; }
 
 // out = alpha * (x + gate * conv5x3_dil(GELU(GroupNorm(x) * (1 + affine)))), statistics of out -> stats_out (may be null)
 void launch_conv_comb(const TV& x, const double* stats_in, long long n_per_group, const float* gamma, const float* affine, long long affine_bstride,
@@ -321,9 +607,14 @@ void launch_conv_comb(const TV& x, const double* stats_in, long long n_per_group
     p.n_items = x.B * dil * p.tiles_t;
     static const int dbg = getenv("AID_COMB_DEBUG") ? atoi(getenv("AID_COMB_DEBUG")) : 0;
     p.dbg = dbg;
-    static SmemConfig configured;
-    ensure_dyn_smem(conv_comb_kernel, CB_SMEM, configured);
-    conv_comb_kernel<<<std::min(p.n_items, num_sms), CB_THREADS, CB_SMEM, s>>>(p);
+    static SmemConfig configured, configured96;
+    if (x.C == C9) {     // wp: launch_pack_weight_comb layout
+        ensure_dyn_smem(conv_comb96_kernel, C9_SMEM, configured96);
+        conv_comb96_kernel<<<std::min(p.n_items, num_sms), C9_THREADS, C9_SMEM, s>>>(p);
+    } else {             // wp: launch_pack_weight_tc2 layout
+        ensure_dyn_smem(conv_comb_kernel, CB_SMEM, configured);
+        conv_comb_kernel<<<std::min(p.n_items, num_sms), CB_THREADS, CB_SMEM, s>>>(p);
+    }
     AID_COUNT_LAUNCH(1);
 }
 

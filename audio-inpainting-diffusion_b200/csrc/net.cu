@@ -50,6 +50,7 @@ struct ConvW {
     int widx = -1; float* wp = nullptr; __half* wtc = nullptr; int Cin = 0, Cout = 0, KF = 1, KT = 1;
     float* wpT = nullptr;   // K-major weights of the transposed (data-gradient) convolution, built on the first VJP call
     __half* wtcT = nullptr; // conv_mode 2: the same for the tcgen05 path (dilated 5x3 layers only)
+    __half* wcomb = nullptr; // conv_mode 2: packing of the fused layer kernel (conv_comb.cu) where it differs from wtc (96-channel 5x3 layers)
 };
 struct LinRef { int w = -1, b = -1; int off = -1, N = 0; };
 struct NormRef { int widx = -1; float* gamma = nullptr; };
@@ -310,7 +311,8 @@ static void finalize_net(Net& n) {
         auto tc_halves = [&](const ConvW* c) {
             return n.cfg.conv_mode == 2 ? tc2_weight_halves(c->Cout, c->Cin, c->KF, c->KT) : (size_t)parts * n.weights[c->widx].numel();
         };
-        for (auto* c : convs) if (conv_tc_supported(c->Cin, c->Cout, c->KF, c->KT)) tc_total += al(tc_halves(c));
+        auto comb96 = [&](const ConvW* c) { return n.cfg.conv_mode == 2 && c->KF == 5 && c->KT == 3 && c->Cin == 96 && c->Cout == 96; };
+        for (auto* c : convs) if (conv_tc_supported(c->Cin, c->Cout, c->KF, c->KT)) tc_total += al(tc_halves(c)) + (comb96(c) ? al(comb_weight_halves(96)) : 0);
         if (tc_total) AID_CUDA_CHECK(cudaMalloc(&n.dweights_tc, tc_total * sizeof(__half)));
         AID_CUDA_CHECK(cudaMalloc(&n.d_sat, 2 * sizeof(unsigned long long)));
         AID_CUDA_CHECK(cudaMemset(n.d_sat, 0, 2 * sizeof(unsigned long long)));
@@ -325,6 +327,13 @@ static void finalize_net(Net& n) {
             AID_CUDA_CHECK(cudaGetLastError());
             AID_CUDA_CHECK(cudaDeviceSynchronize());
             toff += al(tc_halves(c));
+            if (comb96(c)) {
+                c->wcomb = n.dweights_tc + toff;
+                launch_pack_weight_comb(stage, c->wcomb, 96, 0);
+                AID_CUDA_CHECK(cudaGetLastError());
+                AID_CUDA_CHECK(cudaDeviceSynchronize());
+                toff += al(comb_weight_halves(96));
+            }
         }
     }
     AID_CUDA_CHECK(cudaFree(stage));
@@ -505,7 +514,7 @@ static void conv_comb_layer(Ctx& c, const TV& x, const double* stats_in, long lo
         rec.bytes = 4.0 * (px * (w.Cin + w.Cout + w.Cout) + (double)w.Cin * w.Cout * w.KF * w.KT);
         AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
     }
-    launch_conv_comb(x, stats_in, n_grp, gamma, affine, abstride, w.wtc, dil, out, ep, n.num_sms, c.s);
+    launch_conv_comb(x, stats_in, n_grp, gamma, affine, abstride, w.wcomb ? w.wcomb : w.wtc, dil, out, ep, n.num_sms, c.s);
     if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
@@ -613,7 +622,11 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
             const int pf = tc_pad_rows(T, k.H[i].KF, dil);
             __half* a_lo = parts == 2 ? a_hi + planar_halves(N, pf) : nullptr;
             static const bool env_comb = !(getenv("AID_COMB") && atoi(getenv("AID_COMB")) == 0);
-            if (cmode == 2 && env_comb && !tp && !use_cl && !k.k1x1 && !sat && conv_comb_supported(N, F, T, dil)) {
+            // 96 channels (AID_COMB96=0 turns it off): the fused kernel streams its 270 KB of weights and is bound by shared-memory
+            // bandwidth like conv_tc2; in the network at batch 32 it measured +1.4 % over pass + conv_tc2 (cta_group::2), and it differs
+            // from that path in fp32 accumulation order (2e-6 per layer)
+            static const bool env_comb96 = !(getenv("AID_COMB96") && atoi(getenv("AID_COMB96")) == 0);
+            if (cmode == 2 && env_comb && !tp && !use_cl && !k.k1x1 && !sat && conv_comb_supported(N, F, T, dil) && (N != 96 || (env_comb96 && k.H[i].wcomb))) {
                 // fused layer (conv_comb.cu): normalisation, modulation, GELU and the operand conversion happen inside the convolution;
                 // the t-tile halos forbid an in-place update, so the layers alternate between the block's two buffers
                 TV o = (cur.p == x.p) ? a : x;
@@ -1531,6 +1544,11 @@ int aid_debug_dilated_layer(const float* x_dev, const float* w_dev, int B, int C
         AID_CUDA_CHECK(cudaMalloc(&wtc, tc2_weight_halves(C, C, 5, 3) * sizeof(__half)));
         AID_CUDA_CHECK(cudaMalloc(&a, tc2_act_halves(B, C, F, T, pf) * sizeof(__half)));
         launch_pack_weight_tc2(w_dev, wtc, C, C, 5, 3, nullptr);
+        __half* wcomb = nullptr;
+        if (fused && C == 96) {
+            AID_CUDA_CHECK(cudaMalloc(&wcomb, comb_weight_halves(96) * sizeof(__half)));
+            launch_pack_weight_comb(w_dev, wcomb, 96, nullptr);
+        }
         launch_group_stats(x, st, nullptr);
         const long long n_grp = (long long)(C / 8) * F * T;
         ConvEpilogue ep; ep.gate = gate_dev; ep.gate_bstride = 0; ep.alpha = alpha; ep.R = x; ep.stats = stats_out_dev;
@@ -1538,7 +1556,7 @@ int aid_debug_dilated_layer(const float* x_dev, const float* w_dev, int B, int C
         for (int rep = 0; rep < (ms_out ? 2 : 1); ++rep) {
             if (stats_out_dev) AID_CUDA_CHECK(cudaMemsetAsync(stats_out_dev, 0, (size_t)B * 16 * sizeof(double), nullptr));
             AID_CUDA_CHECK(cudaEventRecord(e0, nullptr));
-            if (fused) launch_conv_comb(x, st, n_grp, gamma_dev, affine_dev, 0, wtc, dil, out, ep, sms, nullptr);
+            if (fused) launch_conv_comb(x, st, n_grp, gamma_dev, affine_dev, 0, wcomb ? wcomb : wtc, dil, out, ep, sms, nullptr);
             else {
                 launch_gn_act_tc2(x, st, n_grp, gamma_dev, affine_dev, 0, true, pf, a, nullptr);
                 launch_conv_tc2(a, pf, wtc, B, C, F, T, 5, 3, dil, out, ep, sms, nullptr);
@@ -1548,7 +1566,7 @@ int aid_debug_dilated_layer(const float* x_dev, const float* w_dev, int B, int C
             AID_CUDA_CHECK(cudaEventSynchronize(e1));
         }
         if (ms_out) AID_CUDA_CHECK(cudaEventElapsedTime(ms_out, e0, e1));
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(st); cudaFree(wtc); cudaFree(a);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(st); cudaFree(wtc); cudaFree(a); if (wcomb) cudaFree(wcomb);
         return AID_OK;
     } catch (const CudaError& e) { fprintf(stderr, "aid_debug_dilated_layer: CUDA error %s at %s:%d\n", cudaGetErrorString(e.code), e.file, e.line); return AID_ERR_CUDA; }
     catch (const std::exception& e) { fprintf(stderr, "aid_debug_dilated_layer: %s\n", e.what()); return AID_ERR_INVALID; }

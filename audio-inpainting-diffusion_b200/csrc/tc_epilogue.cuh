@@ -63,13 +63,15 @@ struct EpiUnit {
     int ab; uint32_t aph;           // accumulator handshake: barrier index and phase
     bool first, last;               // first / last unit that uses this accumulator handshake (wait tmem_full / arrive tmem_empty)
 };
-template <bool CG2, int BW, int NB, int GCN, class IT>
+template <bool CG2, int BW, int NB, int GCN, class IT, int EWARPS = 8>
 __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const int e, const int lane, const uint32_t tmem_base, float* gsm_base,
                                               double* sacc_base, uint64_t* tmem_full, uint64_t* tmem_empty) {
-    constexpr int NCOLS = BW * NB;                  // columns of this warp (half of the n-tile)
+    constexpr int NCOLS = BW * NB;                  // columns of this warp (the n-tile split over EWARPS / 4 column groups)
+    constexpr int SST = EWARPS * 32;                // stride of the double accumulators: [k][epilogue threads]
+    constexpr bool DIRECT = (NCOLS / GCN) > 4;      // many groups per warp: batch sums go straight to the shared-memory doubles
     constexpr int NG = NCOLS / GCN;                 // statistics groups they span
     constexpr int GPB = BW / GCN;                   // groups per batch
-    static_assert(NB % 2 == 0 && BW % 8 == 0 && BW <= 32 && BW % GCN == 0 && NG >= 1 && NG <= 4, "epilogue_fast shape");
+    static_assert(NB % 2 == 0 && BW % 4 == 0 && BW <= 32 && BW % GCN == 0 && NG >= 1 && NG <= 8 && 2 * NG * SST * 8 <= 16384, "epilogue_fast shape");
     const int q = e & 3, cw = e >> 2, cbeg = cw * NCOLS;
     const float al = p.alpha, gs = T2_OUT_SCALE * p.alpha;
     const uint32_t osc = (uint32_t)p.out.sc, rsc = (uint32_t)p.R.sc;   // plane strides; a clip's tensor has < 2^31 elements
@@ -77,13 +79,14 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
     float* gsm = gsm_base + e * 128;
     const uint32_t gsm_addr = smem_u32(gsm);
-    double* sacc = sacc_base + (e * 32 + lane);   // [k][256 threads]
-    float S[NG], Q[NG];
+    double* sacc = sacc_base + (e * 32 + lane);   // [k][SST threads]
+    constexpr int NSQ = DIRECT ? 1 : NG;
+    float S[NSQ], Q[NSQ];
 #pragma unroll
-    for (int k = 0; k < NG; ++k) { S[k] = 0.f; Q[k] = 0.f; }
+    for (int k = 0; k < NSQ; ++k) { S[k] = 0.f; Q[k] = 0.f; }
     if (do_stats) {
 #pragma unroll
-        for (int k = 0; k < 2 * NG; ++k) sacc[k * 256] = 0.0;
+        for (int k = 0; k < 2 * NG; ++k) sacc[k * SST] = 0.0;
     }
     int b_cur = -1, nt_cur = 0, gate_key = -2;
     auto flush_stats = [&]() {
@@ -91,7 +94,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
             double v[2 * NG];
 #pragma unroll
             for (int k = 0; k < 2 * NG; ++k) {
-                v[k] = sacc[k * 256]; sacc[k * 256] = 0.0;
+                v[k] = sacc[k * SST]; sacc[k * SST] = 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
             }
@@ -154,6 +157,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
             if constexpr (BW == 32) tmem_ld32_nowait(c_tcol + bi * BW, acc);
             else if constexpr (BW == 24) { tmem_ld16_nowait(c_tcol + bi * BW, acc); tmem_ld8p_nowait(c_tcol + bi * BW + 16, acc + 16); }
             else if constexpr (BW == 16) tmem_ld16_nowait(c_tcol + bi * BW, acc);
+            else if constexpr (BW == 12) { tmem_ld8p_nowait(c_tcol + bi * BW, acc); tmem_ld4p_nowait(c_tcol + bi * BW + 8, acc + 8); }
             else tmem_ld8p_nowait(c_tcol + bi * BW, acc);
             float g[BW];
 #pragma unroll
@@ -184,14 +188,21 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
                         qa = __ffma2_rn(w[k], w[k], qa); qb = __ffma2_rn(w[k + 1], w[k + 1], qb);
                     }
                     const float2 s2 = __fadd2_rn(sa, sb), q2 = __fadd2_rn(qa, qb);
-                    S[bi * GPB + gg] = fmaf(s2.x + s2.y, m, S[bi * GPB + gg]);
-                    Q[bi * GPB + gg] = fmaf(q2.x + q2.y, m, Q[bi * GPB + gg]);
+                    if constexpr (DIRECT) {
+                        sacc[(2 * (bi * GPB + gg)) * SST] += (double)((s2.x + s2.y) * m);
+                        sacc[(2 * (bi * GPB + gg) + 1) * SST] += (double)((q2.x + q2.y) * m);
+                    } else {
+                        S[bi * GPB + gg] = fmaf(s2.x + s2.y, m, S[bi * GPB + gg]);
+                        Q[bi * GPB + gg] = fmaf(q2.x + q2.y, m, Q[bi * GPB + gg]);
+                    }
                 }
             }
         }
-        if (do_stats) {
+        if constexpr (!DIRECT) {
+            if (do_stats) {
 #pragma unroll
-            for (int k = 0; k < NG; ++k) { sacc[(2 * k) * 256] += (double)S[k]; sacc[(2 * k + 1) * 256] += (double)Q[k]; S[k] = 0.f; Q[k] = 0.f; }
+                for (int k = 0; k < NG; ++k) { sacc[(2 * k) * SST] += (double)S[k]; sacc[(2 * k + 1) * SST] += (double)Q[k]; S[k] = 0.f; Q[k] = 0.f; }
+            }
         }
         if (c_last) {      // one arrival per warp: 256 per-thread arrivals on one mbarrier serialise in the shared-memory pipe
             tc_fence_before();

@@ -100,6 +100,9 @@ __device__ __forceinline__ bool elect_one_sync() {
 __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 static constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 
+// K-major SWIZZLE_64B (rows of 64 bytes, 8-row groups 512 bytes apart, XOR of address bits [4,6) with bits [7,9)): high word
+static constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);
+
 // tcgen05.mma with the descriptors given as their low words (the high word of a K-major SWIZZLE_128B descriptor with SBO = 1024 is
 // a constant): the 64-bit descriptors are assembled inside the asm, so a uniform low word stays in a uniform register
 __device__ __forceinline__ void tc_mma_f16_lo(uint32_t d_tmem, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t accumulate) {
@@ -149,6 +152,16 @@ __device__ __forceinline__ void tc_mma_kx2(uint32_t d0, uint32_t d1, uint32_t al
     if constexpr (CG == 2 && NK == 2) asm volatile(AID_MMA2_HEAD("2") AID_MMA2_STEP("2", "2") "}" AID_OPS2);
 #undef AID_OPS2
 }
+// two k-steps of a 32-channel group stored with 64-byte rows (SWIZZLE_64B descriptors), cta_group::1
+__device__ __forceinline__ void tc_mma_k2_sw64(uint32_t d, uint32_t alo, uint32_t blo, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 a, b;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t setp.eq.b32 q, 0, 0;\n\t mov.b64 da, {%1, %5};\n\t mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "add.u32 a, %1, 2;\n\t add.u32 b, %2, 2;\n\t mov.b64 da, {a, %5};\n\t mov.b64 db, {b, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, q;\n\t}" ::"r"(d), "r"(alo), "r"(blo), "r"(idesc), "r"(acc), "r"(DESC_HI_SW64)
+        : "memory");
+}
 // one (kf, group) stage of the 5x3 layers: the three kt taps (activation descriptor advanced by one 128-byte pixel row = 8
 // units, weight descriptor by ktd) for the accumulators whose unit is in range (v0 / v1)
 template <int CG, int NK>
@@ -185,6 +198,9 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
           "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4p_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld8p_nowait(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

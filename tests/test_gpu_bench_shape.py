@@ -80,21 +80,25 @@ def test_paper_network_262144_blockwise_vs_oracle(aid, cuda, nets):
 
 def test_bench_batch_32_rows_equal_solo_clips(aid, cuda, nets):
     """The bench batch (32 x 262144, shared sigma, conv_mode 2): clips are independent -- row k of the batch equals
-    the clip evaluated alone, up to the run-to-run noise of the statistic atomics (measured 2e-5); no value saturates."""
+    the clip evaluated alone (deterministic, batch-invariant statistics: measured 0.0); no value saturates."""
     net = nets[2]
     x = torch.cat([seeded((1, L), 100 + k, 0.5) for k in range(32)]).to(cuda)
     cn = torch.tensor([[-0.3]], device=cuda)
     net._ensure_weights(cuda)
-    net.saturation_counts(enable=True)
-    full = net(x, cn)
+    net.saturation_counts(enable=True)       # counting runs the un-fused path (operand pass + conv_tc2) for every layer
+    full_counted = net(x, cn)
     act, wts = net.saturation_counts(enable=False)
     assert (act, wts) == (0, 0)
+    full = net(x, cn)                        # the bench path (fused layers where they apply)
     assert torch.isfinite(full).all()
+    e = rel_l2(full, full_counted)
+    print(f"fused layers vs operand pass + conv_tc2, whole batch: {e:.2e}")
+    assert e < 1e-3
     for k in (0, 13, 31):
         solo = net(x[k:k + 1], cn)
         e = rel_l2(full[k:k + 1], solo)
         print(f"row {k} of the batch vs solo: {e:.2e}")
-        assert e < 1e-4, (k, e)
+        assert e < 1e-5, (k, e)
     # and the golden clip placed inside a batch still matches the reference
     g = np.load(GOLD)
     xb = x[:4].clone()

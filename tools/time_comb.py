@@ -6,8 +6,7 @@ import torch, aid_b200
 from aid_b200 import _lib
 L = _lib.lib()
 dev = torch.device("cuda:0")
-for B, Fd, T, dil in [(8, 64, 4096, 1), (8, 64, 4096, 2), (8, 128, 2048, 1), (8, 128, 2048, 4), (32, 64, 4096, 2)]:
-    Cn = 64
+for B, Fd, T, dil, Cn in [(8, 64, 4096, 2, 64), (8, 128, 2048, 4, 64), (32, 64, 4096, 2, 64), (8, 128, 2048, 4, 96), (8, 192, 1024, 8, 96), (8, 256, 512, 16, 96), (32, 128, 2048, 2, 96)]:
     x = torch.randn(B, Cn, Fd, T, device=dev); w = torch.randn(Cn, Cn, 5, 3, device=dev) * 0.03
     gamma = torch.ones(Cn, device=dev); aff = torch.zeros(Cn, device=dev); gate = torch.randn(Cn, device=dev)
     out = torch.empty_like(x); st = torch.zeros(B, 8, 2, dtype=torch.float64, device=dev)
