@@ -95,6 +95,9 @@ void launch_conv_simt(const TV& a, const float* wp, int KF, int KT, int dil, con
                       cudaStream_t s);
 // thin convolutions (conv_thin.cu); returns false when the shape is not covered
 bool launch_conv_thin(const TV& a, const float* wp, int KF, int KT, int dil, const TV& out, const ConvEpilogue& ep, cudaStream_t s);
+// attention proj_in (N -> 8, 1x1) reading the un-normalised tensor: the group norm (no activation) is folded into per-clip weights
+bool launch_conv_thin_out_normed(const TV& a, const double* stats, long long n_per_group, const float* gamma, const float* affine, long long affine_bstride,
+                                 const float* wp, const TV& out, cudaStream_t s);
 void launch_attention(const TV& h, const float* qk, const TV& out, cudaStream_t s);
 // tcgen05 version (attention.cu): Q K^T with split-fp16 operands, softmax from TMEM, P V with fp16 operands
 bool attention_tc_supported(int F, int T);

@@ -22,10 +22,12 @@ __device__ __forceinline__ void thin_stats_flush(float s, float q, int g, double
 template <int KF, int KT, int CIN, int PX>
 __global__ void __launch_bounds__(TH) conv_thin_in_kernel(TV a, const float* __restrict__ wp, int dil, TV out, ConvEpilogue ep) {
     constexpr int K = CIN * KF * KT;
-    extern __shared__ float ws[];  // [K][Cout]
+    // weights duplicated as (w, w) pairs: the multiply-accumulate loop runs on the packed fp32x2 pipe of sm_100 (one LDS.64 + PX / 2
+    // FFMA2 per tap instead of one LDS + PX FFMA; the same IEEE fma per lane) -- these kernels are bound by instruction issue
+    extern __shared__ float2 ws2[];  // [K][Cout]
     __shared__ double sst[8][2];
     const int Cout = out.C, F = a.F, T = a.T, b = blockIdx.z;
-    for (int i = threadIdx.x; i < K * Cout; i += TH) ws[i] = __ldg(wp + i);
+    for (int i = threadIdx.x; i < K * Cout; i += TH) { const float w = __ldg(wp + i); ws2[i] = make_float2(w, w); }
     if (threadIdx.x < 16) sst[threadIdx.x >> 1][threadIdx.x & 1] = 0.0;
     __syncthreads();
     const int tq = T / PX;
@@ -63,13 +65,19 @@ __global__ void __launch_bounds__(TH) conv_thin_in_kernel(TV a, const float* __r
 #pragma unroll 1
     for (int co = 0; co < Cout; ++co) {
         float acc[PX];
+        {
+            static_assert(PX % 2 == 0, "conv_thin_in: pixel pairs");
+            float2 acc2[PX / 2];
 #pragma unroll
-        for (int px = 0; px < PX; ++px) acc[px] = 0.f;
+            for (int pp = 0; pp < PX / 2; ++pp) acc2[pp] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float w = ws[k * Cout + co];
+            for (int k = 0; k < K; ++k) {
+                const float2 w2 = ws2[k * Cout + co];
 #pragma unroll
-            for (int px = 0; px < PX; ++px) acc[px] = fmaf(w, in[k][px], acc[px]);
+                for (int pp = 0; pp < PX / 2; ++pp) acc2[pp] = __ffma2_rn(w2, make_float2(in[k][2 * pp], in[k][2 * pp + 1]), acc2[pp]);
+            }
+#pragma unroll
+            for (int pp = 0; pp < PX / 2; ++pp) { acc[2 * pp] = acc2[pp].x; acc[2 * pp + 1] = acc2[pp].y; }
         }
         if (live) {
             const float g = gate ? gate[co] : 1.f;
@@ -111,12 +119,33 @@ __global__ void __launch_bounds__(TH) conv_thin_in_kernel(TV a, const float* __r
     }
 }
 
+// Optional input normalisation folded into the weights (attention proj_in, unet.py:343-345: a_in(GroupNorm(x) * gamma * (1 + affine))):
+// a bias-free group norm without activation is one scale per (clip, channel), so w'[ci][co] = w[ci][co] * scale[b][ci] and the
+// kernel reads the un-normalised tensor -- the separate normalisation pass (4 B read + 4 B written per element) disappears.
+struct ThinInScale { const double* stats; double n_per_group; const float* gamma; const float* affine; long long affine_bstride; };
+
 // One thread = 4 consecutive pixels, COUT accumulators each; streams the Cin input planes once.  1x1 only, no statistics.
 template <int COUT>
-__global__ void __launch_bounds__(TH) conv_thin_out_kernel(TV a, const float* __restrict__ wp, TV out, ConvEpilogue ep) {
+__global__ void __launch_bounds__(TH) conv_thin_out_kernel(TV a, const float* __restrict__ wp, TV out, ConvEpilogue ep, ThinInScale sc) {
     extern __shared__ float ws[];  // [Cin][COUT]
+    __shared__ float s_inv[8];
     const int Cin = a.C, F = a.F, T = a.T, b = blockIdx.z;
-    for (int i = threadIdx.x; i < Cin * COUT; i += TH) ws[i] = __ldg(wp + i);
+    if (sc.stats) {
+        if (threadIdx.x < 8) {      // 1 / (unbiased std + eps) of the 8 groups, the arithmetic of gn_act_kernel
+            const double s1 = sc.stats[((long long)b * 8 + threadIdx.x) * 2 + 0], s2 = sc.stats[((long long)b * 8 + threadIdx.x) * 2 + 1];
+            double var = (s2 - s1 * s1 / sc.n_per_group) / (sc.n_per_group - 1.0);
+            var = var > 0.0 ? var : 0.0;
+            s_inv[threadIdx.x] = 1.f / ((float)sqrt(var) + 1e-7f);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < Cin * COUT; i += TH) {
+            const int ci = i / COUT;
+            const float mod = sc.affine ? (1.f + sc.affine[b * sc.affine_bstride + ci]) : 1.f;
+            ws[i] = __ldg(wp + i) * (sc.gamma[ci] * mod * s_inv[ci / (Cin / 8)]);
+        }
+    } else {
+        for (int i = threadIdx.x; i < Cin * COUT; i += TH) ws[i] = __ldg(wp + i);
+    }
     __syncthreads();
     const int tq = T / 4;
     const long long pq = (long long)blockIdx.x * TH + threadIdx.x;
@@ -162,12 +191,24 @@ static bool aligned16(const TV& v) {
 
 template <int KF, int KT, int CIN, int PX>
 static void launch_thin_in(const TV& a, const float* wp, int dil, const TV& out, const ConvEpilogue& ep, cudaStream_t s) {
-    const size_t smem = (size_t)CIN * KF * KT * out.C * sizeof(float);
+    const size_t smem = (size_t)CIN * KF * KT * out.C * sizeof(float2);
     static SmemConfig configured;
     ensure_dyn_smem(conv_thin_in_kernel<KF, KT, CIN, PX>, smem, configured, 48 * 1024);
     const long long n = (long long)a.F * (a.T / PX);
     conv_thin_in_kernel<KF, KT, CIN, PX><<<dim3((unsigned)((n + TH - 1) / TH), 1, a.B), TH, smem, s>>>(a, wp, dil, out, ep);
     AID_COUNT_LAUNCH(1);
+}
+
+// out[b, 0..8) = W (GroupNorm8(x) * gamma * (1 + affine)) for a 1x1 convolution N -> 8 (attention proj_in) with the normalisation folded
+// into per-clip weights; false when the shape is not covered (caller normalises separately)
+bool launch_conv_thin_out_normed(const TV& a, const double* stats, long long n_per_group, const float* gamma, const float* affine, long long affine_bstride,
+                                 const float* wp, const TV& out, cudaStream_t s) {
+    if (!aligned16(a) || !aligned16(out) || out.C != 8 || a.T % 4 != 0 || a.C % 8 != 0 || a.C * out.C * 4 > 48 * 1024) return false;
+    const long long n = (long long)a.F * (a.T / 4);
+    dim3 grid((unsigned)((n + TH - 1) / TH), 1, a.B);
+    conv_thin_out_kernel<8><<<grid, TH, (size_t)a.C * out.C * sizeof(float), s>>>(a, wp, out, ConvEpilogue(), ThinInScale{stats, (double)n_per_group, gamma, affine, affine_bstride});
+    AID_COUNT_LAUNCH(1);
+    return true;
 }
 
 // returns false when the shape is not one of the thin cases (caller falls back to the general CUDA-core kernel)
@@ -178,8 +219,8 @@ bool launch_conv_thin(const TV& a, const float* wp, int KF, int KT, int dil, con
         const long long n = (long long)a.F * (T / 4);
         dim3 grid((unsigned)((n + TH - 1) / TH), 1, a.B);
         const size_t smem = (size_t)a.C * out.C * sizeof(float);
-        if (out.C == 2) conv_thin_out_kernel<2><<<grid, TH, smem, s>>>(a, wp, out, ep);
-        else conv_thin_out_kernel<8><<<grid, TH, smem, s>>>(a, wp, out, ep);
+        if (out.C == 2) conv_thin_out_kernel<2><<<grid, TH, smem, s>>>(a, wp, out, ep, ThinInScale{});
+        else conv_thin_out_kernel<8><<<grid, TH, smem, s>>>(a, wp, out, ep, ThinInScale{});
         AID_COUNT_LAUNCH(1);
         return true;
     }

@@ -570,9 +570,17 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
     if (tp) bt->x0 = cur;
     if (k.attn) {
         const int heads = k.a_in.Cout;
-        RUN(launch_gn_act(cur, cur.stats, n_grp, k.norm2.gamma, c.mod + k.affine2.off, c.modstride(), false, a, c.s));
         TV h = make_tv(c.allocf((long long)B * heads * F * T), B, heads, F, T);
-        conv(c, a, k.a_in, 1, h, ConvEpilogue());
+        // plain forward: the normalisation is folded into the projection's weights (conv_thin.cu); the taped forward keeps the
+        // normalised tensor, which its backward reads
+        static const bool env_fold = !(getenv("AID_ATT_FOLD") && atoi(getenv("AID_ATT_FOLD")) == 0);
+        bool folded = false;
+        if (!tp && env_fold && !c.dry())
+            folded = launch_conv_thin_out_normed(cur, cur.stats, n_grp, k.norm2.gamma, c.mod + k.affine2.off, c.modstride(), k.a_in.wp, h, c.s);
+        if (!folded) {     // (both are no-ops in the planner's dry run)
+            RUN(launch_gn_act(cur, cur.stats, n_grp, k.norm2.gamma, c.mod + k.affine2.off, c.modstride(), false, a, c.s));
+            conv(c, a, k.a_in, 1, h, ConvEpilogue());
+        }
         TV hflat = make_tv(h.p, B, heads * F, 1, T);
         TV qk = make_tv(c.allocf((long long)B * 2 * heads * F * T), B, 2 * heads * F, 1, T);
         if (k.qk.wtc) {

@@ -342,7 +342,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": {0: "dilated 5x3 conv residual layers (conv_simt_kernel<5,3,8>)", 1: "dilated 5x3 conv (tcgen05, conv_tc_kernel, 3 MMAs per tap)",
-                                    2: "dilated 5x3 conv (tcgen05, conv_tc2_kernel, 1 fp16 MMA per tap)"}[args.conv_mode],
+                                    2: "dilated 5x3 residual layers (tcgen05, 1 fp16 MMA per tap: conv_tc2_kernel / conv_tc2_cg2_kernel, and the fused conv_comb kernels whose time includes the group-norm / GELU operand generation)"}[args.conv_mode],
                          "achieved": conv_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": conv_tflops / pk["tensor"],
                          "peak_source": f"{pk['src']} bf16 dense GEMM, sustained", "traffic": traffic,
                          "algorithmic_gbs": (by.value / 1e9) / (t_ms.value / 1e3) if t_ms.value > 0 else 0.0,
