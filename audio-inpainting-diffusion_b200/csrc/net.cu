@@ -461,6 +461,14 @@ struct Ctx {
 
 #define RUN(call) do { if (!c.dry()) { call; } } while (0)
 
+// fraction of the KF row taps of a dilated convolution that fall inside the plane (the kernels skip the others): the profile
+// records count the multiply-adds that are actually executed, not the nominal 2*Cin*Cout*KF*KT per pixel
+static double valid_tap_fraction(int F, int KF, int dil) {
+    double s = 0;
+    for (int kf = 0; kf < KF; ++kf) s += std::max(0, F - std::abs(kf - KF / 2) * dil);
+    return s / ((double)KF * F);
+}
+
 static void conv(Ctx& c, const TV& a, const ConvW& w, int dil, const TV& out, ConvEpilogue ep) {
     if (a.C != w.Cin || out.C != w.Cout || a.F != out.F || a.T != out.T || a.B != out.B)
         throw std::runtime_error("conv: shape mismatch");
@@ -473,7 +481,7 @@ static void conv(Ctx& c, const TV& a, const ConvW& w, int dil, const TV& out, Co
         rec.e0 = get(); rec.e1 = get();
         rec.kind = (w.KF == 5 && w.Cin > 2) ? 0 : 1;   // 0 = dilated 5x3 residual layers (K1), 1 = everything else
         const double px = (double)a.B * a.F * a.T;
-        rec.flops = 2.0 * w.Cin * w.Cout * w.KF * w.KT * px;
+        rec.flops = 2.0 * w.Cin * w.Cout * w.KF * w.KT * px * valid_tap_fraction(a.F, w.KF, dil);
         rec.bytes = 4.0 * (px * (w.Cin + w.Cout + (ep.R.p ? w.Cout : 0) + (ep.R2.p ? w.Cout : 0)) + (double)w.Cin * w.Cout * w.KF * w.KT);
         AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
     }
@@ -491,7 +499,7 @@ static void conv_tc(Ctx& c, const __half* a_hi, const __half* a_lo, int PF, cons
         rec.e0 = get(); rec.e1 = get(); rec.kind = 0;
         const double px = (double)out.B * out.F * out.T;
         rec.kind = (w.KF == 5) ? 0 : 1;
-        rec.flops = 2.0 * w.Cin * w.Cout * w.KF * w.KT * px;
+        rec.flops = 2.0 * w.Cin * w.Cout * w.KF * w.KT * px * valid_tap_fraction(out.F, w.KF, dil);
         rec.bytes = 4.0 * (px * (w.Cin + w.Cout + (ep.R.p ? w.Cout : 0)) + (double)w.Cin * w.Cout * w.KF * w.KT);
         AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
     }
@@ -500,7 +508,8 @@ static void conv_tc(Ctx& c, const __half* a_hi, const __half* a_lo, int PF, cons
     if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
-// conv_mode 2, 64-channel blocks: one fused kernel per dilated layer (conv_comb.cu); recorded like the other dilated convolutions
+// conv_mode 2, 64 / 96-channel blocks: one fused kernel per dilated layer (conv_comb.cu); recorded as kind 2 (its time includes the
+// normalisation / GELU / operand conversion of the layer; bytes = the layer's algorithmic 4 B read + 4 B written per element)
 static void conv_comb_layer(Ctx& c, const TV& x, const double* stats_in, long long n_grp, const float* gamma, const float* affine, long long abstride,
                             const ConvW& w, int dil, const TV& out, const ConvEpilogue& ep) {
     if (c.dry()) return;
@@ -508,10 +517,10 @@ static void conv_comb_layer(Ctx& c, const TV& x, const double* stats_in, long lo
     Net::ProfRec rec{};
     if (n.prof) {
         auto get = [&]() { cudaEvent_t e; if (n.prof_pool.empty()) { AID_CUDA_CHECK(cudaEventCreate(&e)); } else { e = n.prof_pool.back(); n.prof_pool.pop_back(); } return e; };
-        rec.e0 = get(); rec.e1 = get(); rec.kind = 0;
+        rec.e0 = get(); rec.e1 = get(); rec.kind = 2;
         const double px = (double)out.B * out.F * out.T;
-        rec.flops = 2.0 * w.Cin * w.Cout * w.KF * w.KT * px;
-        rec.bytes = 4.0 * (px * (w.Cin + w.Cout + w.Cout) + (double)w.Cin * w.Cout * w.KF * w.KT);
+        rec.flops = 2.0 * w.Cin * w.Cout * w.KF * w.KT * px * valid_tap_fraction(out.F, w.KF, dil);
+        rec.bytes = 4.0 * px * (w.Cin + w.Cout) + 2.0 * (double)w.Cin * w.Cout * w.KF * w.KT;
         AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
     }
     launch_conv_comb(x, stats_in, n_grp, gamma, affine, abstride, w.wcomb ? w.wcomb : w.wtc, dil, out, ep, n.num_sms, c.s);

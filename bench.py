@@ -273,6 +273,8 @@ def main():
     launches = lib.aid_launch_count() - launches0
     n_l, t_ms, fl, by = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
     _lib.check(lib.aid_profile_read(net._handle, 0, C.byref(n_l), C.byref(t_ms), C.byref(fl), C.byref(by)), net._handle)
+    n_f, t_f, fl_f, by_f = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()      # fused dilated layers (conv_comb.cu)
+    _lib.check(lib.aid_profile_read(net._handle, 2, C.byref(n_f), C.byref(t_f), C.byref(fl_f), C.byref(by_f)), net._handle)
     lib.aid_profile(net._handle, 0)
     clk = clocks.stop() if clocks else None
 
@@ -342,7 +344,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": {0: "dilated 5x3 conv residual layers (conv_simt_kernel<5,3,8>)", 1: "dilated 5x3 conv (tcgen05, conv_tc_kernel, 3 MMAs per tap)",
-                                    2: "dilated 5x3 residual layers (tcgen05, 1 fp16 MMA per tap: conv_tc2_kernel / conv_tc2_cg2_kernel, and the fused conv_comb kernels whose time includes the group-norm / GELU operand generation)"}[args.conv_mode],
+                                    2: "dilated 5x3 conv of the 128 / 256-channel residual layers (tcgen05, 1 fp16 MMA per tap: conv_tc2_kernel, conv_tc2_cg2_kernel); FLOPs = executed taps only"}[args.conv_mode],
                          "achieved": conv_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": conv_tflops / pk["tensor"],
                          "peak_source": f"{pk['src']} bf16 dense GEMM, sustained", "traffic": traffic,
                          "algorithmic_gbs": (by.value / 1e9) / (t_ms.value / 1e3) if t_ms.value > 0 else 0.0,
@@ -354,6 +356,18 @@ def main():
                                            "algorithmic_gbs": B * GB_PER_CLIP.get(L, 0) / (ms / 1e3),
                                            "frac_of_hbm_roof": B * GB_PER_CLIP.get(L, 0) / (ms / 1e3) / pk["hbm"]}},
         }
+        if t_f.value > 0:
+            # the 64 / 96-channel residual layers run as ONE kernel each (normalise + modulate + GELU + convert + convolve + epilogue):
+            # their bound is the layer's HBM traffic (4 B read + 4 B written per element), reported next to their tensor throughput
+            gbs = (by_f.value / 1e9) / (t_f.value / 1e3)
+            line["fused_layers"] = {"kernel": "conv_comb_kernel / conv_comb96_kernel (fused dilated residual layers, 64 / 96 channels)",
+                                    "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                                    "tflops": (fl_f.value / 1e12) / (t_f.value / 1e3), "launches_timed": int(n_f.value),
+                                    "traffic": (json.load(open(prof_json)).get("fused_layers_mode2_bytes_per_launch") if os.path.exists(prof_json) else None),
+                                    "kernel_ms_per_step": t_f.value / args.steps, "kernel_share_of_step": (t_f.value / args.steps) / ms}
+            line["roofline"]["dilated_layers_all"] = {"tflops": ((fl.value + fl_f.value) / 1e12) / ((t_ms.value + t_f.value) / 1e3),
+                                                      "kernel_ms_per_step": (t_ms.value + t_f.value) / args.steps,
+                                                      "kernel_share_of_step": ((t_ms.value + t_f.value) / args.steps) / ms}
         if fp32_grade is not None:
             line["fp32_grade"] = fp32_grade
         if world == 1 and not args.no_cpu_baseline:

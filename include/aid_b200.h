@@ -218,8 +218,10 @@ int aid_debug_dilated_layer(const float* x_dev, const float* w_dev, int B, int C
 
 /* Per-launch timing of the convolution kernels with CUDA events on the launching stream (bench.py's roofline).
  * aid_profile(h, 1) clears and starts recording, aid_profile(h, 0) stops; aid_profile_read sums the recorded launches
- * of one kind (0 = dilated 5x3 residual-layer convolutions, 1 = all other convolutions): count, device ms, algorithmic
- * FLOPs (2*Cin*Cout*taps*pixels) and algorithmic bytes (operand + result + residual tensors + weights, fp32). */
+ * of one kind (0 = dilated 5x3 residual-layer convolutions on conv_tc2 / conv_tc / conv_simt, 1 = all other convolutions, 2 = fused
+ * dilated residual layers of conv_comb.cu, whose time includes normalisation, GELU and operand conversion): count, device ms,
+ * executed FLOPs (2*Cin*Cout*taps*pixels, row taps outside the plane not counted) and algorithmic bytes (kind 0 / 1: operand +
+ * result + residual tensors + weights in fp32; kind 2: 4 B read + 4 B written per element + fp16 weights). */
 int aid_profile(aid_handle* h, int enable);
 int aid_profile_read(aid_handle* h, int kind, uint64_t* launches, double* ms, double* flops, double* bytes);
 
