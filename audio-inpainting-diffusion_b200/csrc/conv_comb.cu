@@ -311,8 +311,9 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_comb_kernel(const __grid_c
 // ---- 96 channels -------------------------------------------------------------------------------------------------------------------
 // The same scheme with K = 96 as a 64-channel group (128-byte rows, SWIZZLE_128B) plus a 32-channel group (64-byte rows,
 // SWIZZLE_64B: the padded 128-channel layout of conv_tc2 would not leave room for the ring), and the weights (270 KB) streamed
-// through a four-slot ring, one slot per (kf, kt): [96 couts][64 cins] then [96 couts][32 cins].  MMA order per output row:
-// kf, kt, group (conv_tc2: kf, group, kt), so the result agrees with the two-kernel path to fp32 accumulation order, not bitwise.
+// through a four-slot ring, one slot per (kf, kt): [96 couts][64 cins] then [96 couts][32 cins]; two consecutive output rows of
+// the comb share every slot.  MMA order per output row: kf, kt, group (conv_tc2: kf, group, kt), so the result agrees with the
+// two-kernel path to fp32 accumulation order, not bitwise.
 //   warps 0-7   epilogue (TMEM lane quadrant x column half, 4 batches of 12 columns = one statistics group each; 4 epilogue warps
 //               measured twice as slow: the epilogue is a latency-bound stream per warp)
 //   warps 8-13  transform, warp w = operand chunks w and w + 6 (two 8-channel chunks: 17 warps keep 96 registers per thread);
@@ -397,15 +398,16 @@ __global__ void __launch_bounds__(C9_THREADS, 1) conv_comb96_kernel(const __grid
     };
 
     if (warp == C9_WARP_W) {
-        // ===================== weight producer: one 18 KB slot per (kf, kt) of every output row =====================
+        // ===================== weight producer: one 18 KB slot per (kf, kt) of every PAIR of output rows =====================
         if (lane == 0) {
             int ws = 0; uint32_t wph = 0;
             for (int item = item0; item < p.n_items; item += istep) {
                 const CombItem ci = comb_item(p, item);
-                for (int k = 0; k < ci.K; ++k)
+                for (int k0 = 0; k0 < ci.K; k0 += 2)
                     for (int kf = 0; kf < 5; ++kf) {
-                        const int j = k + kf - 2;
-                        if (j < 0 || j >= ci.K) continue;
+                        const int j0 = k0 + kf - 2, j1 = j0 + 1;       // input rows of the taps of output rows k0 and k0 + 1
+                        const bool v0 = j0 >= 0 && j0 < ci.K, v1 = k0 + 1 < ci.K && j1 >= 0 && j1 < ci.K;
+                        if (!(v0 || v1)) continue;
                         for (int kt = 0; kt < 3; ++kt) {
                             mbar_wait(w_empty + ws, wph ^ 1);
                             mbar_expect_tx(w_full + ws, (uint32_t)C9_WSLOT);
@@ -538,39 +540,66 @@ __global__ void __launch_bounds__(C9_THREADS, 1) conv_comb96_kernel(const __grid
             }
         }
     } else if (warp == C9_WARP_MMA) {
-        // ===================== MMA issuer: per output row 5 kf x 3 kt x (4 + 2) k-steps of M = 128, N = 96, K = 16 =====================
+        // ===================== MMA issuer: 5 kf x 3 kt x (4 + 2) k-steps of M = 128, N = 96, K = 16 per output row =====================
+        // Output rows are issued in PAIRS (k0, k0 + 1) that share every weight slot (the stream of 270 KB per row through a 72 KB ring
+        // bounded the kernel: the issuer waited for weights a quarter of its time): per (kf, kt) slot six MMAs for row k0 (input row
+        // k0 + kf - 2) and six for row k0 + 1 (input row k0 + kf - 1).  The pair needs input rows k0 - 2 .. k0 + 3 -- one more than the
+        // ring holds: row k0 - 2 is read last by (k0, kf = 0) and row k0 - 1 by (k0, kf = 1), their slots are released right there, and
+        // row k0 + 3, first needed at kf = 4, is transformed into the freed slot meanwhile.
         if (elect_one_sync()) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(C9 >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t a0desc = desc_lo_sw128(smem_u32(ring0)), a1desc = desc_lo_sw128(smem_u32(ring1)), wdesc = desc_lo_sw128(smem_u32(wring));
-            int n0 = 0, ready = 0, ab = 0, ws = 0; uint32_t aph = 0, wph = 0;
+            int n0 = 0, ready = 0, ws = 0, g = 0; uint32_t wph = 0;      // g: output rows issued so far (accumulator g % NACC, phase (g / NACC) & 1)
             long long t_te = 0, t_rr = 0, t_w = 0, t_all = clock64();
+            auto wait_row = [&](int n) {
+                if (n >= ready) { const long long t0 = clock64(); mbar_wait(row_ready + n % CB_RING, (uint32_t)(n / CB_RING) & 1u); t_rr += clock64() - t0; ready = n + 1; tc_fence_after(); }
+            };
             for (int item = item0; item < p.n_items; item += istep) {
                 const CombItem ci = comb_item(p, item);
-                for (int k = 0; k < ci.K; ++k) {
-                    { const long long t0 = clock64(); mbar_wait(tmem_empty + ab, aph ^ 1); t_te += clock64() - t0; }
+                for (int k0 = 0; k0 < ci.K; k0 += 2) {
+                    const bool two = k0 + 1 < ci.K;
+                    const int ab0 = g % C9_NACC, ab1 = (g + 1) % C9_NACC;
+                    { const long long t0 = clock64();
+                      mbar_wait(tmem_empty + ab0, (uint32_t)((g / C9_NACC) & 1) ^ 1u);
+                      if (two) mbar_wait(tmem_empty + ab1, (uint32_t)(((g + 1) / C9_NACC) & 1) ^ 1u);
+                      t_te += clock64() - t0; }
                     tc_fence_after();
-                    const uint32_t d = tmem_base + (uint32_t)(ab * C9_ACC_STRIDE);
-                    uint32_t acc = 0u;
+                    const uint32_t d0 = tmem_base + (uint32_t)(ab0 * C9_ACC_STRIDE), d1 = tmem_base + (uint32_t)(ab1 * C9_ACC_STRIDE);
+                    uint32_t acc0 = 0u, acc1 = 0u;
                     for (int kf = 0; kf < 5; ++kf) {
-                        const int j = k + kf - 2;
-                        if (j < 0 || j >= ci.K) continue;
-                        const int n = n0 + j, slot = n % CB_RING;
-                        if (n >= ready) { const long long t0 = clock64(); mbar_wait(row_ready + slot, (uint32_t)(n / CB_RING) & 1u); t_rr += clock64() - t0; ready = n + 1; tc_fence_after(); }
-                        const uint32_t a0 = a0desc + (uint32_t)slot * (C9_SLOT0 >> 4), a1 = a1desc + (uint32_t)slot * (C9_SLOT1 >> 4);
+                        const int j0 = k0 + kf - 2, j1 = j0 + 1;
+                        const bool v0 = j0 >= 0 && j0 < ci.K, v1 = two && j1 >= 0 && j1 < ci.K;
+                        if (!(v0 || v1)) continue;
+                        const int s0 = (n0 + j0) % CB_RING, s1 = (n0 + j1) % CB_RING;      // (unused when the row is out of range)
+                        if (v0) wait_row(n0 + j0);
+                        if (v1) wait_row(n0 + j1);
+                        const uint32_t a00 = a0desc + (uint32_t)s0 * (C9_SLOT0 >> 4), a01 = a1desc + (uint32_t)s0 * (C9_SLOT1 >> 4);
+                        const uint32_t a10 = a0desc + (uint32_t)s1 * (C9_SLOT0 >> 4), a11 = a1desc + (uint32_t)s1 * (C9_SLOT1 >> 4);
                         for (int kt = 0; kt < 3; ++kt) {
                             { const long long t0 = clock64(); mbar_wait(w_full + ws, wph); t_w += clock64() - t0; }
                             tc_fence_after();
                             const uint32_t b0 = wdesc + (uint32_t)ws * (C9_WSLOT >> 4), b1 = b0 + (C9_WTAP0 >> 4);
-                            tc_mma_k<1, 4>(d, a0 + (uint32_t)kt * 8u, b0, idesc, acc);        // tap kt: one 128-byte pixel row further
-                            tc_mma_k2_sw64(d, a1 + (uint32_t)kt * 4u, b1, idesc, 1u);          // ... one 64-byte row further
-                            acc = 1u;
+                            if (v0) {
+                                tc_mma_k<1, 4>(d0, a00 + (uint32_t)kt * 8u, b0, idesc, acc0);      // tap kt: one 128-byte pixel row further
+                                tc_mma_k2_sw64(d0, a01 + (uint32_t)kt * 4u, b1, idesc, 1u);        // ... one 64-byte row further
+                                acc0 = 1u;
+                            }
+                            if (v1) {
+                                tc_mma_k<1, 4>(d1, a10 + (uint32_t)kt * 8u, b0, idesc, acc1);
+                                tc_mma_k2_sw64(d1, a11 + (uint32_t)kt * 4u, b1, idesc, 1u);
+                                acc1 = 1u;
+                            }
                             tc_commit(w_empty + ws);
                             if (++ws == C9_NW) { ws = 0; wph ^= 1; }
                         }
-                        if (kf == 0 || k == ci.K - 1) tc_commit(slot_free + slot);
+                        // last readers inside a pair: input row k0 - 2 at (k0, kf = 0), input row k0 - 1 at (k0, kf = 1)
+                        if (kf <= 1 && v0) tc_commit(slot_free + s0);
                     }
-                    tc_commit(tmem_full + ab);
-                    if (++ab == C9_NACC) { ab = 0; aph ^= 1; }
+                    tc_commit(tmem_full + ab0);
+                    if (two) tc_commit(tmem_full + ab1);
+                    g += two ? 2 : 1;
+                    if (k0 + 2 >= ci.K)         // last pair of the comb: rows k0 .. K-1 have no later reader
+                        for (int j = k0; j < ci.K; ++j) tc_commit(slot_free + (n0 + j) % CB_RING);
                 }
                 n0 += ci.K;
             }
