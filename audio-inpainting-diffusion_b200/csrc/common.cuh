@@ -137,6 +137,7 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
 // fused dilated residual layer (conv_comb.cu): normalise + modulate + GELU + operand conversion inside the convolution kernel;
 // ep.R must be x itself, out must not overlap x
 bool conv_comb_supported(int C, int F, int T, int dil);
+bool conv_comb_worthwhile(int B, int T, int dil, int num_sms);   // enough combs to fill the device
 // 96 channels: the fused kernel has its own weight packing (64-channel group + 32-channel group per tap); 64 channels: launch_pack_weight_tc2's
 size_t comb_weight_halves(int C);
 void launch_pack_weight_comb(const float* w, __half* wp, int C, cudaStream_t s);

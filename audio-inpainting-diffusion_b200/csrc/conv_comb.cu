@@ -311,9 +311,10 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_comb_kernel(const __grid_c
 // ---- 96 channels -------------------------------------------------------------------------------------------------------------------
 // The same scheme with K = 96 as a 64-channel group (128-byte rows, SWIZZLE_128B) plus a 32-channel group (64-byte rows,
 // SWIZZLE_64B: the padded 128-channel layout of conv_tc2 would not leave room for the ring), and the weights (270 KB) streamed
-// through a four-slot ring, one slot per (kf, kt): [96 couts][64 cins] then [96 couts][32 cins]; two consecutive output rows of
-// the comb share every slot.  MMA order per output row: kf, kt, group (conv_tc2: kf, group, kt), so the result agrees with the
-// two-kernel path to fp32 accumulation order, not bitwise.
+// through a two-slot ring, one slot per (kf, channel group): three taps of [96 couts][64 cins] (36 KB), then three of [96 couts][32
+// cins] (18 KB); two consecutive output rows of the comb share every slot.  MMA order per accumulator: kf, group, kt, k-step --
+// the order of conv_tc2, so the fused layer reproduces the two-kernel path bit for bit and results do not depend on which of
+// the two a batch size selects.
 //   warps 0-7   epilogue (TMEM lane quadrant x column half, 4 batches of 12 columns = one statistics group each; 4 epilogue warps
 //               measured twice as slow: the epilogue is a latency-bound stream per warp)
 //   warps 8-13  transform, warp w = operand chunks w and w + 6 (two 8-channel chunks: 17 warps keep 96 registers per thread);
@@ -321,22 +322,25 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_comb_kernel(const __grid_c
 //   warp 14 halo pixels, 15 weight producer, 16 MMA issuer
 static constexpr int C9 = 96, C9_EPI = 8, C9_TR = 6, C9_WARP_HALO = 14, C9_WARP_W = 15, C9_WARP_MMA = 16, C9_THREADS = 17 * 32;
 static constexpr int C9_SLOT0 = 17408, C9_SLOT1 = 9216;      // group 0: 136 rows x 128 B; group 1: 144 rows x 64 B (130 used), 1 KB aligned
-static constexpr int C9_WTAP0 = C9 * 128, C9_WTAP1 = C9 * 64, C9_WSLOT = C9_WTAP0 + C9_WTAP1;   // 12288 + 6144 = 18432 bytes per (kf, kt)
-static constexpr int C9_NW = 4, C9_NACC = 4, C9_ACC_STRIDE = 128;
+static constexpr int C9_WTAP0 = C9 * 128, C9_WTAP1 = C9 * 64;     // one tap of the 64- / 32-channel group: 12288 / 6144 bytes
+static constexpr int C9_WG0 = 3 * C9_WTAP0, C9_WG1 = 3 * C9_WTAP1, C9_WKF = C9_WG0 + C9_WG1;   // per kf: 36864 + 18432 bytes
+static constexpr int C9_WSLOT = C9_WG0;                            // ring slot (a group-1 stage fills half of it)
+static constexpr int C9_NW = 2, C9_NACC = 4, C9_ACC_STRIDE = 128;
 static constexpr size_t C9_SMEM = 1024 + (size_t)CB_RING * (C9_SLOT0 + C9_SLOT1) + (size_t)C9_NW * C9_WSLOT + CB_BAR_BYTES + CB_GATE_BYTES + CB_STAT_BYTES;
 
-size_t comb_weight_halves(int C) { return C == C9 ? (size_t)15 * C9_WSLOT / 2 : (size_t)15 * CB_C * 64; }
+size_t comb_weight_halves(int C) { return C == C9 ? (size_t)5 * C9_WKF / 2 : (size_t)15 * CB_C * 64; }
 
-// w[co][ci][5][3] fp32 -> per (kf, kt): [96][64] halves (x 2^10), 16-byte chunks swizzled by (co & 7), then [96][32] halves, chunks by ((co >> 1) & 3)
+// w[co][ci][5][3] fp32 -> per kf: [kt][96][64] halves (x 2^10), 16-byte chunks swizzled by (co & 7), then [kt][96][32] halves, chunks by ((co >> 1) & 3)
 __global__ void pack_weight_comb96_kernel(const float* __restrict__ w, __half* __restrict__ wp) {
     const int total = 15 * C9 * C9;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int ci = i % C9, co = (i / C9) % C9, tap = i / (C9 * C9);     // tap = kf * 3 + kt
+        const int kf = tap / 3, kt = tap % 3;
         float v = w[((long long)co * C9 + ci) * 15 + tap] * T2_W_SCALE;
         v = fminf(fmaxf(v, -60000.f), 60000.f);
         size_t o;
-        if (ci < 64) o = (size_t)tap * (C9_WSLOT / 2) + (size_t)co * 64 + ((((ci >> 3) ^ (co & 7)) << 3) | (ci & 7));
-        else { const int c = ci - 64; o = (size_t)tap * (C9_WSLOT / 2) + C9_WTAP0 / 2 + (size_t)co * 32 + ((((c >> 3) ^ ((co >> 1) & 3)) << 3) | (c & 7)); }
+        if (ci < 64) o = (size_t)kf * (C9_WKF / 2) + (size_t)kt * (C9_WTAP0 / 2) + (size_t)co * 64 + ((((ci >> 3) ^ (co & 7)) << 3) | (ci & 7));
+        else { const int c = ci - 64; o = (size_t)kf * (C9_WKF / 2) + C9_WG0 / 2 + (size_t)kt * (C9_WTAP1 / 2) + (size_t)co * 32 + ((((c >> 3) ^ ((co >> 1) & 3)) << 3) | (c & 7)); }
         wp[o] = __float2half_rn(v);
     }
 }
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(C9_THREADS, 1) conv_comb96_kernel(const __grid
     };
 
     if (warp == C9_WARP_W) {
-        // ===================== weight producer: one 18 KB slot per (kf, kt) of every PAIR of output rows =====================
+        // ===================== weight producer: one slot per (kf, channel group) of every PAIR of output rows =====================
         if (lane == 0) {
             int ws = 0; uint32_t wph = 0;
             for (int item = item0; item < p.n_items; item += istep) {
@@ -408,10 +412,11 @@ __global__ void __launch_bounds__(C9_THREADS, 1) conv_comb96_kernel(const __grid
                         const int j0 = k0 + kf - 2, j1 = j0 + 1;       // input rows of the taps of output rows k0 and k0 + 1
                         const bool v0 = j0 >= 0 && j0 < ci.K, v1 = k0 + 1 < ci.K && j1 >= 0 && j1 < ci.K;
                         if (!(v0 || v1)) continue;
-                        for (int kt = 0; kt < 3; ++kt) {
+                        for (int g = 0; g < 2; ++g) {
+                            const uint32_t bytes = g ? (uint32_t)C9_WG1 : (uint32_t)C9_WG0;
                             mbar_wait(w_empty + ws, wph ^ 1);
-                            mbar_expect_tx(w_full + ws, (uint32_t)C9_WSLOT);
-                            bulk_g2s(wring + (size_t)ws * C9_WSLOT, reinterpret_cast<const uint8_t*>(p.w) + (size_t)(kf * 3 + kt) * C9_WSLOT, C9_WSLOT, w_full + ws);
+                            mbar_expect_tx(w_full + ws, bytes);
+                            bulk_g2s(wring + (size_t)ws * C9_WSLOT, reinterpret_cast<const uint8_t*>(p.w) + (size_t)kf * C9_WKF + (g ? C9_WG0 : 0), bytes, w_full + ws);
                             if (++ws == C9_NW) { ws = 0; wph ^= 1; }
                         }
                     }
@@ -575,19 +580,19 @@ __global__ void __launch_bounds__(C9_THREADS, 1) conv_comb96_kernel(const __grid
                         if (v1) wait_row(n0 + j1);
                         const uint32_t a00 = a0desc + (uint32_t)s0 * (C9_SLOT0 >> 4), a01 = a1desc + (uint32_t)s0 * (C9_SLOT1 >> 4);
                         const uint32_t a10 = a0desc + (uint32_t)s1 * (C9_SLOT0 >> 4), a11 = a1desc + (uint32_t)s1 * (C9_SLOT1 >> 4);
-                        for (int kt = 0; kt < 3; ++kt) {
+                        for (int g = 0; g < 2; ++g) {        // 64-channel group (four k-steps per tap), then the 32-channel group (two)
                             { const long long t0 = clock64(); mbar_wait(w_full + ws, wph); t_w += clock64() - t0; }
                             tc_fence_after();
-                            const uint32_t b0 = wdesc + (uint32_t)ws * (C9_WSLOT >> 4), b1 = b0 + (C9_WTAP0 >> 4);
-                            if (v0) {
-                                tc_mma_k<1, 4>(d0, a00 + (uint32_t)kt * 8u, b0, idesc, acc0);      // tap kt: one 128-byte pixel row further
-                                tc_mma_k2_sw64(d0, a01 + (uint32_t)kt * 4u, b1, idesc, 1u);        // ... one 64-byte row further
-                                acc0 = 1u;
-                            }
-                            if (v1) {
-                                tc_mma_k<1, 4>(d1, a10 + (uint32_t)kt * 8u, b0, idesc, acc1);
-                                tc_mma_k2_sw64(d1, a11 + (uint32_t)kt * 4u, b1, idesc, 1u);
-                                acc1 = 1u;
+                            const uint32_t b = wdesc + (uint32_t)ws * (C9_WSLOT >> 4);
+#pragma unroll
+                            for (int kt = 0; kt < 3; ++kt) {        // tap kt: one pixel row (128 / 64 bytes) further in the window
+                                if (g == 0) {
+                                    if (v0) { tc_mma_k<1, 4>(d0, a00 + (uint32_t)kt * 8u, b + (uint32_t)kt * (C9_WTAP0 >> 4), idesc, acc0); acc0 = 1u; }
+                                    if (v1) { tc_mma_k<1, 4>(d1, a10 + (uint32_t)kt * 8u, b + (uint32_t)kt * (C9_WTAP0 >> 4), idesc, acc1); acc1 = 1u; }
+                                } else {
+                                    if (v0) tc_mma_k2_sw64(d0, a01 + (uint32_t)kt * 4u, b + (uint32_t)kt * (C9_WTAP1 >> 4), idesc, 1u);
+                                    if (v1) tc_mma_k2_sw64(d1, a11 + (uint32_t)kt * 4u, b + (uint32_t)kt * (C9_WTAP1 >> 4), idesc, 1u);
+                                }
                             }
                             tc_commit(w_empty + ws);
                             if (++ws == C9_NW) { ws = 0; wph ^= 1; }
@@ -622,6 +627,9 @@ __global__ void __launch_bounds__(C9_THREADS, 1) conv_comb96_kernel(const __grid
 }
 
 bool conv_comb_supported(int C, int F, int T, int dil) { return (C == CB_C || C == C9) && T % 128 == 0 && dil >= 1 && F >= 1; }
+// A comb is one CTA's serial work item: with few clips there are fewer combs (B * dil * T / 128) than SMs and the un-fused path, whose
+// tiles are single rows, is faster (measured at batch 1: 18.4 ms per forward with the fused layers, 12.9 ms without).
+bool conv_comb_worthwhile(int B, int T, int dil, int num_sms) { return (long long)B * dil * (T / 128) * 4 >= 3ll * num_sms; }
 
 // out = alpha * (x + gate * conv5x3_dil(GELU(GroupNorm(x) * (1 + affine)))), statistics of out -> stats_out (may be null)
 void launch_conv_comb(const TV& x, const double* stats_in, long long n_per_group, const float* gamma, const float* affine, long long affine_bstride,

@@ -22,12 +22,13 @@ __device__ __forceinline__ void thin_stats_flush(float s, float q, int g, double
 template <int KF, int KT, int CIN, int PX>
 __global__ void __launch_bounds__(TH) conv_thin_in_kernel(TV a, const float* __restrict__ wp, int dil, TV out, ConvEpilogue ep) {
     constexpr int K = CIN * KF * KT;
-    // weights duplicated as (w, w) pairs: the multiply-accumulate loop runs on the packed fp32x2 pipe of sm_100 (one LDS.64 + PX / 2
-    // FFMA2 per tap instead of one LDS + PX FFMA; the same IEEE fma per lane) -- these kernels are bound by instruction issue
-    extern __shared__ float2 ws2[];  // [K][Cout]
+    // (tried: the multiply-accumulate on the packed fp32x2 pipe with the weights duplicated as (w, w) pairs in shared memory -- one
+    // LDS.64 + PX / 2 FFMA2 per tap instead of one LDS + PX FFMA.  Measured slower, 1.89 -> 2.47 ms over the seven pyramid
+    // convolutions at B = 8: twice the shared memory per block, fewer resident blocks.)
+    extern __shared__ float ws[];  // [K][Cout]
     __shared__ double sst[8][2];
     const int Cout = out.C, F = a.F, T = a.T, b = blockIdx.z;
-    for (int i = threadIdx.x; i < K * Cout; i += TH) { const float w = __ldg(wp + i); ws2[i] = make_float2(w, w); }
+    for (int i = threadIdx.x; i < K * Cout; i += TH) ws[i] = __ldg(wp + i);
     if (threadIdx.x < 16) sst[threadIdx.x >> 1][threadIdx.x & 1] = 0.0;
     __syncthreads();
     const int tq = T / PX;
@@ -65,19 +66,13 @@ __global__ void __launch_bounds__(TH) conv_thin_in_kernel(TV a, const float* __r
 #pragma unroll 1
     for (int co = 0; co < Cout; ++co) {
         float acc[PX];
-        {
-            static_assert(PX % 2 == 0, "conv_thin_in: pixel pairs");
-            float2 acc2[PX / 2];
 #pragma unroll
-            for (int pp = 0; pp < PX / 2; ++pp) acc2[pp] = make_float2(0.f, 0.f);
+        for (int px = 0; px < PX; ++px) acc[px] = 0.f;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const float2 w2 = ws2[k * Cout + co];
+        for (int k = 0; k < K; ++k) {
+            const float w = ws[k * Cout + co];
 #pragma unroll
-                for (int pp = 0; pp < PX / 2; ++pp) acc2[pp] = __ffma2_rn(w2, make_float2(in[k][2 * pp], in[k][2 * pp + 1]), acc2[pp]);
-            }
-#pragma unroll
-            for (int pp = 0; pp < PX / 2; ++pp) { acc[2 * pp] = acc2[pp].x; acc[2 * pp + 1] = acc2[pp].y; }
+            for (int px = 0; px < PX; ++px) acc[px] = fmaf(w, in[k][px], acc[px]);
         }
         if (live) {
             const float g = gate ? gate[co] : 1.f;
@@ -191,7 +186,7 @@ static bool aligned16(const TV& v) {
 
 template <int KF, int KT, int CIN, int PX>
 static void launch_thin_in(const TV& a, const float* wp, int dil, const TV& out, const ConvEpilogue& ep, cudaStream_t s) {
-    const size_t smem = (size_t)CIN * KF * KT * out.C * sizeof(float2);
+    const size_t smem = (size_t)CIN * KF * KT * out.C * sizeof(float);
     static SmemConfig configured;
     ensure_dyn_smem(conv_thin_in_kernel<KF, KT, CIN, PX>, smem, configured, 48 * 1024);
     const long long n = (long long)a.F * (a.T / PX);

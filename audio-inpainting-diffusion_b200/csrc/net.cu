@@ -643,7 +643,8 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
             // bandwidth like conv_tc2; in the network at batch 32 it measured +1.4 % over pass + conv_tc2 (cta_group::2), and it differs
             // from that path in fp32 accumulation order (2e-6 per layer)
             static const bool env_comb96 = !(getenv("AID_COMB96") && atoi(getenv("AID_COMB96")) == 0);
-            if (cmode == 2 && env_comb && !tp && !use_cl && !k.k1x1 && !sat && conv_comb_supported(N, F, T, dil) && (N != 96 || (env_comb96 && k.H[i].wcomb))) {
+            if (cmode == 2 && env_comb && !tp && !use_cl && !k.k1x1 && !sat && conv_comb_supported(N, F, T, dil) && (N != 96 || (env_comb96 && k.H[i].wcomb)) &&
+                conv_comb_worthwhile(B, T, dil, c.n->num_sms)) {
                 // fused layer (conv_comb.cu): normalisation, modulation, GELU and the operand conversion happen inside the convolution;
                 // the t-tile halos forbid an in-place update, so the layers alternate between the block's two buffers
                 TV o = (cur.p == x.p) ? a : x;
@@ -652,6 +653,9 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
                 cur = o;
                 continue;
             }
+            // (the fused layers are the LAST ones of a block -- a comb gets more parallel with the dilation -- so the operand buffer is never
+            // needed again once one of them has used it as its output plane)
+            if (cur.p == abuf) throw std::runtime_error("resblock: un-fused layer after a fused one");
             if (cmode == 2) {
                 if (cur_is_cl) RUN(launch_gn_act_tc2_cl(xcl, B, N, F, T, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s));
                 else RUN(launch_gn_act_tc2(cur, cur_stats, n_grp, k.norm[i].gamma, c.mod + k.affine[i].off, c.modstride(), true, pf, a_hi, c.s, sat));
