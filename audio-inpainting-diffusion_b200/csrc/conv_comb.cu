@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) conv_comb_kernel(const __grid_c
                 const float* xr = xb + (long long)(ci.r + k * p.dil) * p.T;
                 if (k + 2 < ci.K) {     // lane -> (channel lane / 4, 128-byte line lane % 4) of the row after the next
                     const float* nx = xr - lane + 2ll * p.dil * p.T + (long long)(lane >> 2) * sc + (lane & 3) * 32;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nx));
                 }
                 const float* xn = xr + (long long)p.dil * p.T;
                 const bool more = k + 1 < ci.K;
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(C9_THREADS, 1) conv_comb96_kernel(const __grid
                 if (k + 2 < ci.K && lane < 16) {     // L2 prefetch of the row after the next: lane -> (chunk half lane / 8 ... 16 channels x 4 lines = 64 lines, 4 per lane)
                     const float* nx = p.x.p + (long long)ci.b * p.x.sb + (long long)(frow + 2 * p.dil) * p.T + ci.t0 + (long long)(8 * (w + 6 * (lane >> 3)) + (lane & 7)) * sc;
 #pragma unroll
-                    for (int l4 = 0; l4 < 4; ++l4) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + l4 * 32));
+                    for (int l4 = 0; l4 < 4; ++l4) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nx + l4 * 32));
                 }
                 const bool more = k + 1 < ci.K;
                 const int slot = n % CB_RING;
