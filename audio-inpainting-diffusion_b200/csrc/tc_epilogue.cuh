@@ -39,12 +39,6 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
 }
 
 
-// output stores of the epilogue: plain.  (Streaming stores, st.global.cs, measured neutral in the fused kernels and 5-8 % slower on
-// the 128-cout conv_tc2 layers.)
-#ifndef AID_EPI_STORE
-#define AID_EPI_STORE(ptr, val) (*(ptr) = (val))
-#endif
-
 // ---- fast epilogue ------------------------------------------------------------------------------------------------------------
 // The generic epilogue below handles every layout and group width with run-time bookkeeping; its inner loop compiled to ~20
 // instructions per output element with indirect branches in the statistics (ncu: 148 M warp instructions for 134 M outputs of a
@@ -179,7 +173,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
             if (c_ok) {
                 const uint32_t ob = c_oo + (uint32_t)(bi * BW) * osc;
 #pragma unroll
-                for (int j = 0; j < BW / 2; ++j) { AID_EPI_STORE(c_po + ob + (uint32_t)(2 * j) * osc, v2[j].x); AID_EPI_STORE(c_po + ob + (uint32_t)(2 * j + 1) * osc, v2[j].y); }
+                for (int j = 0; j < BW / 2; ++j) { c_po[ob + (uint32_t)(2 * j) * osc] = v2[j].x; c_po[ob + (uint32_t)(2 * j + 1) * osc] = v2[j].y; }     // 32-bit offsets: one IMAD.WIDE per store
             }
             if (do_stats) {
 #pragma unroll
