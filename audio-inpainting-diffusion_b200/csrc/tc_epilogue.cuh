@@ -173,7 +173,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
             if (c_ok) {
                 const uint32_t ob = c_oo + (uint32_t)(bi * BW) * osc;
 #pragma unroll
-                for (int j = 0; j < BW / 2; ++j) { c_po[ob + (uint32_t)(2 * j) * osc] = v2[j].x; c_po[ob + (uint32_t)(2 * j + 1) * osc] = v2[j].y; }     // 32-bit offsets: one IMAD.WIDE per store
+                for (int j = 0; j < BW / 2; ++j) { c_po[ob + (uint32_t)(2 * j) * osc] = v2[j].x; c_po[ob + (uint32_t)(2 * j + 1) * osc] = v2[j].y; }     // 32-bit offsets: one IMAD.WIDE per store.  (Streaming stores, st.global.cs, measured 2-5 % slower on every layer.)
             }
             if (do_stats) {
 #pragma unroll
