@@ -180,6 +180,61 @@ __global__ void __launch_bounds__(TH) conv_thin_out_kernel(TV a, const float* __
     }
 }
 
+// 5x3 (dilation 1) convolution N -> 2: the data gradient of the pyramid projections (unet.py:676, 794), which the general CUDA-core kernel
+// served at 0.04 TB/s (15 % of the whole backward).  One thread = 4 consecutive pixels of one row, both output channels; per input
+// channel it reads the five tap rows (6 pixels each, served by L1 / L2 after the first row) and does 15 x 4 x 2 FMAs.
+__global__ void __launch_bounds__(TH) conv_thin_out53_kernel(TV a, const float* __restrict__ wp, TV out, ConvEpilogue ep) {
+    extern __shared__ float ws[];  // [Cin * 15][2]
+    const int Cin = a.C, F = a.F, T = a.T, b = blockIdx.z;
+    for (int i = threadIdx.x; i < Cin * 30; i += TH) ws[i] = __ldg(wp + i);
+    __syncthreads();
+    const int tq = T / 4;
+    const long long pq = (long long)blockIdx.x * TH + threadIdx.x;
+    if (pq >= (long long)F * tq) return;
+    const int f = (int)(pq / tq), t0 = (int)(pq % tq) * 4;
+    float acc[2][4];
+#pragma unroll
+    for (int co = 0; co < 2; ++co)
+#pragma unroll
+        for (int px = 0; px < 4; ++px) acc[co][px] = 0.f;
+    const float* pa = a.p + (long long)b * a.sb;
+    for (int ci = 0; ci < Cin; ++ci) {
+        const float* pc = pa + (long long)ci * a.sc;
+        const float* w = ws + ci * 30;
+#pragma unroll
+        for (int kf = 0; kf < 5; ++kf) {
+            const int ff = f + kf - 2;
+            if (ff < 0 || ff >= F) continue;
+            const float* row = pc + (long long)ff * T + t0;
+            const float4 m = __ldg(reinterpret_cast<const float4*>(row));
+            const float win[6] = {t0 > 0 ? __ldg(row - 1) : 0.f, m.x, m.y, m.z, m.w, t0 + 4 < T ? __ldg(row + 4) : 0.f};
+#pragma unroll
+            for (int kt = 0; kt < 3; ++kt) {
+                const float w0 = w[(kf * 3 + kt) * 2 + 0], w1 = w[(kf * 3 + kt) * 2 + 1];
+#pragma unroll
+                for (int px = 0; px < 4; ++px) { acc[0][px] = fmaf(w0, win[px + kt], acc[0][px]); acc[1][px] = fmaf(w1, win[px + kt], acc[1][px]); }
+            }
+        }
+    }
+    const long long prow = (long long)f * T + t0;
+    const float* gate = ep.gate ? ep.gate + (long long)b * ep.gate_bstride : nullptr;
+#pragma unroll
+    for (int co = 0; co < 2; ++co) {
+        const float g = gate ? gate[co] : 1.f;
+        float4 v = make_float4(acc[co][0] * g, acc[co][1] * g, acc[co][2] * g, acc[co][3] * g);
+        if (ep.R.p) {
+            const float4 r = *reinterpret_cast<const float4*>(ep.R.p + (long long)b * ep.R.sb + (long long)co * ep.R.sc + prow);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        v.x *= ep.alpha; v.y *= ep.alpha; v.z *= ep.alpha; v.w *= ep.alpha;
+        if (ep.R2.p) {
+            const float4 r = *reinterpret_cast<const float4*>(ep.R2.p + (long long)b * ep.R2.sb + (long long)co * ep.R2.sc + prow);
+            v.x += ep.beta * r.x; v.y += ep.beta * r.y; v.z += ep.beta * r.z; v.w += ep.beta * r.w;
+        }
+        *reinterpret_cast<float4*>(out.p + (long long)b * out.sb + (long long)co * out.sc + prow) = v;
+    }
+}
+
 static bool aligned16(const TV& v) {
     return v.p == nullptr || ((reinterpret_cast<uintptr_t>(v.p) & 15) == 0 && (v.sb & 3) == 0 && (v.sc & 3) == 0);
 }
@@ -216,6 +271,12 @@ bool launch_conv_thin(const TV& a, const float* wp, int KF, int KT, int dil, con
         const size_t smem = (size_t)a.C * out.C * sizeof(float);
         if (out.C == 2) conv_thin_out_kernel<2><<<grid, TH, smem, s>>>(a, wp, out, ep, ThinInScale{});
         else conv_thin_out_kernel<8><<<grid, TH, smem, s>>>(a, wp, out, ep, ThinInScale{});
+        AID_COUNT_LAUNCH(1);
+        return true;
+    }
+    if (KF == 5 && KT == 3 && dil == 1 && out.C == 2 && !ep.stats && T % 4 == 0 && a.C * 30 * 4 <= 48 * 1024) {
+        const long long n = (long long)a.F * (T / 4);
+        conv_thin_out53_kernel<<<dim3((unsigned)((n + TH - 1) / TH), 1, a.B), TH, (size_t)a.C * 30 * sizeof(float), s>>>(a, wp, out, ep);
         AID_COUNT_LAUNCH(1);
         return true;
     }

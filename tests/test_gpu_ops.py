@@ -57,6 +57,8 @@ CONV_CASES = [
     (1, 2, 40, 20, 6, 5, 3, 1, False, True, False, True),      # thin-in 5x3, T = 6 (pair-vectorised)
     (2, 48, 8, 7, 12, 1, 1, 1, False, False, False, False),    # thin-out N -> 8
     (1, 24, 2, 6, 8, 1, 1, 1, False, True, True, False),       # thin-out N -> 2 with both residuals
+    (2, 64, 2, 30, 64, 5, 3, 1, False, False, True, False),    # thin-out 5x3 N -> 2 accumulating into R2 (pyramid projection gradient)
+    (1, 40, 2, 7, 8, 5, 3, 1, True, True, True, False),        # ... gate and both residuals, F of the order of the tap span
 ])
 def test_conv2d(cuda, case, mode):
     B, Cin, Cout, Fd, T, KF, KT, dil, use_gate, use_R, use_R2, use_stats = case

@@ -56,7 +56,7 @@ def test_groupnorm_act_backward(cuda, gelu):
 
 
 @pytest.mark.parametrize("case", [(2, 16, 1, 1, 1), (16, 2, 1, 1, 1), (8, 16, 1, 1, 1), (16, 8, 1, 1, 1), (2, 16, 5, 3, 1), (16, 16, 5, 3, 4),
-                                  (24, 40, 1, 1, 1), (32, 32, 5, 3, 16)])
+                                  (24, 40, 1, 1, 1), (32, 32, 5, 3, 16), (2, 96, 5, 3, 1)])
 def test_conv_backward_input(cuda, case):
     _l, L = _lib()
     Cin, Cout, KF, KT, dil = case
