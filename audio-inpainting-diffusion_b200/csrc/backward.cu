@@ -17,8 +17,19 @@ static constexpr int BT = 256;
 static constexpr int kChunk = 8192;
 
 __device__ __forceinline__ float gelu_grad(float z) {
-    // d/dz [0.5 z (1 + erf(z / sqrt 2))] = 0.5 (1 + erf(z / sqrt 2)) + z exp(-z^2 / 2) / sqrt(2 pi)
-    return 0.5f * (1.f + erff(z * 0.70710678118654752440f)) + z * 0.39894228040143267794f * expf(-0.5f * z * z);
+    // d/dz [0.5 z (1 + erf(z / sqrt 2))] = 0.5 (1 + erf(z / sqrt 2)) + z exp(-z^2 / 2) / sqrt(2 pi).
+    // erf by Abramowitz & Stegun 7.1.26 (1.5e-7 absolute): with u = |z| / sqrt 2 its exponential exp(-u^2) IS exp(-z^2 / 2), so the
+    // whole derivative costs one MUFU.EX2 and one MUFU.RCP (erff + expf were ~40 instructions and bound these passes).
+    const float az = fabsf(z);
+    float t, ex;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, az, 1.f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-0.72134752044448170368f * z * z));      // log2(e) / 2
+    float pl = fmaf(t, 1.061405429f, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    const float erf_abs = fmaf(-pl * t, ex, 1.f);
+    return fmaf(0.5f, copysignf(erf_abs, z), 0.5f) + z * 0.39894228040143267794f * ex;
 }
 
 // (sum, sumsq) of a statistics slot -> mean, unbiased std
@@ -53,7 +64,7 @@ void launch_scale_channels(const TV& in, const float* vec, long long vstride, fl
 // reduce: D[b][grp] += partial sums (double atomics on fp32 block partials).        grid: (chunks, C, B)
 __global__ void __launch_bounds__(BT)
 gn_bwd_reduce_kernel(TV g, TV x, const double* __restrict__ stats, double npg, const float* __restrict__ gamma, const float* __restrict__ affine,
-                     long long abstride, int gelu, double* __restrict__ D) {
+                     long long abstride, int gelu, double* __restrict__ D, int vec) {
     const int c = blockIdx.y, b = blockIdx.z;
     const int grp = c / (x.C / 8);
     float mean, stdv;
@@ -66,6 +77,19 @@ gn_bwd_reduce_kernel(TV g, TV x, const double* __restrict__ stats, double npg, c
     const float* pg = g.p + (long long)b * g.sb + (long long)c * g.sc;
     const long long start = (long long)blockIdx.x * kChunk, end = min(P, start + kChunk);
     float acc = 0.f;
+    if (vec) {      // planes and chunks are multiples of 4 elements, 16-byte aligned
+        for (long long e = start + 4 * threadIdx.x; e < end; e += 4 * BT) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(px + e));
+            const float4 gv = __ldg(reinterpret_cast<const float4*>(pg + e));
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float gz = gs[i];
+                if (gelu) gz *= gelu_grad(xs[i] * sw);
+                acc = fmaf(gz * w, xs[i], acc);
+            }
+        }
+    } else
     for (long long e = start + threadIdx.x; e < end; e += BT) {
         const float xv = px[e];
         float gz = pg[e];
@@ -86,7 +110,7 @@ gn_bwd_reduce_kernel(TV g, TV x, const double* __restrict__ stats, double npg, c
 // apply: out = cres * gres + dx   (gres may be null; out may alias gres or g)
 __global__ void __launch_bounds__(BT)
 gn_bwd_apply_kernel(TV g, TV x, const double* __restrict__ stats, double npg, const float* __restrict__ gamma, const float* __restrict__ affine,
-                    long long abstride, int gelu, const double* __restrict__ D, TV gres, float cres, TV out, unsigned int* __restrict__ amax) {
+                    long long abstride, int gelu, const double* __restrict__ D, TV gres, float cres, TV out, unsigned int* __restrict__ amax, int vec) {
     const int c = blockIdx.y, b = blockIdx.z;
     float vmax = 0.f;
     const int grp = c / (x.C / 8);
@@ -102,6 +126,26 @@ gn_bwd_apply_kernel(TV g, TV x, const double* __restrict__ stats, double npg, co
     const float* pr = gres.p ? gres.p + (long long)b * gres.sb + (long long)c * gres.sc : nullptr;
     float* po = out.p + (long long)b * out.sb + (long long)c * out.sc;
     const long long start = (long long)blockIdx.x * kChunk, end = min(P, start + kChunk);
+    if (vec) {      // (out may alias g or gres: every element is read before it is written, by the same thread)
+        for (long long e = start + 4 * threadIdx.x; e < end; e += 4 * BT) {
+            const float4 xv = *reinterpret_cast<const float4*>(px + e);
+            const float4 gv = *reinterpret_cast<const float4*>(pg + e);
+            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pr) rv = *reinterpret_cast<const float4*>(pr + e);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w}, rs[4] = {rv.x, rv.y, rv.z, rv.w};
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float gz = gs[i];
+                if (gelu) gz *= gelu_grad(xs[i] * sw);
+                float v = sw * gz - k2 * (xs[i] - mean);
+                if (pr) v = fmaf(cres, rs[i], v);
+                o[i] = v;
+                vmax = fmaxf(vmax, fabsf(v));
+            }
+            *reinterpret_cast<float4*>(po + e) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    } else
     for (long long e = start + threadIdx.x; e < end; e += BT) {
         const float xv = px[e];
         float gz = pg[e];
@@ -123,8 +167,10 @@ void launch_gn_bwd(const TV& g, const TV& x, const double* stats, long long n_pe
     const long long P = (long long)x.F * x.T;
     const dim3 grid((unsigned)((P + kChunk - 1) / kChunk), x.C, x.B);
     AID_CUDA_CHECK(cudaMemsetAsync(D_scratch, 0, (size_t)x.B * 8 * sizeof(double), s));
-    gn_bwd_reduce_kernel<<<grid, BT, 0, s>>>(g, x, stats, (double)n_per_group, gamma, affine, abstride, gelu ? 1 : 0, D_scratch);
-    gn_bwd_apply_kernel<<<grid, BT, 0, s>>>(g, x, stats, (double)n_per_group, gamma, affine, abstride, gelu ? 1 : 0, D_scratch, gres, cres, out, amax_out);
+    auto al4 = [](const TV& v) { return v.p == nullptr || ((reinterpret_cast<uintptr_t>(v.p) & 15) == 0 && (v.sb & 3) == 0 && (v.sc & 3) == 0); };
+    const int vec = (P % 4 == 0 && al4(g) && al4(x) && al4(gres) && al4(out)) ? 1 : 0;
+    gn_bwd_reduce_kernel<<<grid, BT, 0, s>>>(g, x, stats, (double)n_per_group, gamma, affine, abstride, gelu ? 1 : 0, D_scratch, vec);
+    gn_bwd_apply_kernel<<<grid, BT, 0, s>>>(g, x, stats, (double)n_per_group, gamma, affine, abstride, gelu ? 1 : 0, D_scratch, gres, cres, out, amax_out, vec);
     AID_COUNT_LAUNCH(2);
 }
 
