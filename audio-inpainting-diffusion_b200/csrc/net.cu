@@ -828,8 +828,9 @@ static size_t plan_forward(Net& n, int B, int* slots) {
 // ======================================================================================================
 // Input gradient (VJP) of the denoiser: reconstruction guidance, sampler.py:57-113 (torch.autograd.grad(norm, x) through
 // edm.py:133-148 and unet.py:730-845).  The taped forward keeps every block input / layer input alive in the workspace; the
-// backward below walks the network in reverse.  All backward arithmetic is fp32 on CUDA cores (the data-gradient convolutions
-// are the forward convolution kernels run with transposed, tap-mirrored weights).
+// backward below walks the network in reverse.  The data-gradient convolutions are the forward convolution kernels run with
+// transposed, tap-mirrored weights: fp32 CUDA cores in conv_mode 0 / 1 and for the thin-channel layers, tcgen05 with fp16 operands
+// and per-tensor gradient scaling for the dilated and the wide 1x1 layers in conv_mode 2; everything else is fp32.
 // Convention: every backward routine ACCUMULATES into its destination (zero-initialised by the caller), through the
 // convolution epilogue's R2 input or the beta argument of the adjoint kernels.
 
