@@ -210,7 +210,7 @@ int aid_debug_time_gn_tc2(const float* x_dev, int B, int C, int F, int T, int PF
 /* Debug / parity / tuning of one dilated residual layer of conv_mode 2 (unet.py:470-482),
  *   out = alpha * (x + gate[c] * conv5x3_dil(GELU(GroupNorm8(x) * gamma * (1 + affine))))          x, out: [B, C, F, T], w: [C, C, 5, 3]
  * fused = 0: operand pass (gn_act_tc2) + conv_tc2_kernel;  fused = 1: conv_comb_kernel (normalisation, GELU and operand conversion
- * inside the convolution; C = 64, T % 128 == 0).  stats_out_dev ([B][8][2] doubles, may be NULL) receives (sum, sumsq) of out per
+ * inside the convolution; C = 64 or 96, T % 128 == 0).  stats_out_dev ([B][8][2] doubles, may be NULL) receives (sum, sumsq) of out per
  * group.  ms_out (may be NULL): device time of the layer (pass + convolution, or the fused kernel) of a second, timed run. */
 int aid_debug_dilated_layer(const float* x_dev, const float* w_dev, int B, int C, int F, int T, int dil, const float* gamma_dev,
                             const float* affine_dev, const float* gate_dev, float alpha, int fused, float* out_dev, double* stats_out_dev,
