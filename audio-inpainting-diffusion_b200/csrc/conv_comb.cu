@@ -1,4 +1,5 @@
-// Fused dilated residual layer of conv_mode 2 for 64-channel blocks (unet.py:470-482): group-norm apply, adaLN modulation, GELU and the
+// Fused dilated residual layer of conv_mode 2 for 64-channel (below) and 96-channel (second half of the file) blocks (unet.py:470-482):
+// group-norm apply, adaLN modulation, GELU and the
 // conversion to the fp16 tensor-core operand happen INSIDE the convolution kernel, so a layer reads its input once and writes
 // its output once (8 B per element instead of 6 B for the operand pass + 10 B for conv_tc2_kernel).
 //
@@ -10,7 +11,8 @@
 // All 15 weight taps (64 x 64 fp16 each, 120 KB) stay resident in shared memory for the whole launch.
 //   warps 0-7   epilogue (tc_epilogue.cuh: TMEM -> out = alpha * (acc * gate + x), statistics of the output for the next layer)
 //   warps 8-15  transform: warp w owns channels 8w .. 8w+7 (one 16-byte operand chunk), lane l the pixels l, l+32, l+64, l+96 of
-//               the tile; raw values are held one row ahead in registers, the row after that is pulled into L2
+//               the tile; raw values are held one row ahead in registers, the row after that is pulled into L2 with evict_last
+//               priority (the epilogue re-reads the row as the residual three output rows later: L2 hits)
 //   warp 16     loads the weights once, then transforms the two halo pixels (t0 - 1, t0 + 128) of every row
 //   warp 17     one elected thread issues the MMAs: per output row 5 kf x 3 kt x 4 k-steps of M = 128, N = 64, K = 16
 // Ring protocol (global row sequence number n per CTA, slot = n % 5): row_ready[slot] <- the 8 transform warps + the halo warp;
