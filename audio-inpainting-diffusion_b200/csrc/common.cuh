@@ -136,6 +136,12 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
 
 // fused dilated residual layer (conv_comb.cu): normalise + modulate + GELU + operand conversion inside the convolution kernel;
 // ep.R must be x itself, out must not overlap x
+// fused init block of an encoder level (conv_init.cu): proj_in (2 -> N) + one gated 1x1 residual layer + res_conv, one pass over the input
+bool init_block_supported(int N, int T);
+size_t init_block_scratch_floats(int B, int N);
+void launch_init_block(const TV& x2, const float* w_in, const float* w_res, const __half* wH, const float* gamma, const float* affine,
+                       long long affine_bstride, const float* gate, long long gate_bstride, const TV& out, double* stats_out, float* scratch,
+                       int num_sms, cudaStream_t s);
 bool conv_comb_supported(int C, int F, int T, int dil);
 bool conv_comb_worthwhile(int B, int T, int dil, int num_sms);   // enough combs to fill the device
 // 96 channels: the fused kernel has its own weight packing (64-channel group + 32-channel group per tap); 64 channels: launch_pack_weight_tc2's

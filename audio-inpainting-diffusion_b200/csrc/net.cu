@@ -146,6 +146,7 @@ struct Net {
     // weight values clamped at finalize
     unsigned long long* d_sat = nullptr;
     bool count_sat = false;
+    bool fuse_init = true, fuse_comb = true;   // aid_debug_fusion: run the un-fused twins of conv_init.cu / conv_comb.cu (parity tests)
     unsigned long long weight_sat = 0;
     // input-gradient path (aid_unet_forward_tape / aid_unet_backward)
     Tape tape;
@@ -527,12 +528,42 @@ static void conv_comb_layer(Ctx& c, const TV& x, const double* stats_in, long lo
     if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
 }
 
+// conv_mode 2, init block of an encoder level with 64 / 96 / 128 channels (conv_init.cu): recorded as kind 1 with the block's algorithmic
+// traffic (8 B read per pixel, 4 N B written)
+static void init_block_fused(Ctx& c, const ResBlk& k, const TV& in, const TV& out) {
+    float* scratch = c.allocf((long long)init_block_scratch_floats(in.B, k.N));
+    if (!c.dry()) {
+        Net& n = *c.n;
+        Net::ProfRec rec{};
+        if (n.prof) {
+            auto get = [&]() { cudaEvent_t e; if (n.prof_pool.empty()) { AID_CUDA_CHECK(cudaEventCreate(&e)); } else { e = n.prof_pool.back(); n.prof_pool.pop_back(); } return e; };
+            rec.e0 = get(); rec.e1 = get(); rec.kind = 1;
+            const double px = (double)in.B * in.F * in.T;
+            rec.flops = 2.0 * px * k.N * (k.N + 4.0);
+            rec.bytes = 4.0 * px * (2.0 + k.N);
+            AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
+        }
+        launch_init_block(in, k.proj_in.wp, k.res_conv.wp, k.H[0].wtc, k.norm[0].gamma, c.mod + k.affine[0].off, c.modstride(),
+                          c.mod + k.gate[0].off, c.modstride(), out, out.stats, scratch, n.num_sms, c.s);
+        if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
+    }
+    c.release(scratch);
+}
+
 // unet.py:452-493.  `accum` (decoder out blocks, unet.py:817): out = (accum + block(x)) / sqrt(2), may alias out.
 // `bt` (taped forward, input-gradient path): every intermediate the backward needs gets its own buffer and is recorded.
 static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = nullptr, BlkTape* bt = nullptr) {
     const int B = in.B, F = in.F, T = in.T, N = k.N;
     const bool tp = bt != nullptr;
     if (in.C != k.dim || out.C != k.dim_out) throw std::runtime_error("resblock: channel mismatch");
+    {   // encoder init blocks (2 CQT channels -> N, one gated 1x1 layer): a single fused kernel in conv_mode 2 (AID_INIT_FUSED=0: the five un-fused launches)
+        static const bool env_init = !(getenv("AID_INIT_FUSED") && atoi(getenv("AID_INIT_FUSED")) == 0);
+        if (env_init && c.n->fuse_init && c.n->cfg.conv_mode == 2 && !tp && !c.n->count_sat && !accum && k.k1x1 && k.dim == 2 && k.nd == 1 && !k.attn && !k.after &&
+            k.dim_out == N && k.H[0].wtc && init_block_supported(N, T)) {
+            init_block_fused(c, k, in, out);
+            return;
+        }
+    }
     const long long plane = (long long)B * N * F * T;
     const long long n_grp = (long long)(N / 8) * F * T;
     float* xbuf = c.allocf(plane);
@@ -643,7 +674,7 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
             // bandwidth like conv_tc2; in the network at batch 32 it measured +1.4 % over pass + conv_tc2 (cta_group::2), and it differs
             // from that path in fp32 accumulation order (2e-6 per layer)
             static const bool env_comb96 = !(getenv("AID_COMB96") && atoi(getenv("AID_COMB96")) == 0);
-            if (cmode == 2 && env_comb && !tp && !use_cl && !k.k1x1 && !sat && conv_comb_supported(N, F, T, dil) && (N != 96 || (env_comb96 && k.H[i].wcomb)) &&
+            if (cmode == 2 && env_comb && c.n->fuse_comb && !tp && !use_cl && !k.k1x1 && !sat && conv_comb_supported(N, F, T, dil) && (N != 96 || (env_comb96 && k.H[i].wcomb)) &&
                 conv_comb_worthwhile(B, T, dil, c.n->num_sms)) {
                 // fused layer (conv_comb.cu): normalisation, modulation, GELU and the operand conversion happen inside the convolution;
                 // the t-tile halos forbid an in-place update, so the layers alternate between the block's two buffers
@@ -1620,6 +1651,64 @@ int aid_debug_dilated_layer(const float* x_dev, const float* w_dev, int B, int C
     catch (const std::exception& e) { fprintf(stderr, "aid_debug_dilated_layer: %s\n", e.what()); return AID_ERR_INVALID; }
 }
 
+/* debug / parity / tuning: the init block of an encoder level in conv_mode 2 (unet.py:452-493 with dim = 2, one 1x1 layer):
+   fused = 1: conv_init.cu; fused = 0: the five un-fused launches of resblock().  Weights in the checkpoint layout
+   (w_in, w_res: [N][2], wH: [N][N]); gamma, affine, gate: [N] (shared by the batch). */
+int aid_debug_init_block(const float* x2_dev, const float* w_in_dev, const float* w_res_dev, const float* wH_dev, int B, int N, int F, int T,
+                         const float* gamma_dev, const float* affine_dev, const float* gate_dev, int fused, float* out_dev,
+                         double* stats_out_dev, float* ms_out) {
+    if (!x2_dev || !w_in_dev || !w_res_dev || !wH_dev || !gamma_dev || !out_dev || N % 8 != 0) return AID_ERR_INVALID;
+    try {
+        if (!conv_tc_supported(N, N, 1, 1) || (fused && !init_block_supported(N, T))) throw std::invalid_argument("shape not supported");
+        TV x2 = make_tv(const_cast<float*>(x2_dev), B, 2, F, T), out = make_tv(out_dev, B, N, F, T);
+        int sms = 148, dev = 0;
+        AID_CUDA_CHECK(cudaGetDevice(&dev));
+        AID_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int pf = tc_pad_rows(T, 1, 1);
+        const size_t plane = (size_t)B * N * F * T;
+        double* st = nullptr; __half *wtc = nullptr, *a = nullptr; float *wk = nullptr, *scratch = nullptr, *y = nullptr, *x = nullptr;
+        AID_CUDA_CHECK(cudaMalloc(&st, (size_t)B * 16 * sizeof(double)));
+        AID_CUDA_CHECK(cudaMalloc(&wtc, tc2_weight_halves(N, N, 1, 1) * sizeof(__half)));
+        AID_CUDA_CHECK(cudaMalloc(&wk, (size_t)4 * N * sizeof(float)));
+        AID_CUDA_CHECK(cudaMalloc(&scratch, init_block_scratch_floats(B, N) * sizeof(float)));
+        if (!fused) {
+            AID_CUDA_CHECK(cudaMalloc(&a, tc2_act_halves(B, N, F, T, pf) * sizeof(__half)));
+            AID_CUDA_CHECK(cudaMalloc(&y, plane * sizeof(float)));
+            AID_CUDA_CHECK(cudaMalloc(&x, plane * sizeof(float)));
+        }
+        launch_pack_weight_tc2(wH_dev, wtc, N, N, 1, 1, nullptr);
+        pack_conv_weight_kernel<<<1, 256>>>(w_in_dev, wk, N, 2, 1);
+        pack_conv_weight_kernel<<<1, 256>>>(w_res_dev, wk + 2 * N, N, 2, 1);
+        const long long n_grp = (long long)(N / 8) * F * T;
+        cudaEvent_t e0, e1; AID_CUDA_CHECK(cudaEventCreate(&e0)); AID_CUDA_CHECK(cudaEventCreate(&e1));
+        for (int rep = 0; rep < (ms_out ? 2 : 1); ++rep) {
+            if (stats_out_dev) AID_CUDA_CHECK(cudaMemsetAsync(stats_out_dev, 0, (size_t)B * 16 * sizeof(double), nullptr));
+            AID_CUDA_CHECK(cudaMemsetAsync(st, 0, (size_t)B * 16 * sizeof(double), nullptr));
+            AID_CUDA_CHECK(cudaEventRecord(e0, nullptr));
+            if (fused) {
+                launch_init_block(x2, wk, wk + 2 * N, wtc, gamma_dev, affine_dev, 0, gate_dev, 0, out, stats_out_dev, scratch, sms, nullptr);
+            } else {
+                TV yv = make_tv(y, B, N, F, T), xv = make_tv(x, B, N, F, T);
+                ConvEpilogue e1p; e1p.stats = st;
+                if (!launch_conv_thin(x2, wk, 1, 1, 1, yv, e1p, nullptr)) throw std::invalid_argument("thin conv not applicable");
+                launch_gn_act_tc2(yv, st, n_grp, gamma_dev, affine_dev, 0, true, pf, a, nullptr);
+                ConvEpilogue e2p; e2p.gate = gate_dev; e2p.gate_bstride = 0; e2p.alpha = kInvSqrt2; e2p.R = yv;
+                launch_conv_tc2(a, pf, wtc, B, N, F, T, 1, 1, 1, xv, e2p, sms, nullptr);
+                ConvEpilogue e3p; e3p.R = xv; e3p.alpha = kInvSqrt2; e3p.stats = stats_out_dev;
+                if (!launch_conv_thin(x2, wk + 2 * N, 1, 1, 1, out, e3p, nullptr)) throw std::invalid_argument("thin conv not applicable");
+            }
+            AID_CUDA_CHECK(cudaEventRecord(e1, nullptr));
+            AID_CUDA_CHECK(cudaGetLastError());
+            AID_CUDA_CHECK(cudaEventSynchronize(e1));
+        }
+        if (ms_out) AID_CUDA_CHECK(cudaEventElapsedTime(ms_out, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(st); cudaFree(wtc); cudaFree(wk); cudaFree(scratch);
+        if (a) cudaFree(a); if (y) cudaFree(y); if (x) cudaFree(x);
+        return AID_OK;
+    } catch (const CudaError& e) { fprintf(stderr, "aid_debug_init_block: CUDA error %s at %s:%d\n", cudaGetErrorString(e.code), e.file, e.line); return AID_ERR_CUDA; }
+    catch (const std::exception& e) { fprintf(stderr, "aid_debug_init_block: %s\n", e.what()); return AID_ERR_INVALID; }
+}
+
 /* debug / tuning: conv_tc2 pipeline profile (cycles per role, summed over CTAs; enabled by AID_TC_DEBUG bit 2048), read and cleared */
 int aid_debug_tc2_profile(uint64_t* out16) {
     if (!out16) return AID_ERR_INVALID;
@@ -1812,6 +1901,13 @@ int aid_debug_saturation(aid_handle* h, int enable, uint64_t* act_count, uint64_
         if (enable && !n.count_sat) { AID_CUDA_CHECK(cudaDeviceSynchronize()); AID_CUDA_CHECK(cudaMemset(n.d_sat, 0, sizeof(unsigned long long))); }
         n.count_sat = enable != 0;
     });
+}
+
+int aid_debug_fusion(aid_handle* h, int init_blocks, int dilated_layers) {
+    if (!h) return AID_ERR_INVALID;
+    if (init_blocks >= 0) h->net.fuse_init = init_blocks != 0;
+    if (dilated_layers >= 0) h->net.fuse_comb = dilated_layers != 0;
+    return AID_OK;
 }
 
 int aid_debug_probe(aid_handle* h, const char* name, float* dst_dev) {

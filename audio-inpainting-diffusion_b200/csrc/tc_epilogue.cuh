@@ -54,6 +54,9 @@ struct EpiArgs {
     const float* gate; long long gate_bstride;
     float alpha; double* stats;
     int Ntile, n_ntiles;
+    // RES = 1 (conv_init.cu): the residual is not loaded but synthesised from a 2-channel tensor x2 of the same [F][T] geometry,
+    // R[c] = x2[0] * c0tab[b][c] + x2[1] * c1tab[b][c]  (tables per clip, tab_bstride apart)
+    TV x2 = TV(); const float* c0tab = nullptr; const float* c1tab = nullptr; long long tab_bstride = 0;
 };
 struct EpiUnit {
     int b, nt;                      // clip, n-tile
@@ -63,7 +66,7 @@ struct EpiUnit {
     int ab; uint32_t aph;           // accumulator handshake: barrier index and phase
     bool first, last;               // first / last unit that uses this accumulator handshake (wait tmem_full / arrive tmem_empty)
 };
-template <bool CG2, int BW, int NB, int GCN, class IT, int EWARPS = 8>
+template <bool CG2, int BW, int NB, int GCN, class IT, int EWARPS = 8, int RES = 0, int GSTRIDE = 128>
 __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const int e, const int lane, const uint32_t tmem_base, float* gsm_base,
                                               double* sacc_base, uint64_t* tmem_full, uint64_t* tmem_empty) {
     constexpr int NCOLS = BW * NB;                  // columns of this warp (the n-tile split over EWARPS / 4 column groups)
@@ -77,7 +80,8 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
     const uint32_t osc = (uint32_t)p.out.sc, rsc = (uint32_t)p.R.sc;   // plane strides; a clip's tensor has < 2^31 elements
     const bool has_r = p.R.p != nullptr, has_gate = p.gate != nullptr, do_stats = p.stats != nullptr;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
-    float* gsm = gsm_base + e * 128;
+    static_assert(RES == 0 || GSTRIDE >= 3 * BW * NB, "epilogue_fast: table stride");
+    float* gsm = gsm_base + e * GSTRIDE;      // [gate NCOLS] (RES = 1: [c0 NCOLS][c1 NCOLS] behind it)
     const uint32_t gsm_addr = smem_u32(gsm);
     double* sacc = sacc_base + (e * 32 + lane);   // [k][SST threads]
     constexpr int NSQ = DIRECT ? 1 : NG;
@@ -108,6 +112,7 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
     // descriptor of the next unit (its first batch of residuals is prefetched during our last batch)
     float* n_po = nullptr; const float* n_pr = nullptr; uint32_t n_oo = 0, n_ro = 0; uint32_t n_tcol = 0, n_aph = 0; int n_b = 0, n_nt = 0, n_ab = 0;
     bool n_valid = false, n_ok = false, n_first = false, n_last = false;
+    float n_x0 = 0.f, n_x1 = 0.f;      // RES = 1: the unit's two input channels at this thread's pixel
     auto advance = [&]() {
         EpiUnit u;
         n_valid = it.next(u);
@@ -118,6 +123,10 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
         n_po = p.out.p + (long long)u.b * p.out.sb; n_oo = co0 * osc + (uint32_t)u.pix;
         n_pr = p.R.p + (long long)u.b * p.R.sb; n_ro = co0 * rsc + (uint32_t)u.pix;
         n_tcol = tq + u.tcol;
+        if constexpr (RES == 1) {
+            const float* q = p.x2.p + (long long)u.b * p.x2.sb + u.pix;
+            n_x0 = __ldg(q); n_x1 = __ldg(q + p.x2.sc);
+        }
     };
     float ra[BW], rb[BW];
     auto load_batch = [&](float (&dst)[BW], const float* src, uint32_t off) {
@@ -130,11 +139,12 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
         }
     };
     advance();
-    if (n_valid) load_batch(ra, n_pr, n_ro);
+    if (RES == 0 && n_valid) load_batch(ra, n_pr, n_ro);
     while (n_valid) {
         float* c_po = n_po; const float* c_pr = n_pr; const uint32_t c_oo = n_oo, c_ro = n_ro;
         const uint32_t c_tcol = n_tcol, c_aph = n_aph; const int c_b = n_b, c_nt = n_nt, c_ab = n_ab;
         const bool c_ok = n_ok, c_first = n_first, c_last = n_last;
+        const float c_x0 = n_x0, c_x1 = n_x1;
         advance();
         if (c_first) { mbar_wait(tmem_full + c_ab, c_aph); tc_fence_after(); }
         if (c_b != b_cur || c_nt != nt_cur) { flush_stats(); b_cur = c_b; nt_cur = c_nt; }
@@ -144,6 +154,12 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
             __syncwarp();
             for (int k = lane; k < NCOLS; k += 32)
                 gsm[k] = has_gate ? __ldg(p.gate + (long long)c_b * p.gate_bstride + c_nt * p.Ntile + cbeg + k) * gs : gs;
+            if constexpr (RES == 1) {
+                for (int k = lane; k < NCOLS; k += 32) {
+                    gsm[NCOLS + k] = __ldg(p.c0tab + (long long)c_b * p.tab_bstride + cbeg + k);
+                    gsm[2 * NCOLS + k] = __ldg(p.c1tab + (long long)c_b * p.tab_bstride + cbeg + k);
+                }
+            }
             __syncwarp();
         }
         const float m = c_ok ? 1.f : 0.f;
@@ -151,8 +167,20 @@ __device__ __forceinline__ void epilogue_fast(const EpiArgs& p, IT& it, const in
         for (int bi = 0; bi < NB; ++bi) {
             float (&cur)[BW] = (bi & 1) ? rb : ra;
             float (&nxt)[BW] = (bi & 1) ? ra : rb;
-            if (bi + 1 < NB) load_batch(nxt, c_pr, c_ro + (uint32_t)((bi + 1) * BW) * rsc);
-            else if (n_valid) load_batch(nxt, n_pr, n_ro);
+            if constexpr (RES == 1) {       // synthesise this batch's residual from the unit's two input values and the per-clip tables
+#pragma unroll
+                for (int j = 0; j < BW; j += 4) {
+                    float a0[4], a1[4];
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a0[0]), "=f"(a0[1]), "=f"(a0[2]), "=f"(a0[3]) : "r"(gsm_addr + (uint32_t)(NCOLS + bi * BW + j) * 4u));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a1[0]), "=f"(a1[1]), "=f"(a1[2]), "=f"(a1[3]) : "r"(gsm_addr + (uint32_t)(2 * NCOLS + bi * BW + j) * 4u));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cur[j + i] = fmaf(c_x0, a0[i], c_x1 * a1[i]);
+                }
+                (void)nxt;
+            } else {
+                if (bi + 1 < NB) load_batch(nxt, c_pr, c_ro + (uint32_t)((bi + 1) * BW) * rsc);
+                else if (n_valid) load_batch(nxt, n_pr, n_ro);
+            }
             uint32_t acc[BW];
             if constexpr (BW == 32) tmem_ld32_nowait(c_tcol + bi * BW, acc);
             else if constexpr (BW == 24) { tmem_ld16_nowait(c_tcol + bi * BW, acc); tmem_ld8p_nowait(c_tcol + bi * BW + 16, acc + 16); }

@@ -216,6 +216,21 @@ int aid_debug_dilated_layer(const float* x_dev, const float* w_dev, int B, int C
                             const float* affine_dev, const float* gate_dev, float alpha, int fused, float* out_dev, double* stats_out_dev,
                             float* ms_out);
 
+/* debug / parity / tuning: the init block of an encoder level in conv_mode 2 (reference unet.py:452-493 as instantiated at unet.py:673-675:
+ * dim = 2 CQT channels, one gated 1x1 residual layer, res_conv):  y = proj_in(x2);  x = (y + gate * H(GELU(GN8(y) gamma (1 + affine)))) / sqrt 2;
+ * out = (x + res_conv(x2)) / sqrt 2.  fused = 0: the five launches of the un-fused path;  fused = 1: init_block_kernel (conv_init.cu; N = 64, 96
+ * or 128, T % 128 == 0), which reads x2 once and never materialises y.  Weights in the checkpoint layout (w_in, w_res: [N][2], wH: [N][N]);
+ * gamma, affine, gate: [N].  stats_out_dev ([B][8][2] doubles, may be NULL): (sum, sumsq) of out per group.  ms_out (may be NULL): device time
+ * of a second, timed run. */
+int aid_debug_init_block(const float* x2_dev, const float* w_in_dev, const float* w_res_dev, const float* wH_dev, int B, int N, int F, int T,
+                         const float* gamma_dev, const float* affine_dev, const float* gate_dev, int fused, float* out_dev,
+                         double* stats_out_dev, float* ms_out);
+
+/* debug / parity: choose between the fused kernels of conv_mode 2 and their un-fused twins for later forwards of this handle
+ * (1 = fused, the default; 0 = un-fused; -1 = leave).  init_blocks: init_block_kernel vs five launches; dilated_layers: conv_comb_kernel /
+ * conv_comb96_kernel vs operand pass + conv_tc2_kernel. */
+int aid_debug_fusion(aid_handle* h, int init_blocks, int dilated_layers);
+
 /* Per-launch timing of the convolution kernels with CUDA events on the launching stream (bench.py's roofline).
  * aid_profile(h, 1) clears and starts recording, aid_profile(h, 0) stops; aid_profile_read sums the recorded launches
  * of one kind (0 = dilated 5x3 residual-layer convolutions on conv_tc2 / conv_tc / conv_simt, 1 = all other convolutions, 2 = fused
