@@ -203,21 +203,21 @@ __global__ void __launch_bounds__(IB_THREADS, 1) init_block_kernel(const __grid_
 }
 
 // Per clip: second moments of x2 -> group statistics of y = W_in x2 -> the transform's constants and the epilogue's coefficient tables.
-// One block per clip; fixed-order double reductions (deterministic, independent of the batch).
-__global__ void __launch_bounds__(256) init_prep_kernel(TV x2, const float* __restrict__ w_in, const float* __restrict__ w_res, const float* __restrict__ gamma,
-                                                        const float* __restrict__ affine, long long affine_bstride, int N, double npg,
-                                                        float* __restrict__ ttab, float* __restrict__ c0tab, float* __restrict__ c1tab) {
-    const int b = blockIdx.x, P = x2.F * x2.T;
+// init_moments_kernel: IB_MSEG blocks per clip, each reduces a contiguous segment (fixed-order double tree); init_prep_kernel: one block
+// per clip adds the segment sums in ascending order -- deterministic and independent of the batch.
+static constexpr int IB_MSEG = 64;
+__global__ void __launch_bounds__(256) init_moments_kernel(TV x2, double* __restrict__ part) {     // part: [B][IB_MSEG][5]
+    const int b = blockIdx.y, P = x2.F * x2.T;
+    const int seg = (P + IB_MSEG - 1) / IB_MSEG, e0 = blockIdx.x * seg, e1 = min(P, e0 + seg);
     const float* p0 = x2.p + (long long)b * x2.sb;
     const float* p1 = p0 + x2.sc;
     double m[5] = {0, 0, 0, 0, 0};
-    for (int e = threadIdx.x; e < P; e += 256) {
-        const double a = (double)p0[e], c = (double)p1[e];
+#pragma unroll 4
+    for (int e = e0 + threadIdx.x; e < e1; e += 256) {
+        const double a = (double)__ldg(p0 + e), c = (double)__ldg(p1 + e);
         m[0] += a; m[1] += c; m[2] += a * a; m[3] += a * c; m[4] += c * c;
     }
     __shared__ double red[5][256];
-    __shared__ double M[5];
-    __shared__ float inv[8];
 #pragma unroll
     for (int k = 0; k < 5; ++k) red[k][threadIdx.x] = m[k];
     __syncthreads();
@@ -227,7 +227,20 @@ __global__ void __launch_bounds__(256) init_prep_kernel(TV x2, const float* __re
             for (int k = 0; k < 5; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x < 5) M[threadIdx.x] = red[threadIdx.x][0];
+    if (threadIdx.x < 5) part[((long long)b * IB_MSEG + blockIdx.x) * 5 + threadIdx.x] = red[threadIdx.x][0];
+}
+
+__global__ void __launch_bounds__(128) init_prep_kernel(const double* __restrict__ part, const float* __restrict__ w_in, const float* __restrict__ w_res,
+                                                        const float* __restrict__ gamma, const float* __restrict__ affine, long long affine_bstride, int N,
+                                                        double npg, float* __restrict__ ttab, float* __restrict__ c0tab, float* __restrict__ c1tab) {
+    const int b = blockIdx.x;
+    __shared__ double M[5];
+    __shared__ float inv[8];
+    if (threadIdx.x < 5) {
+        double v = 0;
+        for (int s = 0; s < IB_MSEG; ++s) v += part[((long long)b * IB_MSEG + s) * 5 + threadIdx.x];
+        M[threadIdx.x] = v;
+    }
     __syncthreads();
     if (threadIdx.x < 8) {      // group g: channels [g N / 8, (g + 1) N / 8); unbiased std of y over the group, as BiasFreeGroupNorm
         const int gcn = N / 8;
@@ -242,7 +255,7 @@ __global__ void __launch_bounds__(256) init_prep_kernel(TV x2, const float* __re
         inv[threadIdx.x] = 1.f / ((float)sqrt(var) + 1e-7f);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < N; c += 256) {
+    for (int c = threadIdx.x; c < N; c += 128) {
         const float mod = affine ? (1.f + affine[(long long)b * affine_bstride + c]) : 1.f;
         const float s = gamma[c] * mod * inv[c / (N / 8)];
         float* t = ttab + ((long long)b * N + c) * 4;
@@ -253,7 +266,7 @@ __global__ void __launch_bounds__(256) init_prep_kernel(TV x2, const float* __re
 }
 
 bool init_block_supported(int N, int T) { return (N == 64 || N == 96 || N == 128) && T % 128 == 0; }
-size_t init_block_scratch_floats(int B, int N) { return (size_t)B * N * 6; }   // ttab (4) + c0tab + c1tab
+size_t init_block_scratch_floats(int B, int N) { return (size_t)B * N * 6 + (size_t)B * IB_MSEG * 5 * 2; }   // ttab (4) + c0tab + c1tab + segment moments (doubles)
 
 template <int N>
 static void launch_init_block_n(const InitArgs& p, int num_sms, cudaStream_t s) {
@@ -273,14 +286,16 @@ void launch_init_block(const TV& x2, const float* w_in, const float* w_res, cons
     if (!init_block_supported(N, x2.T) || x2.C != 2 || x2.F != out.F || x2.T != out.T) throw CudaError(cudaErrorInvalidValue, "init_block: unsupported shape", __FILE__, __LINE__);
     float* ttab = scratch; float* c0 = scratch + (size_t)B * N * 4; float* c1 = c0 + (size_t)B * N;
     const double npg = (double)(N / 8) * x2.F * x2.T;
-    init_prep_kernel<<<B, 256, 0, s>>>(x2, w_in, w_res, gamma, affine, affine_bstride, N, npg, ttab, c0, c1);
+    double* part = reinterpret_cast<double*>(c1 + (size_t)B * N);      // (B * N * 6 floats: a multiple of 8 bytes, N % 8 == 0)
+    init_moments_kernel<<<dim3(IB_MSEG, B), 256, 0, s>>>(x2, part);
+    init_prep_kernel<<<B, 128, 0, s>>>(part, w_in, w_res, gamma, affine, affine_bstride, N, npg, ttab, c0, c1);
     InitArgs p{};
     p.x2 = x2; p.out = out; p.ttab = ttab; p.c0tab = c0; p.c1tab = c1; p.gate = gate; p.gate_bstride = gate_bstride; p.w = wH; p.stats_out = stats_out;
     p.B = B; p.N = N; p.F = x2.F; p.T = x2.T; p.tiles_t = x2.T / 128; p.n_units = B * x2.F * p.tiles_t;
     if (N == 64) launch_init_block_n<64>(p, num_sms, s);
     else if (N == 96) launch_init_block_n<96>(p, num_sms, s);
     else launch_init_block_n<128>(p, num_sms, s);
-    AID_COUNT_LAUNCH(2);
+    AID_COUNT_LAUNCH(3);
 }
 
 }  // namespace aid

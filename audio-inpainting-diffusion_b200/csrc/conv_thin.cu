@@ -22,6 +22,8 @@ __device__ __forceinline__ void thin_stats_flush(float s, float q, int g, double
 template <int KF, int KT, int CIN, int PX>
 __global__ void __launch_bounds__(TH) conv_thin_in_kernel(TV a, const float* __restrict__ wp, int dil, TV out, ConvEpilogue ep) {
     constexpr int K = CIN * KF * KT;
+    // (tried: 4 output channels per pass, one LDS.128 of weights per 4 PX multiply-adds instead of one LDS per PX: no change, 58.1 vs 57.7 ms
+    // per forward at B = 8 -- the kernel is not bound by the shared-memory pipe; its stores are 512-byte runs in Cout planes 1 MB apart)
     // (tried: the multiply-accumulate on the packed fp32x2 pipe with the weights duplicated as (w, w) pairs in shared memory -- one
     // LDS.64 + PX / 2 FFMA2 per tap instead of one LDS + PX FFMA.  Measured slower, 1.89 -> 2.47 ms over the seven pyramid
     // convolutions at B = 8: twice the shared memory per block, fewer resident blocks.)
