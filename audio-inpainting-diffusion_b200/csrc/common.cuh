@@ -142,6 +142,12 @@ size_t init_block_scratch_floats(int B, int N);
 void launch_init_block(const TV& x2, const float* w_in, const float* w_res, const __half* wH, const float* gamma, const float* affine,
                        long long affine_bstride, const float* gate, long long gate_bstride, const TV& out, double* stats_out, float* scratch,
                        int num_sms, cudaStream_t s);
+// fused out block of the decoder / bottleneck (out_block.cu): one gated 1x1 layer + proj_out / res_conv N -> 2 collapsed into one pass over x
+bool out_block_supported(const TV& x, const TV& out, const TV& accum);
+size_t out_block_scratch_floats(int B, int N);
+void launch_out_block(const TV& x, const double* stats, long long n_per_group, const float* gamma, const float* affine, long long affine_bstride,
+                      const float* gate, long long gate_bstride, const float* hw, const float* pw, const float* rw, const TV& out, const TV& accum,
+                      float* scratch, cudaStream_t s);
 bool conv_comb_supported(int C, int F, int T, int dil);
 bool conv_comb_worthwhile(int B, int T, int dil, int num_sms);   // enough combs to fill the device
 // 96 channels: the fused kernel has its own weight packing (64-channel group + 32-channel group per tap); 64 channels: launch_pack_weight_tc2's

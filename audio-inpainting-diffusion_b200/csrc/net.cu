@@ -146,7 +146,7 @@ struct Net {
     // weight values clamped at finalize
     unsigned long long* d_sat = nullptr;
     bool count_sat = false;
-    bool fuse_init = true, fuse_comb = true;   // aid_debug_fusion: run the un-fused twins of conv_init.cu / conv_comb.cu (parity tests)
+    bool fuse_init = true, fuse_comb = true, fuse_out = true;   // aid_debug_fusion: run the un-fused twins of conv_init.cu / conv_comb.cu (parity tests)
     unsigned long long weight_sat = 0;
     // input-gradient path (aid_unet_forward_tape / aid_unet_backward)
     Tape tape;
@@ -550,12 +550,41 @@ static void init_block_fused(Ctx& c, const ResBlk& k, const TV& in, const TV& ou
     c.release(scratch);
 }
 
+// conv_mode 2, out blocks (N -> 2 after one gated 1x1 layer; out_block.cu): recorded as kind 1 with the block's algorithmic traffic
+static void out_block_fused(Ctx& c, const ResBlk& k, const TV& in, const TV& out, const TV& accum) {
+    float* scratch = c.allocf((long long)out_block_scratch_floats(in.B, k.N));
+    if (!c.dry()) {
+        Net& n = *c.n;
+        Net::ProfRec rec{};
+        if (n.prof) {
+            auto get = [&]() { cudaEvent_t e; if (n.prof_pool.empty()) { AID_CUDA_CHECK(cudaEventCreate(&e)); } else { e = n.prof_pool.back(); n.prof_pool.pop_back(); } return e; };
+            rec.e0 = get(); rec.e1 = get(); rec.kind = 1;
+            const double px = (double)in.B * in.F * in.T;
+            rec.flops = 2.0 * px * k.N * 4.0;
+            rec.bytes = 4.0 * px * (k.N + 2.0 + (accum.p ? 2.0 : 0.0));
+            AID_CUDA_CHECK(cudaEventRecord(rec.e0, c.s));
+        }
+        launch_out_block(in, in.stats, (long long)(k.N / 8) * in.F * in.T, k.norm[0].gamma, c.mod + k.affine[0].off, c.modstride(),
+                         c.mod + k.gate[0].off, c.modstride(), k.H[0].wp, k.proj_out.wp, k.res_conv.wp, out, accum, scratch, c.s);
+        if (n.prof) { AID_CUDA_CHECK(cudaEventRecord(rec.e1, c.s)); n.prof_recs.push_back(rec); }
+    }
+    c.release(scratch);
+}
+
 // unet.py:452-493.  `accum` (decoder out blocks, unet.py:817): out = (accum + block(x)) / sqrt(2), may alias out.
 // `bt` (taped forward, input-gradient path): every intermediate the backward needs gets its own buffer and is recorded.
 static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = nullptr, BlkTape* bt = nullptr) {
     const int B = in.B, F = in.F, T = in.T, N = k.N;
     const bool tp = bt != nullptr;
     if (in.C != k.dim || out.C != k.dim_out) throw std::runtime_error("resblock: channel mismatch");
+    {   // out blocks (N -> 2 after one gated 1x1 layer): the layer collapses into the projection, one pass over x (AID_OUT_FUSED=0: four launches)
+        static const bool env_outb = !(getenv("AID_OUT_FUSED") && atoi(getenv("AID_OUT_FUSED")) == 0);
+        if (env_outb && c.n->fuse_out && c.n->cfg.conv_mode == 2 && !tp && !c.n->count_sat && k.after && k.dim_out == 2 && k.k1x1 && k.nd == 1 && !k.attn &&
+            k.dim == N && in.stats && !out.stats && out_block_supported(in, out, accum ? *accum : TV())) {
+            out_block_fused(c, k, in, out, accum ? *accum : TV());
+            return;
+        }
+    }
     {   // encoder init blocks (2 CQT channels -> N, one gated 1x1 layer): a single fused kernel in conv_mode 2 (AID_INIT_FUSED=0: the five un-fused launches)
         static const bool env_init = !(getenv("AID_INIT_FUSED") && atoi(getenv("AID_INIT_FUSED")) == 0);
         if (env_init && c.n->fuse_init && c.n->cfg.conv_mode == 2 && !tp && !c.n->count_sat && !accum && k.k1x1 && k.dim == 2 && k.nd == 1 && !k.attn && !k.after &&
@@ -1709,6 +1738,68 @@ int aid_debug_init_block(const float* x2_dev, const float* w_in_dev, const float
     catch (const std::exception& e) { fprintf(stderr, "aid_debug_init_block: %s\n", e.what()); return AID_ERR_INVALID; }
 }
 
+/* debug / parity / tuning: an out block in conv_mode 2 (unet.py:452-493 with one 1x1 layer, proj_out and res_conv N -> 2; accum_dev != NULL:
+   out = (accum + block(x)) / sqrt 2, unet.py:817).  fused = 1: out_block.cu; fused = 0: the four un-fused launches of resblock().
+   Weights in the checkpoint layout (wH: [N][N], wP, wR: [2][N]); gamma, affine, gate: [N]. */
+int aid_debug_out_block(const float* x_dev, const float* wH_dev, const float* wP_dev, const float* wR_dev, int B, int N, int F, int T,
+                        const float* gamma_dev, const float* affine_dev, const float* gate_dev, const float* accum_dev, int fused, float* out_dev,
+                        float* ms_out) {
+    if (!x_dev || !wH_dev || !wP_dev || !wR_dev || !gamma_dev || !out_dev || N % 8 != 0) return AID_ERR_INVALID;
+    try {
+        TV x = make_tv(const_cast<float*>(x_dev), B, N, F, T), out = make_tv(out_dev, B, 2, F, T);
+        TV acc = accum_dev ? make_tv(const_cast<float*>(accum_dev), B, 2, F, T) : TV();
+        if (!conv_tc_supported(N, N, 1, 1) || (fused && !out_block_supported(x, out, acc))) throw std::invalid_argument("shape not supported");
+        int sms = 148, dev = 0;
+        AID_CUDA_CHECK(cudaGetDevice(&dev));
+        AID_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int pf = tc_pad_rows(T, 1, 1);
+        const size_t plane = (size_t)B * N * F * T;
+        double* st = nullptr; __half *wtc = nullptr, *a = nullptr; float *wk = nullptr, *scratch = nullptr, *x1 = nullptr, *t = nullptr;
+        AID_CUDA_CHECK(cudaMalloc(&st, (size_t)B * 16 * sizeof(double)));
+        AID_CUDA_CHECK(cudaMemset(st, 0, (size_t)B * 16 * sizeof(double)));
+        AID_CUDA_CHECK(cudaMalloc(&wtc, tc2_weight_halves(N, N, 1, 1) * sizeof(__half)));
+        AID_CUDA_CHECK(cudaMalloc(&wk, ((size_t)N * N + 4 * N) * sizeof(float)));
+        AID_CUDA_CHECK(cudaMalloc(&scratch, out_block_scratch_floats(B, N) * sizeof(float)));
+        if (!fused) {
+            AID_CUDA_CHECK(cudaMalloc(&a, tc2_act_halves(B, N, F, T, pf) * sizeof(__half)));
+            AID_CUDA_CHECK(cudaMalloc(&x1, plane * sizeof(float)));
+            AID_CUDA_CHECK(cudaMalloc(&t, (size_t)B * 2 * F * T * sizeof(float)));
+        }
+        float *hk = wk, *pk = wk + (size_t)N * N, *rk = pk + 2 * N;
+        launch_pack_weight_tc2(wH_dev, wtc, N, N, 1, 1, nullptr);
+        pack_conv_weight_kernel<<<64, 256>>>(wH_dev, hk, N, N, 1);
+        pack_conv_weight_kernel<<<1, 256>>>(wP_dev, pk, 2, N, 1);
+        pack_conv_weight_kernel<<<1, 256>>>(wR_dev, rk, 2, N, 1);
+        launch_group_stats(x, st, nullptr);
+        const long long n_grp = (long long)(N / 8) * F * T;
+        cudaEvent_t e0, e1; AID_CUDA_CHECK(cudaEventCreate(&e0)); AID_CUDA_CHECK(cudaEventCreate(&e1));
+        for (int rep = 0; rep < (ms_out ? 2 : 1); ++rep) {
+            if (acc.p && rep > 0) break;     // accum is read per run; with out aliasing it a second run would accumulate twice (timing: pass accum = NULL)
+            AID_CUDA_CHECK(cudaEventRecord(e0, nullptr));
+            if (fused) {
+                launch_out_block(x, st, n_grp, gamma_dev, affine_dev, 0, gate_dev, 0, hk, pk, rk, out, acc, scratch, nullptr);
+            } else {
+                TV x1v = make_tv(x1, B, N, F, T), tv = make_tv(t, B, 2, F, T);
+                launch_gn_act_tc2(x, st, n_grp, gamma_dev, affine_dev, 0, true, pf, a, nullptr);
+                ConvEpilogue e1p; e1p.gate = gate_dev; e1p.gate_bstride = 0; e1p.alpha = kInvSqrt2; e1p.R = x;
+                launch_conv_tc2(a, pf, wtc, B, N, F, T, 1, 1, 1, x1v, e1p, sms, nullptr);
+                if (!launch_conv_thin(x1v, pk, 1, 1, 1, tv, ConvEpilogue(), nullptr)) throw std::invalid_argument("thin conv not applicable");
+                ConvEpilogue e3p; e3p.R = tv;
+                if (acc.p) { e3p.alpha = 0.5f; e3p.beta = kInvSqrt2; e3p.R2 = acc; } else e3p.alpha = kInvSqrt2;
+                if (!launch_conv_thin(x, rk, 1, 1, 1, out, e3p, nullptr)) throw std::invalid_argument("thin conv not applicable");
+            }
+            AID_CUDA_CHECK(cudaEventRecord(e1, nullptr));
+            AID_CUDA_CHECK(cudaGetLastError());
+            AID_CUDA_CHECK(cudaEventSynchronize(e1));
+        }
+        if (ms_out) AID_CUDA_CHECK(cudaEventElapsedTime(ms_out, e0, e1));
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(st); cudaFree(wtc); cudaFree(wk); cudaFree(scratch);
+        if (a) cudaFree(a); if (x1) cudaFree(x1); if (t) cudaFree(t);
+        return AID_OK;
+    } catch (const CudaError& e) { fprintf(stderr, "aid_debug_out_block: CUDA error %s at %s:%d\n", cudaGetErrorString(e.code), e.file, e.line); return AID_ERR_CUDA; }
+    catch (const std::exception& e) { fprintf(stderr, "aid_debug_out_block: %s\n", e.what()); return AID_ERR_INVALID; }
+}
+
 /* debug / tuning: conv_tc2 pipeline profile (cycles per role, summed over CTAs; enabled by AID_TC_DEBUG bit 2048), read and cleared */
 int aid_debug_tc2_profile(uint64_t* out16) {
     if (!out16) return AID_ERR_INVALID;
@@ -1903,10 +1994,11 @@ int aid_debug_saturation(aid_handle* h, int enable, uint64_t* act_count, uint64_
     });
 }
 
-int aid_debug_fusion(aid_handle* h, int init_blocks, int dilated_layers) {
+int aid_debug_fusion(aid_handle* h, int init_blocks, int dilated_layers, int out_blocks) {
     if (!h) return AID_ERR_INVALID;
     if (init_blocks >= 0) h->net.fuse_init = init_blocks != 0;
     if (dilated_layers >= 0) h->net.fuse_comb = dilated_layers != 0;
+    if (out_blocks >= 0) h->net.fuse_out = out_blocks != 0;
     return AID_OK;
 }
 

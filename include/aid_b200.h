@@ -226,10 +226,20 @@ int aid_debug_init_block(const float* x2_dev, const float* w_in_dev, const float
                          const float* gamma_dev, const float* affine_dev, const float* gate_dev, int fused, float* out_dev,
                          double* stats_out_dev, float* ms_out);
 
+/* debug / parity / tuning: an out block of the decoder / bottleneck in conv_mode 2 (reference unet.py:452-493 as instantiated at unet.py:690, 719:
+ * one gated 1x1 residual layer N -> N, then proj_out and res_conv N -> 2):  x1 = (x + gate * H(GELU(GN8(x) gamma (1 + affine)))) / sqrt 2;
+ * blk = (proj_out(x1) + res_conv(x)) / sqrt 2;  out = blk, or (accum + blk) / sqrt 2 when accum_dev != NULL (unet.py:817; out_dev may alias it).
+ * fused = 0: the four launches of the un-fused path (fp16 operands for H);  fused = 1: out_block_kernel (out_block.cu), which folds
+ * P diag(gate) H into a per-clip 2 x N matrix and reads x once, all in fp32.  Weights in the checkpoint layout (wH: [N][N], wP, wR: [2][N]);
+ * gamma, affine, gate: [N].  ms_out (may be NULL, needs accum_dev == NULL): device time of a second, timed run. */
+int aid_debug_out_block(const float* x_dev, const float* wH_dev, const float* wP_dev, const float* wR_dev, int B, int N, int F, int T,
+                        const float* gamma_dev, const float* affine_dev, const float* gate_dev, const float* accum_dev, int fused, float* out_dev,
+                        float* ms_out);
+
 /* debug / parity: choose between the fused kernels of conv_mode 2 and their un-fused twins for later forwards of this handle
  * (1 = fused, the default; 0 = un-fused; -1 = leave).  init_blocks: init_block_kernel vs five launches; dilated_layers: conv_comb_kernel /
- * conv_comb96_kernel vs operand pass + conv_tc2_kernel. */
-int aid_debug_fusion(aid_handle* h, int init_blocks, int dilated_layers);
+ * conv_comb96_kernel vs operand pass + conv_tc2_kernel; out_blocks: out_block_kernel vs four launches. */
+int aid_debug_fusion(aid_handle* h, int init_blocks, int dilated_layers, int out_blocks);
 
 /* Per-launch timing of the convolution kernels with CUDA events on the launching stream (bench.py's roofline).
  * aid_profile(h, 1) clears and starts recording, aid_profile(h, 0) stops; aid_profile_read sums the recorded launches

@@ -89,18 +89,18 @@ def test_bench_batch_32_rows_equal_solo_clips(aid, cuda, nets):
     full_counted = net(x, cn)
     act, wts = net.saturation_counts(enable=False)
     assert (act, wts) == (0, 0)
-    net.set_fusion(init_blocks=False)
+    net.set_fusion(init_blocks=False, out_blocks=False)
     part = net(x, cn)                        # fused dilated layers (conv_comb.cu) over un-fused init blocks: bit-compatible with the counted run
     e = rel_l2(part, full_counted)
     print(f"fused dilated layers vs operand pass + conv_tc2, whole batch: {e:.2e}")
     assert e < 1e-6
     del part
-    net.set_fusion(init_blocks=True)
-    full = net(x, cn)                        # the bench path (fused init blocks and fused layers where they apply)
+    net.set_fusion(init_blocks=True, out_blocks=True)
+    full = net(x, cn)                        # the bench path (fused init / out blocks and fused layers where they apply)
     assert torch.isfinite(full).all()
     # init_block_kernel rounds y = proj_in(x2) differently in the last fp32 bit (tests/test_gpu_init_block.py: <= 2e-5 per block); the fp16
     # operand roundings of the ~100 layers behind it turn any such perturbation into their own noise floor, the same ~1e-4 that separates
-    # conv_mode 2 from the fp32 reference
+    # conv_mode 2 from the fp32 reference.  out_block_kernel evaluates its 1x1 layer in fp32 instead of fp16 operands (tests/test_gpu_out_block.py).
     e = rel_l2(full, full_counted)
     print(f"fused init blocks + fused dilated layers vs the un-fused path, whole batch: {e:.2e}")
     assert e < 5e-4
