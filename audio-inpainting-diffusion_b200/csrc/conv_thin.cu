@@ -6,6 +6,7 @@
 //                                N -> 8 (unet.py:322, 345)
 // Same fused epilogue as the other convolution kernels: out = alpha*(acc*gate + R) + beta*R2, group statistics.
 // Weights are the K-major packing wp[(ci*KF*KT + tap)*Cout + co] used by conv_simt.cu.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace aid {
@@ -19,15 +20,13 @@ __device__ __forceinline__ void thin_stats_flush(float s, float q, int g, double
 }
 
 // One thread = PX consecutive pixels of one row, all output channels.  grid: (ceil(F*T/PX / 256), 1, B)
-template <int KF, int KT, int CIN, int PX>
-__global__ void __launch_bounds__(TH) conv_thin_in_kernel(TV a, const float* __restrict__ wp, int dil, TV out, ConvEpilogue ep) {
+template <int KF, int KT, int CIN, int PX, int CO>
+__global__ void __launch_bounds__(TH, CO == 4 ? 3 : 1) conv_thin_in_kernel(TV a, const float* __restrict__ wp, int dil, TV out, ConvEpilogue ep) {
     constexpr int K = CIN * KF * KT;
-    // (tried: 4 output channels per pass, one LDS.128 of weights per 4 PX multiply-adds instead of one LDS per PX: no change, 58.1 vs 57.7 ms
-    // per forward at B = 8 -- the kernel is not bound by the shared-memory pipe; its stores are 512-byte runs in Cout planes 1 MB apart)
     // (tried: the multiply-accumulate on the packed fp32x2 pipe with the weights duplicated as (w, w) pairs in shared memory -- one
     // LDS.64 + PX / 2 FFMA2 per tap instead of one LDS + PX FFMA.  Measured slower, 1.89 -> 2.47 ms over the seven pyramid
     // convolutions at B = 8: twice the shared memory per block, fewer resident blocks.)
-    extern __shared__ float ws[];  // [K][Cout]
+    extern __shared__ __align__(16) float ws[];  // [K][Cout]
     __shared__ double sst[8][2];
     const int Cout = out.C, F = a.F, T = a.T, b = blockIdx.z;
     for (int i = threadIdx.x; i < K * Cout; i += TH) ws[i] = __ldg(wp + i);
@@ -65,46 +64,61 @@ __global__ void __launch_bounds__(TH) conv_thin_in_kernel(TV a, const float* __r
     const float* pr = ep.R.p ? ep.R.p + (long long)b * ep.R.sb + prow : nullptr;
     const float* pr2 = ep.R2.p ? ep.R2.p + (long long)b * ep.R2.sb + prow : nullptr;
     const float* gate = ep.gate ? ep.gate + (long long)b * ep.gate_bstride : nullptr;
+    // CO output channels per pass.  Their residual loads are all issued before the first store of the pass: R / R2 may alias out, so the
+    // compiler cannot move a load above a store by itself, and with one channel per pass every thread had a single load in flight
+    // (16-32 KB per SM, far from what HBM latency x bandwidth needs).  The weights of the CO channels are adjacent: one LDS.128 per tap.
 #pragma unroll 1
-    for (int co = 0; co < Cout; ++co) {
-        float acc[PX];
+    for (int co0 = 0; co0 < Cout; co0 += CO) {
+        float acc[CO][PX], r1[CO][PX];
 #pragma unroll
-        for (int px = 0; px < PX; ++px) acc[px] = 0.f;
+        for (int c = 0; c < CO; ++c) {
+            const int co = co0 + c;
+#pragma unroll
+            for (int px = 0; px < PX; ++px) { acc[c][px] = 0.f; r1[c][px] = 0.f; }
+            if (live && pr) {
+                if constexpr (PX == 4) { const float4 q = *reinterpret_cast<const float4*>(pr + (long long)co * ep.R.sc); r1[c][0] = q.x; r1[c][1] = q.y; r1[c][2] = q.z; r1[c][3] = q.w; }
+                else if constexpr (PX == 2) { const float2 q = *reinterpret_cast<const float2*>(pr + (long long)co * ep.R.sc); r1[c][0] = q.x; r1[c][1] = q.y; }
+                else r1[c][0] = pr[(long long)co * ep.R.sc];
+            }
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const float w = ws[k * Cout + co];
+            float w[CO];
+            if constexpr (CO == 4) { const float4 q = *reinterpret_cast<const float4*>(ws + k * Cout + co0); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+            else w[0] = ws[k * Cout + co0];
 #pragma unroll
-            for (int px = 0; px < PX; ++px) acc[px] = fmaf(w, in[k][px], acc[px]);
+            for (int c = 0; c < CO; ++c)
+#pragma unroll
+                for (int px = 0; px < PX; ++px) acc[c][px] = fmaf(w[c], in[k][px], acc[c][px]);
         }
-        if (live) {
-            const float g = gate ? gate[co] : 1.f;
-            float v[PX], r1[PX], r2[PX];
 #pragma unroll
-            for (int px = 0; px < PX; ++px) { r1[px] = 0.f; r2[px] = 0.f; }
-            if (pr) {
-                if constexpr (PX == 4) { const float4 q = *reinterpret_cast<const float4*>(pr + (long long)co * ep.R.sc); r1[0] = q.x; r1[1] = q.y; r1[2] = q.z; r1[3] = q.w; }
-                else if constexpr (PX == 2) { const float2 q = *reinterpret_cast<const float2*>(pr + (long long)co * ep.R.sc); r1[0] = q.x; r1[1] = q.y; }
-                else r1[0] = pr[(long long)co * ep.R.sc];
-            }
-            if (pr2) {
-                if constexpr (PX == 4) { const float4 q = *reinterpret_cast<const float4*>(pr2 + (long long)co * ep.R2.sc); r2[0] = q.x; r2[1] = q.y; r2[2] = q.z; r2[3] = q.w; }
-                else if constexpr (PX == 2) { const float2 q = *reinterpret_cast<const float2*>(pr2 + (long long)co * ep.R2.sc); r2[0] = q.x; r2[1] = q.y; }
-                else r2[0] = pr2[(long long)co * ep.R2.sc];
-            }
+        for (int c = 0; c < CO; ++c) {
+            const int co = co0 + c;
+            if (live) {
+                const float g = gate ? gate[co] : 1.f;
+                float v[PX], r2[PX];
 #pragma unroll
-            for (int px = 0; px < PX; ++px) {
-                const float x = (acc[px] * g + r1[px]) * ep.alpha + ep.beta * r2[px];
-                v[px] = x;
-                ssum += x; ssq = fmaf(x, x, ssq);
+                for (int px = 0; px < PX; ++px) r2[px] = 0.f;
+                if (pr2) {      // (the gradient accumulators of the backward pass; not on the forward path)
+                    if constexpr (PX == 4) { const float4 q = *reinterpret_cast<const float4*>(pr2 + (long long)co * ep.R2.sc); r2[0] = q.x; r2[1] = q.y; r2[2] = q.z; r2[3] = q.w; }
+                    else if constexpr (PX == 2) { const float2 q = *reinterpret_cast<const float2*>(pr2 + (long long)co * ep.R2.sc); r2[0] = q.x; r2[1] = q.y; }
+                    else r2[0] = pr2[(long long)co * ep.R2.sc];
+                }
+#pragma unroll
+                for (int px = 0; px < PX; ++px) {
+                    const float x = (acc[c][px] * g + r1[c][px]) * ep.alpha + ep.beta * r2[px];
+                    v[px] = x;
+                    ssum += x; ssq = fmaf(x, x, ssq);
+                }
+                float* o = po + (long long)co * out.sc;
+                if constexpr (PX == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                else if constexpr (PX == 2) *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
+                else o[0] = v[0];
             }
-            float* o = po + (long long)co * out.sc;
-            if constexpr (PX == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            else if constexpr (PX == 2) *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
-            else o[0] = v[0];
-        }
-        if (ep.stats && ((co + 1) % gcn == 0 || co + 1 == Cout)) {
-            thin_stats_flush(ssum, ssq, min(co / gcn, 7), sst);
-            ssum = 0.f; ssq = 0.f;
+            if (ep.stats && ((co + 1) % gcn == 0 || co + 1 == Cout)) {     // (warp-uniform)
+                thin_stats_flush(ssum, ssq, min(co / gcn, 7), sst);
+                ssum = 0.f; ssq = 0.f;
+            }
         }
     }
     if (ep.stats) {
@@ -124,7 +138,7 @@ struct ThinInScale { const double* stats; double n_per_group; const float* gamma
 // One thread = 4 consecutive pixels, COUT accumulators each; streams the Cin input planes once.  1x1 only, no statistics.
 template <int COUT>
 __global__ void __launch_bounds__(TH) conv_thin_out_kernel(TV a, const float* __restrict__ wp, TV out, ConvEpilogue ep, ThinInScale sc) {
-    extern __shared__ float ws[];  // [Cin][COUT]
+    extern __shared__ __align__(16) float ws[];  // [Cin][COUT]
     __shared__ float s_inv[8];
     const int Cin = a.C, F = a.F, T = a.T, b = blockIdx.z;
     if (sc.stats) {
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(TH) conv_thin_out_kernel(TV a, const float* __
 // served at 0.04 TB/s (15 % of the whole backward).  One thread = 4 consecutive pixels of one row, both output channels; per input
 // channel it reads the five tap rows (6 pixels each, served by L1 / L2 after the first row) and does 15 x 4 x 2 FMAs.
 __global__ void __launch_bounds__(TH) conv_thin_out53_kernel(TV a, const float* __restrict__ wp, TV out, ConvEpilogue ep) {
-    extern __shared__ float ws[];  // [Cin * 15][2]
+    extern __shared__ __align__(16) float ws[];  // [Cin * 15][2]
     const int Cin = a.C, F = a.F, T = a.T, b = blockIdx.z;
     for (int i = threadIdx.x; i < Cin * 30; i += TH) ws[i] = __ldg(wp + i);
     __syncthreads();
@@ -245,9 +259,17 @@ template <int KF, int KT, int CIN, int PX>
 static void launch_thin_in(const TV& a, const float* wp, int dil, const TV& out, const ConvEpilogue& ep, cudaStream_t s) {
     const size_t smem = (size_t)CIN * KF * KT * out.C * sizeof(float);
     static SmemConfig configured;
-    ensure_dyn_smem(conv_thin_in_kernel<KF, KT, CIN, PX>, smem, configured, 48 * 1024);
     const long long n = (long long)a.F * (a.T / PX);
-    conv_thin_in_kernel<KF, KT, CIN, PX><<<dim3((unsigned)((n + TH - 1) / TH), 1, a.B), TH, smem, s>>>(a, wp, dil, out, ep);
+    const dim3 grid((unsigned)((n + TH - 1) / TH), 1, a.B);
+    static const bool env_co4 = !(getenv("AID_THIN_CO4") && atoi(getenv("AID_THIN_CO4")) == 0);
+    if (out.C % 4 == 0 && env_co4) {
+        ensure_dyn_smem(conv_thin_in_kernel<KF, KT, CIN, PX, 4>, smem, configured, 48 * 1024);
+        conv_thin_in_kernel<KF, KT, CIN, PX, 4><<<grid, TH, smem, s>>>(a, wp, dil, out, ep);
+    } else {
+        static SmemConfig configured1;
+        ensure_dyn_smem(conv_thin_in_kernel<KF, KT, CIN, PX, 1>, smem, configured1, 48 * 1024);
+        conv_thin_in_kernel<KF, KT, CIN, PX, 1><<<grid, TH, smem, s>>>(a, wp, dil, out, ep);
+    }
     AID_COUNT_LAUNCH(1);
 }
 
