@@ -75,7 +75,7 @@ _SIGS = {
                                           C.POINTER(C.c_float)]),
     "aid_debug_init_block": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P, C.POINTER(C.c_float)]),
     "aid_debug_out_block": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, C.POINTER(C.c_float)]),
-    "aid_debug_fusion": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
+    "aid_debug_fusion": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "aid_profile": (C.c_int, [_P, C.c_int]),
     "aid_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "aid_debug_probe": (C.c_int, [_P, C.c_char_p, _P]),

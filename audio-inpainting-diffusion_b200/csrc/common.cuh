@@ -136,6 +136,9 @@ void launch_conv_tc2(const __half* a, int PF, const __half* wp, int B, int Cin, 
 
 // fused dilated residual layer (conv_comb.cu): normalise + modulate + GELU + operand conversion inside the convolution kernel;
 // ep.R must be x itself, out must not overlap x
+// operand of [upsample2x(up) | x] without the fp32 copy of the upsampled half (conv_tc2.cu)
+bool to_planar_tc2_up_supported(const TV& up, const TV& x);
+void launch_to_planar_tc2_up(const TV& up, const TV& x, int PF, __half* a, cudaStream_t s);
 // fused init block of an encoder level (conv_init.cu): proj_in (2 -> N) + one gated 1x1 residual layer + res_conv, one pass over the input
 bool init_block_supported(int N, int T);
 size_t init_block_scratch_floats(int B, int N);

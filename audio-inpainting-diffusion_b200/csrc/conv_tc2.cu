@@ -839,16 +839,22 @@ __device__ __forceinline__ bool ld_ok(int i, int n) { return i < n; }
 // private layout (chunk slot = (chunk + pixel / 4) & 7) is conflict free for both sides; the way out applies the operand
 // swizzle, writes 128 contiguous bytes per pixel and the zero pad pixels next to the first / last pixel of a row.
 // grid: (B * G, chunk shares), block 256.  vec == 0 (T or the view not 16-byte aligned): scalar loads, same mapping.
-template <bool COUNT>
+// UP (plain conversion only): the operand's first up.C channels are not read from x but computed on the fly as the 2x time-upsampling
+// (unet.py:128-150, the arithmetic of resample_up4_kernel) of up -- a [B][up.C][F][T / 2] tensor -- and x supplies the channels behind them:
+// the decoder's concatenation [upsampled decoder stream | encoder skip] is consumed only through this operand (proj_in / res_conv of the
+// level's main block), so its upsampled half never exists in fp32.
+struct UpSrc { const float* p; long long sb, sc; int C, T; };
+template <bool COUNT, bool UP>
 __global__ void __launch_bounds__(256, 3)
 gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, const float* __restrict__ gamma,
                   const float* __restrict__ affine, long long affine_bstride, int gelu, int PF, int G, int vec, uint32_t mg_T,
-                  __half* __restrict__ a, unsigned long long* __restrict__ sat) {
+                  __half* __restrict__ a, unsigned long long* __restrict__ sat, UpSrc up) {
     unsigned int nsat = 0;   // COUNT: values this thread clamped to the finite fp16 range (aid_debug_saturation)
     const int T = x.T, Tp = T + 2, rows_total = x.F + 2 * PF;
     const int n_src = x.F * T;                        // source pixels of one channel plane
     const int g = blockIdx.x % G, b = blockIdx.x / G;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int upC = UP ? up.C : 0, Ctot = x.C + upC;  // operand channels: [0, upC) upsampled from up, [upC, Ctot) from x
     __shared__ float s_scale[64];
     __shared__ float s_inv[8];
     __shared__ __align__(16) uint8_t tile[128 * 128];   // [pixel][slot][16 B]
@@ -863,7 +869,7 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
     if (threadIdx.x < 64) {
         float sc = 0.f;
         const int c = g * 64 + threadIdx.x;
-        if (c < x.C) {
+        if (c < Ctot) {
             sc = 1.f;
             if (stats) {
                 const float mod = affine ? (1.f + affine[b * affine_bstride + c]) : 1.f;
@@ -885,7 +891,9 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
         cu[j] = fabsf(sj) * 0.84932180028801904272f;
         chh[j] = gelu ? 8.f * sj : T2_A_SCALE * sj;
     }
-    const bool chok = g * 64 + w * 8 < x.C;      // C is a multiple of 8: a chunk is either all real or all padding
+    const int c0 = g * 64 + w * 8;               // first channel of this warp's chunk
+    const bool chok = c0 < Ctot;                 // C is a multiple of 8: a chunk is either all real or all padding
+    const bool from_up = UP && c0 < upC;         // (warp-uniform; upC is a multiple of 8)
     uint8_t* dst = reinterpret_cast<uint8_t*>(a + ((long long)b * G + g) * rows_total * Tp * 64);
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     if (PF > 0) {                                // zero rows above and below the plane, shared by the blocks of the plane
@@ -894,7 +902,7 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
         const int n16 = PF * Tp * 8;
         for (int i = blockIdx.y * 256 + threadIdx.x; i < n16; i += gridDim.y * 256) { top[i] = zero4; bot[i] = zero4; }
     }
-    const float* src = x.p + (long long)b * x.sb + (long long)(g * 64 + w * 8) * x.sc + 4 * lane;
+    const float* src = x.p + (long long)b * x.sb + (long long)(c0 - upC) * x.sc + 4 * lane;
     const int nchunk = (n_src + 127) >> 7;
     const int slot_w = ((w + lane) & 7) << 4;    // this thread's pixels are 4 lane + i: pixel / 4 == lane
     const int cp = threadIdx.x & 7;              // way out: 16-byte position inside the 128-byte pixel row
@@ -902,7 +910,42 @@ gn_act_tc2_kernel(TV x, const double* __restrict__ stats, double n_per_group, co
     for (int ch = blockIdx.y; ch < nchunk; ch += gridDim.y) {
         const int s0 = ch << 7, st = s0 + 4 * lane;
         float v[8][4];
-        if (chok) {
+        if (UP && from_up) {
+            // 4 outputs m = 4v .. 4v+3 of row f from the 6 inputs x[2v-2 .. 2v+3] of the half-rate row (reflect padded); T % 4 == 0.
+            // A lane loads its own pair x[2v], x[2v+1] (one coalesced LDG.64 per channel) and takes the pairs left and right of it from
+            // its neighbour lanes; the lanes at a row end or at the edge of the warp's 128-pixel run load theirs (six scalar loads
+            // per channel and lane cost six 256-byte L1 accesses per warp instead of one).
+            const bool act = st < n_src;
+            const uint2 ft = fast_divmod((uint32_t)(act ? st : 0), (uint32_t)T, mg_T);
+            const int vq = (int)ft.y >> 2, Th = up.T;
+            const float* row = up.p + (long long)b * up.sb + (long long)c0 * up.sc + (long long)ft.x * Th;
+            const bool own_l = act && (lane == 0 || vq == 0), own_r = act && (lane == 31 || vq == (T >> 2) - 1);
+            int il0 = 2 * vq - 2, il1 = 2 * vq - 1, ir0 = 2 * vq + 2, ir1 = 2 * vq + 3;       // reflect: -n for n < 0, 2 (Th - 1) - n for n >= Th
+            il0 = il0 < 0 ? -il0 : il0; il1 = il1 < 0 ? -il1 : il1;
+            ir0 = ir0 >= Th ? 2 * (Th - 1) - ir0 : ir0; ir1 = ir1 >= Th ? 2 * (Th - 1) - ir1 : ir1;
+            constexpr float kc[8] = {-0.01171875f, -0.03515625f, 0.11328125f, 0.43359375f, 0.43359375f, 0.11328125f, -0.03515625f, -0.01171875f};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float* rj = row + (long long)j * up.sc;
+                float2 mine = make_float2(0.f, 0.f);
+                if (act) mine = __ldg(reinterpret_cast<const float2*>(rj + 2 * vq));
+                float wv[6];
+                wv[0] = __shfl_up_sync(0xffffffffu, mine.x, 1); wv[1] = __shfl_up_sync(0xffffffffu, mine.y, 1);
+                wv[4] = __shfl_down_sync(0xffffffffu, mine.x, 1); wv[5] = __shfl_down_sync(0xffffffffu, mine.y, 1);
+                wv[2] = mine.x; wv[3] = mine.y;
+                if (own_l) { wv[0] = __ldg(rj + il0); wv[1] = __ldg(rj + il1); }
+                if (own_r) { wv[4] = __ldg(rj + ir0); wv[5] = __ldg(rj + ir1); }
+                float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    y[0] += kc[7 - 2 * q] * wv[q];
+                    y[1] += kc[6 - 2 * q] * wv[q + 1];
+                    y[2] += kc[7 - 2 * q] * wv[q + 1];
+                    y[3] += kc[6 - 2 * q] * wv[q + 2];
+                }
+                v[j][0] = act ? y[0] : 0.f; v[j][1] = act ? y[1] : 0.f; v[j][2] = act ? y[2] : 0.f; v[j][3] = act ? y[3] : 0.f;
+            }
+        } else if (chok) {
             if (vec) {
                 const bool ld = st < n_src;      // n_src is a multiple of 4 here
 #pragma unroll
@@ -1061,10 +1104,30 @@ void launch_gn_act_tc2(const TV& x, const double* stats, long long n_per_group, 
     const int shares = (int)std::min<long long>(nchunk, std::max<long long>(1, ((long long)device_sm_count() * env_bps + planes - 1) / planes));
     const int vec = (x.T % 4 == 0 && x.sb % 4 == 0 && x.sc % 4 == 0 && (reinterpret_cast<uintptr_t>(x.p) & 15) == 0) ? 1 : 0;
     dim3 grid((unsigned)planes, shares);
-    if (sat) gn_act_tc2_kernel<true><<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, vec,
-                                                       div_magic((uint32_t)x.T), a, sat);
-    else gn_act_tc2_kernel<false><<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, vec,
-                                                       div_magic((uint32_t)x.T), a, nullptr);
+    if (sat) gn_act_tc2_kernel<true, false><<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, vec,
+                                                              div_magic((uint32_t)x.T), a, sat, UpSrc{});
+    else gn_act_tc2_kernel<false, false><<<grid, 256, 0, s>>>(x, stats, (double)n_per_group, gamma, affine, affine_bstride, gelu ? 1 : 0, PF, G, vec,
+                                                              div_magic((uint32_t)x.T), a, nullptr, UpSrc{});
+    AID_COUNT_LAUNCH(1);
+}
+
+// Operand of the concatenation [upsample2x(up) | x] (channels up.C + x.C) without materialising the upsampled half: see UpSrc.
+// up: [B][Cu][F][T / 2], x: [B][Cx][F][T]; Cu % 8 == 0, T % 4 == 0, x 16-byte aligned.
+bool to_planar_tc2_up_supported(const TV& up, const TV& x) {
+    return up.B == x.B && up.F == x.F && 2 * up.T == x.T && up.C % 8 == 0 && x.C % 8 == 0 && x.T % 4 == 0 && up.T >= 4 && x.sb % 4 == 0 && x.sc % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(x.p) & 15) == 0 && (reinterpret_cast<uintptr_t>(up.p) & 7) == 0 && up.sb % 2 == 0 && up.sc % 2 == 0;
+}
+void launch_to_planar_tc2_up(const TV& up, const TV& x, int PF, __half* a, cudaStream_t s) {
+    if (!to_planar_tc2_up_supported(up, x)) throw CudaError(cudaErrorInvalidValue, "to_planar_tc2_up: unsupported shape", __FILE__, __LINE__);
+    const int rows_total = x.F + 2 * PF, Tp = x.T + 2, G = (x.C + up.C + 63) / 64;
+    static const int env_bps = getenv("AID_GN_BPS") ? atoi(getenv("AID_GN_BPS")) : 16;
+    if ((long long)rows_total * Tp >= (1ll << 31) / 128)
+        throw CudaError(cudaErrorInvalidValue, "to_planar_tc2_up: plane too large for 32-bit pixel indices", __FILE__, __LINE__);
+    const int nchunk = (x.F * x.T + 127) / 128;
+    const long long planes = (long long)x.B * G;
+    const int shares = (int)std::min<long long>(nchunk, std::max<long long>(1, ((long long)device_sm_count() * env_bps + planes - 1) / planes));
+    gn_act_tc2_kernel<false, true><<<dim3((unsigned)planes, shares), 256, 0, s>>>(x, nullptr, 1.0, nullptr, nullptr, 0, 0, PF, G, 1, div_magic((uint32_t)x.T), a, nullptr,
+                                                                                UpSrc{up.p, up.sb, up.sc, up.C, up.T});
     AID_COUNT_LAUNCH(1);
 }
 

@@ -146,7 +146,7 @@ struct Net {
     // weight values clamped at finalize
     unsigned long long* d_sat = nullptr;
     bool count_sat = false;
-    bool fuse_init = true, fuse_comb = true, fuse_out = true;   // aid_debug_fusion: run the un-fused twins of conv_init.cu / conv_comb.cu (parity tests)
+    bool fuse_init = true, fuse_comb = true, fuse_out = true, fuse_up = true;   // aid_debug_fusion: run the un-fused twins of conv_init.cu / conv_comb.cu (parity tests)
     unsigned long long weight_sat = 0;
     // input-gradient path (aid_unet_forward_tape / aid_unet_backward)
     Tape tape;
@@ -573,7 +573,9 @@ static void out_block_fused(Ctx& c, const ResBlk& k, const TV& in, const TV& out
 
 // unet.py:452-493.  `accum` (decoder out blocks, unet.py:817): out = (accum + block(x)) / sqrt(2), may alias out.
 // `bt` (taped forward, input-gradient path): every intermediate the backward needs gets its own buffer and is recorded.
-static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = nullptr, BlkTape* bt = nullptr) {
+// `up_src` (conv_mode 2, plain forward): the first up_src->C channels of `in` were NOT written; they are the 2x time-upsampling of *up_src,
+// which the operand conversion computes on the fly (launch_to_planar_tc2_up) -- the block must consume `in` only through that operand.
+static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = nullptr, BlkTape* bt = nullptr, const TV* up_src = nullptr) {
     const int B = in.B, F = in.F, T = in.T, N = k.N;
     const bool tp = bt != nullptr;
     if (in.C != k.dim || out.C != k.dim_out) throw std::runtime_error("resblock: channel mismatch");
@@ -623,8 +625,11 @@ static void resblock(Ctx& c, const ResBlk& k, TV in, TV out, const TV* accum = n
         pin_buf = c.allocf(operand_floats(k.dim, pf1, F));
         pin_hi = reinterpret_cast<__half*>(pin_buf);
         pin_lo = parts == 2 ? pin_hi + planar_halves(k.dim, pf1) : nullptr;
-        RUN(to_operand(in, pf1, pin_hi, pin_lo));
+        if (up_src) RUN(launch_to_planar_tc2_up(*up_src, slice_c(in, up_src->C, in.C - up_src->C), pf1, pin_hi, c.s));
+        else RUN(to_operand(in, pf1, pin_hi, pin_lo));
     }
+    if (up_src && !(cmode == 2 && !tp && k.dim != N && k.dim != k.dim_out && k.proj_in.wtc && k.res_conv.wtc && !k.after))
+        throw std::runtime_error("resblock: deferred upsampling needs a block that reads its input through the fp16 operand only");
     TV cur;
     if (k.dim != N) {
         TV xo = fresh();
@@ -851,24 +856,36 @@ static void forward(Ctx& c, const float* x, const float* c_noise, float* out, fl
     TV Xout = make_tv(c.allocf((long long)B * 2 * Fl * Tl), B, 2, Fl, Tl);
     resblock(c, n.mid_out, Xm, Xout, nullptr, tp ? &tp->mid_out : nullptr);
     float2* Y = (float2*)c.ar.alloc((size_t)B * n.tabs.ytotal * sizeof(float2));
+    TV up_src; float* up_hold = nullptr;           // deferred upsampling of the decoder stream (see below)
     for (int i = 0; i < no; ++i) {
         const int j = no - 1 - i, Fj = bins * (j + 1), Tj = Tof(j);
         const int dout = j == 0 ? cf.Ns[0] : cf.Ns[j - 1];
         TV Xdec = make_tv(c.allocf((long long)B * dout * Fj * Tj), B, dout, Fj, Tj); Xdec.stats = c.new_slot();
-        resblock(c, n.ups_main[i], cat[j], Xdec, nullptr, tp ? &tp->ups_main[i] : nullptr);
+        resblock(c, n.ups_main[i], cat[j], Xdec, nullptr, tp ? &tp->ups_main[i] : nullptr, up_hold ? &up_src : nullptr);
+        if (up_hold) { c.release(up_hold); up_hold = nullptr; }
         probe(c, "dec" + std::to_string(i), Xdec);
         keep(cat[j].p);
         resblock(c, n.ups_out[i], Xdec, Xout, &Xout, tp ? &tp->ups_out[i] : nullptr);
         RUN(launch_cqt_synth_oct(n.tabs, n.fft, i, slice_f(Xout, 0, bins), Y, c.s));
         if (j > 0) {
             TV Xn = slice_c(cat[j - 1], 0, cf.Ns[j - 1]);
-            RUN(launch_resample_up(slice_f(Xdec, bins, Fj - bins), Xn, c.s));
+            // conv_mode 2: the upsampled decoder stream is consumed only as the fp16 operand of the next level's proj_in / res_conv, so it is
+            // produced there, inside the operand conversion, from the half-rate rows (AID_UP_FUSED=0: resample_up + conversion of the fp32 copy)
+            static const bool env_up = !(getenv("AID_UP_FUSED") && atoi(getenv("AID_UP_FUSED")) == 0);
+            const ResBlk& nb = n.ups_main[i + 1];
+            const TV usrc = slice_f(Xdec, bins, Fj - bins);
+            if (env_up && n.fuse_up && cf.conv_mode == 2 && !tp && !n.count_sat && nb.proj_in.wtc && nb.res_conv.wtc && !nb.after && nb.dim != nb.N &&
+                nb.dim != nb.dim_out && to_planar_tc2_up_supported(usrc, slice_c(cat[j - 1], cf.Ns[j - 1], cat[j - 1].C - cf.Ns[j - 1]))) {
+                up_src = usrc; up_hold = Xdec.p;       // Xdec stays alive until the next main block has converted its input
+            } else {
+                RUN(launch_resample_up(usrc, Xn, c.s));
+            }
             TV Xo2 = make_tv(c.allocf((long long)B * 2 * (Fj - bins) * 2 * Tj), B, 2, Fj - bins, 2 * Tj);
             RUN(launch_resample_up(slice_f(Xout, bins, Fj - bins), Xo2, c.s));
             c.release(Xout.p);
             Xout = Xo2;
         }
-        keep(Xdec.p);
+        if (!up_hold) keep(Xdec.p);
     }
     c.release(Xout.p);
     RUN(launch_cqt_synth_gather(n.tabs, B, Y, spec, c.s));
@@ -1994,11 +2011,12 @@ int aid_debug_saturation(aid_handle* h, int enable, uint64_t* act_count, uint64_
     });
 }
 
-int aid_debug_fusion(aid_handle* h, int init_blocks, int dilated_layers, int out_blocks) {
+int aid_debug_fusion(aid_handle* h, int init_blocks, int dilated_layers, int out_blocks, int upsampling) {
     if (!h) return AID_ERR_INVALID;
     if (init_blocks >= 0) h->net.fuse_init = init_blocks != 0;
     if (dilated_layers >= 0) h->net.fuse_comb = dilated_layers != 0;
     if (out_blocks >= 0) h->net.fuse_out = out_blocks != 0;
+    if (upsampling >= 0) h->net.fuse_up = upsampling != 0;
     return AID_OK;
 }
 

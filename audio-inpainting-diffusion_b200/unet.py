@@ -379,12 +379,12 @@ class Unet_CQT_oct_with_attention(nn.Module):
             _lib.check(L.aid_debug_saturation(self._handle, 1 if enable else 0, C.byref(a), C.byref(w)), self._handle)
         return int(a.value), int(w.value)
 
-    def set_fusion(self, init_blocks=None, dilated_layers=None, out_blocks=None):
+    def set_fusion(self, init_blocks=None, dilated_layers=None, out_blocks=None, upsampling=None):
         """Parity tests: run the un-fused twins of the fused conv_mode 2 kernels in later forwards (aid_debug_fusion); None leaves a switch."""
         if self._handle is None:
             raise _lib.AidError("set_fusion needs an uploaded model (run a forward or _ensure_weights first)")
         enc = lambda v: -1 if v is None else int(bool(v))
-        _lib.check(_lib.lib().aid_debug_fusion(self._handle, enc(init_blocks), enc(dilated_layers), enc(out_blocks)), self._handle)
+        _lib.check(_lib.lib().aid_debug_fusion(self._handle, enc(init_blocks), enc(dilated_layers), enc(out_blocks), enc(upsampling)), self._handle)
 
     def forward_with_probes(self, inputs, sigma):
         """Debug/parity helper: forward plus the per-block intermediates {"enc<i>", "mid", "dec<i>"} (see aid_debug_probe)."""

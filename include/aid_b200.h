@@ -238,8 +238,9 @@ int aid_debug_out_block(const float* x_dev, const float* wH_dev, const float* wP
 
 /* debug / parity: choose between the fused kernels of conv_mode 2 and their un-fused twins for later forwards of this handle
  * (1 = fused, the default; 0 = un-fused; -1 = leave).  init_blocks: init_block_kernel vs five launches; dilated_layers: conv_comb_kernel /
- * conv_comb96_kernel vs operand pass + conv_tc2_kernel; out_blocks: out_block_kernel vs four launches. */
-int aid_debug_fusion(aid_handle* h, int init_blocks, int dilated_layers, int out_blocks);
+ * conv_comb96_kernel vs operand pass + conv_tc2_kernel; out_blocks: out_block_kernel vs four launches; upsampling: the decoder stream upsampled
+ * inside the operand conversion of the next level's main block vs resample_up + conversion of its fp32 copy. */
+int aid_debug_fusion(aid_handle* h, int init_blocks, int dilated_layers, int out_blocks, int upsampling);
 
 /* Per-launch timing of the convolution kernels with CUDA events on the launching stream (bench.py's roofline).
  * aid_profile(h, 1) clears and starts recording, aid_profile(h, 0) stops; aid_profile_read sums the recorded launches

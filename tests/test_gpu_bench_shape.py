@@ -90,7 +90,7 @@ def test_bench_batch_32_rows_equal_solo_clips(aid, cuda, nets):
     act, wts = net.saturation_counts(enable=False)
     assert (act, wts) == (0, 0)
     net.set_fusion(init_blocks=False, out_blocks=False)
-    part = net(x, cn)                        # fused dilated layers (conv_comb.cu) over un-fused init blocks: bit-compatible with the counted run
+    part = net(x, cn)                        # fused dilated layers (conv_comb.cu) and in-conversion upsampling over un-fused init / out blocks: bit-compatible with the counted run
     e = rel_l2(part, full_counted)
     print(f"fused dilated layers vs operand pass + conv_tc2, whole batch: {e:.2e}")
     assert e < 1e-6
