@@ -1,8 +1,14 @@
 #!/bin/bash
-# fused init block (conv_init.cu): parity at the bench shape and the oracle tests, then the bench line with and without it
+# cta_group::2 bring-up: parity tests first (bounded), then per-layer timings with the pair mode on / off
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_bench_shape.py tests/test_gpu_unet.py -m gpu -x -q -s 2>&1 | grep -v "^$" | tail -25
-echo "== bench, fused init blocks"
-timeout 600 python bench.py --steps 8 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r2_bench_initfused.json
-echo "== bench, AID_INIT_FUSED=0"
-AID_INIT_FUSED=0 timeout 600 python bench.py --steps 8 --warmup 3 2>&1 | tail -1 | tee gpurun_out/r2_bench_initunfused.json
+timeout 900 python -m pytest tests/test_gpu_tc.py -m gpu -x -q --timeout 90 --timeout-method thread -k "cta_pair or single_cta" 2>&1 | tail -15
+echo "== cg2 on"
+AID_TC2_CG2=1 AID_TC_DEBUG=4096 timeout 120 python tools/time_conv.py 3 5x3 2>&1 | tail -14
+echo "== cg2 off"
+AID_TC2_CG2=0 timeout 120 python tools/time_conv.py 3 5x3 2>&1 | tail -8
+echo "== cg2 on, nA 4"
+AID_TC2_CG2=1 AID_TC2_NA=4 timeout 120 python tools/time_conv.py 3 5x3 2>&1 | tail -8
+echo "== profile cg2 on"
+AID_TC2_CG2=1 AID_TC_DEBUG=2048 TC_SHAPES="8,64,64,4096,2;8,128,256,512,16;8,256,384,128,64" timeout 120 python tools/time_conv.py 3 2>&1 | tail -8
+echo "== profile cg2 off"
+AID_TC2_CG2=0 AID_TC_DEBUG=2048 TC_SHAPES="8,64,64,4096,2;8,128,256,512,16;8,256,384,128,64" timeout 120 python tools/time_conv.py 3 2>&1 | tail -8

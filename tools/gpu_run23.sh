@@ -1,7 +1,13 @@
 #!/bin/bash
-# fused out block: block-level parity + timing, bench-shape invariants + golden, forward time with / without
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_out_block.py -m gpu -q -s 2>&1 | grep "fused\|passed\|failed\|Error\|assert" | tail -24
-timeout 900 python -m pytest tests/test_gpu_bench_shape.py tests/test_gpu_unet.py -m gpu -x -q -s 2>&1 | grep "whole batch\|rel-L2\|passed\|failed\|Error\|assert" | head -30
-echo "== fused"; timeout 300 python tools/time_forward.py 1 8 32
-echo "== AID_OUT_FUSED=0"; AID_OUT_FUSED=0 timeout 300 python tools/time_forward.py 1 8 32
+# pure epilogue (no MMAs, no operand loads: AID_TC_DEBUG 2|4|8 = 14) of the N = 96 / N = 64 layers: what is it bound by
+S="8,96,128,2048,4;8,64,64,4096,2"
+for ew in 8 16; do
+export AID_TC2_EW=$ew
+echo "== EW $ew: epilogue only";           AID_TC_DEBUG=14 TC_SHAPES=$S timeout 120 python tools/time_conv.py 3 2>&1 | tail -2
+echo "== EW $ew: no residual";  NOR=1 AID_TC_DEBUG=14 TC_SHAPES=$S timeout 120 python tools/time_conv.py 3 2>&1 | tail -2
+echo "== EW $ew: no stats";  NOSTATS=1 AID_TC_DEBUG=14 TC_SHAPES=$S timeout 120 python tools/time_conv.py 3 2>&1 | tail -2
+echo "== EW $ew: no stores";  AID_TC_DEBUG=270 TC_SHAPES=$S timeout 120 python tools/time_conv.py 3 2>&1 | tail -2
+echo "== EW $ew: no tmem ld";  AID_TC_DEBUG=526 TC_SHAPES=$S timeout 120 python tools/time_conv.py 3 2>&1 | tail -2
+echo "== EW $ew: no stores, no residual, no stats";  NOR=1 NOSTATS=1 AID_TC_DEBUG=270 TC_SHAPES=$S timeout 120 python tools/time_conv.py 3 2>&1 | tail -2
+echo "== EW $ew: no residual, no stats";  NOR=1 NOSTATS=1 AID_TC_DEBUG=14 TC_SHAPES=$S timeout 120 python tools/time_conv.py 3 2>&1 | tail -2
+done
