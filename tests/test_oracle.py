@@ -182,3 +182,64 @@ def test_spectral_mask_oracle_and_kernel_definition_match_reference_golden(name)
     assert torch.equal(got, want)
     if name != "ragged":                      # the per-sample python loop: keep the CPU suite short
         assert rel_l2(_stft_kernel_definition(x, mask, n_fft, hop), want) < 1e-6
+
+
+# ---- the algebra behind the fused thin-end blocks (csrc/out_block.cu, csrc/conv_init.cu), checked on the oracle's resnet_block in fp64 ----
+def _block_sd(p, dim, dim_out, N, seed):
+    import math
+    sd = {}
+    if dim != N: sd[p + ".proj_in.weight"] = seeded((N, dim, 1, 1), seed + 1, 1 / math.sqrt(dim)).double()
+    if dim != dim_out: sd[p + ".res_conv.weight"] = seeded((dim_out, dim, 1, 1), seed + 2, 1 / math.sqrt(dim)).double()
+    if N != dim_out: sd[p + ".proj_out.weight"] = seeded((dim_out, N, 1, 1), seed + 3, 1 / math.sqrt(N)).double()
+    sd[p + ".H.0.weight"] = seeded((N, N, 1, 1), seed + 4, 1 / math.sqrt(N)).double()
+    sd[p + ".norm.0.gamma"] = (1 + 0.2 * seeded((1, N, 1, 1), seed + 5)).double()
+    for nm, s in (("affine", 6), ("gate", 7)):
+        sd[f"{p}.{nm}.0.weight"] = seeded((N, 256), seed + s, 0.05).double()
+        sd[f"{p}.{nm}.0.bias"] = seeded((N,), seed + s + 10, 0.5).double()
+    return sd
+
+
+def test_out_block_collapses_into_two_2xN_matrices():
+    """out_block.cu: with only two channels leaving the block, proj_out((x + gate * H a) / sqrt 2) + res_conv(x) is
+    W1 x + W2_b a with W1 = R + P / sqrt 2 and W2_b = P diag(gate_b) H / sqrt 2 (unet.py:470-493)."""
+    from oracle import unet_oracle as uo
+    N, B, Fd, T = 32, 3, 5, 24
+    sd = _block_sd("blk", N, 2, N, 300)
+    x, emb = seeded((B, N, Fd, T), 310).double(), seeded((B, 256), 311).double()
+    x[1] *= 3.0
+    ref = uo.resnet_block(sd, "blk", x, emb, dim=N, dim_out=2, num_dils=1, k1x1=True, after=True)
+    a = torch.nn.functional.gelu(uo.group_norm(x, sd["blk.norm.0.gamma"]) * (uo.linear(sd, "blk.affine.0", emb)[:, :, None, None] + 1))
+    gate = uo.linear(sd, "blk.gate.0", emb)                                                # [B, N]
+    P, R, H = sd["blk.proj_out.weight"][:, :, 0, 0], sd["blk.res_conv.weight"][:, :, 0, 0], sd["blk.H.0.weight"][:, :, 0, 0]
+    A = 1 / uo.SQRT2
+    W1 = A * (R + A * P)
+    W2 = A * A * torch.einsum("kn,bn,nm->bkm", P, gate, H)                                 # per clip
+    out = torch.einsum("kn,bnft->bkft", W1, x) + torch.einsum("bkm,bmft->bkft", W2, a)
+    assert rel_l2(out, ref) < 1e-13
+
+
+def test_init_block_statistics_follow_from_the_input_moments():
+    """conv_init.cu: y = proj_in(x2) is a linear map of two channels, so the unbiased group variance of y (unet.py:147-163) follows from the
+    five second moments of x2, and the block output is a function of the pixel's two input values plus the N x N layer."""
+    from oracle import unet_oracle as uo
+    N, B, Fd, T = 32, 2, 6, 20
+    sd = _block_sd("blk", 2, N, N, 400)
+    x2, emb = seeded((B, 2, Fd, T), 410).double(), seeded((B, 256), 411).double()
+    x2[:, 1] = 0.4 * x2[:, 1] + 0.3 * x2[:, 0]
+    ref = uo.resnet_block(sd, "blk", x2, emb, dim=2, dim_out=N, num_dils=1, k1x1=True)
+    Wi, Wr, H = sd["blk.proj_in.weight"][:, :, 0, 0], sd["blk.res_conv.weight"][:, :, 0, 0], sd["blk.H.0.weight"][:, :, 0, 0]
+    M1 = x2.sum(dim=(2, 3))                                                                # [B, 2]
+    M2 = torch.einsum("bift,bjft->bij", x2, x2)                                            # [B, 2, 2]
+    gcn, npg = N // 8, (N // 8) * Fd * T
+    s1 = torch.einsum("nc,bc->bn", Wi, M1).reshape(B, 8, gcn).sum(-1)
+    s2 = torch.einsum("ni,bij,nj->bn", Wi, M2, Wi).reshape(B, 8, gcn).sum(-1)
+    std = ((s2 - s1 * s1 / npg) / (npg - 1)).sqrt()                                        # [B, 8]
+    y = torch.einsum("nc,bcft->bnft", Wi, x2)
+    assert torch.allclose(std, y.reshape(B, 8, -1).std(-1), rtol=1e-12)
+    scale = (sd["blk.norm.0.gamma"] * (uo.linear(sd, "blk.affine.0", emb)[:, :, None, None] + 1)) / (std.repeat_interleave(gcn, 1)[:, :, None, None] + 1e-7)
+    a = torch.nn.functional.gelu(y * scale)
+    gate = uo.linear(sd, "blk.gate.0", emb)[:, :, None, None]
+    A = 1 / uo.SQRT2
+    c = Wi + uo.SQRT2 * Wr                                                                 # the epilogue's coefficient tables
+    out = 0.5 * gate * torch.einsum("nm,bmft->bnft", H, a) + 0.5 * torch.einsum("nc,bcft->bnft", c, x2)
+    assert rel_l2(out, ref) < 1e-13
